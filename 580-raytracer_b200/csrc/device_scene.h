@@ -1,0 +1,51 @@
+// Device-resident scene: what rt580_upload_scene leaves in HBM.
+//
+// Layout (64 B per triangle record, 64 B per 2-child node):
+//   PrimRec[n_leaf]   Morton-sorted primitive records, 4 x float4 each, so a leaf visit is
+//                     four coalescable 16-byte loads.  Zero-area triangles are dropped
+//                     (N == 0 => |N.d| < EPSILON always, Raytracer.cpp:365-373).
+//   BvhNode[n_leaf-1] LBVH inner nodes, both child boxes inline (Aila-Laine layout).
+//   vn / prim_material / materials / lights : shading data addressed by the reference's
+//                     primitive ORDER index (shape order, triangle order), which is also
+//                     the tie-break key for equal distances (cpp:494, cpp:513).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rt580 {
+
+#define RT_PRIM_TRIANGLE 0
+#define RT_PRIM_SPHERE   1
+#define RT_PRIM_SLOWPATH 2   // flag bit: triangle whose totalArea is outside [1e-30,1e30] -> exact division path
+
+// triangle: a = (v0.xyz, D)  b = (v1.xyz, totalArea)  c = (v2.xyz, bits(prim order))  d = (N.xyz, bits(type|flags))
+//           v* world space (cpp:353-355), N = normalize(cross(E1,E2)) (cpp:362-365),
+//           D = -dot(N, v0) (cpp:377), totalArea (cpp:389)
+// sphere  : a = (centre.xyz, radius) b = (r*r,0,0,0) c = (0,0,0, bits(prim order)) d = (0,0,0, bits(type))
+struct __align__(16) PrimRec { float4 a, b, c, d; };
+
+// kids.x / kids.y: >= 0 inner node index, < 0 leaf (~index into PrimRec)
+struct __align__(16) BvhNode {
+    float4 xy0;   // child0: lo.x hi.x lo.y hi.y
+    float4 xy1;   // child1: lo.x hi.x lo.y hi.y
+    float4 z01;   // child0 lo.z hi.z, child1 lo.z hi.z
+    int4 kids;    // child0, child1, unused, unused
+};
+
+struct DeviceScene {
+    const PrimRec* prims;
+    const BvhNode* nodes;
+    int32_t n_leaf;            // primitives in the BVH
+    int32_t n_prims;           // primitives in reference order (incl. dropped ones)
+    const float4* vn;          // [n_prims][3] object-space vertex normals (Q10); unused for spheres
+    const int32_t* prim_material;   // [n_prims]
+    const float* materials;    // [n_materials][8] Cs.rgb Ka Kd Ks Kt n
+    int32_t n_materials;
+    const int32_t* light_type; // [n_lights]
+    const float* light_f;      // [n_lights][10]
+    int32_t n_lights;
+    int32_t n_ambient;
+    int32_t n_nonambient;
+};
+
+}  // namespace rt580

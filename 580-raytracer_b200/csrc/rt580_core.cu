@@ -1,0 +1,1005 @@
+// librt580 core: context, scene upload, and the wavefront frame pipeline that replaces the
+// loop body of Raytracer::Render (Raytracer.cpp:921-932) and the recursion of
+// Raytracer::Raycast (cpp:28-129).
+//
+// The recursive reflect/refract Raycast becomes a breadth-first wavefront over "hit nodes":
+//
+//   level 0   k_trace<primary>     GenerateRay (cpp:832-858) + closest hit per pixel
+//   level L   k_shade              per hit node: shadow rays (cpp:53-81) + CalculateLocalColor,
+//                                  spawn reflection / refraction rays (cpp:94-112) into the
+//                                  ray queue with warp-ballot compaction
+//             k_trace<secondary>   closest hit of the queued rays -> level L+1 nodes
+//   order     k_subtree (bottom-up), scan over pixels, k_preorder (top-down): gives every hit
+//             node its ordinal in the reference's traversal order (scanline pixels x pre-order
+//             nodes), i.e. its position in the single AO random stream
+//   AO        k_ao                 one thread per (node, ambient light, sample): any-hit ray,
+//                                  stream position by modular exponentiation (Appendix C)
+//   resolve   k_resolve (bottom-up per level): the integer Pixel algebra of cpp:39-51 and
+//             cpp:114-128, child colour written into the parent's slot, roots into the frame
+//
+// AO never influences ray geometry (cpp:45 only scales a colour), so the tree of every pixel
+// is known before a single AO ray is traced; that is what makes the stream addressable.
+#include "../../include/rt580.h"
+#include "device_scene.h"
+#include "build.h"
+#include "trace.cuh"
+#include "shade.cuh"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <string>
+#include <mutex>
+
+using namespace rt580;
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+extern "C" const char* rt580_last_error(void) { return g_err; }
+void rt580_set_error(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); }
+#define FAIL(code, ...) do { snprintf(g_err, sizeof g_err, __VA_ARGS__); return (code); } while (0)
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return RT580_FAILURE; } } while (0)
+
+// ---------------------------------------------------------------------------------------
+// frame data
+// ---------------------------------------------------------------------------------------
+struct __align__(16) Node {       // 64 B per hit Raycast node
+    float4 P;   // hitPoint.xyz                      w: bits(primitive order index)
+    float4 N;   // RaycastHitInfo::normal.xyz        w: bits(parent node, -1 for a root)
+    float4 D;   // direction of the ray that hit     w: bits(local pixel index)
+    float4 B;   // alpha, beta, gamma (triangles)    w: bits(flags)
+};
+#define NF_SPHERE   1u            // flags bit 0: hit a sphere
+#define NF_REFR     2u            // flags bit 1: this node is its parent's refraction child
+#define NF_BOUNCE_SHIFT 8         // flags bits 8..15: bounces left at this node
+
+struct __align__(16) NodeAux {    // 32 B
+    short local[4];               // sum over non-ambient lights of lit ? CalculateLocalColor : 0
+    short refl[4];                // reflectionColor (cpp:91,103): rgb; [3] = 0 none, 1 miss(BG), 2 hit child
+    short refr[4];                // refractionColor (cpp:92,111)
+    uint32_t sub_refl;            // hit nodes in the reflection subtree
+    uint32_t sub_refr;            // hit nodes in the refraction subtree
+};
+
+struct __align__(16) QRay {       // 32 B queue entry
+    float4 o;   // origin.xyz    w: bits(parent node)
+    float4 d;   // direction.xyz w: bits(flags for the child: NF_REFR, bounces left)
+};
+
+struct FrameParams {
+    int W, H;
+    int row_first, row_step, n_rows;
+    int depth, spp, rng_mode;
+    float cam[3];
+    float inv[9];
+    const float* ndc_x;   // [W]  (float)(NDCX * aspect * tan(fov/2))   cpp:834-839, 846
+    const float* ndc_y;   // [H]  (float)(NDCY * tan(fov/2))            cpp:835, 840, 846
+};
+
+template <typename T> struct DBuf {
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n, size_t keep, cudaStream_t s) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = cap ? cap : 1024;
+        while (ncap < n) ncap = ncap + ncap / 2 + 1024;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; }
+        if (p) { cudaStreamSynchronize(s); cudaFree(p); }
+        p = q; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct rt580_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    // scene
+    DeviceScene sc{};
+    PrimRec* d_prims = nullptr; BvhNode* d_nodes = nullptr;
+    float4* d_vn = nullptr; int32_t* d_prim_material = nullptr; float* d_materials = nullptr;
+    int32_t* d_light_type = nullptr; float* d_light_f = nullptr;
+    bool have_scene = false;
+    float build_ms = 0.f; unsigned bvh_depth = 0; float pad_extent = 0.f;
+    // frame
+    FrameParams fp{};
+    int traversal = 0;
+    DBuf<float> ndc;
+    DBuf<Node> nodes; DBuf<NodeAux> aux; DBuf<QRay> queue;
+    DBuf<uint64_t> pre;            // per node: ordinal of its first AO call / n_ambient
+    DBuf<uint32_t> ao_state;       // per AO call: engine state at its first draw
+    DBuf<uint32_t> ao_hits;        // per AO call: occluded samples
+    DBuf<uint32_t> pix_hits;       // per local pixel: hit nodes
+    DBuf<uint32_t> pix_scan;       // exclusive scan of pix_hits
+    DBuf<uint32_t> scan_tmp;
+    DBuf<uint64_t> row_vals;       // per local row: hit nodes / base
+    DBuf<int16_t> fb;              // [n_rows][W][3]
+    DBuf<unsigned int> counters;   // [0] node count, [1] queue count
+    std::vector<size_t> level_off; // node index where each level starts (+ end)
+    std::vector<uint64_t> level_rays;
+    bool frame_begun = false;
+    cudaEvent_t ev[12];
+    rt580_stats stats{};
+    uint32_t launches = 0;
+    std::vector<uint64_t> last_ao_base;   // host copy for the checker
+};
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+// warp-aggregated slot allocation; must be reached by all 32 lanes of the warp
+__device__ __forceinline__ unsigned warp_alloc(unsigned int* counter, bool want) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0u) return 0u;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned base = 0u;
+    if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+}
+
+#define RT_SMEM_PRIMS 64   // scenes up to this many primitives are staged in shared memory
+
+template <int MODE /*0 bvh, 1 linear from smem, 2 linear from global*/, bool ANY>
+__device__ __forceinline__ bool trace_ray(const DeviceScene& sc, const PrimRec* smem_prims, V3 O, V3 d, float tmax,
+                                          HitRec& hit) {
+    if (MODE == 0) return traverse_bvh<ANY>(sc, O, d, tmax, hit);
+    if (MODE == 1) return traverse_linear<ANY, false>(smem_prims, sc.n_leaf, O, d, tmax, hit);
+    return traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit);
+}
+
+template <int MODE>
+__device__ __forceinline__ const PrimRec* stage_prims(const DeviceScene& sc, PrimRec* smem) {
+    if (MODE == 1) {
+        const float4* src = reinterpret_cast<const float4*>(sc.prims);
+        float4* dst = reinterpret_cast<float4*>(smem);
+        for (int i = threadIdx.x; i < sc.n_leaf * 4; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    return smem;
+}
+
+// Fill the node of a closest hit: what IntersectTriangle / IntersectSphere leave in
+// RaycastHitInfo (cpp:399-407, cpp:456-462) for the winning primitive.
+__device__ __forceinline__ void fill_node(const PrimRec* __restrict__ prims, const HitRec& h, V3 O, V3 d,
+                                          int parent, int pixel, unsigned flags, Node& nd) {
+    const PrimRec* p = prims + h.leaf;
+    const float4 ra = p->a, rb = p->b, rc = p->c, rd = p->d;
+    const V3 P = O + d * h.t;                                     // cpp:387 / cpp:456
+    V3 Nn; float al = 0.f, be = 0.f, ga = 0.f;
+    if (__float_as_int(rd.w) & RT_PRIM_SPHERE) {
+        Nn = normalize(P - mk(ra.x, ra.y, ra.z));                 // cpp:459-460
+        flags |= NF_SPHERE;
+    } else {
+        const V3 N = mk(rd.x, rd.y, rd.z);
+        const V3 v0 = mk(ra.x, ra.y, ra.z), v1 = mk(rb.x, rb.y, rb.z), v2 = mk(rc.x, rc.y, rc.z);
+        al = (0.5f * dot(cross(v1 - P, v2 - P), N)) / rb.w;       // cpp:392
+        be = (0.5f * dot(cross(P - v0, v2 - v0), N)) / rb.w;      // cpp:393
+        ga = (0.5f * dot(cross(v1 - v0, P - v0), N)) / rb.w;      // cpp:394
+        Nn = normalize(N);                                        // cpp:402-403 (normalised twice, Q25)
+    }
+    nd.P = make_float4(P.x, P.y, P.z, __int_as_float(h.prim));
+    nd.N = make_float4(Nn.x, Nn.y, Nn.z, __int_as_float(parent));
+    nd.D = make_float4(d.x, d.y, d.z, __int_as_float(pixel));
+    nd.B = make_float4(al, be, ga, __uint_as_float(flags));
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+// Closest-hit wavefront step.  PRIMARY: one thread per local pixel, ray from GenerateRay.
+// Otherwise one thread per queued reflection / refraction ray.
+template <int MODE, bool PRIMARY>
+__global__ void __launch_bounds__(128)
+k_trace(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, unsigned n_items,
+        Node* __restrict__ nodes, NodeAux* __restrict__ aux, unsigned int* __restrict__ counters,
+        uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap)
+{
+    __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
+    const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n_items;
+    V3 O = mk(0, 0, 0), d = mk(0, 0, 0);
+    int parent = -1, pixel = 0; unsigned flags = 0;
+    if (active) {
+        if (PRIMARY) {
+            pixel = (int)i;
+            const int x = pixel % fp.W, row = pixel / fp.W;
+            const int y = fp.row_first + row * fp.row_step;
+            // cpp:846-852: direction(NDCX, NDCY, -1) through the inverse view matrix, normalised
+            const float dx = __ldg(fp.ndc_x + x), dy = __ldg(fp.ndc_y + y), dz = -1.0f;
+            const V3 w = mk(fp.inv[0] * dx + fp.inv[1] * dy + fp.inv[2] * dz,
+                            fp.inv[3] * dx + fp.inv[4] * dy + fp.inv[5] * dz,
+                            fp.inv[6] * dx + fp.inv[7] * dy + fp.inv[8] * dz);      // h:227-232
+            d = normalize(w);
+            O = mk(fp.cam[0], fp.cam[1], fp.cam[2]);                                // cpp:843
+            flags = (unsigned)fp.depth << NF_BOUNCE_SHIFT;
+        } else {
+            const float4 qo = queue[i].o, qd = queue[i].d;
+            O = mk(qo.x, qo.y, qo.z); d = mk(qd.x, qd.y, qd.z);
+            parent = __float_as_int(qo.w); flags = __float_as_uint(qd.w);
+        }
+    }
+    HitRec h; bool hit = false;
+    if (active) hit = trace_ray<MODE, false>(sc, sp, O, d, 0.f, h);
+    const unsigned slot = warp_alloc(&counters[0], hit);
+    if (!active) return;
+    if (hit) {
+        if (slot >= node_cap) return;   // cannot happen: capacity is ensured before the launch
+        if (!PRIMARY) pixel = __float_as_int(nodes[parent].D.w);
+        Node nd;
+        fill_node(MODE == 1 ? sp : sc.prims, h, O, d, parent, pixel, flags, nd);
+        nodes[slot] = nd;
+        if (!PRIMARY) {
+            short* s = (flags & NF_REFR) ? aux[parent].refr : aux[parent].refl;
+            s[3] = 2;
+        }
+    } else {
+        if (PRIMARY) {
+            fb[3 * (size_t)pixel + 0] = 254; fb[3 * (size_t)pixel + 1] = 64; fb[3 * (size_t)pixel + 2] = 205;   // BG_COLOR h:597
+            pix_hits[pixel] = 0u;
+        } else {
+            short* s = (flags & NF_REFR) ? aux[parent].refr : aux[parent].refl;
+            s[0] = 254; s[1] = 64; s[2] = 205; s[3] = 1;     // cpp:30-32 at depth > 0
+        }
+    }
+}
+
+// Per hit node of one level: direct lighting with shadow rays, then spawn the children.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __restrict__ nodes,
+        NodeAux* __restrict__ aux, QRay* __restrict__ queue, unsigned int* __restrict__ counters)
+{
+    __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
+    const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
+    const unsigned i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n1;
+    bool want_refl = false, want_refr = false;
+    V3 P = mk(0, 0, 0), N = mk(0, 0, 0), D = mk(0, 0, 0);
+    unsigned flags = 0; int bounces = 0;
+    Material M{};
+    if (active) {
+        const Node nd = nodes[i];
+        P = mk(nd.P.x, nd.P.y, nd.P.z); N = mk(nd.N.x, nd.N.y, nd.N.z); D = mk(nd.D.x, nd.D.y, nd.D.z);
+        flags = __float_as_uint(nd.B.w);
+        bounces = (int)((flags >> NF_BOUNCE_SHIFT) & 0xffu);
+        const int prim = __float_as_int(nd.P.w);
+        M = load_material(sc.materials, __ldg(sc.prim_material + prim));
+        // shading normal (cpp:225-236)
+        V3 sn = N;
+        if (!(flags & NF_SPHERE)) {
+            const float4 a = __ldg(sc.vn + 3 * (size_t)prim), b = __ldg(sc.vn + 3 * (size_t)prim + 1),
+                         c = __ldg(sc.vn + 3 * (size_t)prim + 2);
+            sn = normalize((mk(a.x, a.y, a.z) * nd.B.x + mk(b.x, b.y, b.z) * nd.B.y) + mk(c.x, c.y, c.z) * nd.B.z);   // cpp:334-336
+        }
+        Pix local = mkpix(0, 0, 0);                                   // SHADOW_COLOR h:598
+        const V3 cam = mk(fp.cam[0], fp.cam[1], fp.cam[2]);
+        for (int li = 0; li < sc.n_lights; li++) {                    // cpp:39
+            const Light L = load_light(sc.light_type, sc.light_f, li);
+            if (L.type == RT580_LIGHT_AMBIENT) continue;              // handled by k_ao / k_resolve
+            V3 lightDir = mk(0, 0, 0);
+            if (L.type == RT580_LIGHT_DIRECTIONAL) lightDir = -L.direction;          // cpp:56-60
+            else if (L.type == RT580_LIGHT_POINT) lightDir = L.position - P;         // cpp:62-64
+            lightDir = normalize(lightDir);                                          // cpp:65
+            const V3 so = P + lightDir * RT_SHADOW_OFFSET;                           // cpp:67
+            const V3 sd = normalize(lightDir);                                       // Ray ctor h:431-433
+            const float distToLight = length(L.position - P);                        // cpp:71
+            HitRec sh;
+            // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
+            const float tmax = (L.type == RT580_LIGHT_POINT) ? distToLight : __int_as_float(0x7f800000);
+            const bool occluded = trace_ray<MODE, true>(sc, sp, so, sd, tmax, sh);
+            if (!occluded) local = pix_add(local, calculate_local_color(P, sn, L, M, cam));   // cpp:77
+        }
+        NodeAux a;
+        a.local[0] = local.r; a.local[1] = local.g; a.local[2] = local.b; a.local[3] = 0;
+        a.refl[0] = a.refl[1] = a.refl[2] = a.refl[3] = 0;            // Pixel() (cpp:91-92)
+        a.refr[0] = a.refr[1] = a.refr[2] = a.refr[3] = 0;
+        a.sub_refl = 0; a.sub_refr = 0;
+        aux[i] = a;
+        if (bounces > 0) { want_refl = M.Ks > 0; want_refr = M.Kt > 0; }     // cpp:87, 94, 108
+    }
+    // reflection first, refraction second: queue order is irrelevant to the result (ordinals
+    // come from the tree), compaction only keeps the next trace launch dense
+    const unsigned s0 = warp_alloc(&counters[1], want_refl);
+    const unsigned s1 = warp_alloc(&counters[1], want_refr);
+    if (!active) return;
+    const unsigned child_flags = (unsigned)(bounces - 1) << NF_BOUNCE_SHIFT;
+    if (want_refl) {
+        const V3 rdir = normalize(reflect(D, N));                             // cpp:96-97
+        const V3 ro = P + rdir * RT_SHADOW_OFFSET;                            // cpp:98
+        const V3 rd = normalize(rdir);                                        // Ray ctor
+        QRay q; q.o = make_float4(ro.x, ro.y, ro.z, __int_as_float((int)i));
+        q.d = make_float4(rd.x, rd.y, rd.z, __uint_as_float(child_flags));
+        queue[s0] = q;
+    }
+    if (want_refr) {
+        const V3 tdir = calculate_refraction(D, N, RT_IOR);                   // cpp:109
+        const V3 to = P + tdir * RT_SHADOW_OFFSET;                            // cpp:110
+        const V3 td = normalize(tdir);                                        // Ray ctor (zero stays zero, Q20)
+        QRay q; q.o = make_float4(to.x, to.y, to.z, __int_as_float((int)i));
+        q.d = make_float4(td.x, td.y, td.z, __uint_as_float(child_flags | NF_REFR));
+        queue[s1] = q;
+    }
+}
+
+// bottom-up: hit nodes per subtree -> parent slot, or per pixel for roots
+__global__ void k_subtree(unsigned n0, unsigned n1, const Node* __restrict__ nodes, NodeAux* __restrict__ aux,
+                          uint32_t* __restrict__ pix_hits)
+{
+    const unsigned i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const uint32_t cnt = 1u + aux[i].sub_refl + aux[i].sub_refr;
+    const int parent = __float_as_int(nodes[i].N.w);
+    if (parent < 0) pix_hits[__float_as_int(nodes[i].D.w)] = cnt;
+    else if (__float_as_uint(nodes[i].B.w) & NF_REFR) aux[parent].sub_refr = cnt;
+    else aux[parent].sub_refl = cnt;
+}
+
+// ---- exclusive scan of uint32 (three small kernels, 1024 elements per block) -------------
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 4
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ block_sums, unsigned n)
+{
+    __shared__ uint32_t warp_sums[SCAN_BLOCK / 32];
+    const unsigned base = (blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; sum += v[k]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < SCAN_BLOCK / 32) ? warp_sums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < SCAN_BLOCK / 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < SCAN_BLOCK / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t excl = incl - sum + (warp ? warp_sums[warp - 1] : 0u);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
+    if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = excl;
+}
+__global__ void k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ block_offs, unsigned n) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += block_offs[i / (SCAN_BLOCK * SCAN_ITEMS)];
+}
+
+// per local row: hit nodes of the row = scan[end] - scan[begin] (+ last element)
+__global__ void k_row_counts(const uint32_t* __restrict__ pix_hits, const uint32_t* __restrict__ pix_scan, int W,
+                             int n_rows, uint64_t* __restrict__ row_counts)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const size_t first = (size_t)r * W, last = first + W - 1;
+    row_counts[r] = (uint64_t)(pix_scan[last] + pix_hits[last] - pix_scan[first]);
+}
+
+// top-down: ordinal of every hit node in the reference's traversal order
+__global__ void k_preorder(unsigned n0, unsigned n1, const Node* __restrict__ nodes, const NodeAux* __restrict__ aux,
+                           const uint32_t* __restrict__ pix_scan, const uint64_t* __restrict__ row_base, FrameParams fp,
+                           int n_ambient, uint64_t* __restrict__ pre, uint32_t* __restrict__ ao_state)
+{
+    const unsigned i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const int parent = __float_as_int(nodes[i].N.w);
+    uint64_t ord;
+    if (parent < 0) {
+        const int pixel = __float_as_int(nodes[i].D.w);
+        const int row = pixel / fp.W;
+        if (fp.rng_mode == RT580_RNG_REFERENCE_LCG)
+            ord = row_base[row] + (uint64_t)(pix_scan[pixel] - pix_scan[(size_t)row * fp.W]);
+        else {
+            const uint64_t gp = (uint64_t)(fp.row_first + row * fp.row_step) * fp.W + (pixel % fp.W);
+            ord = gp * 32ull;     // counter mode: at most 31 nodes per pixel (depth <= 4)
+        }
+    } else {
+        ord = pre[parent] + 1ull;                                              // node, then reflection subtree,
+        if (__float_as_uint(nodes[i].B.w) & NF_REFR) ord += aux[parent].sub_refl;   // then refraction subtree
+    }
+    pre[i] = ord;
+    for (int a = 0; a < n_ambient; a++) {
+        const uint64_t call = ord * (uint64_t)n_ambient + a;      // one AO call per ambient light (cpp:41-45, Q6)
+        ao_state[(size_t)i * n_ambient + a] = lcg_state_at(2ull * (uint64_t)fp.spp * call);
+    }
+}
+
+// Occlusion pass: one thread per AO sample ray (cpp:320-328).
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_ao(DeviceScene sc, FrameParams fp, unsigned long long n_rays, int n_ambient, const Node* __restrict__ nodes,
+     const uint32_t* __restrict__ ao_state, uint32_t* __restrict__ ao_hits)
+{
+    __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
+    const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n_rays;
+    unsigned call = 0xffffffffu; bool hit = false;
+    if (active) {
+        call = (unsigned)(i / (unsigned)fp.spp);
+        const unsigned k = (unsigned)(i % (unsigned)fp.spp);
+        const unsigned node = call / (unsigned)n_ambient;
+        // state after the 2k draws of the preceding samples of this call: s0 * 16807^(2k)
+        uint32_t st = lcg_mulmod(__ldg(ao_state + call), lcg_state_at(2ull * k));
+        const float4 nP = __ldg(&nodes[node].P), nN = __ldg(&nodes[node].N);
+        const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
+        const V3 dir = random_in_hemisphere(st, N);                            // cpp:321
+        const V3 org = P + dir * RT_SHADOW_OFFSET;                             // cpp:322
+        const V3 rd = normalize(dir);                                          // Ray ctor h:431-433
+        HitRec h;
+        hit = trace_ray<MODE, true>(sc, sp, org, rd, __int_as_float(0x7f800000), h);   // cpp:325
+    }
+    // count the occluded samples of each AO call inside the warp, one atomic per (warp, call)
+    const unsigned peers = __match_any_sync(0xffffffffu, call);
+    const unsigned votes = __ballot_sync(0xffffffffu, hit);
+    if (active && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
+        const unsigned c = __popc(votes & peers);
+        if (c) atomicAdd(ao_hits + call, c);
+    }
+}
+
+// bottom-up per level: cpp:39-51 (ambient term), cpp:85-128 (Fresnel blend in Pixel algebra)
+__global__ void k_resolve(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __restrict__ nodes,
+                          NodeAux* __restrict__ aux, const uint32_t* __restrict__ ao_hits, int n_ambient,
+                          int16_t* __restrict__ fb)
+{
+    const unsigned i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const Node nd = nodes[i];
+    const NodeAux a = aux[i];
+    const unsigned flags = __float_as_uint(nd.B.w);
+    const int bounces = (int)((flags >> NF_BOUNCE_SHIFT) & 0xffu);
+    const Material M = load_material(sc.materials, __ldg(sc.prim_material + __float_as_int(nd.P.w)));
+    Pix local = mkpix(a.local[0], a.local[1], a.local[2]);
+    int amb = 0;
+    for (int li = 0; li < sc.n_lights; li++) {
+        if (__ldg(sc.light_type + li) != RT580_LIGHT_AMBIENT) continue;
+        const Light L = load_light(sc.light_type, sc.light_f, li);
+        V3 c = ((M.Cs * M.Ka) * L.color) * L.intensity;                              // cpp:42
+        const float occlusion = (float)ao_hits[(size_t)i * n_ambient + amb];         // cpp:326 summed
+        const float ao = 1.0f - (occlusion / (float)fp.spp);                         // cpp:329
+        c = c * ao;                                                                  // cpp:45
+        local = pix_add(local, pix_from_v3(c));                                      // cpp:48-49
+        amb++;
+    }
+    if (bounces > 0) {                                                               // cpp:87
+        float kr, kt;
+        const V3 N = mk(nd.N.x, nd.N.y, nd.N.z), D = mk(nd.D.x, nd.D.y, nd.D.z);
+        compute_fresnel(RT_IOR, N, D, kr, kt);                                       // cpp:114
+        const Pix reflC = mkpix(a.refl[0], a.refl[1], a.refl[2]);
+        const Pix refrC = mkpix(a.refr[0], a.refr[1], a.refr[2]);
+        const Pix fr = pix_muls(pix_muls(reflC, kr), M.Ks);                          // cpp:116
+        const Pix ft = pix_muls(pix_muls(refrC, kt), M.Kt);                          // cpp:117
+        float albedo = 1 - M.Ks - M.Kt;                                              // cpp:120
+        albedo = fmaxf(albedo, 0.0f);                                                // cpp:121
+        local = pix_add(pix_add(pix_muls(local, albedo), pix_muls(fr, M.Ks)), pix_muls(ft, M.Kt));   // cpp:124
+    }
+    const Pix out = pix_clamp(local);                                                // cpp:128
+    const int parent = __float_as_int(nd.N.w);
+    if (parent < 0) {
+        const size_t px = (size_t)__float_as_int(nd.D.w);
+        fb[3 * px] = out.r; fb[3 * px + 1] = out.g; fb[3 * px + 2] = out.b;          // cpp:925
+    } else {
+        short* s = (flags & NF_REFR) ? aux[parent].refr : aux[parent].refl;
+        s[0] = out.r; s[1] = out.g; s[2] = out.b;
+    }
+}
+
+// checker kernels: arbitrary rays
+template <int MODE, bool ANY>
+__global__ void __launch_bounds__(128)
+k_trace_rays(DeviceScene sc, long long n, const float* __restrict__ org, const float* __restrict__ dir,
+             const float* __restrict__ tmax, int32_t* __restrict__ prim_out, float* __restrict__ t_out,
+             uint8_t* __restrict__ hit_out)
+{
+    __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
+    const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 O = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    HitRec h;
+    const bool hit = trace_ray<MODE, ANY>(sc, sp, O, d, ANY ? tmax[i] : 0.f, h);
+    if (ANY) hit_out[i] = hit ? 1 : 0;
+    else { prim_out[i] = hit ? h.prim : -1; t_out[i] = hit ? h.t : 0.f; }
+}
+
+__global__ void k_hemisphere(float nx, float ny, float nz, unsigned long long step, int n, float* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t st = lcg_state_at(step);
+    for (int k = 0; k < n; k++) {
+        const V3 v = random_in_hemisphere(st, mk(nx, ny, nz));
+        out[3 * k] = v.x; out[3 * k + 1] = v.y; out[3 * k + 2] = v.z;
+    }
+}
+__global__ void k_powf(long long n, const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = powf_glibc(x[i], y[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static int pick_mode(const rt580_context* c, int traversal) {
+    if (traversal == RT580_TRAVERSAL_BVH) return 0;
+    if (traversal == RT580_TRAVERSAL_BRUTE_FORCE) return c->sc.n_leaf <= RT_SMEM_PRIMS ? 1 : 2;
+    return c->sc.n_leaf <= RT_SMEM_PRIMS ? 1 : 0;     // AUTO
+}
+
+extern "C" int rt580_create(int device, rt580_context** out)
+{
+    if (!out) FAIL(RT580_INVALID_ARG, "rt580_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        FAIL(RT580_FAILURE, "rt580_create: no CUDA device (%s); this library has no CPU fallback",
+             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) FAIL(RT580_INVALID_ARG, "rt580_create: device %d out of range [0,%d)", device, n);
+    CU(cudaSetDevice(device));
+    rt580_context* c = new rt580_context();
+    c->device = device;
+    CU(cudaGetDeviceProperties(&c->prop, device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+    *out = c;
+    return RT580_SUCCESS;
+}
+
+static void free_scene(rt580_context* c) {
+    cudaFree(c->d_prims); cudaFree(c->d_nodes); cudaFree(c->d_vn); cudaFree(c->d_prim_material);
+    cudaFree(c->d_materials); cudaFree(c->d_light_type); cudaFree(c->d_light_f);
+    c->d_prims = nullptr; c->d_nodes = nullptr; c->d_vn = nullptr; c->d_prim_material = nullptr;
+    c->d_materials = nullptr; c->d_light_type = nullptr; c->d_light_f = nullptr;
+    c->have_scene = false;
+}
+
+extern "C" void rt580_destroy(rt580_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    c->ndc.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
+    c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
+    c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
+    for (auto& ev : c->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int rt580_device_info(rt580_context* c, int32_t* sm_count, int32_t* sm_clock_mhz, uint64_t* hbm_bytes)
+{
+    if (!c) FAIL(RT580_INVALID_ARG, "rt580_device_info: ctx is NULL");
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (sm_clock_mhz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device); *sm_clock_mhz = khz / 1000; }
+    if (hbm_bytes) *hbm_bytes = (uint64_t)c->prop.totalGlobalMem;
+    return RT580_SUCCESS;
+}
+
+template <typename T> static cudaError_t upload(T** dst, const void* src, size_t count, cudaStream_t s) {
+    *dst = nullptr;
+    cudaError_t e = cudaMalloc((void**)dst, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (count) e = cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    return e;
+}
+
+extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
+{
+    if (!c || !s) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: NULL argument");
+    if (s->n_tris < 0 || s->n_spheres < 0 || s->n_prims != s->n_tris + s->n_spheres || s->n_lights < 0 || s->n_materials < 0)
+        FAIL(RT580_INVALID_ARG, "rt580_upload_scene: inconsistent counts");
+    if (s->n_prims > 0x7ffffff0ll) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: too many primitives");
+    CU(cudaSetDevice(c->device));
+    free_scene(c);
+    cudaStream_t st = c->stream;
+    float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr, *sph = nullptr; int32_t *tprim = nullptr, *sprim = nullptr;
+    CU(upload(&v0, s->tri_v0, (size_t)s->n_tris, st));
+    CU(upload(&v1, s->tri_v1, (size_t)s->n_tris, st));
+    CU(upload(&v2, s->tri_v2, (size_t)s->n_tris, st));
+    CU(upload(&tprim, s->tri_prim, (size_t)s->n_tris, st));
+    CU(upload(&sph, s->sph_center_r, (size_t)s->n_spheres, st));
+    CU(upload(&sprim, s->sph_prim, (size_t)s->n_spheres, st));
+    // shading tables addressed by primitive order index
+    std::vector<float> vn((size_t)s->n_prims * 12, 0.f);
+    std::vector<int32_t> pm((size_t)s->n_prims, 0);
+    for (int64_t t = 0; t < s->n_tris; t++) {
+        const int32_t p = s->tri_prim[t];
+        if (p < 0 || p >= s->n_prims) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: tri_prim[%lld] out of range", (long long)t);
+        memcpy(&vn[(size_t)p * 12 + 0], s->tri_n0 + 4 * t, 16);
+        memcpy(&vn[(size_t)p * 12 + 4], s->tri_n1 + 4 * t, 16);
+        memcpy(&vn[(size_t)p * 12 + 8], s->tri_n2 + 4 * t, 16);
+        pm[p] = s->tri_material[t];
+    }
+    for (int64_t k = 0; k < s->n_spheres; k++) {
+        const int32_t p = s->sph_prim[k];
+        if (p < 0 || p >= s->n_prims) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: sph_prim[%lld] out of range", (long long)k);
+        pm[p] = s->sph_material[k];
+    }
+    for (auto m : pm) if (m < 0 || m >= s->n_materials) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: material index out of range");
+    CU(upload(&c->d_vn, vn.data(), (size_t)s->n_prims * 3, st));
+    CU(upload(&c->d_prim_material, pm.data(), (size_t)s->n_prims, st));
+    CU(upload(&c->d_materials, s->materials, (size_t)s->n_materials * 8, st));
+    CU(upload(&c->d_light_type, s->light_type, (size_t)s->n_lights, st));
+    CU(upload(&c->d_light_f, s->light_f, (size_t)s->n_lights * 10, st));
+
+    BuildInput in{};
+    in.tri_v0 = v0; in.tri_v1 = v1; in.tri_v2 = v2; in.tri_prim = tprim; in.n_tris = s->n_tris;
+    in.sph = sph; in.sph_prim = sprim; in.n_spheres = s->n_spheres;
+    // ray origins never leave the hull of the scene and the camera (bvh_build.cu header)
+    for (int k = 0; k < 3; k++) in.origin_hint[k] = s->origin_hint[k];
+    BuildOutput bo{};
+    CU(cudaEventRecord(c->ev[10], st));
+    char err[256] = "";
+    if (!build_bvh(in, &bo, st, err, sizeof err)) FAIL(RT580_FAILURE, "rt580_upload_scene: %s", err);
+    CU(cudaEventRecord(c->ev[11], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventElapsedTime(&c->build_ms, c->ev[10], c->ev[11]));
+    cudaFree(v0); cudaFree(v1); cudaFree(v2); cudaFree(tprim); cudaFree(sph); cudaFree(sprim);
+    if (bo.max_depth > RT_STACK_SIZE)
+        FAIL(RT580_FAILURE, "rt580_upload_scene: LBVH depth %u exceeds the traversal stack (%d)", bo.max_depth, RT_STACK_SIZE);
+    c->d_prims = bo.prims; c->d_nodes = bo.nodes; c->bvh_depth = bo.max_depth; c->pad_extent = bo.extent;
+    c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_prims = (int32_t)s->n_prims;
+    c->sc.vn = c->d_vn; c->sc.prim_material = c->d_prim_material; c->sc.materials = c->d_materials;
+    c->sc.n_materials = s->n_materials; c->sc.light_type = c->d_light_type; c->sc.light_f = c->d_light_f;
+    c->sc.n_lights = s->n_lights;
+    c->sc.n_ambient = 0;
+    for (int i = 0; i < s->n_lights; i++) if (s->light_type[i] == RT580_LIGHT_AMBIENT) c->sc.n_ambient++;
+    c->sc.n_nonambient = s->n_lights - c->sc.n_ambient;
+    c->have_scene = true;
+    c->frame_begun = false;
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_build_ms(rt580_context* c, float* ms) {
+    if (!c || !ms) FAIL(RT580_INVALID_ARG, "rt580_build_ms: NULL argument");
+    *ms = c->build_ms;
+    return RT580_SUCCESS;
+}
+
+static inline unsigned nblk(unsigned long long n, unsigned b) { return (unsigned)((n + b - 1) / b); }
+
+template <int MODE> static void launch_trace(rt580_context* c, bool primary, unsigned n_items, unsigned node_cap) {
+    if (primary)
+        k_trace<MODE, true><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, c->nodes.p, c->aux.p,
+                                                                      c->counters.p, c->pix_hits.p, c->fb.p, node_cap);
+    else
+        k_trace<MODE, false><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, c->nodes.p, c->aux.p,
+                                                                       c->counters.p, c->pix_hits.p, c->fb.p, node_cap);
+    c->launches++;
+}
+template <int MODE> static void launch_shade(rt580_context* c, unsigned n0, unsigned n1) {
+    k_shade<MODE><<<nblk(n1 - n0, 128), 128, 0, c->stream>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p);
+    c->launches++;
+}
+template <int MODE> static void launch_ao(rt580_context* c, unsigned long long n_rays) {
+    k_ao<MODE><<<nblk(n_rays, 128), 128, 0, c->stream>>>(c->sc, c->fp, n_rays, c->sc.n_ambient, c->nodes.p, c->ao_state.p, c->ao_hits.p);
+    c->launches++;
+}
+#define DISPATCH_MODE(mode, fn, ...) do { if ((mode) == 0) fn<0>(__VA_ARGS__); else if ((mode) == 1) fn<1>(__VA_ARGS__); else fn<2>(__VA_ARGS__); } while (0)
+
+static int exclusive_scan_u32(rt580_context* c, const uint32_t* in, uint32_t* out, unsigned n)
+{
+    // recursive block scan; levels live in scan_tmp
+    const unsigned per = SCAN_BLOCK * SCAN_ITEMS;
+    std::vector<unsigned> sizes; sizes.push_back(n);
+    while (sizes.back() > 1) sizes.push_back(nblk(sizes.back(), per));
+    size_t total = 0; for (size_t l = 1; l < sizes.size(); l++) total += 2 * (size_t)sizes[l];
+    CU(c->scan_tmp.ensure(total + 2, 0, c->stream));
+    std::vector<uint32_t*> sums(sizes.size(), nullptr), offs(sizes.size(), nullptr);
+    uint32_t* p = c->scan_tmp.p;
+    for (size_t l = 1; l < sizes.size(); l++) { sums[l] = p; p += sizes[l]; offs[l] = p; p += sizes[l]; }
+    const uint32_t* src = in; uint32_t* dst = out;
+    // up-sweep
+    for (size_t l = 0; l + 1 < sizes.size(); l++) {
+        k_scan_block<<<sizes[l + 1], SCAN_BLOCK, 0, c->stream>>>(src, dst, sums[l + 1], sizes[l]); c->launches++;
+        src = sums[l + 1]; dst = offs[l + 1];
+    }
+    if (sizes.size() == 1) { CU(cudaMemsetAsync(out, 0, sizeof(uint32_t) * n, c->stream)); return RT580_SUCCESS; }
+    // the top level has one element: its exclusive scan is 0
+    CU(cudaMemsetAsync(offs.back(), 0, sizeof(uint32_t), c->stream));
+    // down-sweep
+    for (size_t l = sizes.size() - 1; l >= 1; l--) {
+        uint32_t* target = (l == 1) ? out : offs[l - 1];
+        k_scan_add<<<nblk(sizes[l - 1], 256), 256, 0, c->stream>>>(target, offs[l], sizes[l - 1]); c->launches++;
+    }
+    return RT580_SUCCESS;
+}
+
+static int read_counter(rt580_context* c, int which, unsigned* out) {
+    CU(cudaMemcpyAsync(out, c->counters.p + which, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p, uint64_t* row_hit_nodes)
+{
+    if (!c || !p) FAIL(RT580_INVALID_ARG, "rt580_render_begin: NULL argument");
+    if (!c->have_scene) FAIL(RT580_FAILURE, "rt580_render_begin: no scene uploaded");
+    if (p->width <= 0 || p->height <= 0) FAIL(RT580_INVALID_ARG, "rt580_render_begin: bad resolution %dx%d", p->width, p->height);
+    if (p->depth < 0 || p->depth > 4) FAIL(RT580_INVALID_ARG, "rt580_render_begin: depth %d outside [0,4] (reference: 4, h:563)", p->depth);
+    if (p->ao_spp < 1 || p->ao_spp > 65536) FAIL(RT580_INVALID_ARG, "rt580_render_begin: ao_spp %d outside [1,65536]", p->ao_spp);
+    if (p->rng_mode != RT580_RNG_REFERENCE_LCG && p->rng_mode != RT580_RNG_COUNTER) FAIL(RT580_INVALID_ARG, "rt580_render_begin: bad rng_mode");
+    if (p->traversal < 0 || p->traversal > 2) FAIL(RT580_INVALID_ARG, "rt580_render_begin: bad traversal");
+    for (int k = 0; k < 3; k++)
+        if (!(fabsf(p->camera_from[k]) + 1.0f <= c->pad_extent))
+            FAIL(RT580_INVALID_ARG, "rt580_render_begin: camera_from[%d]=%g lies outside the extent (%g) the BVH boxes were padded for; "
+                 "pass the camera as rt580_flat_scene::origin_hint", k, p->camera_from[k], c->pad_extent);
+    CU(cudaSetDevice(c->device));
+    FrameParams& fp = c->fp;
+    fp.W = p->width; fp.H = p->height;
+    if (p->n_rows == 0) { fp.row_first = 0; fp.row_step = 1; fp.n_rows = p->height; }
+    else { fp.row_first = p->row_first; fp.row_step = p->row_step; fp.n_rows = p->n_rows; }
+    if (fp.n_rows < 0 || fp.row_step < 1 || fp.row_first < 0 || (fp.n_rows > 0 && fp.row_first + (long long)(fp.n_rows - 1) * fp.row_step >= fp.H))
+        FAIL(RT580_INVALID_ARG, "rt580_render_begin: rows (first %d step %d count %d) outside the %d-row frame", fp.row_first, fp.row_step, fp.n_rows, fp.H);
+    const unsigned long long npix64 = (unsigned long long)fp.n_rows * fp.W;
+    if (npix64 > 0x7fffff00ull) FAIL(RT580_INVALID_ARG, "rt580_render_begin: too many pixels for one context");
+    const unsigned npix = (unsigned)npix64;
+    fp.depth = p->depth; fp.spp = p->ao_spp; fp.rng_mode = p->rng_mode;
+    memcpy(fp.cam, p->camera_from, sizeof fp.cam);
+    memcpy(fp.inv, p->inv_view3x3, sizeof fp.inv);
+    c->traversal = p->traversal;
+    const int mode = pick_mode(c, p->traversal);
+    cudaStream_t st = c->stream;
+    c->launches = 0;
+    memset(&c->stats, 0, sizeof c->stats);
+
+    // primary-ray tables: cpp:834-846 evaluated in double on the host, exactly as the reference
+    // does per pixel (tan is libm's; hoisting is bit-exact because it is a pure function of x / y)
+    {
+        std::vector<float> t((size_t)fp.W + fp.H);
+        const float half = p->fov_degrees / 2;
+        const float rad = (float)(half * (3.14159265 / 180));                 // ToRadian h:581-583
+        const float aspect = (float)fp.W / (float)fp.H;                       // cpp:836
+        for (int x = 0; x < fp.W; x++) { double n = (2.0 * x) / fp.W - 1; n *= aspect * tan(rad); t[x] = (float)n; }
+        for (int y = 0; y < fp.H; y++) { double n = 1 - (2.0 * y) / fp.H; n *= tan(rad); t[(size_t)fp.W + y] = (float)n; }
+        CU(c->ndc.ensure(t.size(), 0, st));
+        CU(cudaMemcpyAsync(c->ndc.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        fp.ndc_x = c->ndc.p; fp.ndc_y = c->ndc.p + fp.W;
+    }
+    CU(c->counters.ensure(4, 0, st));
+    CU(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned), st));
+    CU(c->pix_hits.ensure(npix + 1, 0, st));
+    CU(c->pix_scan.ensure(npix + 1, 0, st));
+    CU(c->fb.ensure((size_t)npix * 3 + 1, 0, st));
+    CU(c->nodes.ensure(npix + 1, 0, st));
+    CU(c->aux.ensure(npix + 1, 0, st));
+    CU(c->row_vals.ensure((size_t)fp.n_rows + 1, 0, st));
+
+    CU(cudaEventRecord(c->ev[0], st));
+    c->level_off.clear(); c->level_rays.clear();
+    c->level_off.push_back(0);
+    unsigned n_nodes = 0;
+    if (npix) {
+        DISPATCH_MODE(mode, launch_trace, c, true, npix, (unsigned)c->nodes.cap);
+        if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
+    }
+    c->level_rays.push_back(npix);
+    c->level_off.push_back(n_nodes);
+    for (int L = 0; L <= fp.depth; L++) {
+        const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
+        if (n1 == n0) break;
+        CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
+        if (L < fp.depth) CU(c->queue.ensure(2 * (size_t)(n1 - n0), 0, st));
+        else CU(c->queue.ensure(1, 0, st));
+        DISPATCH_MODE(mode, launch_shade, c, n0, n1);
+        if (L == fp.depth) break;
+        unsigned q = 0;
+        if (read_counter(c, 1, &q)) return RT580_FAILURE;
+        if (q == 0) break;
+        CU(c->nodes.ensure((size_t)n1 + q, n1, st));
+        CU(c->aux.ensure((size_t)n1 + q, n1, st));
+        DISPATCH_MODE(mode, launch_trace, c, false, q, (unsigned)c->nodes.cap);
+        if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
+        c->level_rays.push_back(q);
+        c->level_off.push_back(n_nodes);
+    }
+    CU(cudaEventRecord(c->ev[1], st));
+    // order: subtree sizes bottom-up, per-pixel exclusive scan, per-row totals
+    const int n_levels = (int)c->level_off.size() - 1;
+    for (int L = n_levels - 1; L >= 0; L--) {
+        const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
+        if (n1 > n0) { k_subtree<<<nblk(n1 - n0, 256), 256, 0, st>>>(n0, n1, c->nodes.p, c->aux.p, c->pix_hits.p); c->launches++; }
+    }
+    if (npix) {
+        if (exclusive_scan_u32(c, c->pix_hits.p, c->pix_scan.p, npix)) return RT580_FAILURE;
+        k_row_counts<<<nblk(fp.n_rows, 128), 128, 0, st>>>(c->pix_hits.p, c->pix_scan.p, fp.W, fp.n_rows, c->row_vals.p); c->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev[6], st));
+    std::vector<uint64_t> rows((size_t)fp.n_rows);
+    if (fp.n_rows) CU(cudaMemcpyAsync(rows.data(), c->row_vals.p, sizeof(uint64_t) * fp.n_rows, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (row_hit_nodes) for (int r = 0; r < fp.n_rows; r++) row_hit_nodes[r] = rows[r];
+    c->frame_begun = true;
+    // ray accounting: one ray == one IntersectScene call of the reference (cpp:30, cpp:75, cpp:325)
+    c->stats.rays_primary = npix;
+    for (size_t l = 1; l < c->level_rays.size(); l++) c->stats.rays_secondary += c->level_rays[l];
+    c->stats.hit_nodes = n_nodes;
+    c->stats.rays_shadow = (uint64_t)n_nodes * c->sc.n_nonambient;
+    c->stats.ao_calls = (uint64_t)n_nodes * c->sc.n_ambient;
+    c->stats.rays_ao = c->stats.ao_calls * (uint64_t)fp.spp;
+    c->stats.bvh_max_depth = c->bvh_depth;
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base, int16_t* fb_out, int fb_on_device,
+                                   rt580_stats* stats)
+{
+    if (!c) FAIL(RT580_INVALID_ARG, "rt580_render_finish: ctx is NULL");
+    if (!c->frame_begun) FAIL(RT580_FAILURE, "rt580_render_finish: no frame begun");
+    CU(cudaSetDevice(c->device));
+    FrameParams& fp = c->fp;
+    cudaStream_t st = c->stream;
+    const int mode = pick_mode(c, c->traversal);
+    const unsigned npix = (unsigned)fp.n_rows * fp.W;
+    const unsigned n_nodes = (unsigned)c->level_off.back();
+    const int n_amb = c->sc.n_ambient;
+    const int n_levels = (int)c->level_off.size() - 1;
+    if (fp.rng_mode == RT580_RNG_REFERENCE_LCG && !row_ao_base && fp.n_rows)
+        FAIL(RT580_INVALID_ARG, "rt580_render_finish: row_ao_base required in RT580_RNG_REFERENCE_LCG mode");
+    if (row_ao_base && fp.n_rows)
+        CU(cudaMemcpyAsync(c->row_vals.p, row_ao_base, sizeof(uint64_t) * fp.n_rows, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c->ev[2], st));
+    const unsigned long long n_calls = (unsigned long long)n_nodes * n_amb;
+    CU(c->pre.ensure((size_t)n_nodes + 1, 0, st));
+    CU(c->ao_state.ensure((size_t)n_calls + 1, 0, st));
+    CU(c->ao_hits.ensure((size_t)n_calls + 1, 0, st));
+    CU(cudaMemsetAsync(c->ao_hits.p, 0, sizeof(uint32_t) * (n_calls + 1), st));
+    for (int L = 0; L < n_levels; L++) {
+        const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
+        if (n1 > n0) {
+            k_preorder<<<nblk(n1 - n0, 128), 128, 0, st>>>(n0, n1, c->nodes.p, c->aux.p, c->pix_scan.p, c->row_vals.p, fp, n_amb,
+                                                          c->pre.p, c->ao_state.p);
+            c->launches++;
+        }
+    }
+    CU(cudaEventRecord(c->ev[3], st));
+    const unsigned long long n_ao = n_calls * (unsigned long long)fp.spp;
+    if (n_ao > 0xffffffffull * 128ull) FAIL(RT580_FAILURE, "rt580_render_finish: AO ray count exceeds one launch");
+    if (n_ao) DISPATCH_MODE(mode, launch_ao, c, n_ao);
+    CU(cudaEventRecord(c->ev[4], st));
+    for (int L = n_levels - 1; L >= 0; L--) {
+        const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
+        if (n1 > n0) {
+            k_resolve<<<nblk(n1 - n0, 128), 128, 0, st>>>(c->sc, fp, n0, n1, c->nodes.p, c->aux.p, c->ao_hits.p, n_amb, c->fb.p);
+            c->launches++;
+        }
+    }
+    CU(cudaEventRecord(c->ev[5], st));
+    if (fb_out && npix)
+        CU(cudaMemcpyAsync(fb_out, c->fb.p, sizeof(int16_t) * 3 * (size_t)npix,
+                           fb_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.ms_structure = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.ms_order = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[6]); c->stats.ms_order += ms;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.ms_ao = ms; c->stats.ms_ao_kernel = ms;
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->stats.ms_resolve = ms;
+    c->stats.ms_total = c->stats.ms_structure + c->stats.ms_order + c->stats.ms_ao + c->stats.ms_resolve;
+    c->stats.kernel_launches = c->launches;
+    if (stats) *stats = c->stats;
+    c->frame_begun = false;
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_render(rt580_context* c, const rt580_render_params* p, int16_t* fb_out, rt580_stats* stats)
+{
+    if (!c || !p) FAIL(RT580_INVALID_ARG, "rt580_render: NULL argument");
+    const int n_rows = p->n_rows ? p->n_rows : p->height;
+    std::vector<uint64_t> rows((size_t)(n_rows > 0 ? n_rows : 0) + 1);
+    int st = rt580_render_begin(c, p, rows.data());
+    if (st != RT580_SUCCESS) return st;
+    // single context: the rows it owns are the whole stream
+    uint64_t run = 0;
+    for (int r = 0; r < n_rows; r++) { uint64_t v = rows[r]; rows[r] = run; run += v; }
+    return rt580_render_finish(c, rows.data(), fb_out, 0, stats);
+}
+
+extern "C" int rt580_last_frame_ao_base(rt580_context* c, uint64_t* out)
+{
+    if (!c || !out) FAIL(RT580_INVALID_ARG, "rt580_last_frame_ao_base: NULL argument");
+    CU(cudaSetDevice(c->device));
+    const FrameParams& fp = c->fp;
+    const size_t npix = (size_t)fp.n_rows * fp.W;
+    if (!npix) return RT580_SUCCESS;
+    std::vector<uint32_t> scan(npix); std::vector<uint64_t> rows((size_t)fp.n_rows);
+    CU(cudaMemcpy(scan.data(), c->pix_scan.p, sizeof(uint32_t) * npix, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rows.data(), c->row_vals.p, sizeof(uint64_t) * fp.n_rows, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < npix; i++) {
+        const size_t r = i / fp.W;
+        out[i] = (rows[r] + (uint64_t)(scan[i] - scan[r * fp.W])) * (uint64_t)c->sc.n_ambient;
+    }
+    return RT580_SUCCESS;
+}
+
+// ---- checkers ---------------------------------------------------------------------------
+template <int MODE> static void launch_rays(rt580_context* c, bool any, long long n, const float* o, const float* d,
+                                            const float* tmax, int32_t* prim, float* t, uint8_t* hit) {
+    if (any) k_trace_rays<MODE, true><<<nblk(n, 128), 128, 0, c->stream>>>(c->sc, n, o, d, tmax, prim, t, hit);
+    else k_trace_rays<MODE, false><<<nblk(n, 128), 128, 0, c->stream>>>(c->sc, n, o, d, tmax, prim, t, hit);
+}
+
+static int trace_rays_common(rt580_context* c, bool any, int64_t n, const float* org3, const float* dir3, const float* tmax,
+                             int traversal, int32_t* prim_out, float* t_out, uint8_t* hit_out)
+{
+    if (!c || !org3 || !dir3 || n < 0) FAIL(RT580_INVALID_ARG, "rt580_trace: bad argument");
+    if (!c->have_scene) FAIL(RT580_FAILURE, "rt580_trace: no scene uploaded");
+    if (n == 0) return RT580_SUCCESS;
+    CU(cudaSetDevice(c->device));
+    float *o = nullptr, *d = nullptr, *tm = nullptr, *t = nullptr; int32_t* pr = nullptr; uint8_t* h = nullptr;
+    CU(cudaMalloc(&o, sizeof(float) * 3 * n)); CU(cudaMalloc(&d, sizeof(float) * 3 * n));
+    CU(cudaMemcpy(o, org3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d, dir3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    if (any) { CU(cudaMalloc(&tm, sizeof(float) * n)); CU(cudaMemcpy(tm, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)); CU(cudaMalloc(&h, n)); }
+    else { CU(cudaMalloc(&t, sizeof(float) * n)); CU(cudaMalloc(&pr, sizeof(int32_t) * n)); }
+    const int mode = pick_mode(c, traversal);
+    DISPATCH_MODE(mode, launch_rays, c, any, (long long)n, o, d, tm, pr, t, h);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    if (any) CU(cudaMemcpy(hit_out, h, n, cudaMemcpyDeviceToHost));
+    else { CU(cudaMemcpy(prim_out, pr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(t_out, t, sizeof(float) * n, cudaMemcpyDeviceToHost)); }
+    cudaFree(o); cudaFree(d); cudaFree(tm); cudaFree(t); cudaFree(pr); cudaFree(h);
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_trace_closest(rt580_context* c, int64_t n, const float* org3, const float* dir3, int traversal,
+                                   int32_t* prim_out, float* t_out)
+{
+    if (!prim_out || !t_out) FAIL(RT580_INVALID_ARG, "rt580_trace_closest: NULL output");
+    return trace_rays_common(c, false, n, org3, dir3, nullptr, traversal, prim_out, t_out, nullptr);
+}
+extern "C" int rt580_trace_any(rt580_context* c, int64_t n, const float* org3, const float* dir3, const float* tmax,
+                               int traversal, uint8_t* hit_out)
+{
+    if (!hit_out || !tmax) FAIL(RT580_INVALID_ARG, "rt580_trace_any: NULL argument");
+    return trace_rays_common(c, true, n, org3, dir3, tmax, traversal, nullptr, nullptr, hit_out);
+}
+
+extern "C" int rt580_hemisphere_stream(rt580_context* c, const float normal[3], uint64_t step, int32_t n, float* out3)
+{
+    if (!c || !normal || !out3 || n < 0) FAIL(RT580_INVALID_ARG, "rt580_hemisphere_stream: bad argument");
+    if (n == 0) return RT580_SUCCESS;
+    CU(cudaSetDevice(c->device));
+    float* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(float) * 3 * n));
+    k_hemisphere<<<1, 32, 0, c->stream>>>(normal[0], normal[1], normal[2], step, n, d);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out3, d, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_powf(rt580_context* c, int64_t n, const float* x, const float* y, float* out)
+{
+    if (!c || !x || !y || !out || n < 0) FAIL(RT580_INVALID_ARG, "rt580_powf: bad argument");
+    if (n == 0) return RT580_SUCCESS;
+    CU(cudaSetDevice(c->device));
+    float *dx = nullptr, *dy = nullptr, *dz = nullptr;
+    CU(cudaMalloc(&dx, sizeof(float) * n)); CU(cudaMalloc(&dy, sizeof(float) * n)); CU(cudaMalloc(&dz, sizeof(float) * n));
+    CU(cudaMemcpy(dx, x, sizeof(float) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dy, y, sizeof(float) * n, cudaMemcpyHostToDevice));
+    k_powf<<<nblk(n, 256), 256, 0, c->stream>>>((long long)n, dx, dy, dz);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dz, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(dz);
+    return RT580_SUCCESS;
+}

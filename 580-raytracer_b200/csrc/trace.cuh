@@ -1,0 +1,173 @@
+// Ray / primitive tests and BVH traversal.  Device restatement of
+//   IntersectTriangle  Raytracer.cpp:348-409 (+ CalcTriangleAreaSigned cpp:937-942, NearlyEquals cpp:16-18)
+//   IntersectSphere    Raytracer.cpp:419-464 (+ GreaterThanZero Raytracer.h:558-560)
+//   IntersectScene     Raytracer.cpp:473-526
+// The leaf tests are the reference's arithmetic operation for operation (the TU is built
+// with -fmad=false); the LBVH above them only prunes.  Closest hit = lexicographic minimum
+// of (t, primitive order index), which is what the reference's first-wins strict '<' loop
+// returns (cpp:494, cpp:513).
+#pragma once
+#include "device_scene.h"
+#include "rt_math.cuh"
+#include <cfloat>
+
+namespace rt580 {
+
+#define RT_STACK_SIZE 64
+#define RT_SLAB_WIDEN 4.76837158e-7f   // 2^-21: > 3 roundings of (plane - o) * (1/d), see DESIGN.md
+
+struct HitRec {
+    float t;
+    int leaf;    // index into DeviceScene::prims
+    int prim;    // primitive order index (tie-break key, shading lookup)
+};
+
+// true iff (float)(0.5 * (double)dval) / total < 0, i.e. the reference's barycentric sign test
+// (cpp:392-396 with cpp:941's double 0.5).  Fast path: no underflow possible => sign logic.
+__device__ __forceinline__ bool bary_negative(float dval, float total, bool slow) {
+    if (!slow && fabsf(dval) >= 1e-30f) return (dval < 0.0f) != (total < 0.0f);
+    float h = 0.5f * dval;          // == (float)(0.5 * (double)dval)
+    return (h / total) < 0.0f;
+}
+
+// Does the reference accept this primitive for the ray, and at which t?  (no best-so-far logic)
+// t_limit: candidates with t > t_limit (or, at t == t_limit, prim >= prim_limit) are not worth
+// the barycentric work because the caller would discard them anyway.
+template <bool GLOBAL> __device__ __forceinline__ float4 ld4(const float4* p) {
+    if (GLOBAL) return __ldg(p);      // read-only path (LDG.E.128.CONSTANT)
+    return *p;                        // shared-memory staged records
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ bool prim_test(const PrimRec* __restrict__ p, V3 O, V3 d, float t_limit, int prim_limit,
+                                          float& t_out, int& prim_out)
+{
+    const float4 ra = ld4<GLOBAL>(&p->a);
+    const float4 rd = ld4<GLOBAL>(&p->d);
+    const float4 rc = ld4<GLOBAL>(&p->c);
+    const int flags = __float_as_int(rd.w);
+    const int prim = __float_as_int(rc.w);
+    if (!(flags & RT_PRIM_SPHERE)) {
+        const V3 N = mk(rd.x, rd.y, rd.z);
+        const float nd = dot(N, d);                               // cpp:367
+        if (fabsf(nd - 0.0f) <= RT_EPS_F) return false;           // cpp:371
+        const float t = -(dot(N, O) + ra.w) / nd;                 // cpp:381
+        if (t <= RT_EPS_F) return false;                          // cpp:382
+        if (!(t < t_limit || (t == t_limit && prim < prim_limit))) return false;
+        const float4 rb = ld4<GLOBAL>(&p->b);
+        const V3 v0 = mk(ra.x, ra.y, ra.z), v1 = mk(rb.x, rb.y, rb.z), v2 = mk(rc.x, rc.y, rc.z);
+        const V3 P = O + d * t;                                   // cpp:387
+        const bool slow = (flags & RT_PRIM_SLOWPATH) != 0;
+        // CalcTriangleAreaSigned(A,B,C,N) = 0.5 * dot(cross(B-A, C-A), N)   (cpp:937-942)
+        const float da = dot(cross(v1 - P, v2 - P), N);           // alpha: (P, v1, v2)   cpp:392
+        if (bary_negative(da, rb.w, slow)) return false;
+        const float db = dot(cross(P - v0, v2 - v0), N);          // beta : (v0, P, v2)   cpp:393
+        if (bary_negative(db, rb.w, slow)) return false;
+        const float dg = dot(cross(v1 - v0, P - v0), N);          // gamma: (v0, v1, P)   cpp:394
+        if (bary_negative(dg, rb.w, slow)) return false;          // cpp:396
+        t_out = t; prim_out = prim;
+        return true;
+    } else {
+        const V3 C = mk(ra.x, ra.y, ra.z);
+        const V3 oc = O - C;                                      // cpp:421
+        const float b = 2.0f * dot(d, oc);                        // cpp:422
+        const float c = dot(oc, oc) - (ra.w * ra.w);              // cpp:423
+        const float disc = (b * b) - (4.0f * c);                  // cpp:426
+        if (disc <= RT_EPS_F) return false;                       // cpp:427
+        const float sq = sqrtf(disc);                             // cpp:429
+        const float t0 = (-b + sq) / 2.0f;                        // cpp:430
+        const float t1 = (-b - sq) / 2.0f;                        // cpp:431
+        const bool g0 = t0 > RT_EPS_F, g1 = t1 > RT_EPS_F;        // h:558-560
+        if (!g0 && !g1) return false;                             // cpp:433
+        const float t = !g0 ? t1 : (!g1 ? t0 : fminf(t0, t1));    // cpp:438-453
+        if (!(t < t_limit || (t == t_limit && prim < prim_limit))) return false;
+        t_out = t; prim_out = prim;
+        return true;
+    }
+}
+
+// Conservative ray/box slab test.  (plane - o) * inv has <= 3 roundings, so widening the
+// interval by 2^-21 relative makes the float result a superset of the exact one.
+__device__ __forceinline__ bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz,
+                                     V3 O, V3 inv, float tcull, float& tnear)
+{
+    const float ax = (lox - O.x) * inv.x, bx = (hix - O.x) * inv.x;
+    const float ay = (loy - O.y) * inv.y, by = (hiy - O.y) * inv.y;
+    const float az = (loz - O.z) * inv.z, bz = (hiz - O.z) * inv.z;
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    tn = __fmaf_rn(fabsf(tn), -RT_SLAB_WIDEN, tn);
+    tf = __fmaf_rn(fabsf(tf), RT_SLAB_WIDEN, tf);
+    tnear = tn;
+    return (tn <= tf) && (tf >= 0.0f) && (tn <= tcull);
+}
+
+// Closest hit (ANY == false): best = lexicographic min (t, prim) over accepted primitives.
+// Any hit     (ANY == true) : true as soon as one primitive is accepted with t <= tmax
+//                             (cpp:75 and cpp:325 use only that boolean).
+template <bool ANY>
+__device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, float tmax, HitRec& best)
+{
+    best.t = ANY ? tmax : __int_as_float(0x7f800000);
+    best.leaf = -1;
+    best.prim = 0x7fffffff;
+    if (sc.n_leaf <= 0) return false;
+    const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[RT_STACK_SIZE];
+    int sp = 0;
+    int node = 0;
+    bool found = false;
+    for (;;) {
+        const BvhNode* __restrict__ nd = sc.nodes + node;
+        const float4 xy0 = __ldg(&nd->xy0), xy1 = __ldg(&nd->xy1), z01 = __ldg(&nd->z01);
+        const int4 kids = __ldg(&nd->kids);
+        float tn0, tn1;
+        const bool h0 = slab(xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, O, inv, best.t, tn0);
+        const bool h1 = slab(xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, O, inv, best.t, tn1);
+        int next;
+        if (h0 && h1) {
+            int nearc = kids.x, farc = kids.y;
+            if (tn1 < tn0) { nearc = kids.y; farc = kids.x; }
+            if (sp < RT_STACK_SIZE) stack[sp++] = farc;   // depth is checked at build time (<= RT_STACK_SIZE)
+            next = nearc;
+        } else if (h0) next = kids.x;
+        else if (h1) next = kids.y;
+        else { if (sp == 0) break; next = stack[--sp]; }
+        // leaves
+        bool done = false;
+        while (next < 0) {
+            const int leaf = ~next;
+            float t; int prim;
+            if (prim_test<true>(sc.prims + leaf, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+                if (ANY) return true;   // prim_test's limit is "t < tmax || t == tmax" (prim_limit = INT_MAX)
+                best.t = t; best.leaf = leaf; best.prim = prim; found = true;
+            }
+            if (sp == 0) { done = true; break; }
+            next = stack[--sp];
+        }
+        if (done) break;
+        node = next;
+    }
+    return found;
+}
+
+// The reference's own linear loop (cpp:476-521) over `n` records, e.g. staged in shared memory.
+template <bool ANY, bool GLOBAL>
+__device__ __forceinline__ bool traverse_linear(const PrimRec* __restrict__ prims, int n, V3 O, V3 d, float tmax,
+                                                HitRec& best)
+{
+    best.t = ANY ? tmax : __int_as_float(0x7f800000);
+    best.leaf = -1;
+    best.prim = 0x7fffffff;
+    bool found = false;
+    for (int i = 0; i < n; i++) {
+        float t; int prim;
+        if (prim_test<GLOBAL>(prims + i, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+            if (ANY) return true;
+            best.t = t; best.leaf = i; best.prim = prim; found = true;
+        }
+    }
+    return found;
+}
+
+}  // namespace rt580

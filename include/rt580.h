@@ -1,0 +1,177 @@
+/* rt580.h - C ABI of the B200-native 580-Raytracer hot path (librt580.so).
+ *
+ * The reference has no plugin / FFI interface: its API is the public surface of
+ * `class Raytracer` (Raytracer.h:557-588) as driven by main() (Raytracer.cpp:944-953).
+ * This repo keeps that class (580-raytracer_b200/csrc/raytracer.h) and cuts the C ABI
+ * INSIDE Raytracer::Render (Raytracer.cpp:916-935), between InitializeRenderer()
+ * (cpp:917) and FlushFrameBufferToPPM() (cpp:934): everything the double loop at
+ * cpp:921-932 does - GenerateRay, Raycast, IntersectScene/Triangle/Sphere,
+ * CalculateLocalColor, CalculateAmbientOcclusion, ComputeFresnel, CalculateRefraction -
+ * happens behind rt580_render*().
+ *
+ * Conventions (match the reference): every call returns RT580_SUCCESS / RT580_FAILURE /
+ * RT580_INVALID_ARG (Raytracer.h:8-10); diagnostics go to rt580_last_error(); calls are
+ * synchronous and a context is not re-entrant (the reference Render is neither,
+ * Raytracer.h:592).  All pointers are host memory borrowed for the call unless a
+ * parameter says "device".  The library owns all device memory.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails.
+ *
+ * All "cpp:" / "h:" citations are /root/reference/580 Raytracer/Raytracer.{cpp,h}.
+ */
+#ifndef RT580_H
+#define RT580_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT580_SUCCESS     0   /* h:8  RT_SUCCESS     */
+#define RT580_FAILURE     1   /* h:9  RT_FAILURE     */
+#define RT580_INVALID_ARG 2   /* h:10 RT_INVALID_ARG */
+
+/* Light::Type, h:520-524 */
+#define RT580_LIGHT_DIRECTIONAL 0
+#define RT580_LIGHT_POINT       1
+#define RT580_LIGHT_AMBIENT     2
+
+/* How the ambient-occlusion sample stream (cpp:269-292, cpp:315-330) is addressed. */
+#define RT580_RNG_REFERENCE_LCG 0   /* replays the reference's single sequential
+                                       std::default_random_engine stream (h:592, cpp:787):
+                                       AO call j of the frame in scanline/pre-order starts at
+                                       engine step 2*spp*j.  Needs the global prefix of AO-call
+                                       counts, i.e. one exchange between ranks.              */
+#define RT580_RNG_COUNTER       1   /* same generator, position = f(pixel, node): no
+                                       cross-pixel dependency, no exchange, different noise. */
+
+/* How closest/any hits are searched (cpp:473-526 is a linear loop; results are identical). */
+#define RT580_TRAVERSAL_AUTO        0   /* brute force from shared memory for tiny scenes, LBVH otherwise */
+#define RT580_TRAVERSAL_BVH         1
+#define RT580_TRAVERSAL_BRUTE_FORCE 2   /* the reference's own linear loop, on the GPU (checker / tiny scenes) */
+
+typedef struct rt580_context rt580_context;
+
+/* Scene after the load-time flatten (replaces the per-ray work of cpp:477-480 and
+ * cpp:353-355): world-space triangle vertices = ComputeModelMatrix(shape).TransformPoint(v)
+ * (cpp:528-586, h:234-248), sphere centre = translation column of that matrix, radius
+ * unscaled (cpp:421-423).  Primitive order = (shape order, triangle order) - it decides
+ * ties (cpp:494, cpp:513).  Every float4 array is 16-byte records. */
+typedef struct rt580_flat_scene {
+    int64_t        n_prims;        /* triangles + spheres, in reference order            */
+    int64_t        n_tris;
+    const float*   tri_v0;         /* [n_tris][4] world xyz, w ignored                   */
+    const float*   tri_v1;         /* [n_tris][4]                                         */
+    const float*   tri_v2;         /* [n_tris][4]                                         */
+    const float*   tri_n0;         /* [n_tris][4] OBJECT-space vertex normals (cpp:227)  */
+    const float*   tri_n1;
+    const float*   tri_n2;
+    const int32_t* tri_prim;       /* [n_tris] index of the triangle in primitive order  */
+    const int32_t* tri_material;   /* [n_tris] material (= shape) index                  */
+    int64_t        n_spheres;
+    const float*   sph_center_r;   /* [n_spheres][4] world centre xyz, radius            */
+    const int32_t* sph_prim;       /* [n_spheres]                                         */
+    const int32_t* sph_material;   /* [n_spheres]                                         */
+    int32_t        n_materials;
+    const float*   materials;      /* [n_materials][8] Cs.rgb Ka Kd Ks Kt n (h:442-463)  */
+    int32_t        n_lights;
+    const int32_t* light_type;     /* [n_lights] RT580_LIGHT_*, JSON order (cpp:39)      */
+    const float*   light_f;        /* [n_lights][10] color.rgb intensity position.xyz direction.xyz */
+    float          origin_hint[3]; /* Camera::from (h:506): together with the scene bounds it bounds
+                                      every ray origin, which sizes the conservative padding of the
+                                      BVH boxes; a render whose camera lies outside is refused */
+} rt580_flat_scene;
+
+typedef struct rt580_render_params {
+    int32_t width, height;         /* Display xRes,yRes (h:420-425) - the ctor's, not the JSON's (Q23) */
+    float   fov_degrees;           /* Display::fov, 60 in the reference (cpp:786)          */
+    float   camera_from[3];        /* Camera::from (h:506): ray origin + Phong view point  */
+    float   inv_view3x3[9];        /* upper-left 3x3 of Inverse(viewMatrix), row major (cpp:849-851) */
+    int32_t depth;                 /* Raycast bounces, 4 in the reference (h:563)          */
+    int32_t ao_spp;                /* CalculateAmbientOcclusion samples, 128 in the reference (cpp:317) */
+    int32_t rng_mode;              /* RT580_RNG_*                                          */
+    int32_t traversal;             /* RT580_TRAVERSAL_*                                    */
+    /* rows rendered by this context: row_first + k*row_step, k in [0,n_rows).
+     * n_rows == 0 means the whole frame (row_first 0, step 1). */
+    int32_t row_first, row_step, n_rows;
+} rt580_render_params;
+
+typedef struct rt580_stats {
+    uint64_t rays_primary;         /* IntersectScene calls from cpp:30 at depth 0          */
+    uint64_t rays_secondary;       /* cpp:30 via cpp:103 / cpp:111                         */
+    uint64_t rays_shadow;          /* cpp:75                                               */
+    uint64_t rays_ao;              /* cpp:325                                              */
+    uint64_t hit_nodes;            /* Raycast nodes that hit something                     */
+    uint64_t ao_calls;
+    float    ms_structure;         /* primary+secondary closest-hit + shading + shadow     */
+    float    ms_order;             /* subtree counts, scan, pre-order ordinals             */
+    float    ms_ao;                /* occlusion pass                                       */
+    float    ms_resolve;           /* integer Pixel algebra bottom-up                      */
+    float    ms_total;             /* device time of the frame (CUDA events)               */
+    float    ms_ao_kernel;         /* the dominant kernel alone                            */
+    uint32_t kernel_launches;      /* kernels launched for the frame                       */
+    uint32_t bvh_max_depth;
+    uint32_t reserved0, reserved1;
+} rt580_stats;
+
+/* ---- context ------------------------------------------------------------------------- */
+int  rt580_create(int device, rt580_context** out);
+void rt580_destroy(rt580_context* ctx);
+const char* rt580_last_error(void);
+/* device properties the benchmark needs for its FP32 roofline: SM count, max SM MHz */
+int  rt580_device_info(rt580_context* ctx, int32_t* sm_count, int32_t* sm_clock_mhz, uint64_t* hbm_bytes);
+
+/* ---- scene: H2D + per-triangle constants (cpp:362-365, 377, 389) + LBVH build ----------- */
+int  rt580_upload_scene(rt580_context* ctx, const rt580_flat_scene* scene);
+/* device ms of the last upload's build kernels (setup, morton, sort, hierarchy, refit, pack) */
+int  rt580_build_ms(rt580_context* ctx, float* ms);
+
+/* ---- frame: replaces the loop body of Raytracer::Render (cpp:921-932) ------------------ */
+/* One call = whole frame (or the rows in params) on this context's GPU.
+ * fb_out: [n_rows][width][3] int16 raw Pixel{short r,g,b} (h:373-374), host memory. */
+int  rt580_render(rt580_context* ctx, const rt580_render_params* params, int16_t* fb_out, rt580_stats* stats);
+
+/* Split form for several ranks (one context per GPU, rows partitioned):
+ *   begin  : structure pass; row_hit_nodes[n_rows] = AO-relevant hit nodes per owned row
+ *   finish : row_ao_base[n_rows] = for each owned row the number of hit nodes in ALL rows
+ *            before it in scanline order (the exchange: all-gather of row_hit_nodes, then a
+ *            prefix sum); ignored (may be NULL) in RT580_RNG_COUNTER mode.
+ *            fb_out may be host memory, or device memory when fb_on_device != 0 (so the
+ *            caller can hand it to NCCL without staging). */
+int  rt580_render_begin(rt580_context* ctx, const rt580_render_params* params, uint64_t* row_hit_nodes);
+int  rt580_render_finish(rt580_context* ctx, const uint64_t* row_ao_base, int16_t* fb_out, int fb_on_device,
+                         rt580_stats* stats);
+
+/* ---- checkers (used by the parity tests; same kernels as the frame path) ---------------- */
+/* Closest hit of n arbitrary rays: prim_out = primitive order index or -1, t_out = distance. */
+int  rt580_trace_closest(rt580_context* ctx, int64_t n, const float* org3, const float* dir3, int traversal,
+                         int32_t* prim_out, float* t_out);
+/* Any hit with t <= tmax (cpp:75 / cpp:325 use only the bool). */
+int  rt580_trace_any(rt580_context* ctx, int64_t n, const float* org3, const float* dir3, const float* tmax,
+                     int traversal, uint8_t* hit_out);
+/* Per-pixel global ordinal of the first AO call of the last rendered frame (local rows). */
+int  rt580_last_frame_ao_base(rt580_context* ctx, uint64_t* pixel_ao_base /* [n_rows*width] */);
+/* n AO directions of the stream starting at engine step `step` (cpp:283-292). */
+int  rt580_hemisphere_stream(rt580_context* ctx, const float normal[3], uint64_t step, int32_t n, float* out3);
+/* device powf used by the Phong term (cpp:253), element-wise */
+int  rt580_powf(rt580_context* ctx, int64_t n, const float* x, const float* y, float* out);
+
+/* ---- class mirror: the reference's public API over the C ABI (h:557-588) ---------------- */
+typedef struct rt580_raytracer rt580_raytracer;
+rt580_raytracer* rt580_raytracer_new(int width, int height);                 /* h:588 ctor            */
+void rt580_raytracer_delete(rt580_raytracer* rt);
+int  rt580_raytracer_set_assets_path(rt580_raytracer* rt, const char* dir);  /* ASSETS_PATH, h:15     */
+int  rt580_raytracer_set_options(rt580_raytracer* rt, int depth, int ao_spp, int rng_mode, int traversal,
+                                 int device);                                /* h:563, cpp:317        */
+int  rt580_raytracer_load_scene_json(rt580_raytracer* rt, const char* scene);/* h:572 LoadSceneJSON   */
+int  rt580_raytracer_render(rt580_raytracer* rt, const char* output_ppm);    /* h:586 Render          */
+int  rt580_raytracer_flush_ppm(rt580_raytracer* rt, const char* output_ppm); /* h:573                 */
+const int16_t* rt580_raytracer_framebuffer(rt580_raytracer* rt);             /* Display::frameBuffer  */
+int  rt580_raytracer_stats(rt580_raytracer* rt, rt580_stats* stats);
+/* the flattened scene + camera the class hands to rt580_upload_scene / rt580_render */
+int  rt580_raytracer_flat_scene(rt580_raytracer* rt, rt580_flat_scene* out);
+int  rt580_raytracer_render_params(rt580_raytracer* rt, rt580_render_params* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT580_H */
