@@ -21,11 +21,13 @@ LIB_PATH = os.path.join(HERE, "librt580.so")
 RT_SUCCESS, RT_FAILURE, RT_INVALID_ARG = 0, 1, 2
 RNG_REFERENCE_LCG, RNG_COUNTER = 0, 1
 TRAVERSAL_AUTO, TRAVERSAL_BVH, TRAVERSAL_BRUTE_FORCE = 0, 1, 2
+FARFIELD_EXACT, FARFIELD_OFF = 0, 1
 LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AMBIENT = 0, 1, 2
 
 # every symbol include/rt580.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "rt580_create", "rt580_destroy", "rt580_last_error", "rt580_device_info", "rt580_upload_scene", "rt580_build_ms",
+    "rt580_scene_info_get",
     "rt580_render", "rt580_render_begin", "rt580_render_finish", "rt580_trace_closest", "rt580_trace_any",
     "rt580_last_frame_ao_base", "rt580_hemisphere_stream", "rt580_powf",
     "rt580_raytracer_new", "rt580_raytracer_delete", "rt580_raytracer_set_assets_path", "rt580_raytracer_set_options",
@@ -61,13 +63,24 @@ class RenderParams(ctypes.Structure):
         ("camera_from", ctypes.c_float * 3), ("inv_view3x3", ctypes.c_float * 9),
         ("depth", ctypes.c_int32), ("ao_spp", ctypes.c_int32), ("rng_mode", ctypes.c_int32),
         ("traversal", ctypes.c_int32), ("row_first", ctypes.c_int32), ("row_step", ctypes.c_int32),
-        ("n_rows", ctypes.c_int32),
+        ("n_rows", ctypes.c_int32), ("farfield", ctypes.c_int32),
     ]
 
     def copy(self):
         c = RenderParams()
         ctypes.memmove(ctypes.addressof(c), ctypes.addressof(self), ctypes.sizeof(RenderParams))
         return c
+
+
+class SceneInfo(ctypes.Structure):
+    _fields_ = [
+        ("n_leaf", ctypes.c_int64), ("n_dropped", ctypes.c_int64), ("n_always", ctypes.c_int64),
+        ("far_tmin", ctypes.c_float), ("pad", ctypes.c_float), ("extent", ctypes.c_float),
+        ("build_ms", ctypes.c_float), ("bvh_max_depth", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
 class Stats(ctypes.Structure):
@@ -113,6 +126,7 @@ def lib():
         L.rt580_device_info.argtypes = [vp, vp, vp, vp]
         L.rt580_upload_scene.argtypes = [vp, ctypes.POINTER(FlatScene)]
         L.rt580_build_ms.argtypes = [vp, vp]
+        L.rt580_scene_info_get.argtypes = [vp, ctypes.POINTER(SceneInfo)]
         L.rt580_render.argtypes = [vp, ctypes.POINTER(RenderParams), vp, ctypes.POINTER(Stats)]
         L.rt580_render_begin.argtypes = [vp, ctypes.POINTER(RenderParams), vp]
         L.rt580_render_finish.argtypes = [vp, vp, vp, i32, ctypes.POINTER(Stats)]
@@ -126,7 +140,7 @@ def lib():
         L.rt580_raytracer_delete.argtypes = [vp]
         L.rt580_raytracer_delete.restype = None
         L.rt580_raytracer_set_assets_path.argtypes = [vp, ctypes.c_char_p]
-        L.rt580_raytracer_set_options.argtypes = [vp, i32, i32, i32, i32, i32]
+        L.rt580_raytracer_set_options.argtypes = [vp, i32, i32, i32, i32, i32, i32]
         L.rt580_raytracer_load_scene_json.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_render.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_flush_ppm.argtypes = [vp, ctypes.c_char_p]
@@ -171,6 +185,11 @@ class Context:
 
     def upload_scene(self, flat: FlatScene):
         _check(lib().rt580_upload_scene(self._h, ctypes.byref(flat)))
+
+    def scene_info(self):
+        info = SceneInfo()
+        _check(lib().rt580_scene_info_get(self._h, ctypes.byref(info)))
+        return info
 
     def build_ms(self):
         ms = ctypes.c_float()
@@ -252,7 +271,8 @@ class Raytracer:
         if not self._h:
             raise Rt580Error(RT_FAILURE, "rt580_raytracer_new failed")
         self.width, self.height = width, height
-        self._opts = dict(depth=4, ao_spp=128, rng_mode=RNG_REFERENCE_LCG, traversal=TRAVERSAL_AUTO, device=0)
+        self._opts = dict(depth=4, ao_spp=128, rng_mode=RNG_REFERENCE_LCG, traversal=TRAVERSAL_AUTO, device=0,
+                          farfield=FARFIELD_EXACT)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -271,7 +291,7 @@ class Raytracer:
     def SetOptions(self, **kw):
         self._opts.update(kw)
         o = self._opts
-        return lib().rt580_raytracer_set_options(self._h, o["depth"], o["ao_spp"], o["rng_mode"], o["traversal"], o["device"])
+        return lib().rt580_raytracer_set_options(self._h, o["depth"], o["ao_spp"], o["rng_mode"], o["traversal"], o["device"], o["farfield"])
 
     def LoadSceneJSON(self, scene_path):
         return lib().rt580_raytracer_load_scene_json(self._h, scene_path.encode())

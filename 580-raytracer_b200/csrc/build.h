@@ -15,6 +15,10 @@ struct BuildInput {            // device pointers (already uploaded)
 struct BuildOutput {
     PrimRec* prims;            // [n_leaf] Morton order (cudaMalloc'ed, caller frees)
     BvhNode* nodes;            // [max(n_leaf-1,1)]
+    float4* far;               // [n_leaf] far-field filter records
+    float far_tmin;            // min over triangles of T_far
+    int n_always;              // triangles that are far-field candidates for every ray (slivers)
+    int32_t* always_idx;       // [n_always] their indices into prims
     int n_leaf;
     int n_dropped;             // zero-area triangles
     unsigned int max_depth;

@@ -14,12 +14,27 @@
 //   k_pack           64-byte traversal nodes with both child boxes inline
 //   k_depth          max leaf depth (bounds the traversal stack)
 //
-// Conservative boxes: the reference accepts a hit from float arithmetic, so a ray may be
-// accepted although, in exact arithmetic, it misses the triangle by a few ulp of the
-// coordinates involved.  Every primitive box is therefore padded by pad = 2^-19 * E, where
-// E bounds |coordinate| of anything a ray can start from or hit (scene bounds + camera),
-// and sphere boxes use r_box^2 = r^2 + 2^-18 (2E+1)^2 to cover the cancellation error of
-// the discriminant at cpp:422-426.  See DESIGN.md "Why the BVH returns the same hit".
+// Why the tree returns the reference's hit (DESIGN.md has the derivation):
+// the reference accepts a hit from float arithmetic (cpp:392-396), so the set of points P the
+// test accepts is not the triangle but, with u = 2^-24, L = distance of P from the triangle,
+// r = its diameter, h = the smaller altitude onto the two edges meeting at v0:
+//   NEAR  L <= L_near = 2048 u r^2 / h     rounding slop around the triangle (beta/gamma at
+//                                          cpp:393-394 confine P to the wedge at v0 up to a
+//                                          relative 10u; alpha at cpp:392 cuts the wedge off
+//                                          with an absolute error <= 9u |v-P|^2 / |v1v2|)
+//   FAR   L >= R_safe = h / (13u)          cpp:392's cross product of two long, almost parallel
+//                                          vectors is rounding noise there: the wedge is no
+//                                          longer cut off
+//   and nothing in between.
+// NEAR is covered by padding every box with pad = 2^-18 E + L_near (E bounds every coordinate a
+// ray can start from or hit; the first term covers the off-plane error of t at cpp:381-387).
+// FAR cannot be covered by any box: those are rays almost parallel to the triangle's plane that
+// "hit" it 10^4..10^7 units away; the reference reports them (they decide hit/miss of rays that
+// leave the scene, i.e. tree structure and AO), so the device replays them: each triangle gets
+// a filter record (N, thr) with thr = 4E / (R_safe - 4E) >= |N.O + D| / T_far, and a ray that
+// found nothing nearer than far_tmin tests every triangle with |N.d| <= thr exactly (trace.cuh).
+// Sphere boxes use r_box^2 = r^2 + 2^-18 (2E+1)^2: the cancellation error of the
+// discriminant at cpp:422-426 for the ray origins possible in the scene.
 #include "device_scene.h"
 #include "rt_math.cuh"
 #include "build.h"
@@ -90,6 +105,7 @@ struct SetupParams {
     float inv_ext[3];   // 2^21 / extent
     float pad;          // box padding (see file header)
     float sph_extra;    // added to r^2 for sphere boxes
+    float E;            // bound on |coordinate| of ray origins and hit points
 };
 
 __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __restrict__ v1,
@@ -97,7 +113,7 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
                              const float4* __restrict__ sph, const int32_t* __restrict__ sph_prim, int64_t n_sph,
                              SetupParams sp, PrimRec* __restrict__ rec, float4* __restrict__ box_lo,
                              float4* __restrict__ box_hi, uint64_t* __restrict__ keys, uint32_t* __restrict__ ids,
-                             unsigned int* __restrict__ n_dropped)
+                             float4* __restrict__ far, unsigned int* __restrict__ n_dropped)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_tris + n_sph) return;
@@ -121,10 +137,32 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
         r.b = make_float4(p1.x, p1.y, p1.z, total);
         r.c = make_float4(p2.x, p2.y, p2.z, __int_as_float(tri_prim[i]));
         r.d = make_float4(N.x, N.y, N.z, __int_as_float(flags));
-        lo[0] = fminf(p0.x, fminf(p1.x, p2.x)) - sp.pad; hi[0] = fmaxf(p0.x, fmaxf(p1.x, p2.x)) + sp.pad;
-        lo[1] = fminf(p0.y, fminf(p1.y, p2.y)) - sp.pad; hi[1] = fmaxf(p0.y, fmaxf(p1.y, p2.y)) + sp.pad;
-        lo[2] = fminf(p0.z, fminf(p1.z, p2.z)) - sp.pad; hi[2] = fmaxf(p0.z, fmaxf(p1.z, p2.z)) + sp.pad;
+        // near / far split of the reference's acceptance region (file header):
+        // hmin = the smaller of the altitudes onto the two edges that meet at v0
+        const V3 e0 = p2 - p1;
+        const float la = length(e0), lb = length(e2), lc = length(e1);          // |v1v2|, |v0v2|, |v0v1|
+        const float diam = fmaxf(la, fmaxf(lb, lc));
+        const float area2 = length(cross(e1, e2));
+        const float hmin = 0.99f * area2 / fmaxf(lb, lc);
+        float l_near = 1.2207031e-4f * diam * diam / hmin;                       // 2048 u diam^2 / hmin
+        const float r_safe = hmin * 1290555.0f;                                  // hmin / (13 u)
+        float thr = 4.0f;                                                        // > |N.d| always: candidate for every ray
+        if (hmin > 0.0f && r_safe > 8.0f * sp.E + 12.0f * diam && l_near <= diam) {
+            const float t_far = r_safe - 4.0f * sp.E - 2.0f * diam;
+            thr = 4.0f * sp.E / t_far;
+        } else l_near = fminf(l_near, diam);
+        if (!(l_near >= 0.0f)) l_near = diam;                                    // NaN guard
+        const float pad = sp.pad + l_near;
+        far[i] = make_float4(N.x, N.y, N.z, drop ? -1.0f : thr);
+        if (!drop) {
+            if (thr < 4.0f) atomicMax(n_dropped + 2, (unsigned)__float_as_int(thr));   // positive floats order like ints
+            else atomicAdd(n_dropped + 3, 1u);
+        }
+        lo[0] = fminf(p0.x, fminf(p1.x, p2.x)) - pad; hi[0] = fmaxf(p0.x, fmaxf(p1.x, p2.x)) + pad;
+        lo[1] = fminf(p0.y, fminf(p1.y, p2.y)) - pad; hi[1] = fmaxf(p0.y, fmaxf(p1.y, p2.y)) + pad;
+        lo[2] = fminf(p0.z, fminf(p1.z, p2.z)) - pad; hi[2] = fmaxf(p0.z, fmaxf(p1.z, p2.z)) + pad;
     } else {
+        far[i] = make_float4(0.f, 0.f, 0.f, -1.0f);                              // spheres have no far field
         float4 s = sph[i - n_tris];
         r.a = s;
         r.b = make_float4(s.w * s.w, 0.f, 0.f, 0.f);          // cpp:423 radius*radius
@@ -153,16 +191,26 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
 }
 
 __global__ void k_gather(const PrimRec* __restrict__ rec, const float4* __restrict__ box_lo,
-                         const float4* __restrict__ box_hi, const uint32_t* __restrict__ ids, int n_leaf,
-                         PrimRec* __restrict__ out, float4* __restrict__ nb_lo, float4* __restrict__ nb_hi)
+                         const float4* __restrict__ box_hi, const float4* __restrict__ far_in,
+                         const uint32_t* __restrict__ ids, int n_leaf,
+                         PrimRec* __restrict__ out, float4* __restrict__ far_out, float4* __restrict__ nb_lo,
+                         float4* __restrict__ nb_hi)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_leaf) return;
     uint32_t i = ids[j];
     out[j] = rec[i];
+    far_out[j] = far_in[i];
     // node boxes: inner nodes [0, n_leaf-1), leaves [n_leaf-1, 2 n_leaf-1)
     nb_lo[n_leaf - 1 + j] = box_lo[i];
     nb_hi[n_leaf - 1 + j] = box_hi[i];
+}
+
+__global__ void k_collect_always(const float4* __restrict__ far, int n, int32_t* __restrict__ out,
+                                 unsigned int* __restrict__ count)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && far[j].w >= 4.0f) out[atomicAdd(count, 1u)] = j;
 }
 
 // Karras 2012: length of the common prefix of keys i and j, ties broken by index
@@ -260,12 +308,13 @@ template <typename T> static bool dalloc(T** p, size_t n, char* err, size_t errl
 bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char* err, size_t errlen)
 {
     const int64_t n_in = in.n_tris + in.n_spheres;
-    out->prims = nullptr; out->nodes = nullptr; out->n_leaf = 0; out->max_depth = 0; out->launches = 0;
+    out->prims = nullptr; out->nodes = nullptr; out->far = nullptr; out->far_tmin = 0.f; out->n_always = 0; out->always_idx = nullptr;
+    out->n_leaf = 0; out->max_depth = 0; out->launches = 0;
     if (n_in > 0x7ffffff0ll) { snprintf(err, errlen, "too many primitives (%lld)", (long long)n_in); return false; }
 
     int* d_bounds = nullptr; unsigned int* d_counters = nullptr;
-    if (!dalloc(&d_bounds, 6, err, errlen) || !dalloc(&d_counters, 2, err, errlen)) return false;
-    CK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned int), stream));
+    if (!dalloc(&d_bounds, 6, err, errlen) || !dalloc(&d_counters, 4, err, errlen)) return false;
+    CK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), stream));   // dropped, depth, max thr bits, always-candidates
     {
         const int init[6] = { 0x7f7fffff, 0x7f7fffff, 0x7f7fffff,                     // +FLT_MAX, ordered encoding
                               (int)0x80800000, (int)0x80800000, (int)0x80800000 };    // -FLT_MAX, ordered encoding
@@ -288,7 +337,8 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
     }
     E += 1.0f;   // + SHADOW_CLIPPING_OFFSET steps and slack
     SetupParams sp;
-    sp.pad = E * (1.0f / 524288.0f);                                   // 2^-19 E
+    sp.pad = E * (1.0f / 262144.0f);                                   // 2^-18 E
+    sp.E = E;
     sp.sph_extra = (2.f * E + 1.f) * (2.f * E + 1.f) * (1.0f / 262144.0f);   // 2^-18 (2E+1)^2
     for (int k = 0; k < 3; k++) {
         float l = lo[k] - 2.f * sp.pad, h = hi[k] + 2.f * sp.pad;
@@ -299,15 +349,16 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
     for (int k = 0; k < 3; k++) { out->bounds_lo[k] = lo[k]; out->bounds_hi[k] = hi[k]; }
     if (n_in == 0) { cudaFree(d_bounds); cudaFree(d_counters); return true; }
 
-    PrimRec* rec = nullptr; float4 *blo = nullptr, *bhi = nullptr;
+    PrimRec* rec = nullptr; float4 *blo = nullptr, *bhi = nullptr, *far_in = nullptr;
     uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *ids = nullptr, *ids2 = nullptr;
     if (!dalloc(&rec, n_in, err, errlen) || !dalloc(&blo, n_in, err, errlen) || !dalloc(&bhi, n_in, err, errlen) ||
+        !dalloc(&far_in, n_in, err, errlen) ||
         !dalloc(&keys, n_in, err, errlen) || !dalloc(&keys2, n_in, err, errlen) || !dalloc(&ids, n_in, err, errlen) ||
         !dalloc(&ids2, n_in, err, errlen)) return false;
     {
         int blocks = (int)((n_in + 255) / 256);
         k_prim_setup<<<blocks, 256, 0, stream>>>(in.tri_v0, in.tri_v1, in.tri_v2, in.tri_prim, in.n_tris, in.sph,
-                                                 in.sph_prim, in.n_spheres, sp, rec, blo, bhi, keys, ids, d_counters);
+                                                 in.sph_prim, in.n_spheres, sp, rec, blo, bhi, keys, ids, far_in, d_counters);
         out->launches++;
     }
     size_t tmp_bytes = 0;
@@ -316,21 +367,28 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
     CK(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
     CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, ids2, (int)n_in, 0, 64, stream));
     out->launches += 4;   // cub onesweep: histogram + scan + passes (approximate, library)
-    unsigned int hc[2];
+    unsigned int hc[4];
     CK(cudaMemcpyAsync(hc, d_counters, sizeof hc, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     const int n = (int)(n_in - hc[0]);
     out->n_leaf = n;
     out->n_dropped = (int)hc[0];
+    out->n_always = (int)hc[3];
+    {
+        float max_thr; memcpy(&max_thr, &hc[2], 4);
+        // far-field acceptance needs t >= T_far = 4E / thr; with sliver triangles (candidates for
+        // every ray) there is no lower bound
+        out->far_tmin = max_thr > 0.f ? 4.0f * E / max_thr : 3.0e38f;
+    }
     if (n > 0) {
-        PrimRec* prims = nullptr; BvhNode* nodes = nullptr;
+        PrimRec* prims = nullptr; BvhNode* nodes = nullptr; float4* far = nullptr;
         float4 *nlo = nullptr, *nhi = nullptr; int2* kids = nullptr; int* parent = nullptr; unsigned int* arrive = nullptr;
-        if (!dalloc(&prims, n, err, errlen) || !dalloc(&nodes, n > 1 ? n - 1 : 1, err, errlen) ||
+        if (!dalloc(&prims, n, err, errlen) || !dalloc(&nodes, n > 1 ? n - 1 : 1, err, errlen) || !dalloc(&far, n, err, errlen) ||
             !dalloc(&nlo, 2 * (size_t)n, err, errlen) || !dalloc(&nhi, 2 * (size_t)n, err, errlen) ||
             !dalloc(&kids, n, err, errlen) || !dalloc(&parent, 2 * (size_t)n, err, errlen) ||
             !dalloc(&arrive, n, err, errlen)) return false;
         int blocks = (n + 255) / 256;
-        k_gather<<<blocks, 256, 0, stream>>>(rec, blo, bhi, ids2, n, prims, nlo, nhi); out->launches++;
+        k_gather<<<blocks, 256, 0, stream>>>(rec, blo, bhi, far_in, ids2, n, prims, far, nlo, nhi); out->launches++;
         if (n > 1) {
             CK(cudaMemsetAsync(arrive, 0, sizeof(unsigned int) * n, stream));
             k_hierarchy<<<blocks, 256, 0, stream>>>(keys2, n, kids, parent); out->launches++;
@@ -357,11 +415,19 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
         }
         CK(cudaGetLastError());
         cudaFree(nlo); cudaFree(nhi); cudaFree(kids); cudaFree(parent); cudaFree(arrive);
-        out->prims = prims; out->nodes = nodes;
+        out->prims = prims; out->nodes = nodes; out->far = far;
+        if (out->n_always > 0) {
+            int32_t* idx = nullptr;
+            if (!dalloc(&idx, out->n_always, err, errlen)) return false;
+            CK(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int), stream));
+            k_collect_always<<<blocks, 256, 0, stream>>>(far, n, idx, d_counters); out->launches++;
+            CK(cudaStreamSynchronize(stream));
+            out->always_idx = idx;
+        }
     }
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
-    cudaFree(tmp); cudaFree(rec); cudaFree(blo); cudaFree(bhi); cudaFree(keys); cudaFree(keys2); cudaFree(ids); cudaFree(ids2);
+    cudaFree(tmp); cudaFree(rec); cudaFree(blo); cudaFree(bhi); cudaFree(far_in); cudaFree(keys); cudaFree(keys2); cudaFree(ids); cudaFree(ids2);
     cudaFree(d_bounds); cudaFree(d_counters);
     return true;
 }

@@ -24,10 +24,11 @@ int rt580_raytracer_set_assets_path(rt580_raytracer* h, const char* dir) {
     h->rt->SetAssetsPath(d);
     return RT_SUCCESS;
 }
-int rt580_raytracer_set_options(rt580_raytracer* h, int depth, int ao_spp, int rng_mode, int traversal, int device) {
+int rt580_raytracer_set_options(rt580_raytracer* h, int depth, int ao_spp, int rng_mode, int traversal, int device,
+                                int farfield) {
     if (!h) return RT_INVALID_ARG;
     h->rt->SetBounces(depth); h->rt->SetAmbientOcclusionSamples(ao_spp); h->rt->SetRngMode(rng_mode);
-    h->rt->SetTraversal(traversal); h->rt->SetDevice(device);
+    h->rt->SetTraversal(traversal); h->rt->SetDevice(device); h->rt->SetFarField(farfield);
     return RT_SUCCESS;
 }
 int rt580_raytracer_load_scene_json(rt580_raytracer* h, const char* scene) {

@@ -35,6 +35,12 @@ struct __align__(16) BvhNode {
 struct DeviceScene {
     const PrimRec* prims;
     const BvhNode* nodes;
+    const float4* far;         // [n_leaf] far-field filter records (N.xyz, thr), see bvh_build.cu
+    float far_tmin;            // no far-field acceptance is possible at t < far_tmin (sliver list aside)
+    const int32_t* always_idx; // [n_always] sliver triangles whose far field starts inside the scene:
+    int32_t n_always;          //            tested exactly for every ray
+    float extent;              // E: the boxes and far-field records are valid for ray origins with |coordinate| <= E
+    int32_t farfield;          // 1: replay the reference's far-field acceptances (exact), 0: skip
     int32_t n_leaf;            // primitives in the BVH
     int32_t n_prims;           // primitives in reference order (incl. dropped ones)
     const float4* vn;          // [n_prims][3] object-space vertex normals (Q10); unused for spheres

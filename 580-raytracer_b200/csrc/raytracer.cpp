@@ -365,6 +365,7 @@ int Raytracer::GetRenderParams(rt580_render_params* out) {
     memcpy(out->inv_view3x3, mInvView, sizeof mInvView);
     out->depth = mDepth; out->ao_spp = mAoSpp; out->rng_mode = mRngMode; out->traversal = mTraversal;
     out->row_first = 0; out->row_step = 1; out->n_rows = 0;
+    out->farfield = mFarField;
     return RT_SUCCESS;
 }
 

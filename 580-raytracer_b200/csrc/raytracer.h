@@ -74,6 +74,7 @@ public:
     void SetRngMode(int mode) { mRngMode = mode; }
     void SetTraversal(int t) { mTraversal = t; }
     void SetDevice(int device) { mDevice = device; }
+    void SetFarField(int mode) { mFarField = mode; }
     int  RenderToFrameBuffer();                                        // Render without the PPM
     const Pixel* FrameBuffer() const { return mFrameBuffer.data(); }
     int Width() const { return mWidth; }
@@ -94,7 +95,8 @@ private:
     std::vector<Pixel> mFrameBuffer;                                   // Display::frameBuffer h:423
     Scene* mScene = nullptr;
     int mSceneStatus = RT_SUCCESS;
-    int mDepth = 4, mAoSpp = 128, mRngMode = RT580_RNG_REFERENCE_LCG, mTraversal = RT580_TRAVERSAL_AUTO, mDevice = 0;
+    int mDepth = 4, mAoSpp = 128, mRngMode = RT580_RNG_REFERENCE_LCG, mTraversal = RT580_TRAVERSAL_AUTO, mDevice = 0,
+        mFarField = RT580_FARFIELD_EXACT;
     float mInvView[9] = { 0 };
     bool mViewOk = false;
 

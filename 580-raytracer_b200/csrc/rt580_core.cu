@@ -102,7 +102,8 @@ struct rt580_context {
     cudaDeviceProp prop;
     // scene
     DeviceScene sc{};
-    PrimRec* d_prims = nullptr; BvhNode* d_nodes = nullptr;
+    PrimRec* d_prims = nullptr; BvhNode* d_nodes = nullptr; float4* d_far = nullptr;
+    int n_always = 0, n_dropped = 0; int32_t* d_always = nullptr;
     float4* d_vn = nullptr; int32_t* d_prim_material = nullptr; float* d_materials = nullptr;
     int32_t* d_light_type = nullptr; float* d_light_f = nullptr;
     bool have_scene = false;
@@ -150,7 +151,25 @@ __device__ __forceinline__ unsigned warp_alloc(unsigned int* counter, bool want)
 template <int MODE /*0 bvh, 1 linear from smem, 2 linear from global*/, bool ANY>
 __device__ __forceinline__ bool trace_ray(const DeviceScene& sc, const PrimRec* smem_prims, V3 O, V3 d, float tmax,
                                           HitRec& hit) {
-    if (MODE == 0) return traverse_bvh<ANY>(sc, O, d, tmax, hit);
+    if (MODE == 0) {
+        // A ray that starts outside the extent the boxes were padded for can only be the child of a
+        // far-field "hit" (its origin is 10^4..10^7 units away, where one float ulp is larger than a
+        // triangle): nothing can be bounded there, so it takes the reference's own linear loop.
+        if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent)
+            return traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit);
+        bool found = traverse_bvh<ANY>(sc, O, d, tmax, hit);
+        if (ANY && found) return true;
+        if (sc.farfield) {
+            if (sc.n_always) found = always_scan<ANY>(sc, O, d, hit, found);
+            if (ANY) {
+                if (found) return true;
+                if (tmax >= sc.far_tmin) return farfield_scan<true>(sc, O, d, hit, false);
+                return false;
+            }
+            if (!found || hit.t >= sc.far_tmin) found = farfield_scan<false>(sc, O, d, hit, found);
+        }
+        return found;
+    }
     if (MODE == 1) return traverse_linear<ANY, false>(smem_prims, sc.n_leaf, O, d, tmax, hit);
     return traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit);
 }
@@ -558,9 +577,9 @@ extern "C" int rt580_create(int device, rt580_context** out)
 }
 
 static void free_scene(rt580_context* c) {
-    cudaFree(c->d_prims); cudaFree(c->d_nodes); cudaFree(c->d_vn); cudaFree(c->d_prim_material);
+    cudaFree(c->d_prims); cudaFree(c->d_nodes); cudaFree(c->d_far); cudaFree(c->d_always); cudaFree(c->d_vn); cudaFree(c->d_prim_material);
     cudaFree(c->d_materials); cudaFree(c->d_light_type); cudaFree(c->d_light_f);
-    c->d_prims = nullptr; c->d_nodes = nullptr; c->d_vn = nullptr; c->d_prim_material = nullptr;
+    c->d_prims = nullptr; c->d_nodes = nullptr; c->d_far = nullptr; c->d_always = nullptr; c->d_vn = nullptr; c->d_prim_material = nullptr;
     c->d_materials = nullptr; c->d_light_type = nullptr; c->d_light_f = nullptr;
     c->have_scene = false;
 }
@@ -650,7 +669,10 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     cudaFree(v0); cudaFree(v1); cudaFree(v2); cudaFree(tprim); cudaFree(sph); cudaFree(sprim);
     if (bo.max_depth > RT_STACK_SIZE)
         FAIL(RT580_FAILURE, "rt580_upload_scene: LBVH depth %u exceeds the traversal stack (%d)", bo.max_depth, RT_STACK_SIZE);
-    c->d_prims = bo.prims; c->d_nodes = bo.nodes; c->bvh_depth = bo.max_depth; c->pad_extent = bo.extent;
+    c->d_prims = bo.prims; c->d_nodes = bo.nodes; c->d_far = bo.far; c->bvh_depth = bo.max_depth; c->pad_extent = bo.extent;
+    c->sc.far = bo.far; c->sc.far_tmin = bo.far_tmin; c->sc.farfield = 1; c->sc.extent = bo.extent;
+    c->n_always = bo.n_always; c->n_dropped = bo.n_dropped;
+    c->d_always = bo.always_idx; c->sc.always_idx = bo.always_idx; c->sc.n_always = bo.n_always;
     c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_prims = (int32_t)s->n_prims;
     c->sc.vn = c->d_vn; c->sc.prim_material = c->d_prim_material; c->sc.materials = c->d_materials;
     c->sc.n_materials = s->n_materials; c->sc.light_type = c->d_light_type; c->sc.light_f = c->d_light_f;
@@ -660,6 +682,16 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->sc.n_nonambient = s->n_lights - c->sc.n_ambient;
     c->have_scene = true;
     c->frame_begun = false;
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_scene_info_get(rt580_context* c, rt580_scene_info* out) {
+    if (!c || !out) FAIL(RT580_INVALID_ARG, "rt580_scene_info_get: NULL argument");
+    if (!c->have_scene) FAIL(RT580_FAILURE, "rt580_scene_info_get: no scene uploaded");
+    memset(out, 0, sizeof *out);
+    out->n_leaf = c->sc.n_leaf; out->n_dropped = c->n_dropped; out->n_always = c->n_always;
+    out->far_tmin = c->sc.far_tmin; out->pad = c->pad_extent / 262144.0f; out->extent = c->pad_extent;
+    out->build_ms = c->build_ms; out->bvh_max_depth = c->bvh_depth;
     return RT580_SUCCESS;
 }
 
@@ -751,6 +783,8 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
     memcpy(fp.cam, p->camera_from, sizeof fp.cam);
     memcpy(fp.inv, p->inv_view3x3, sizeof fp.inv);
     c->traversal = p->traversal;
+    if (p->farfield != RT580_FARFIELD_EXACT && p->farfield != RT580_FARFIELD_OFF) FAIL(RT580_INVALID_ARG, "rt580_render_begin: bad farfield");
+    c->sc.farfield = (p->farfield == RT580_FARFIELD_EXACT) ? 1 : 0;
     const int mode = pick_mode(c, p->traversal);
     cudaStream_t st = c->stream;
     c->launches = 0;
@@ -763,8 +797,11 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
         const float half = p->fov_degrees / 2;
         const float rad = (float)(half * (3.14159265 / 180));                 // ToRadian h:581-583
         const float aspect = (float)fp.W / (float)fp.H;                       // cpp:836
-        for (int x = 0; x < fp.W; x++) { double n = (2.0 * x) / fp.W - 1; n *= aspect * tan(rad); t[x] = (float)n; }
-        for (int y = 0; y < fp.H; y++) { double n = 1 - (2.0 * y) / fp.H; n *= tan(rad); t[(size_t)fp.W + y] = (float)n; }
+        // the reference's unqualified tan() is the C library's DOUBLE function of the float radian (Q27);
+        // in a .cu file a bare tan(float) would bind to CUDA's float overload, hence the explicit form
+        const double tan_half = ::tan((double)rad);
+        for (int x = 0; x < fp.W; x++) { double n = (2.0 * x) / fp.W - 1; n *= (double)aspect * tan_half; t[x] = (float)n; }
+        for (int y = 0; y < fp.H; y++) { double n = 1 - (2.0 * y) / fp.H; n *= tan_half; t[(size_t)fp.W + y] = (float)n; }
         CU(c->ndc.ensure(t.size(), 0, st));
         CU(cudaMemcpyAsync(c->ndc.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
@@ -950,6 +987,7 @@ static int trace_rays_common(rt580_context* c, bool any, int64_t n, const float*
     if (any) { CU(cudaMalloc(&tm, sizeof(float) * n)); CU(cudaMemcpy(tm, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)); CU(cudaMalloc(&h, n)); }
     else { CU(cudaMalloc(&t, sizeof(float) * n)); CU(cudaMalloc(&pr, sizeof(int32_t) * n)); }
     const int mode = pick_mode(c, traversal);
+    c->sc.farfield = 1;     // the checkers always run the exact path
     DISPATCH_MODE(mode, launch_rays, c, any, (long long)n, o, d, tm, pr, t, h);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());

@@ -151,6 +151,47 @@ __device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, 
     return found;
 }
 
+// Far-field replay (bvh_build.cu header): the reference's float test also accepts "hits" at
+// t >= far_tmin for rays almost parallel to a triangle's plane.  No box can bound those, so a
+// ray that found nothing nearer tests every triangle whose filter record says it could be one:
+// |N.d| <= thr  (thr >= |N.O + D| / T_far, so t_plane >= T_far implies the filter passes), and
+// runs the reference's exact test on the survivors.  All lanes of a warp read the same record
+// (one broadcast load), so the scan costs ~8 instructions per (ray, triangle).
+template <bool ANY>
+__device__ __forceinline__ bool farfield_scan(const DeviceScene& sc, V3 O, V3 d, HitRec& best, bool found)
+{
+    const float4* __restrict__ far = sc.far;
+    const int n = sc.n_leaf;
+    for (int i = 0; i < n; i++) {
+        const float4 f = __ldg(far + i);
+        const float nd = __fmaf_rn(f.x, d.x, __fmaf_rn(f.y, d.y, f.z * d.z));   // filter only: FMA is fine
+        if (fabsf(nd) <= f.w) {
+            float t; int prim;
+            if (prim_test<true>(sc.prims + i, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+                if (ANY) return true;
+                best.t = t; best.leaf = i; best.prim = prim; found = true;
+            }
+        }
+    }
+    return found;
+}
+
+// Sliver triangles whose far field begins inside the scene (bvh_build.cu: thr >= 4): exact test
+// for every ray, whatever the BVH found.
+template <bool ANY>
+__device__ __forceinline__ bool always_scan(const DeviceScene& sc, V3 O, V3 d, HitRec& best, bool found)
+{
+    for (int k = 0; k < sc.n_always; k++) {
+        const int i = __ldg(sc.always_idx + k);
+        float t; int prim;
+        if (prim_test<true>(sc.prims + i, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+            if (ANY) return true;
+            best.t = t; best.leaf = i; best.prim = prim; found = true;
+        }
+    }
+    return found;
+}
+
 // The reference's own linear loop (cpp:476-521) over `n` records, e.g. staged in shared memory.
 template <bool ANY, bool GLOBAL>
 __device__ __forceinline__ bool traverse_linear(const PrimRec* __restrict__ prims, int n, V3 O, V3 d, float tmax,

@@ -49,6 +49,14 @@ extern "C" {
 #define RT580_TRAVERSAL_BVH         1
 #define RT580_TRAVERSAL_BRUTE_FORCE 2   /* the reference's own linear loop, on the GPU (checker / tiny scenes) */
 
+/* The reference's float triangle test (cpp:392-396) also accepts points 10^4..10^7 units away
+ * when a ray is almost parallel to a triangle's plane (the cross product at cpp:392 is rounding
+ * noise there).  Those "hits" decide hit/miss for rays that leave the scene, so they are part of
+ * the reference's image.  EXACT replays them (bit-identical to the linear loop, costs a scan of
+ * the filter records for every ray that finds nothing nearer); OFF treats them as misses. */
+#define RT580_FARFIELD_EXACT 0
+#define RT580_FARFIELD_OFF   1
+
 typedef struct rt580_context rt580_context;
 
 /* Scene after the load-time flatten (replaces the per-ray work of cpp:477-480 and
@@ -93,7 +101,20 @@ typedef struct rt580_render_params {
     /* rows rendered by this context: row_first + k*row_step, k in [0,n_rows).
      * n_rows == 0 means the whole frame (row_first 0, step 1). */
     int32_t row_first, row_step, n_rows;
+    int32_t farfield;              /* RT580_FARFIELD_*                                     */
 } rt580_render_params;
+
+typedef struct rt580_scene_info {
+    int64_t  n_leaf;               /* primitives in the BVH                                */
+    int64_t  n_dropped;            /* zero-area triangles (never intersectable, cpp:365-373) */
+    int64_t  n_always;             /* sliver triangles that are far-field candidates for every ray */
+    float    far_tmin;             /* smallest t at which a far-field acceptance is possible */
+    float    pad;                  /* global part of the box padding                       */
+    float    extent;               /* E: bound on |coordinate| of ray origins / hit points */
+    float    build_ms;             /* device time of the build kernels                     */
+    uint32_t bvh_max_depth;
+    uint32_t reserved;
+} rt580_scene_info;
 
 typedef struct rt580_stats {
     uint64_t rays_primary;         /* IntersectScene calls from cpp:30 at depth 0          */
@@ -124,6 +145,7 @@ int  rt580_device_info(rt580_context* ctx, int32_t* sm_count, int32_t* sm_clock_
 int  rt580_upload_scene(rt580_context* ctx, const rt580_flat_scene* scene);
 /* device ms of the last upload's build kernels (setup, morton, sort, hierarchy, refit, pack) */
 int  rt580_build_ms(rt580_context* ctx, float* ms);
+int  rt580_scene_info_get(rt580_context* ctx, rt580_scene_info* out);
 
 /* ---- frame: replaces the loop body of Raytracer::Render (cpp:921-932) ------------------ */
 /* One call = whole frame (or the rows in params) on this context's GPU.
@@ -161,7 +183,7 @@ rt580_raytracer* rt580_raytracer_new(int width, int height);                 /* 
 void rt580_raytracer_delete(rt580_raytracer* rt);
 int  rt580_raytracer_set_assets_path(rt580_raytracer* rt, const char* dir);  /* ASSETS_PATH, h:15     */
 int  rt580_raytracer_set_options(rt580_raytracer* rt, int depth, int ao_spp, int rng_mode, int traversal,
-                                 int device);                                /* h:563, cpp:317        */
+                                 int device, int farfield);                  /* h:563, cpp:317        */
 int  rt580_raytracer_load_scene_json(rt580_raytracer* rt, const char* scene);/* h:572 LoadSceneJSON   */
 int  rt580_raytracer_render(rt580_raytracer* rt, const char* output_ppm);    /* h:586 Render          */
 int  rt580_raytracer_flush_ppm(rt580_raytracer* rt, const char* output_ppm); /* h:573                 */

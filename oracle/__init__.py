@@ -188,6 +188,9 @@ def t1_lib():
             ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_void_p]
         lib.orc580_intersect_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 4 + [ctypes.c_int]
+        lib.orc580_render_log.restype = ctypes.c_int64
+        lib.orc580_render_log.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_int64, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 6
         lib.orc580_gamma_encode.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         _t1 = lib
     return _t1
@@ -247,6 +250,25 @@ class Oracle:
         if pix is None:
             out = out.reshape(H, W, 3)
         return out, rays.value, hits
+
+    def render_log(self, W, H, spp, depth, pix=None, ao_base=None, max_rays=1 << 22):
+        """Serial render that logs every IntersectScene call: -> dict(org, dir, prim, t, kind, fb)"""
+        if pix is not None:
+            pix = np.ascontiguousarray(pix, np.int32)
+            n = pix.size
+        else:
+            n = W * H
+        if ao_base is not None:
+            ao_base = np.ascontiguousarray(ao_base, np.uint64)
+        org = np.zeros((max_rays, 3), np.float32); dirs = np.zeros((max_rays, 3), np.float32)
+        prim = np.zeros(max_rays, np.int64); t = np.zeros(max_rays, np.float32); kind = np.zeros(max_rays, np.int32)
+        out = np.zeros((n, 3), np.int16)
+        m = t1_lib().orc580_render_log(self._world, W, H, spp, depth, n, _ptr(pix) if pix is not None else None,
+                                       _ptr(ao_base) if ao_base is not None else None, max_rays, org.ctypes.data,
+                                       dirs.ctypes.data, prim.ctypes.data, t.ctypes.data, kind.ctypes.data, out.ctypes.data)
+        if m < 0:
+            raise RuntimeError("orc580_render_log failed")
+        return {"org": org[:m], "dir": dirs[:m], "prim": prim[:m], "t": t[:m], "kind": kind[:m], "fb": out}
 
     def intersect(self, org, dirs, nthreads=1):
         org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)

@@ -488,7 +488,22 @@ typedef struct {
     uint64_t ao_ordinal;  /* global ordinal of the next AO call */
     uint64_t rays;
     uint32_t hit_nodes;
+    /* optional log of every IntersectScene call (debug / ray-level parity checks) */
+    int64_t log_cap, log_n;
+    float* log_org; float* log_dir; int64_t* log_prim; float* log_t; int32_t* log_kind;
 } rctx;
+
+enum { RAY_PRIMARY_OR_SECONDARY = 0, RAY_SHADOW = 1, RAY_AO = 2 };
+static int intersect_scene_logged(rctx* c, v3 O, v3 d, hitinfo* out, int kind) {
+    int hit = intersect_scene(c->w, O, d, out, &c->rays);
+    if (c->log_org && c->log_n < c->log_cap) {
+        int64_t i = c->log_n++;
+        c->log_org[3 * i] = O.x; c->log_org[3 * i + 1] = O.y; c->log_org[3 * i + 2] = O.z;
+        c->log_dir[3 * i] = d.x; c->log_dir[3 * i + 1] = d.y; c->log_dir[3 * i + 2] = d.z;
+        c->log_prim[i] = hit ? out->prim : -1; c->log_t[i] = hit ? out->distance : 0.0f; c->log_kind[i] = kind;
+    }
+    return hit;
+}
 
 /* cpp:315-330 */
 static float ambient_occlusion(rctx* c, v3 hitPoint, v3 normal) {
@@ -499,7 +514,7 @@ static float ambient_occlusion(rctx* c, v3 hitPoint, v3 normal) {
         v3 org = vadd(hitPoint, vmuls(dir, SHADOW_CLIPPING_OFFSET));
         v3 rd = vnormalize(dir);                  /* Ray ctor h:431-433 */
         hitinfo tmp;
-        if (intersect_scene(c->w, org, rd, &tmp, &c->rays)) occlusion += 1.0f;
+        if (intersect_scene_logged(c, org, rd, &tmp, RAY_AO)) occlusion += 1.0f;
     }
     c->rng = st;
     c->ao_ordinal++;
@@ -511,7 +526,7 @@ static pix raycast(rctx* c, v3 O, v3 d, int bounces) {
     const orc_world* w = c->w;
     hitinfo info;
     pix BG = { 254, 64, 205 };                                     /* h:597 */
-    if (!intersect_scene(w, O, d, &info, &c->rays)) return BG;     /* cpp:30-32 */
+    if (!intersect_scene_logged(c, O, d, &info, RAY_PRIMARY_OR_SECONDARY)) return BG;     /* cpp:30-32 */
     c->hit_nodes++;
     const wmat* M = &w->mats[info.shape];
     pix local = { 0, 0, 0 };                                       /* h:598 */
@@ -532,7 +547,7 @@ static pix raycast(rctx* c, v3 O, v3 d, int bounces) {
             v3 sd = vnormalize(lightDir);                          /* Ray ctor */
             float distToLight = vlength(vsub(L->position, info.hitPoint));        /* cpp:71 */
             hitinfo li_info;
-            if (!intersect_scene(w, so, sd, &li_info, &c->rays) || (li_info.distance > distToLight && L->type == 1))
+            if (!intersect_scene_logged(c, so, sd, &li_info, RAY_SHADOW) || (li_info.distance > distToLight && L->type == 1))
                 local = pix_add(local, calculate_local_color(w, &info, L, M));    /* cpp:75-78 */
             /* else + SHADOW_COLOR (0,0,0) cpp:80 */
         }
@@ -658,6 +673,27 @@ int orc580_render(const orc_world* w, int W, int H, int spp, int depth,
     if (rays_out) *rays_out = total_rays;
     free(base);
     return have_inv ? RT_SUCCESS : RT_FAILURE;
+}
+
+/* Serial render of the listed pixels that also records every IntersectScene call in order. */
+int64_t orc580_render_log(const orc_world* w, int W, int H, int spp, int depth, int64_t npix, const int32_t* pix_ids,
+                          const uint64_t* ao_base, int64_t max_rays, float* org3, float* dir3, int64_t* prim,
+                          float* t, int32_t* kind, int16_t* out) {
+    mat4 inv;
+    if (view_inverse(w, &inv) != RT_SUCCESS) return -1;
+    rctx c; memset(&c, 0, sizeof c);
+    c.w = w; c.spp = spp; c.rng = 1u;
+    c.log_cap = max_rays; c.log_org = org3; c.log_dir = dir3; c.log_prim = prim; c.log_t = t; c.log_kind = kind;
+    if (!pix_ids) npix = (int64_t)W * H;
+    for (int64_t i = 0; i < npix; i++) {
+        int p = pix_ids ? pix_ids[i] : (int)i;
+        if (ao_base) { c.random_access = 1; c.ao_ordinal = ao_base[i]; }
+        v3 O, d;
+        generate_ray(w, &inv, W, H, p % W, p / W, &O, &d);
+        pix r = raycast(&c, O, d, depth);
+        if (out) { out[3 * i] = r.r; out[3 * i + 1] = r.g; out[3 * i + 2] = r.b; }
+    }
+    return c.log_n;
 }
 
 /* cpp:809-823 (Q24) */

@@ -77,6 +77,14 @@ int orc580_render(const orc_world* w, int W, int H, int spp, int depth,
 void orc580_intersect_batch(const orc_world* w, int64_t n, const float* org3, const float* dir3,
                             int64_t* prim_out, float* t_out, int nthreads);
 
+/* Serial render of the listed pixels (NULL = whole frame) that also records every
+ * IntersectScene call in call order: origin, direction, closest primitive (-1 = miss), t,
+ * kind (0 primary/secondary cpp:30, 1 shadow cpp:75, 2 AO cpp:325).  Returns the number of
+ * rays logged (capped at max_rays), -1 on failure. */
+int64_t orc580_render_log(const orc_world* w, int W, int H, int spp, int depth, int64_t npix, const int32_t* pix,
+                          const uint64_t* ao_base, int64_t max_rays, float* org3, float* dir3, int64_t* prim,
+                          float* t, int32_t* kind, int16_t* out);
+
 /* cpp:796-830 gamma encode of a raw frame buffer into 8-bit RGB. */
 void orc580_gamma_encode(const int16_t* fb, int64_t n_channels, uint8_t* out);
 
