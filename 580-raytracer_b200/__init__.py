@@ -27,10 +27,10 @@ LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AMBIENT = 0, 1, 2
 # every symbol include/rt580.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "rt580_create", "rt580_destroy", "rt580_last_error", "rt580_device_info", "rt580_upload_scene", "rt580_build_ms",
-    "rt580_scene_info_get",
-    "rt580_render", "rt580_render_begin", "rt580_render_finish", "rt580_trace_closest", "rt580_trace_any",
+    "rt580_scene_info_get", "rt580_get_stream",
+    "rt580_render", "rt580_render_begin", "rt580_render_finish", "rt580_trace_closest", "rt580_trace_any", "rt580_trace_profile",
     "rt580_last_frame_ao_base", "rt580_hemisphere_stream", "rt580_powf",
-    "rt580_raytracer_new", "rt580_raytracer_delete", "rt580_raytracer_set_assets_path", "rt580_raytracer_set_options",
+    "rt580_raytracer_new", "rt580_raytracer_delete", "rt580_raytracer_set_assets_path", "rt580_raytracer_set_options", "rt580_raytracer_set_quiet",
     "rt580_raytracer_load_scene_json", "rt580_raytracer_render", "rt580_raytracer_flush_ppm",
     "rt580_raytracer_framebuffer", "rt580_raytracer_stats", "rt580_raytracer_flat_scene",
     "rt580_raytracer_render_params",
@@ -90,7 +90,7 @@ class Stats(ctypes.Structure):
         ("ms_structure", ctypes.c_float), ("ms_order", ctypes.c_float), ("ms_ao", ctypes.c_float),
         ("ms_resolve", ctypes.c_float), ("ms_total", ctypes.c_float), ("ms_ao_kernel", ctypes.c_float),
         ("kernel_launches", ctypes.c_uint32), ("bvh_max_depth", ctypes.c_uint32),
-        ("reserved0", ctypes.c_uint32), ("reserved1", ctypes.c_uint32),
+        ("far_scans", ctypes.c_uint32), ("linear_fallbacks", ctypes.c_uint32),
     ]
 
     @property
@@ -124,6 +124,7 @@ def lib():
         L.rt580_destroy.argtypes = [vp]
         L.rt580_destroy.restype = None
         L.rt580_device_info.argtypes = [vp, vp, vp, vp]
+        L.rt580_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
         L.rt580_upload_scene.argtypes = [vp, ctypes.POINTER(FlatScene)]
         L.rt580_build_ms.argtypes = [vp, vp]
         L.rt580_scene_info_get.argtypes = [vp, ctypes.POINTER(SceneInfo)]
@@ -132,6 +133,7 @@ def lib():
         L.rt580_render_finish.argtypes = [vp, vp, vp, i32, ctypes.POINTER(Stats)]
         L.rt580_trace_closest.argtypes = [vp, i64, vp, vp, i32, vp, vp]
         L.rt580_trace_any.argtypes = [vp, i64, vp, vp, vp, i32, vp]
+        L.rt580_trace_profile.argtypes = [vp, i64, vp, vp, vp, vp]
         L.rt580_last_frame_ao_base.argtypes = [vp, vp]
         L.rt580_hemisphere_stream.argtypes = [vp, vp, ctypes.c_uint64, i32, vp]
         L.rt580_powf.argtypes = [vp, i64, vp, vp, vp]
@@ -141,6 +143,7 @@ def lib():
         L.rt580_raytracer_delete.restype = None
         L.rt580_raytracer_set_assets_path.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_set_options.argtypes = [vp, i32, i32, i32, i32, i32, i32]
+        L.rt580_raytracer_set_quiet.argtypes = [vp, i32]
         L.rt580_raytracer_load_scene_json.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_render.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_flush_ppm.argtypes = [vp, ctypes.c_char_p]
@@ -182,6 +185,11 @@ class Context:
         sm, mhz, mem = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_uint64()
         _check(lib().rt580_device_info(self._h, ctypes.addressof(sm), ctypes.addressof(mhz), ctypes.addressof(mem)))
         return {"sm_count": sm.value, "sm_clock_mhz": mhz.value, "hbm_bytes": mem.value}
+
+    def stream(self):
+        s = ctypes.c_void_p()
+        _check(lib().rt580_get_stream(self._h, ctypes.byref(s)))
+        return s.value or 0
 
     def upload_scene(self, flat: FlatScene):
         _check(lib().rt580_upload_scene(self._h, ctypes.byref(flat)))
@@ -244,6 +252,18 @@ class Context:
         _check(lib().rt580_trace_any(self._h, n, org.ctypes.data, dirs.ctypes.data, tmax.ctypes.data, traversal, hit.ctypes.data))
         return hit
 
+    def trace_profile(self, org, dirs, tmax=None):
+        org = np.ascontiguousarray(org, np.float32).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = org.shape[0]
+        cnt = np.zeros((n, 4), np.uint32)
+        tptr = None
+        if tmax is not None:
+            tmax = np.ascontiguousarray(tmax, np.float32)
+            tptr = tmax.ctypes.data
+        _check(lib().rt580_trace_profile(self._h, n, org.ctypes.data, dirs.ctypes.data, tptr, cnt.ctypes.data))
+        return cnt
+
     def last_frame_ao_base(self, n_pixels):
         out = np.zeros(n_pixels, np.uint64)
         _check(lib().rt580_last_frame_ao_base(self._h, out.ctypes.data))
@@ -266,10 +286,11 @@ class Context:
 class Raytracer:
     """The reference's class, method for method (Raytracer.h:557-588), over the C ABI."""
 
-    def __init__(self, width, height):
+    def __init__(self, width, height, quiet=True):
         self._h = lib().rt580_raytracer_new(width, height)
         if not self._h:
             raise Rt580Error(RT_FAILURE, "rt580_raytracer_new failed")
+        lib().rt580_raytracer_set_quiet(self._h, 1 if quiet else 0)
         self.width, self.height = width, height
         self._opts = dict(depth=4, ao_spp=128, rng_mode=RNG_REFERENCE_LCG, traversal=TRAVERSAL_AUTO, device=0,
                           farfield=FARFIELD_EXACT)

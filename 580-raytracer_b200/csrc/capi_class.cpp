@@ -31,6 +31,11 @@ int rt580_raytracer_set_options(rt580_raytracer* h, int depth, int ao_spp, int r
     h->rt->SetTraversal(traversal); h->rt->SetDevice(device); h->rt->SetFarField(farfield);
     return RT_SUCCESS;
 }
+int rt580_raytracer_set_quiet(rt580_raytracer* h, int quiet) {
+    if (!h) return RT_INVALID_ARG;
+    h->rt->SetQuiet(quiet != 0);
+    return RT_SUCCESS;
+}
 int rt580_raytracer_load_scene_json(rt580_raytracer* h, const char* scene) {
     if (!h || !scene) return RT_INVALID_ARG;
     try { return h->rt->LoadSceneJSON(scene); } catch (...) { return RT_FAILURE; }

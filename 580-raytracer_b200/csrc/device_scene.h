@@ -40,6 +40,7 @@ struct DeviceScene {
     const int32_t* always_idx; // [n_always] sliver triangles whose far field starts inside the scene:
     int32_t n_always;          //            tested exactly for every ray
     float extent;              // E: the boxes and far-field records are valid for ray origins with |coordinate| <= E
+    unsigned int* diag;        // [2] device counters: far-field scans, linear fallbacks (rare events)
     int32_t farfield;          // 1: replay the reference's far-field acceptances (exact), 0: skip
     int32_t n_leaf;            // primitives in the BVH
     int32_t n_prims;           // primitives in reference order (incl. dropped ones)

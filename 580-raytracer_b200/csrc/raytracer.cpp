@@ -130,7 +130,7 @@ Raytracer::Matrix Raytracer::ComputeModelMatrix(const Transformation& tr) {
 int Raytracer::LoadMesh(const std::string meshName) {
     if (!mScene) return RT_FAILURE;
     if (mScene->meshMap.find(meshName) != mScene->meshMap.end()) {
-        std::cout << "Mesh map already contains " << meshName << ". Skipped loading" << std::endl;
+        if (!mQuiet) std::cout << "Mesh map already contains " << meshName << ". Skipped loading" << std::endl;
         return RT_SUCCESS;
     }
     std::string text;
@@ -248,7 +248,7 @@ int Raytracer::LoadSceneJSON(const std::string scenePath) {
                 mScene->lights.push_back(light);
             }
         }
-        std::cout << "Scene parsing completed!\n";
+        if (!mQuiet) std::cout << "Scene parsing completed!\n";
         mSceneStatus = status;
         if (status == RT_SUCCESS) status |= FlattenScene();
         return status;

@@ -75,6 +75,7 @@ public:
     void SetTraversal(int t) { mTraversal = t; }
     void SetDevice(int device) { mDevice = device; }
     void SetFarField(int mode) { mFarField = mode; }
+    void SetQuiet(bool q) { mQuiet = q; }                              // silence the loader's cout chatter (cpp:592, 772)
     int  RenderToFrameBuffer();                                        // Render without the PPM
     const Pixel* FrameBuffer() const { return mFrameBuffer.data(); }
     int Width() const { return mWidth; }
@@ -99,6 +100,7 @@ private:
         mFarField = RT580_FARFIELD_EXACT;
     float mInvView[9] = { 0 };
     bool mViewOk = false;
+    bool mQuiet = false;
 
     // flattened scene (host SoA, float4 records) handed to rt580_upload_scene
     std::vector<float> mTriV0, mTriV1, mTriV2, mTriN0, mTriN1, mTriN2, mSphere, mMaterials, mLightF;

@@ -148,30 +148,38 @@ __device__ __forceinline__ unsigned warp_alloc(unsigned int* counter, bool want)
 
 #define RT_SMEM_PRIMS 64   // scenes up to this many primitives are staged in shared memory
 
+// One ray per lane, called by ALL 32 lanes of a warp (inactive lanes pass active = false):
+// the tree answers almost every ray; the rare ones it cannot (trace.cuh: warp_slow_path) are
+// then served by the whole warp.
 template <int MODE /*0 bvh, 1 linear from smem, 2 linear from global*/, bool ANY>
-__device__ __forceinline__ bool trace_ray(const DeviceScene& sc, const PrimRec* smem_prims, V3 O, V3 d, float tmax,
-                                          HitRec& hit) {
-    if (MODE == 0) {
-        // A ray that starts outside the extent the boxes were padded for can only be the child of a
-        // far-field "hit" (its origin is 10^4..10^7 units away, where one float ulp is larger than a
-        // triangle): nothing can be bounded there, so it takes the reference's own linear loop.
-        if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent)
-            return traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit);
-        bool found = traverse_bvh<ANY>(sc, O, d, tmax, hit);
-        if (ANY && found) return true;
-        if (sc.farfield) {
-            if (sc.n_always) found = always_scan<ANY>(sc, O, d, hit, found);
-            if (ANY) {
-                if (found) return true;
-                if (tmax >= sc.far_tmin) return farfield_scan<true>(sc, O, d, hit, false);
-                return false;
+__device__ __forceinline__ bool trace_ray(const DeviceScene& sc, const PrimRec* smem_prims, bool active, V3 O, V3 d,
+                                          float tmax, HitRec& hit, unsigned* cnt = nullptr) {
+    if (MODE == 1) return active ? traverse_linear<ANY, false>(smem_prims, sc.n_leaf, O, d, tmax, hit) : false;
+    if (MODE == 2) return active ? traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit) : false;
+    bool found = false, need = false, linear = false;
+    hit.t = ANY ? tmax : __int_as_float(0x7f800000); hit.leaf = -1; hit.prim = 0x7fffffff;
+    if (active) {
+        if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent) {
+            // starts outside the extent the boxes were padded for: only the child of a far-field
+            // "hit" can (one float ulp out there is larger than a triangle) -> reference's linear loop
+            need = true; linear = true;
+            if (cnt) cnt[3]++;
+            if (sc.diag) atomicAdd(sc.diag + 1, 1u);
+        } else {
+            found = traverse_bvh<ANY>(sc, O, d, tmax, hit, cnt);
+            // a zero direction (total internal reflection, cpp:197-199, Q20) fails |N.d| >= EPSILON for
+            // every triangle (cpp:371): only spheres can "hit" it, and those are all in the tree
+            const bool zero_dir = (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f);
+            if (!(ANY && found) && sc.farfield && !zero_dir) {
+                if (sc.n_always) found = always_scan<ANY>(sc, O, d, hit, found);
+                if (ANY) need = !found && tmax >= sc.far_tmin;
+                else need = !found || hit.t >= sc.far_tmin;
+                if (need) { if (cnt) cnt[2]++; if (sc.diag) atomicAdd(sc.diag, 1u); }
             }
-            if (!found || hit.t >= sc.far_tmin) found = farfield_scan<false>(sc, O, d, hit, found);
         }
-        return found;
     }
-    if (MODE == 1) return traverse_linear<ANY, false>(smem_prims, sc.n_leaf, O, d, tmax, hit);
-    return traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit);
+    if (sc.farfield) found = warp_slow_path<ANY>(sc, need, linear, O, d, hit, found);
+    return found;
 }
 
 template <int MODE>
@@ -246,8 +254,8 @@ k_trace(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, unsigned
             parent = __float_as_int(qo.w); flags = __float_as_uint(qd.w);
         }
     }
-    HitRec h; bool hit = false;
-    if (active) hit = trace_ray<MODE, false>(sc, sp, O, d, 0.f, h);
+    HitRec h;
+    const bool hit = trace_ray<MODE, false>(sc, sp, active, O, d, 0.f, h);
     const unsigned slot = warp_alloc(&counters[0], hit);
     if (!active) return;
     if (hit) {
@@ -282,7 +290,7 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
     const unsigned i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n1;
     bool want_refl = false, want_refr = false;
-    V3 P = mk(0, 0, 0), N = mk(0, 0, 0), D = mk(0, 0, 0);
+    V3 P = mk(0, 0, 0), N = mk(0, 0, 0), D = mk(0, 0, 0), sn = mk(0, 0, 0);
     unsigned flags = 0; int bounces = 0;
     Material M{};
     if (active) {
@@ -293,30 +301,33 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
         const int prim = __float_as_int(nd.P.w);
         M = load_material(sc.materials, __ldg(sc.prim_material + prim));
         // shading normal (cpp:225-236)
-        V3 sn = N;
+        sn = N;
         if (!(flags & NF_SPHERE)) {
             const float4 a = __ldg(sc.vn + 3 * (size_t)prim), b = __ldg(sc.vn + 3 * (size_t)prim + 1),
                          c = __ldg(sc.vn + 3 * (size_t)prim + 2);
             sn = normalize((mk(a.x, a.y, a.z) * nd.B.x + mk(b.x, b.y, b.z) * nd.B.y) + mk(c.x, c.y, c.z) * nd.B.z);   // cpp:334-336
         }
-        Pix local = mkpix(0, 0, 0);                                   // SHADOW_COLOR h:598
-        const V3 cam = mk(fp.cam[0], fp.cam[1], fp.cam[2]);
-        for (int li = 0; li < sc.n_lights; li++) {                    // cpp:39
-            const Light L = load_light(sc.light_type, sc.light_f, li);
-            if (L.type == RT580_LIGHT_AMBIENT) continue;              // handled by k_ao / k_resolve
-            V3 lightDir = mk(0, 0, 0);
-            if (L.type == RT580_LIGHT_DIRECTIONAL) lightDir = -L.direction;          // cpp:56-60
-            else if (L.type == RT580_LIGHT_POINT) lightDir = L.position - P;         // cpp:62-64
-            lightDir = normalize(lightDir);                                          // cpp:65
-            const V3 so = P + lightDir * RT_SHADOW_OFFSET;                           // cpp:67
-            const V3 sd = normalize(lightDir);                                       // Ray ctor h:431-433
-            const float distToLight = length(L.position - P);                        // cpp:71
-            HitRec sh;
-            // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
-            const float tmax = (L.type == RT580_LIGHT_POINT) ? distToLight : __int_as_float(0x7f800000);
-            const bool occluded = trace_ray<MODE, true>(sc, sp, so, sd, tmax, sh);
-            if (!occluded) local = pix_add(local, calculate_local_color(P, sn, L, M, cam));   // cpp:77
-        }
+    }
+    Pix local = mkpix(0, 0, 0);                                       // SHADOW_COLOR h:598
+    const V3 cam = mk(fp.cam[0], fp.cam[1], fp.cam[2]);
+    // the light loop is uniform over the warp (trace_ray is warp-collective)
+    for (int li = 0; li < sc.n_lights; li++) {                        // cpp:39
+        const Light L = load_light(sc.light_type, sc.light_f, li);
+        if (L.type == RT580_LIGHT_AMBIENT) continue;                  // handled by k_ao / k_resolve
+        V3 lightDir = mk(0, 0, 0);
+        if (L.type == RT580_LIGHT_DIRECTIONAL) lightDir = -L.direction;          // cpp:56-60
+        else if (L.type == RT580_LIGHT_POINT) lightDir = L.position - P;         // cpp:62-64
+        lightDir = normalize(lightDir);                                          // cpp:65
+        const V3 so = P + lightDir * RT_SHADOW_OFFSET;                           // cpp:67
+        const V3 sd = normalize(lightDir);                                       // Ray ctor h:431-433
+        const float distToLight = length(L.position - P);                        // cpp:71
+        HitRec sh;
+        // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
+        const float tmax = (L.type == RT580_LIGHT_POINT) ? distToLight : __int_as_float(0x7f800000);
+        const bool occluded = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh);
+        if (active && !occluded) local = pix_add(local, calculate_local_color(P, sn, L, M, cam));   // cpp:77
+    }
+    if (active) {
         NodeAux a;
         a.local[0] = local.r; a.local[1] = local.g; a.local[2] = local.b; a.local[3] = 0;
         a.refl[0] = a.refl[1] = a.refl[2] = a.refl[3] = 0;            // Pixel() (cpp:91-92)
@@ -445,7 +456,8 @@ k_ao(DeviceScene sc, FrameParams fp, unsigned long long n_rays, int n_ambient, c
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n_rays;
-    unsigned call = 0xffffffffu; bool hit = false;
+    unsigned call = 0xffffffffu;
+    V3 org = mk(0, 0, 0), rd = mk(0, 0, 0);
     if (active) {
         call = (unsigned)(i / (unsigned)fp.spp);
         const unsigned k = (unsigned)(i % (unsigned)fp.spp);
@@ -455,11 +467,11 @@ k_ao(DeviceScene sc, FrameParams fp, unsigned long long n_rays, int n_ambient, c
         const float4 nP = __ldg(&nodes[node].P), nN = __ldg(&nodes[node].N);
         const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
         const V3 dir = random_in_hemisphere(st, N);                            // cpp:321
-        const V3 org = P + dir * RT_SHADOW_OFFSET;                             // cpp:322
-        const V3 rd = normalize(dir);                                          // Ray ctor h:431-433
-        HitRec h;
-        hit = trace_ray<MODE, true>(sc, sp, org, rd, __int_as_float(0x7f800000), h);   // cpp:325
+        org = P + dir * RT_SHADOW_OFFSET;                                      // cpp:322
+        rd = normalize(dir);                                                   // Ray ctor h:431-433
     }
+    HitRec h;
+    const bool hit = trace_ray<MODE, true>(sc, sp, active, org, rd, __int_as_float(0x7f800000), h);   // cpp:325
     // count the occluded samples of each AO call inside the warp, one atomic per (warp, call)
     const unsigned peers = __match_any_sync(0xffffffffu, call);
     const unsigned votes = __ballot_sync(0xffffffffu, hit);
@@ -526,12 +538,32 @@ k_trace_rays(DeviceScene sc, long long n, const float* __restrict__ org, const f
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V3 O = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    const bool active = i < n;
+    V3 O = mk(0, 0, 0), d = mk(0, 0, 0);
+    if (active) { O = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]); d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]); }
     HitRec h;
-    const bool hit = trace_ray<MODE, ANY>(sc, sp, O, d, ANY ? tmax[i] : 0.f, h);
+    const bool hit = trace_ray<MODE, ANY>(sc, sp, active, O, d, (ANY && active) ? tmax[i] : 0.f, h);
+    if (!active) return;
     if (ANY) hit_out[i] = hit ? 1 : 0;
     else { prim_out[i] = hit ? h.prim : -1; t_out[i] = hit ? h.t : 0.f; }
+}
+
+// traversal profile of arbitrary rays (BVH path): per ray node visits, leaf tests, far-field scans,
+// linear fallbacks -> tuning data, not part of the frame path
+template <bool ANY>
+__global__ void __launch_bounds__(128)
+k_trace_profile(DeviceScene sc, long long n, const float* __restrict__ org, const float* __restrict__ dir,
+                const float* __restrict__ tmax, unsigned* __restrict__ counts4)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    V3 O = mk(0, 0, 0), d = mk(0, 0, 0);
+    if (active) { O = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]); d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]); }
+    HitRec h;
+    unsigned cnt[4] = { 0, 0, 0, 0 };
+    trace_ray<0, ANY>(sc, nullptr, active, O, d, (ANY && active) ? tmax[i] : 0.f, h, cnt);
+    if (!active) return;
+    for (int k = 0; k < 4; k++) counts4[4 * i + k] = cnt[k];
 }
 
 __global__ void k_hemisphere(float nx, float ny, float nz, unsigned long long step, int n, float* __restrict__ out) {
@@ -604,6 +636,13 @@ extern "C" int rt580_device_info(rt580_context* c, int32_t* sm_count, int32_t* s
     if (sm_count) *sm_count = c->prop.multiProcessorCount;
     if (sm_clock_mhz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device); *sm_clock_mhz = khz / 1000; }
     if (hbm_bytes) *hbm_bytes = (uint64_t)c->prop.totalGlobalMem;
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_get_stream(rt580_context* c, void** cuda_stream)
+{
+    if (!c || !cuda_stream) FAIL(RT580_INVALID_ARG, "rt580_get_stream: NULL argument");
+    *cuda_stream = (void*)c->stream;
     return RT580_SUCCESS;
 }
 
@@ -807,8 +846,9 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
         CU(cudaStreamSynchronize(st));
         fp.ndc_x = c->ndc.p; fp.ndc_y = c->ndc.p + fp.W;
     }
-    CU(c->counters.ensure(4, 0, st));
-    CU(cudaMemsetAsync(c->counters.p, 0, 4 * sizeof(unsigned), st));
+    CU(c->counters.ensure(8, 0, st));
+    CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned), st));
+    c->sc.diag = c->counters.p + 4;
     CU(c->pix_hits.ensure(npix + 1, 0, st));
     CU(c->pix_scan.ensure(npix + 1, 0, st));
     CU(c->fb.ensure((size_t)npix * 3 + 1, 0, st));
@@ -931,6 +971,11 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->stats.ms_resolve = ms;
     c->stats.ms_total = c->stats.ms_structure + c->stats.ms_order + c->stats.ms_ao + c->stats.ms_resolve;
     c->stats.kernel_launches = c->launches;
+    {
+        unsigned dg[2] = { 0, 0 };
+        cudaMemcpy(dg, c->counters.p + 4, sizeof dg, cudaMemcpyDeviceToHost);
+        c->stats.far_scans = dg[0]; c->stats.linear_fallbacks = dg[1];
+    }
     if (stats) *stats = c->stats;
     c->frame_begun = false;
     return RT580_SUCCESS;
@@ -988,6 +1033,7 @@ static int trace_rays_common(rt580_context* c, bool any, int64_t n, const float*
     else { CU(cudaMalloc(&t, sizeof(float) * n)); CU(cudaMalloc(&pr, sizeof(int32_t) * n)); }
     const int mode = pick_mode(c, traversal);
     c->sc.farfield = 1;     // the checkers always run the exact path
+    c->sc.diag = nullptr;
     DISPATCH_MODE(mode, launch_rays, c, any, (long long)n, o, d, tm, pr, t, h);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -1008,6 +1054,28 @@ extern "C" int rt580_trace_any(rt580_context* c, int64_t n, const float* org3, c
 {
     if (!hit_out || !tmax) FAIL(RT580_INVALID_ARG, "rt580_trace_any: NULL argument");
     return trace_rays_common(c, true, n, org3, dir3, tmax, traversal, nullptr, nullptr, hit_out);
+}
+
+extern "C" int rt580_trace_profile(rt580_context* c, int64_t n, const float* org3, const float* dir3, const float* tmax,
+                                   uint32_t* counts4)
+{
+    if (!c || !org3 || !dir3 || !counts4 || n < 0) FAIL(RT580_INVALID_ARG, "rt580_trace_profile: bad argument");
+    if (!c->have_scene) FAIL(RT580_FAILURE, "rt580_trace_profile: no scene uploaded");
+    if (n == 0) return RT580_SUCCESS;
+    CU(cudaSetDevice(c->device));
+    float *o = nullptr, *d = nullptr, *tm = nullptr; unsigned* cn = nullptr;
+    CU(cudaMalloc(&o, sizeof(float) * 3 * n)); CU(cudaMalloc(&d, sizeof(float) * 3 * n)); CU(cudaMalloc(&cn, sizeof(unsigned) * 4 * n));
+    CU(cudaMemcpy(o, org3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d, dir3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    if (tmax) { CU(cudaMalloc(&tm, sizeof(float) * n)); CU(cudaMemcpy(tm, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)); }
+    c->sc.farfield = 1; c->sc.diag = nullptr;
+    if (tmax) k_trace_profile<true><<<nblk(n, 128), 128, 0, c->stream>>>(c->sc, (long long)n, o, d, tm, cn);
+    else k_trace_profile<false><<<nblk(n, 128), 128, 0, c->stream>>>(c->sc, (long long)n, o, d, tm, cn);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(counts4, cn, sizeof(unsigned) * 4 * n, cudaMemcpyDeviceToHost));
+    cudaFree(o); cudaFree(d); cudaFree(tm); cudaFree(cn);
+    return RT580_SUCCESS;
 }
 
 extern "C" int rt580_hemisphere_stream(rt580_context* c, const float normal[3], uint64_t step, int32_t n, float* out3)

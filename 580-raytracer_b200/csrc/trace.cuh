@@ -106,7 +106,8 @@ __device__ __forceinline__ bool slab(float lox, float hix, float loy, float hiy,
 // Any hit     (ANY == true) : true as soon as one primitive is accepted with t <= tmax
 //                             (cpp:75 and cpp:325 use only that boolean).
 template <bool ANY>
-__device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, float tmax, HitRec& best)
+__device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, float tmax, HitRec& best,
+                                             unsigned* cnt = nullptr)
 {
     best.t = ANY ? tmax : __int_as_float(0x7f800000);
     best.leaf = -1;
@@ -118,6 +119,7 @@ __device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, 
     int node = 0;
     bool found = false;
     for (;;) {
+        if (cnt) cnt[0]++;
         const BvhNode* __restrict__ nd = sc.nodes + node;
         const float4 xy0 = __ldg(&nd->xy0), xy1 = __ldg(&nd->xy1), z01 = __ldg(&nd->z01);
         const int4 kids = __ldg(&nd->kids);
@@ -138,6 +140,7 @@ __device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, 
         while (next < 0) {
             const int leaf = ~next;
             float t; int prim;
+            if (cnt) cnt[1]++;
             if (prim_test<true>(sc.prims + leaf, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
                 if (ANY) return true;   // prim_test's limit is "t < tmax || t == tmax" (prim_limit = INT_MAX)
                 best.t = t; best.leaf = leaf; best.prim = prim; found = true;
@@ -151,26 +154,65 @@ __device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, 
     return found;
 }
 
-// Far-field replay (bvh_build.cu header): the reference's float test also accepts "hits" at
-// t >= far_tmin for rays almost parallel to a triangle's plane.  No box can bound those, so a
-// ray that found nothing nearer tests every triangle whose filter record says it could be one:
-// |N.d| <= thr  (thr >= |N.O + D| / T_far, so t_plane >= T_far implies the filter passes), and
-// runs the reference's exact test on the survivors.  All lanes of a warp read the same record
-// (one broadcast load), so the scan costs ~8 instructions per (ray, triangle).
+// Slow path, warp-cooperative.  Two kinds of rays cannot be answered by the tree alone
+// (bvh_build.cu header):
+//   far scan  a ray that found nothing nearer than far_tmin must replay the reference's
+//             far-field acceptances: every triangle whose filter record passes |N.d| <= thr
+//             (thr >= |N.O + D| / T_far, so t_plane >= T_far implies the filter passes) gets
+//             the reference's exact test;
+//   linear    a ray that starts outside the extent the boxes were padded for (the child of a
+//             far-field hit, 10^4..10^7 units away) takes the reference's own linear loop.
+// Such rays are rare and scattered, so instead of one lane walking ~10^6 records while 31 idle,
+// the whole warp serves them one at a time: the ray is broadcast, lane l tests records
+// l, l+32, ... (coalesced 512-byte loads), and a lexicographic (t, prim) warp reduction
+// returns what the reference's first-wins loop would.  Must be called by all 32 lanes.
 template <bool ANY>
-__device__ __forceinline__ bool farfield_scan(const DeviceScene& sc, V3 O, V3 d, HitRec& best, bool found)
+__device__ __forceinline__ bool warp_slow_path(const DeviceScene& sc, bool need, bool linear, V3 O, V3 d,
+                                               HitRec& hit, bool found)
 {
+    unsigned pending = __ballot_sync(0xffffffffu, need);
+    if (pending == 0u) return found;
+    const int lane = threadIdx.x & 31;
     const float4* __restrict__ far = sc.far;
     const int n = sc.n_leaf;
-    for (int i = 0; i < n; i++) {
-        const float4 f = __ldg(far + i);
-        const float nd = __fmaf_rn(f.x, d.x, __fmaf_rn(f.y, d.y, f.z * d.z));   // filter only: FMA is fine
-        if (fabsf(nd) <= f.w) {
-            float t; int prim;
-            if (prim_test<true>(sc.prims + i, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
-                if (ANY) return true;
-                best.t = t; best.leaf = i; best.prim = prim; found = true;
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1u;
+        const V3 Ob = mk(__shfl_sync(0xffffffffu, O.x, src), __shfl_sync(0xffffffffu, O.y, src), __shfl_sync(0xffffffffu, O.z, src));
+        const V3 db = mk(__shfl_sync(0xffffffffu, d.x, src), __shfl_sync(0xffffffffu, d.y, src), __shfl_sync(0xffffffffu, d.z, src));
+        const bool lin = __shfl_sync(0xffffffffu, linear ? 1 : 0, src) != 0;
+        HitRec best;
+        best.t = __shfl_sync(0xffffffffu, hit.t, src);
+        best.prim = __shfl_sync(0xffffffffu, hit.prim, src);
+        best.leaf = -1;
+        bool f = false;
+        for (int i = lane; i < n; i += 32) {
+            if (!lin) {
+                const float4 fr = __ldg(far + i);
+                const float nd = __fmaf_rn(fr.x, db.x, __fmaf_rn(fr.y, db.y, fr.z * db.z));   // filter only: FMA is fine
+                if (!(fabsf(nd) <= fr.w)) continue;
             }
+            float t; int prim;
+            if (prim_test<true>(sc.prims + i, Ob, db, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+                best.t = t; best.leaf = i; best.prim = prim; f = true;
+                if (ANY) break;
+            }
+        }
+        const bool anyf = __any_sync(0xffffffffu, f);
+        if (!ANY) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float t2 = __shfl_xor_sync(0xffffffffu, best.t, o);
+                const int p2 = __shfl_xor_sync(0xffffffffu, best.prim, o);
+                const int l2 = __shfl_xor_sync(0xffffffffu, best.leaf, o);
+                if (t2 < best.t || (t2 == best.t && (p2 < best.prim || (p2 == best.prim && l2 > best.leaf)))) {
+                    best.t = t2; best.prim = p2; best.leaf = l2;
+                }
+            }
+        }
+        if (lane == src && anyf) {
+            found = true;
+            if (!ANY) hit = best;
         }
     }
     return found;

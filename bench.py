@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the 580-Raytracer hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU Render
+
+Metric (BASELINE.json): Mrays/s, one ray = one IntersectScene call of the reference
+(primary + secondary + shadow + AO).  Workload = BASELINE.json configs[3]: synthetic
+1M-triangle + 1k-sphere scene at 3840x2160, depth 4, 16 AO samples per pixel ("c4_room":
+977 instanced teapots + 1000 spheres in a closed room, written by scenegen.py in the
+reference's own JSON schema, seed 580).  A step = one frame.
+
+  value  scene + LBVH resident in HBM; rt580_render_begin/finish per step, frame gathered to rank 0
+  e2e    through the reference-facing call with HOST buffers every step: rt580_upload_scene
+         (H2D of the flattened scene + LBVH build) + rt580_render (D2H of the int16 frame)
+N GPUs: rows interleaved across ranks (strong scaling of the one frame), the AO-stream row
+prefix exchanged with one tiny all_gather, the int16 bands gathered to rank 0 over NCCL.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import ASSETS, PKG_DIR, load_package  # noqa: E402
+
+METRIC, UNIT = "Mrays/s", "Mrays/s"
+WORKLOAD = "c4_room"
+W, H, DEPTH, SPP = 3840, 2160, 4, 16
+CACHE = "/tmp/rt580_bench_scenes"
+
+
+def scene_dir(name):
+    """Write (once) the synthetic scene next to a copy of the teapot mesh it instances."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("scenegen", os.path.join(PKG_DIR, "scenegen.py"))
+    sg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sg)
+    d = os.path.join(CACHE, name)
+    if not os.path.exists(os.path.join(d, name + ".json")):
+        os.makedirs(d, exist_ok=True)
+        shutil.copy(os.path.join(ASSETS, "teapot.json"), d)
+        sg.write_synthetic_scene(d, name, **sg.CONFIGS[name])
+    return d
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.samples, self.stop_flag = gpu, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "samples": len(self.samples),
+                "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_per_ray(n_prims):
+    """F_ray = ceil(log2 N) * 40 + 71 flop, B_ray = ceil(log2 N) * 64 + 64 bytes."""
+    lg = int(np.ceil(np.log2(max(n_prims, 2))))
+    return lg * 40 + 71, lg * 64 + 64
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_pix, nthreads, seed=580):
+    """Time the reference's GenerateRay + Raycast (oracle/_ref, i.e. the reference's own sources)
+    on a bounded pixel sample of the same workload.  Returns (Mrays/s, rays, seconds, kind)."""
+    import oracle
+    d = scene_dir(WORKLOAD)
+    rng = np.random.default_rng(seed)
+    pix = rng.choice(W * H, n_pix, replace=False).astype(np.int32)
+    if oracle.t0_available():
+        st, _, rays, secs = oracle.t0_render_pixels(d, WORKLOAD + ".json", W, H, SPP, DEPTH, pix, nthreads=nthreads)
+        assert st == 0
+        return rays / secs / 1e6, rays, secs, "reference"
+    orc = oracle.Oracle(oracle.load_scene_json(d, WORKLOAD + ".json"))
+    t0 = time.time()
+    _, rays, _ = orc.render(W, H, SPP, DEPTH, pix=pix, ao_base=np.zeros(n_pix, np.uint64), nthreads=nthreads)
+    secs = time.time() - t0
+    return rays / secs / 1e6, rays, secs, "port"
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_pix = max(cores, 2 * cores)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, rays, secs, kind = cpu_reference_sample(n_pix, cores, seed=580 + i)
+        if i >= args.warmup:
+            vals.append((v, rays, secs))
+    value = float(np.mean([v for v, _, _ in vals]))
+    ms = float(np.mean([s for _, _, s in vals]) * 1e3)
+    sample = "%d random pixels of the %dx%d frame per step (%d rays), one reference Raytracer instance per thread" % (
+        n_pix, W, H, vals[-1][1])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "depth": DEPTH, "ao_spp": SPP, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = load_package()
+    d = scene_dir(WORKLOAD) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        d = scene_dir(WORKLOAD)
+
+    # host side of the reference API: LoadSceneJSON + the load-time flatten (host C++)
+    rt = pkg.Raytracer(W, H)
+    rt.SetAssetsPath(d)
+    rt.SetOptions(depth=DEPTH, ao_spp=SPP, device=local, farfield=pkg.FARFIELD_OFF if args.farfield == "off" else pkg.FARFIELD_EXACT)
+    assert rt.LoadSceneJSON(WORKLOAD + ".json") == pkg.RT_SUCCESS
+    flat = rt.flat_scene()
+    params = rt.render_params()
+    ctx = pkg.Context(local)
+    ctx.upload_scene(flat)
+    info = ctx.scene_info()
+    dev = ctx.device_info()
+    ext_stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    p = params.copy()
+    p.row_first, p.row_step, p.n_rows = pkg.rows_for_rank(H, rank, world)
+    band = torch.empty((max(p.n_rows, 1), W, 3), dtype=torch.int16, device="cuda")
+    max_rows = (H + world - 1) // world
+    gather_list = [torch.empty((max_rows, W, 3), dtype=torch.int16, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
+    padded = torch.zeros((max_rows, W, 3), dtype=torch.int16, device="cuda") if world > 1 else None
+
+    def frame():
+        """one step: this rank's rows; returns (stats, frame on rank 0 or None)"""
+        counts = ctx.render_begin(p)
+        if world > 1:
+            mine = torch.zeros(max_rows, dtype=torch.int64, device="cuda")
+            mine[:p.n_rows] = torch.from_numpy(counts.astype(np.int64)).cuda()
+            allc = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allc, mine)                                   # the one exchange of the LCG mode
+            per_rank = [c.cpu().numpy().astype(np.uint64) for c in allc]
+            bases = pkg.row_bases_from_counts(H, world, per_rank)[rank]
+        else:
+            bases = pkg.row_bases_from_counts(H, 1, [counts])[0]
+        _, st = ctx.render_finish(p, bases, device_ptr=band.data_ptr())
+        if world > 1:
+            padded[:p.n_rows].copy_(band[:p.n_rows])
+            dist.gather(padded, gather_list, dst=0)                       # int16 bands to rank 0 over NVLink
+        return st
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        frame()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(ext_stream)
+    stats, launches = [], 0
+    for _ in range(args.steps):
+        st = frame()
+        stats.append(st)
+        launches += st.kernel_launches
+    ev1.record(ext_stream)
+    sync()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = ev0.elapsed_time(ev1)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    step_ms = max(dev_ms, 0.0) / args.steps
+    rays_rank = float(np.mean([s.rays for s in stats]))
+    ao_ms = float(np.mean([s.ms_ao_kernel for s in stats]))
+    ao_rays = float(np.mean([s.rays_ao for s in stats]))
+    t = torch.tensor([step_ms, rays_rank, wall_ms / args.steps, ao_ms, ao_rays], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        step_ms, wall_step_ms, ao_ms = float(tmax[0]), float(tmax[2]), float(tmax[3])
+        rays_total, ao_rays_total = float(tsum[1]), float(tsum[4])
+    else:
+        wall_step_ms, rays_total, ao_rays_total = wall_ms / args.steps, rays_rank, ao_rays
+    value = rays_total / (step_ms * 1e-3) / 1e6
+
+    # e2e: the reference-facing call with host buffers, every step: upload (H2D + LBVH build) + render (D2H)
+    h2d = int(flat.n_tris * (6 * 16 + 8) + flat.n_spheres * (16 + 8) + flat.n_materials * 32 + flat.n_lights * 44)
+    d2h = int(p.n_rows * W * 6)
+    for _ in range(1):
+        ctx.upload_scene(flat); ctx.render(p) if world == 1 else None
+    sync()
+    e0 = time.perf_counter()
+    e_steps = max(1, min(args.steps, 3))
+    for _ in range(e_steps):
+        ctx.upload_scene(flat)
+        if world == 1:
+            ctx.render(p)
+        else:
+            counts = ctx.render_begin(p)
+            mine = torch.zeros(max_rows, dtype=torch.int64, device="cuda")
+            mine[:p.n_rows] = torch.from_numpy(counts.astype(np.int64)).cuda()
+            allc = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allc, mine)
+            bases = pkg.row_bases_from_counts(H, world, [c.cpu().numpy().astype(np.uint64) for c in allc])[rank]
+            ctx.render_finish(p, bases)                                   # host band
+    sync()
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = rays_total / (float(te[0]) * 1e-3) / 1e6
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        f_ray, b_ray = algorithmic_per_ray(int(info.n_leaf))
+        sm_mhz = float(peaks.get("sm_max_mhz") or dev["sm_clock_mhz"])
+        fp32_peak = dev["sm_count"] * 128 * 2 * sm_mhz * 1e6 / 1e12          # TFLOP/s, FMA counted as 2
+        ao_rate = ao_rays_total / (ao_ms * 1e-3) if ao_ms > 0 else 0.0      # rays/s over all ranks (max kernel time)
+        roofline = {"bound": "fp32", "kernel": "k_ao (any-hit LBVH traversal, 1 thread per AO ray)",
+                    "achieved": ao_rate * f_ray / 1e12, "peak": fp32_peak * world, "unit": "TFLOP/s",
+                    "frac": (ao_rate * f_ray / 1e12) / (fp32_peak * world) if fp32_peak else None,
+                    "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (%s); MEASURED_PEAKS.json has no fp32 figure" % (
+                        dev["sm_count"], sm_mhz, peak_src),
+                    "flop_per_ray": f_ray, "rays_per_launch": ao_rays_total, "kernel_ms": ao_ms, "traffic": None,
+                    "hbm": {"achieved": ao_rate * b_ray / 1e9, "peak": float(peaks["hbm_gbs"]) * world, "unit": "GB/s",
+                            "frac": (ao_rate * b_ray / 1e9) / (float(peaks["hbm_gbs"]) * world), "bytes_per_ray": b_ray,
+                            "note": "algorithmic node+triangle bytes; served from L1/L2, not HBM, when the BVH fits L2"}}
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, rays, secs, kind = cpu_reference_sample(max(2 * cores, 8), cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "%d random pixels of the %dx%d c4_room frame, %d rays in %.1f s, one reference Raytracer instance per thread" % (
+                       max(2 * cores, 8), W, H, rays, secs)}
+        st0 = stats[-1]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "scene": "977 teapot instances (1,000,448 triangles) + 1000 spheres + closed room (12 triangles), seed 580",
+                           "width": W, "height": H, "depth": DEPTH, "ao_spp": SPP, "rng": "reference_lcg", "farfield": args.farfield, "far_scans": st0.far_scans, "linear_fallbacks": st0.linear_fallbacks,
+                           "partition": "rows interleaved over %d rank(s)" % world, "l2": "working set > L2: nodes+records %.0f MB, frame data %.0f MB/step" % (
+                               info.n_leaf * 144 / 1e6, st0.hit_nodes * 110 / 1e6)},
+                "rays_per_frame": rays_total, "ms_per_frame_4k": step_ms, "wall_ms_per_step": wall_step_ms,
+                "phases_ms": {"structure": st0.ms_structure, "order": st0.ms_order, "ao": st0.ms_ao, "resolve": st0.ms_resolve},
+                "ray_mix": {"primary": st0.rays_primary, "secondary": st0.rays_secondary, "shadow": st0.rays_shadow, "ao": st0.rays_ao,
+                            "note": "rank 0 share" if world > 1 else "whole frame"},
+                "scene_info": info.as_dict(),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": float(te[0]), "includes": "rt580_upload_scene (H2D + LBVH build) + rt580_render (D2H int16 frame)"},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": sampler.summary() if sampler else None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    global W, H, WORKLOAD
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--farfield", default="exact", choices=["exact", "off"], help="debug only")
+    ap.add_argument("--workload", default=WORKLOAD, help="debug only")
+    ap.add_argument("--width", type=int, default=0, help="debug only: override the frame width")
+    ap.add_argument("--height", type=int, default=0, help="debug only: override the frame height")
+    args = ap.parse_args()
+    WORKLOAD = args.workload
+    if args.width and args.height:
+        W, H = args.width, args.height
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

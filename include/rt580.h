@@ -131,7 +131,8 @@ typedef struct rt580_stats {
     float    ms_ao_kernel;         /* the dominant kernel alone                            */
     uint32_t kernel_launches;      /* kernels launched for the frame                       */
     uint32_t bvh_max_depth;
-    uint32_t reserved0, reserved1;
+    uint32_t far_scans;            /* rays that needed the far-field scan (found nothing nearer) */
+    uint32_t linear_fallbacks;     /* rays that started outside the padded extent (children of far hits) */
 } rt580_stats;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -140,6 +141,8 @@ void rt580_destroy(rt580_context* ctx);
 const char* rt580_last_error(void);
 /* device properties the benchmark needs for its FP32 roofline: SM count, max SM MHz */
 int  rt580_device_info(rt580_context* ctx, int32_t* sm_count, int32_t* sm_clock_mhz, uint64_t* hbm_bytes);
+/* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
+int  rt580_get_stream(rt580_context* ctx, void** cuda_stream);
 
 /* ---- scene: H2D + per-triangle constants (cpp:362-365, 377, 389) + LBVH build ----------- */
 int  rt580_upload_scene(rt580_context* ctx, const rt580_flat_scene* scene);
@@ -170,6 +173,10 @@ int  rt580_trace_closest(rt580_context* ctx, int64_t n, const float* org3, const
 /* Any hit with t <= tmax (cpp:75 / cpp:325 use only the bool). */
 int  rt580_trace_any(rt580_context* ctx, int64_t n, const float* org3, const float* dir3, const float* tmax,
                      int traversal, uint8_t* hit_out);
+/* Traversal profile of n rays through the LBVH path: counts4[4*i..] = node visits, leaf tests,
+ * far-field scans, linear fallbacks of ray i.  tmax == NULL: closest hit, else any hit. */
+int  rt580_trace_profile(rt580_context* ctx, int64_t n, const float* org3, const float* dir3, const float* tmax,
+                         uint32_t* counts4);
 /* Per-pixel global ordinal of the first AO call of the last rendered frame (local rows). */
 int  rt580_last_frame_ao_base(rt580_context* ctx, uint64_t* pixel_ao_base /* [n_rows*width] */);
 /* n AO directions of the stream starting at engine step `step` (cpp:283-292). */
@@ -184,6 +191,7 @@ void rt580_raytracer_delete(rt580_raytracer* rt);
 int  rt580_raytracer_set_assets_path(rt580_raytracer* rt, const char* dir);  /* ASSETS_PATH, h:15     */
 int  rt580_raytracer_set_options(rt580_raytracer* rt, int depth, int ao_spp, int rng_mode, int traversal,
                                  int device, int farfield);                  /* h:563, cpp:317        */
+int  rt580_raytracer_set_quiet(rt580_raytracer* rt, int quiet);              /* mute cpp:592 / cpp:772 prints */
 int  rt580_raytracer_load_scene_json(rt580_raytracer* rt, const char* scene);/* h:572 LoadSceneJSON   */
 int  rt580_raytracer_render(rt580_raytracer* rt, const char* output_ppm);    /* h:586 Render          */
 int  rt580_raytracer_flush_ppm(rt580_raytracer* rt, const char* output_ppm); /* h:573                 */
