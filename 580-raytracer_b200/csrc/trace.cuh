@@ -186,16 +186,34 @@ __device__ __forceinline__ bool warp_slow_path(const DeviceScene& sc, bool need,
         best.prim = __shfl_sync(0xffffffffu, hit.prim, src);
         best.leaf = -1;
         bool f = false;
-        for (int i = lane; i < n; i += 32) {
-            if (!lin) {
-                const float4 fr = __ldg(far + i);
-                const float nd = __fmaf_rn(fr.x, db.x, __fmaf_rn(fr.y, db.y, fr.z * db.z));   // filter only: FMA is fine
-                if (!(fabsf(nd) <= fr.w)) continue;
+        if (!lin) {
+            // far scan: 4 filter records per lane in flight (independent loads), exact test on the survivors
+            for (int base = 0; base < n && !(ANY && f); base += 128) {
+                float4 fr[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int i = base + 32 * k + lane;
+                    fr[k] = (i < n) ? __ldg(far + i) : make_float4(0.f, 0.f, 0.f, -1.0f);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float nd = __fmaf_rn(fr[k].x, db.x, __fmaf_rn(fr[k].y, db.y, fr[k].z * db.z));   // filter only: FMA is fine
+                    if (fabsf(nd) <= fr[k].w) {
+                        const int i = base + 32 * k + lane;
+                        float t; int prim;
+                        if (prim_test<true>(sc.prims + i, Ob, db, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+                            best.t = t; best.leaf = i; best.prim = prim; f = true;
+                        }
+                    }
+                }
             }
-            float t; int prim;
-            if (prim_test<true>(sc.prims + i, Ob, db, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
-                best.t = t; best.leaf = i; best.prim = prim; f = true;
-                if (ANY) break;
+        } else {
+            for (int i = lane; i < n; i += 32) {
+                float t; int prim;
+                if (prim_test<true>(sc.prims + i, Ob, db, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+                    best.t = t; best.leaf = i; best.prim = prim; f = true;
+                    if (ANY) break;
+                }
             }
         }
         const bool anyf = __any_sync(0xffffffffu, f);

@@ -182,7 +182,8 @@ def run_ours(args):
     p.row_first, p.row_step, p.n_rows = pkg.rows_for_rank(H, rank, world)
     band = torch.empty((max(p.n_rows, 1), W, 3), dtype=torch.int16, device="cuda")
     max_rows = (H + world - 1) // world
-    gather_list = [torch.empty((max_rows, W, 3), dtype=torch.int16, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
+    # int16 is not an NCCL dtype: the bands are gathered as bytes
+    gather_list = [torch.empty((max_rows, W, 6), dtype=torch.uint8, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
     padded = torch.zeros((max_rows, W, 3), dtype=torch.int16, device="cuda") if world > 1 else None
 
     def frame():
@@ -200,7 +201,7 @@ def run_ours(args):
         _, st = ctx.render_finish(p, bases, device_ptr=band.data_ptr())
         if world > 1:
             padded[:p.n_rows].copy_(band[:p.n_rows])
-            dist.gather(padded, gather_list, dst=0)                       # int16 bands to rank 0 over NVLink
+            dist.gather(padded.view(torch.uint8), gather_list, dst=0)     # int16 bands (as bytes) to rank 0 over NVLink
         return st
 
     def sync():
