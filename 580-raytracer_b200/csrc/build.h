@@ -10,6 +10,7 @@ struct BuildInput {            // device pointers (already uploaded)
     const int32_t* tri_prim; int64_t n_tris;
     const float4* sph; const int32_t* sph_prim; int64_t n_spheres;
     float origin_hint[3];      // camera position: bounds |ray origin| for the box padding
+    int64_t n_prims;           // primitives in reference order
 };
 
 struct BuildOutput {
@@ -19,6 +20,7 @@ struct BuildOutput {
     float far_tmin;            // min over triangles of T_far
     int n_always;              // triangles that are far-field candidates for every ray (slivers)
     int32_t* always_idx;       // [n_always] their indices into prims
+    int32_t* leaf_of_prim;     // [n_prims] inverse of the Morton permutation (-1 for dropped triangles)
     int n_leaf;
     int n_dropped;             // zero-area triangles
     unsigned int max_depth;

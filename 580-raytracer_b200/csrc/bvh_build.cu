@@ -206,6 +206,11 @@ __global__ void k_gather(const PrimRec* __restrict__ rec, const float4* __restri
     nb_hi[n_leaf - 1 + j] = box_hi[i];
 }
 
+__global__ void k_leaf_of_prim(const PrimRec* __restrict__ prims, int n, int32_t* __restrict__ out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[__float_as_int(prims[j].c.w)] = j;
+}
+
 __global__ void k_collect_always(const float4* __restrict__ far, int n, int32_t* __restrict__ out,
                                  unsigned int* __restrict__ count)
 {
@@ -308,7 +313,7 @@ template <typename T> static bool dalloc(T** p, size_t n, char* err, size_t errl
 bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char* err, size_t errlen)
 {
     const int64_t n_in = in.n_tris + in.n_spheres;
-    out->prims = nullptr; out->nodes = nullptr; out->far = nullptr; out->far_tmin = 0.f; out->n_always = 0; out->always_idx = nullptr;
+    out->prims = nullptr; out->nodes = nullptr; out->far = nullptr; out->far_tmin = 0.f; out->n_always = 0; out->always_idx = nullptr; out->leaf_of_prim = nullptr;
     out->n_leaf = 0; out->max_depth = 0; out->launches = 0;
     if (n_in > 0x7ffffff0ll) { snprintf(err, errlen, "too many primitives (%lld)", (long long)n_in); return false; }
 
@@ -416,6 +421,13 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
         CK(cudaGetLastError());
         cudaFree(nlo); cudaFree(nhi); cudaFree(kids); cudaFree(parent); cudaFree(arrive);
         out->prims = prims; out->nodes = nodes; out->far = far;
+        {
+            int32_t* lop = nullptr;
+            if (!dalloc(&lop, (size_t)in.n_prims, err, errlen)) return false;
+            CK(cudaMemsetAsync(lop, 0xff, sizeof(int32_t) * (size_t)(in.n_prims ? in.n_prims : 1), stream));
+            k_leaf_of_prim<<<blocks, 256, 0, stream>>>(prims, n, lop); out->launches++;
+            out->leaf_of_prim = lop;
+        }
         if (out->n_always > 0) {
             int32_t* idx = nullptr;
             if (!dalloc(&idx, out->n_always, err, errlen)) return false;

@@ -37,6 +37,7 @@ struct DeviceScene {
     const BvhNode* nodes;
     const float4* far;         // [n_leaf] far-field filter records (N.xyz, thr), see bvh_build.cu
     float far_tmin;            // no far-field acceptance is possible at t < far_tmin (sliver list aside)
+    const int32_t* leaf_of_prim; // [n_prims] index into prims of a primitive order index (-1: dropped)
     const int32_t* always_idx; // [n_always] sliver triangles whose far field starts inside the scene:
     int32_t n_always;          //            tested exactly for every ray
     float extent;              // E: the boxes and far-field records are valid for ray origins with |coordinate| <= E

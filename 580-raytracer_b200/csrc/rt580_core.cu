@@ -69,6 +69,27 @@ struct __align__(16) QRay {       // 32 B queue entry
     float4 d;   // direction.xyz w: bits(flags for the child: NF_REFR, bounces left)
 };
 
+// Deferred slow rays (trace.cuh: far scan / linear fallback): recorded by the kernel that meets
+// them, answered by k_slow with one warp per ray over the whole GPU, applied by a finish kernel.
+struct __align__(16) SlowRay {
+    float4 o;   // origin.xyz     w: bits(best t so far / tmax)
+    float4 d;   // direction.xyz  w: bits(best prim so far)
+    int4 c;     // x: bit0 = linear fallback, y/z: consumer ids, w: best leaf so far (-1 none)
+};
+// answer of a slow ray: closest hit = lexicographic minimum of (t, prim) packed so that an integer
+// atomicMin over record slices gives it (t > 0, so the float bits order like the value);
+// any hit = the flag
+struct __align__(16) SlowRes { unsigned long long key; int found; int pad; };
+struct SlowQ { SlowRay* rays; SlowRes* res; unsigned int* count; unsigned cap; };
+__host__ __device__ __forceinline__ unsigned long long slow_key(float t, int prim) {
+#if defined(__CUDA_ARCH__)
+    return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)prim;
+#else
+    unsigned u; memcpy(&u, &t, 4); return ((unsigned long long)u << 32) | (unsigned)prim;
+#endif
+}
+#define SLOW_CAP_MAX (16u << 20)
+
 struct FrameParams {
     int W, H;
     int row_first, row_step, n_rows;
@@ -103,7 +124,7 @@ struct rt580_context {
     // scene
     DeviceScene sc{};
     PrimRec* d_prims = nullptr; BvhNode* d_nodes = nullptr; float4* d_far = nullptr;
-    int n_always = 0, n_dropped = 0; int32_t* d_always = nullptr;
+    int n_always = 0, n_dropped = 0; int32_t* d_always = nullptr; int32_t* d_leaf_of_prim = nullptr;
     float4* d_vn = nullptr; int32_t* d_prim_material = nullptr; float* d_materials = nullptr;
     int32_t* d_light_type = nullptr; float* d_light_f = nullptr;
     bool have_scene = false;
@@ -121,7 +142,9 @@ struct rt580_context {
     DBuf<uint32_t> scan_tmp;
     DBuf<uint64_t> row_vals;       // per local row: hit nodes / base
     DBuf<int16_t> fb;              // [n_rows][W][3]
-    DBuf<unsigned int> counters;   // [0] node count, [1] queue count
+    DBuf<unsigned int> counters;   // [0] node count, [1] queue count, [2] slow-ray count, [4..5] diagnostics
+    DBuf<SlowRay> slow_rays; DBuf<SlowRes> slow_res;
+    uint64_t slow_total = 0;
     std::vector<size_t> level_off; // node index where each level starts (+ end)
     std::vector<uint64_t> level_rays;
     bool frame_begun = false;
@@ -148,15 +171,19 @@ __device__ __forceinline__ unsigned warp_alloc(unsigned int* counter, bool want)
 
 #define RT_SMEM_PRIMS 64   // scenes up to this many primitives are staged in shared memory
 
-// One ray per lane, called by ALL 32 lanes of a warp (inactive lanes pass active = false):
-// the tree answers almost every ray; the rare ones it cannot (trace.cuh: warp_slow_path) are
-// then served by the whole warp.
+// One ray per lane, called by ALL 32 lanes of a warp (inactive lanes pass active = false).
+// The tree answers almost every ray.  The rare ones it cannot (trace.cuh) are pushed to the
+// deferred queue `q` when there is one (returns TR_PENDING: the caller's finish kernel applies
+// the answer), otherwise - or when the queue is full - the warp serves them in place.
+#define TR_MISS 0
+#define TR_HIT 1
+#define TR_PENDING 2
 template <int MODE /*0 bvh, 1 linear from smem, 2 linear from global*/, bool ANY>
-__device__ __forceinline__ bool trace_ray(const DeviceScene& sc, const PrimRec* smem_prims, bool active, V3 O, V3 d,
-                                          float tmax, HitRec& hit, unsigned* cnt = nullptr) {
-    if (MODE == 1) return active ? traverse_linear<ANY, false>(smem_prims, sc.n_leaf, O, d, tmax, hit) : false;
-    if (MODE == 2) return active ? traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit) : false;
-    bool found = false, need = false, linear = false;
+__device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* smem_prims, bool active, V3 O, V3 d,
+                                         float tmax, HitRec& hit, SlowQ q, int ca, int cb, unsigned* cnt = nullptr) {
+    if (MODE == 1) return (active && traverse_linear<ANY, false>(smem_prims, sc.n_leaf, O, d, tmax, hit)) ? TR_HIT : TR_MISS;
+    if (MODE == 2) return (active && traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit)) ? TR_HIT : TR_MISS;
+    bool found = false, need = false, linear = false, pending = false;
     hit.t = ANY ? tmax : __int_as_float(0x7f800000); hit.leaf = -1; hit.prim = 0x7fffffff;
     if (active) {
         if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent) {
@@ -177,9 +204,111 @@ __device__ __forceinline__ bool trace_ray(const DeviceScene& sc, const PrimRec* 
                 if (need) { if (cnt) cnt[2]++; if (sc.diag) atomicAdd(sc.diag, 1u); }
             }
         }
+        if (need && q.rays) {
+            const unsigned slot = atomicAdd(q.count, 1u);
+            if (slot < q.cap) {
+                SlowRay r;
+                r.o = make_float4(O.x, O.y, O.z, hit.t);
+                r.d = make_float4(d.x, d.y, d.z, __int_as_float(hit.prim));
+                r.c = make_int4(linear ? 1 : 0, ca, cb, found ? hit.leaf : -1);
+                q.rays[slot] = r;
+                SlowRes a; a.key = slow_key(hit.t, hit.prim); a.found = 0; a.pad = 0;
+                q.res[slot] = a;
+                pending = true; need = false;
+            }
+        }
     }
     if (sc.farfield) found = warp_slow_path<ANY>(sc, need, linear, O, d, hit, found);
-    return found;
+    return pending ? TR_PENDING : (found ? TR_HIT : TR_MISS);
+}
+
+// Deferred slow rays.  Every slow ray must see every primitive record (far scan: the 16-byte
+// filter record, and the 64-byte primitive record of the survivors; linear fallback: the
+// primitive record), so the kernel is bound by record traffic unless rays share it: a block takes
+// SLOW_RPB rays, streams the records through shared memory in tiles of SLOW_TILE, and each of
+// its 8 warps tests its 4 rays against the tile (lane l takes records l, l+32, ...).  Record
+// traffic per ray drops by SLOW_RPB; the grid is one block per ray batch over the whole GPU.
+#define SLOW_RPB 32
+#define SLOW_TILE 256
+#define SLOW_RPW (SLOW_RPB / 8)
+template <bool ANY>
+__global__ void __launch_bounds__(256)
+k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __restrict__ res, int chunk)
+{
+    __shared__ PrimRec s_prim[SLOW_TILE];
+    __shared__ float4 s_far[SLOW_TILE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned first = blockIdx.x * SLOW_RPB + warp * SLOW_RPW;
+    V3 O[SLOW_RPW], D[SLOW_RPW]; HitRec best[SLOW_RPW]; bool lin[SLOW_RPW], live[SLOW_RPW], got[SLOW_RPW];
+#pragma unroll
+    for (int j = 0; j < SLOW_RPW; j++) {
+        const unsigned e = first + j;
+        live[j] = e < n; got[j] = false; lin[j] = false;
+        O[j] = mk(0, 0, 0); D[j] = mk(0, 0, 0); best[j].t = 0.f; best[j].prim = 0; best[j].leaf = -1;
+        if (live[j]) {
+            const float4 o = __ldg(&rays[e].o), d = __ldg(&rays[e].d);
+            const int4 c = __ldg(&rays[e].c);
+            O[j] = mk(o.x, o.y, o.z); D[j] = mk(d.x, d.y, d.z);
+            best[j].t = o.w; best[j].prim = __float_as_int(d.w);
+            lin[j] = (c.x & 1) != 0;
+        }
+    }
+    // blockIdx.y selects a slice of the records (few slow rays -> more slices, so the GPU stays busy)
+    const int nl = min(sc.n_leaf, ((int)blockIdx.y + 1) * chunk);
+    for (int base = (int)blockIdx.y * chunk; base < nl; base += SLOW_TILE) {
+        {   // stage one tile: thread t brings record base + t
+            const int i = base + (int)threadIdx.x;
+            if (i < nl) {
+                s_far[threadIdx.x] = __ldg(sc.far + i);
+                const float4* src = reinterpret_cast<const float4*>(sc.prims + i);
+                float4* dst = reinterpret_cast<float4*>(&s_prim[threadIdx.x]);
+                dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+            } else s_far[threadIdx.x] = make_float4(0.f, 0.f, 0.f, -1.0f);
+        }
+        __syncthreads();
+        bool block_live = false;
+#pragma unroll
+        for (int j = 0; j < SLOW_RPW; j++) {
+            if (!live[j]) continue;
+            block_live = true;
+#pragma unroll 2
+            for (int k = 0; k < SLOW_TILE / 32; k++) {
+                const int s = k * 32 + lane, i = base + s;
+                if (i >= nl) break;
+                if (!lin[j]) {
+                    const float4 fr = s_far[s];
+                    const float nd = __fmaf_rn(fr.x, D[j].x, __fmaf_rn(fr.y, D[j].y, fr.z * D[j].z));   // filter only: FMA is fine
+                    if (!(fabsf(nd) <= fr.w)) continue;
+                }
+                float t; int prim;
+                if (prim_test<false>(&s_prim[s], O[j], D[j], best[j].t, ANY ? 0x7fffffff : best[j].prim, t, prim)) {
+                    best[j].t = t; best[j].leaf = i; best[j].prim = prim; got[j] = true;
+                }
+            }
+            if (ANY && __any_sync(0xffffffffu, got[j])) live[j] = false;     // any hit: this ray is answered
+        }
+        if (!__syncthreads_or(block_live ? 1 : 0)) break;                     // also the barrier before the next tile
+    }
+#pragma unroll
+    for (int j = 0; j < SLOW_RPW; j++) {
+        const unsigned e = first + j;
+        if (e >= n) continue;
+        const bool anyf = __any_sync(0xffffffffu, got[j]);
+        HitRec b = best[j];
+        if (!ANY) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float t2 = __shfl_xor_sync(0xffffffffu, b.t, o);
+                const int p2 = __shfl_xor_sync(0xffffffffu, b.prim, o);
+                const int l2 = __shfl_xor_sync(0xffffffffu, b.leaf, o);
+                if (t2 < b.t || (t2 == b.t && (p2 < b.prim || (p2 == b.prim && l2 > b.leaf)))) { b.t = t2; b.prim = p2; b.leaf = l2; }
+            }
+        }
+        if (lane == 0 && anyf) {
+            if (ANY) res[e].found = 1;
+            else atomicMin(&res[e].key, slow_key(b.t, b.prim));
+        }
+    }
 }
 
 template <int MODE>
@@ -221,13 +350,43 @@ __device__ __forceinline__ void fill_node(const PrimRec* __restrict__ prims, con
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
+// What cpp:30-32 / cpp:925 do with the answer of a closest-hit ray: a hit becomes a node of the
+// next level, a miss is the background colour (in the frame for a primary ray, in the parent's
+// child slot otherwise).  `slot` comes from warp_alloc (all lanes).
+template <bool PRIMARY>
+__device__ __forceinline__ void commit_closest(const PrimRec* __restrict__ prims, bool hit, const HitRec& h, V3 O, V3 d,
+                                               int parent, int pixel, unsigned flags, unsigned slot, unsigned node_cap,
+                                               Node* __restrict__ nodes, NodeAux* __restrict__ aux,
+                                               uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb)
+{
+    if (hit) {
+        if (slot >= node_cap) return;   // cannot happen: capacity is ensured before the launch
+        if (!PRIMARY) pixel = __float_as_int(nodes[parent].D.w);
+        Node nd;
+        fill_node(prims, h, O, d, parent, pixel, flags, nd);
+        nodes[slot] = nd;
+        if (!PRIMARY) {
+            short* s = (flags & NF_REFR) ? aux[parent].refr : aux[parent].refl;
+            s[3] = 2;
+        }
+    } else {
+        if (PRIMARY) {
+            fb[3 * (size_t)pixel + 0] = 254; fb[3 * (size_t)pixel + 1] = 64; fb[3 * (size_t)pixel + 2] = 205;   // BG_COLOR h:597
+            pix_hits[pixel] = 0u;
+        } else {
+            short* s = (flags & NF_REFR) ? aux[parent].refr : aux[parent].refl;
+            s[0] = 254; s[1] = 64; s[2] = 205; s[3] = 1;     // cpp:30-32 at depth > 0
+        }
+    }
+}
+
 // Closest-hit wavefront step.  PRIMARY: one thread per local pixel, ray from GenerateRay.
 // Otherwise one thread per queued reflection / refraction ray.
 template <int MODE, bool PRIMARY>
 __global__ void __launch_bounds__(128)
 k_trace(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, unsigned n_items,
         Node* __restrict__ nodes, NodeAux* __restrict__ aux, unsigned int* __restrict__ counters,
-        uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap)
+        uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap, SlowQ sq)
 {
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
@@ -255,35 +414,55 @@ k_trace(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, unsigned
         }
     }
     HitRec h;
-    const bool hit = trace_ray<MODE, false>(sc, sp, active, O, d, 0.f, h);
+    const int tr = trace_ray<MODE, false>(sc, sp, active, O, d, 0.f, h, sq, (int)i, 0);
+    const unsigned slot = warp_alloc(&counters[0], tr == TR_HIT);
+    if (!active || tr == TR_PENDING) return;
+    commit_closest<PRIMARY>(MODE == 1 ? sp : sc.prims, tr == TR_HIT, h, O, d, parent, pixel, flags, slot, node_cap, nodes, aux,
+                            pix_hits, fb);
+}
+
+// second half of k_trace for the rays that went through the deferred slow path
+template <bool PRIMARY>
+__global__ void __launch_bounds__(128)
+k_trace_finish(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, const SlowRay* __restrict__ rays,
+               const SlowRes* __restrict__ res, unsigned n_slow, Node* __restrict__ nodes, NodeAux* __restrict__ aux,
+               unsigned int* __restrict__ counters, uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = e < n_slow;
+    bool hit = false; HitRec h; h.t = 0.f; h.leaf = -1; h.prim = 0;
+    V3 O = mk(0, 0, 0), d = mk(0, 0, 0);
+    int parent = -1, pixel = 0; unsigned flags = 0;
+    if (active) {
+        const SlowRay r = rays[e];
+        const SlowRes a = res[e];
+        O = mk(r.o.x, r.o.y, r.o.z); d = mk(r.d.x, r.d.y, r.d.z);
+        h.t = __uint_as_float((unsigned)(a.key >> 32)); h.prim = (int)(unsigned)(a.key & 0xffffffffull);
+        hit = h.prim != 0x7fffffff;
+        h.leaf = hit ? __ldg(sc.leaf_of_prim + h.prim) : -1;
+        const int i = r.c.y;
+        if (PRIMARY) { pixel = i; flags = (unsigned)fp.depth << NF_BOUNCE_SHIFT; }
+        else { parent = __float_as_int(queue[i].o.w); flags = __float_as_uint(queue[i].d.w); }
+    }
     const unsigned slot = warp_alloc(&counters[0], hit);
     if (!active) return;
-    if (hit) {
-        if (slot >= node_cap) return;   // cannot happen: capacity is ensured before the launch
-        if (!PRIMARY) pixel = __float_as_int(nodes[parent].D.w);
-        Node nd;
-        fill_node(MODE == 1 ? sp : sc.prims, h, O, d, parent, pixel, flags, nd);
-        nodes[slot] = nd;
-        if (!PRIMARY) {
-            short* s = (flags & NF_REFR) ? aux[parent].refr : aux[parent].refl;
-            s[3] = 2;
-        }
-    } else {
-        if (PRIMARY) {
-            fb[3 * (size_t)pixel + 0] = 254; fb[3 * (size_t)pixel + 1] = 64; fb[3 * (size_t)pixel + 2] = 205;   // BG_COLOR h:597
-            pix_hits[pixel] = 0u;
-        } else {
-            short* s = (flags & NF_REFR) ? aux[parent].refr : aux[parent].refl;
-            s[0] = 254; s[1] = 64; s[2] = 205; s[3] = 1;     // cpp:30-32 at depth > 0
-        }
-    }
+    commit_closest<PRIMARY>(sc.prims, hit, h, O, d, parent, pixel, flags, slot, node_cap, nodes, aux, pix_hits, fb);
+}
+
+// shading normal of a node (cpp:225-236): interpolated object-space vertex normals for a triangle
+// (InterpolateVector3 cpp:333-338, normalised once there), the geometric hit normal for a sphere
+__device__ __forceinline__ V3 shading_normal(const DeviceScene& sc, const Node& nd, unsigned flags, int prim) {
+    if (flags & NF_SPHERE) return mk(nd.N.x, nd.N.y, nd.N.z);
+    const float4 a = __ldg(sc.vn + 3 * (size_t)prim), b = __ldg(sc.vn + 3 * (size_t)prim + 1),
+                 c = __ldg(sc.vn + 3 * (size_t)prim + 2);
+    return normalize((mk(a.x, a.y, a.z) * nd.B.x + mk(b.x, b.y, b.z) * nd.B.y) + mk(c.x, c.y, c.z) * nd.B.z);   // cpp:334-336
 }
 
 // Per hit node of one level: direct lighting with shadow rays, then spawn the children.
 template <int MODE>
 __global__ void __launch_bounds__(128)
 k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __restrict__ nodes,
-        NodeAux* __restrict__ aux, QRay* __restrict__ queue, unsigned int* __restrict__ counters)
+        NodeAux* __restrict__ aux, QRay* __restrict__ queue, unsigned int* __restrict__ counters, SlowQ sq)
 {
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
@@ -300,13 +479,7 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
         bounces = (int)((flags >> NF_BOUNCE_SHIFT) & 0xffu);
         const int prim = __float_as_int(nd.P.w);
         M = load_material(sc.materials, __ldg(sc.prim_material + prim));
-        // shading normal (cpp:225-236)
-        sn = N;
-        if (!(flags & NF_SPHERE)) {
-            const float4 a = __ldg(sc.vn + 3 * (size_t)prim), b = __ldg(sc.vn + 3 * (size_t)prim + 1),
-                         c = __ldg(sc.vn + 3 * (size_t)prim + 2);
-            sn = normalize((mk(a.x, a.y, a.z) * nd.B.x + mk(b.x, b.y, b.z) * nd.B.y) + mk(c.x, c.y, c.z) * nd.B.z);   // cpp:334-336
-        }
+        sn = shading_normal(sc, nd, flags, prim);
     }
     Pix local = mkpix(0, 0, 0);                                       // SHADOW_COLOR h:598
     const V3 cam = mk(fp.cam[0], fp.cam[1], fp.cam[2]);
@@ -324,8 +497,9 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
         HitRec sh;
         // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
         const float tmax = (L.type == RT580_LIGHT_POINT) ? distToLight : __int_as_float(0x7f800000);
-        const bool occluded = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh);
-        if (active && !occluded) local = pix_add(local, calculate_local_color(P, sn, L, M, cam));   // cpp:77
+        const int tr = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh, sq, (int)i, li);
+        // TR_PENDING: k_shade_finish adds this light's term once the deferred ray is answered
+        if (active && tr == TR_MISS) local = pix_add(local, calculate_local_color(P, sn, L, M, cam));   // cpp:77
     }
     if (active) {
         NodeAux a;
@@ -358,6 +532,38 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
         q.d = make_float4(td.x, td.y, td.z, __uint_as_float(child_flags | NF_REFR));
         queue[s1] = q;
     }
+}
+
+// deferred shadow rays of k_shade: an unoccluded one adds its light's Phong term (cpp:77).  Pixel
+// addition is plain integer addition (h:403-409), so the order of the terms does not matter; two
+// lights of one node may finish concurrently, hence the packed 16-bit atomics (terms are in
+// [0,255], sums stay far below 2^16).
+__global__ void __launch_bounds__(128)
+k_shade_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays, const SlowRes* __restrict__ res,
+               unsigned n_slow, const Node* __restrict__ nodes, NodeAux* __restrict__ aux)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_slow) return;
+    if (res[e].found) return;                                          // occluded: + SHADOW_COLOR (cpp:80)
+    const int i = rays[e].c.y, li = rays[e].c.z;
+    const Node nd = nodes[i];
+    const unsigned flags = __float_as_uint(nd.B.w);
+    const int prim = __float_as_int(nd.P.w);
+    const Material M = load_material(sc.materials, __ldg(sc.prim_material + prim));
+    const V3 sn = shading_normal(sc, nd, flags, prim);
+    const Light L = load_light(sc.light_type, sc.light_f, li);
+    const Pix c = calculate_local_color(mk(nd.P.x, nd.P.y, nd.P.z), sn, L, M, mk(fp.cam[0], fp.cam[1], fp.cam[2]));
+    unsigned int* w = reinterpret_cast<unsigned int*>(aux[i].local);
+    atomicAdd(w, (unsigned)(unsigned short)c.r | ((unsigned)(unsigned short)c.g << 16));
+    atomicAdd(w + 1, (unsigned)(unsigned short)c.b);
+}
+
+// deferred AO rays of k_ao: a hit is one more occluded sample of its AO call (cpp:325-326)
+__global__ void k_ao_finish(const SlowRay* __restrict__ rays, const SlowRes* __restrict__ res, unsigned n_slow,
+                            uint32_t* __restrict__ ao_hits)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_slow && res[e].found) atomicAdd(ao_hits + rays[e].c.y, 1u);
 }
 
 // bottom-up: hit nodes per subtree -> parent slot, or per pixel for roots
@@ -450,7 +656,7 @@ __global__ void k_preorder(unsigned n0, unsigned n1, const Node* __restrict__ no
 template <int MODE>
 __global__ void __launch_bounds__(128)
 k_ao(DeviceScene sc, FrameParams fp, unsigned long long n_rays, int n_ambient, const Node* __restrict__ nodes,
-     const uint32_t* __restrict__ ao_state, uint32_t* __restrict__ ao_hits)
+     const uint32_t* __restrict__ ao_state, uint32_t* __restrict__ ao_hits, SlowQ sq)
 {
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
@@ -471,7 +677,7 @@ k_ao(DeviceScene sc, FrameParams fp, unsigned long long n_rays, int n_ambient, c
         rd = normalize(dir);                                                   // Ray ctor h:431-433
     }
     HitRec h;
-    const bool hit = trace_ray<MODE, true>(sc, sp, active, org, rd, __int_as_float(0x7f800000), h);   // cpp:325
+    const bool hit = trace_ray<MODE, true>(sc, sp, active, org, rd, __int_as_float(0x7f800000), h, sq, (int)call, 0) == TR_HIT;   // cpp:325
     // count the occluded samples of each AO call inside the warp, one atomic per (warp, call)
     const unsigned peers = __match_any_sync(0xffffffffu, call);
     const unsigned votes = __ballot_sync(0xffffffffu, hit);
@@ -542,7 +748,8 @@ k_trace_rays(DeviceScene sc, long long n, const float* __restrict__ org, const f
     V3 O = mk(0, 0, 0), d = mk(0, 0, 0);
     if (active) { O = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]); d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]); }
     HitRec h;
-    const bool hit = trace_ray<MODE, ANY>(sc, sp, active, O, d, (ANY && active) ? tmax[i] : 0.f, h);
+    const SlowQ noq = { nullptr, nullptr, nullptr, 0u };
+    const bool hit = trace_ray<MODE, ANY>(sc, sp, active, O, d, (ANY && active) ? tmax[i] : 0.f, h, noq, 0, 0) == TR_HIT;
     if (!active) return;
     if (ANY) hit_out[i] = hit ? 1 : 0;
     else { prim_out[i] = hit ? h.prim : -1; t_out[i] = hit ? h.t : 0.f; }
@@ -561,7 +768,8 @@ k_trace_profile(DeviceScene sc, long long n, const float* __restrict__ org, cons
     if (active) { O = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]); d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]); }
     HitRec h;
     unsigned cnt[4] = { 0, 0, 0, 0 };
-    trace_ray<0, ANY>(sc, nullptr, active, O, d, (ANY && active) ? tmax[i] : 0.f, h, cnt);
+    const SlowQ noq = { nullptr, nullptr, nullptr, 0u };
+    trace_ray<0, ANY>(sc, nullptr, active, O, d, (ANY && active) ? tmax[i] : 0.f, h, noq, 0, 0, cnt);
     if (!active) return;
     for (int k = 0; k < 4; k++) counts4[4 * i + k] = cnt[k];
 }
@@ -609,9 +817,9 @@ extern "C" int rt580_create(int device, rt580_context** out)
 }
 
 static void free_scene(rt580_context* c) {
-    cudaFree(c->d_prims); cudaFree(c->d_nodes); cudaFree(c->d_far); cudaFree(c->d_always); cudaFree(c->d_vn); cudaFree(c->d_prim_material);
+    cudaFree(c->d_prims); cudaFree(c->d_nodes); cudaFree(c->d_far); cudaFree(c->d_always); cudaFree(c->d_leaf_of_prim); cudaFree(c->d_vn); cudaFree(c->d_prim_material);
     cudaFree(c->d_materials); cudaFree(c->d_light_type); cudaFree(c->d_light_f);
-    c->d_prims = nullptr; c->d_nodes = nullptr; c->d_far = nullptr; c->d_always = nullptr; c->d_vn = nullptr; c->d_prim_material = nullptr;
+    c->d_prims = nullptr; c->d_nodes = nullptr; c->d_far = nullptr; c->d_always = nullptr; c->d_leaf_of_prim = nullptr; c->d_vn = nullptr; c->d_prim_material = nullptr;
     c->d_materials = nullptr; c->d_light_type = nullptr; c->d_light_f = nullptr;
     c->have_scene = false;
 }
@@ -625,6 +833,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     c->ndc.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
+    c->slow_rays.release(); c->slow_res.release();
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -695,7 +904,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
 
     BuildInput in{};
     in.tri_v0 = v0; in.tri_v1 = v1; in.tri_v2 = v2; in.tri_prim = tprim; in.n_tris = s->n_tris;
-    in.sph = sph; in.sph_prim = sprim; in.n_spheres = s->n_spheres;
+    in.sph = sph; in.sph_prim = sprim; in.n_spheres = s->n_spheres; in.n_prims = s->n_prims;
     // ray origins never leave the hull of the scene and the camera (bvh_build.cu header)
     for (int k = 0; k < 3; k++) in.origin_hint[k] = s->origin_hint[k];
     BuildOutput bo{};
@@ -712,6 +921,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->sc.far = bo.far; c->sc.far_tmin = bo.far_tmin; c->sc.farfield = 1; c->sc.extent = bo.extent;
     c->n_always = bo.n_always; c->n_dropped = bo.n_dropped;
     c->d_always = bo.always_idx; c->sc.always_idx = bo.always_idx; c->sc.n_always = bo.n_always;
+    c->d_leaf_of_prim = bo.leaf_of_prim; c->sc.leaf_of_prim = bo.leaf_of_prim;
     c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_prims = (int32_t)s->n_prims;
     c->sc.vn = c->d_vn; c->sc.prim_material = c->d_prim_material; c->sc.materials = c->d_materials;
     c->sc.n_materials = s->n_materials; c->sc.light_type = c->d_light_type; c->sc.light_f = c->d_light_f;
@@ -742,21 +952,27 @@ extern "C" int rt580_build_ms(rt580_context* c, float* ms) {
 
 static inline unsigned nblk(unsigned long long n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
-template <int MODE> static void launch_trace(rt580_context* c, bool primary, unsigned n_items, unsigned node_cap) {
+static SlowQ slowq(rt580_context* c, unsigned cap) {
+    SlowQ q; q.rays = c->slow_rays.p; q.res = c->slow_res.p; q.count = c->counters.p + 2; q.cap = cap;
+    return q;
+}
+template <int MODE> static void launch_trace(rt580_context* c, bool primary, unsigned n_items, unsigned node_cap, unsigned slow_cap) {
     if (primary)
         k_trace<MODE, true><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, c->nodes.p, c->aux.p,
-                                                                      c->counters.p, c->pix_hits.p, c->fb.p, node_cap);
+                                                                      c->counters.p, c->pix_hits.p, c->fb.p, node_cap, slowq(c, slow_cap));
     else
         k_trace<MODE, false><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, c->nodes.p, c->aux.p,
-                                                                       c->counters.p, c->pix_hits.p, c->fb.p, node_cap);
+                                                                       c->counters.p, c->pix_hits.p, c->fb.p, node_cap, slowq(c, slow_cap));
     c->launches++;
 }
-template <int MODE> static void launch_shade(rt580_context* c, unsigned n0, unsigned n1) {
-    k_shade<MODE><<<nblk(n1 - n0, 128), 128, 0, c->stream>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p);
+template <int MODE> static void launch_shade(rt580_context* c, unsigned n0, unsigned n1, unsigned slow_cap) {
+    k_shade<MODE><<<nblk(n1 - n0, 128), 128, 0, c->stream>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p,
+                                                             slowq(c, slow_cap));
     c->launches++;
 }
-template <int MODE> static void launch_ao(rt580_context* c, unsigned long long n_rays) {
-    k_ao<MODE><<<nblk(n_rays, 128), 128, 0, c->stream>>>(c->sc, c->fp, n_rays, c->sc.n_ambient, c->nodes.p, c->ao_state.p, c->ao_hits.p);
+template <int MODE> static void launch_ao(rt580_context* c, unsigned long long n_rays, unsigned slow_cap) {
+    k_ao<MODE><<<nblk(n_rays, 128), 128, 0, c->stream>>>(c->sc, c->fp, n_rays, c->sc.n_ambient, c->nodes.p, c->ao_state.p, c->ao_hits.p,
+                                                         slowq(c, slow_cap));
     c->launches++;
 }
 #define DISPATCH_MODE(mode, fn, ...) do { if ((mode) == 0) fn<0>(__VA_ARGS__); else if ((mode) == 1) fn<1>(__VA_ARGS__); else fn<2>(__VA_ARGS__); } while (0)
@@ -792,6 +1008,45 @@ static int exclusive_scan_u32(rt580_context* c, const uint32_t* in, uint32_t* ou
 static int read_counter(rt580_context* c, int which, unsigned* out) {
     CU(cudaMemcpyAsync(out, c->counters.p + which, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return RT580_SUCCESS;
+}
+
+// Reserve the deferred-ray queue for a launch that may record up to `max_rays` slow rays.
+static int slow_prepare(rt580_context* c, unsigned long long max_rays, unsigned* cap_out)
+{
+    unsigned cap = (unsigned)(max_rays < (unsigned long long)SLOW_CAP_MAX ? max_rays : (unsigned long long)SLOW_CAP_MAX);
+    if (!c->sc.farfield || c->sc.n_leaf <= RT_SMEM_PRIMS) cap = 0;       // linear modes never defer
+    if (cap) {
+        CU(c->slow_rays.ensure(cap, 0, c->stream));
+        CU(c->slow_res.ensure(cap, 0, c->stream));
+    }
+    CU(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned), c->stream));
+    *cap_out = cap;
+    return RT580_SUCCESS;
+}
+// Answer the recorded slow rays (one warp each); returns how many there were.
+static int slow_run(rt580_context* c, bool any, unsigned cap, unsigned* n_out)
+{
+    *n_out = 0;
+    if (!cap) return RT580_SUCCESS;
+    unsigned n = 0;
+    if (read_counter(c, 2, &n)) return RT580_FAILURE;
+    if (n > cap) n = cap;
+    if (n) {
+        const unsigned batches = nblk(n, SLOW_RPB);
+        unsigned slices = nblk(4u * (unsigned)c->prop.multiProcessorCount, batches);
+        const unsigned max_slices = nblk((unsigned)c->sc.n_leaf, SLOW_TILE);
+        if (slices > max_slices) slices = max_slices;
+        if (slices > 256u) slices = 256u;
+        if (slices < 1u) slices = 1u;
+        const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_leaf, slices), SLOW_TILE) * SLOW_TILE);
+        const dim3 grid(batches, slices);
+        if (any) k_slow<true><<<grid, 256, 0, c->stream>>>(c->sc, c->slow_rays.p, n, c->slow_res.p, chunk);
+        else k_slow<false><<<grid, 256, 0, c->stream>>>(c->sc, c->slow_rays.p, n, c->slow_res.p, chunk);
+        c->launches++;
+        c->slow_total += n;
+    }
+    *n_out = n;
     return RT580_SUCCESS;
 }
 
@@ -859,9 +1114,18 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
     CU(cudaEventRecord(c->ev[0], st));
     c->level_off.clear(); c->level_rays.clear();
     c->level_off.push_back(0);
-    unsigned n_nodes = 0;
+    unsigned n_nodes = 0, slow_cap = 0, n_slow = 0;
+    c->slow_total = 0;
     if (npix) {
-        DISPATCH_MODE(mode, launch_trace, c, true, npix, (unsigned)c->nodes.cap);
+        if (slow_prepare(c, npix, &slow_cap)) return RT580_FAILURE;
+        DISPATCH_MODE(mode, launch_trace, c, true, npix, (unsigned)c->nodes.cap, slow_cap);
+        if (slow_run(c, false, slow_cap, &n_slow)) return RT580_FAILURE;
+        if (n_slow) {
+            k_trace_finish<true><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
+                                                                   c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
+                                                                   (unsigned)c->nodes.cap);
+            c->launches++;
+        }
         if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
     }
     c->level_rays.push_back(npix);
@@ -872,14 +1136,28 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
         CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
         if (L < fp.depth) CU(c->queue.ensure(2 * (size_t)(n1 - n0), 0, st));
         else CU(c->queue.ensure(1, 0, st));
-        DISPATCH_MODE(mode, launch_shade, c, n0, n1);
+        if (slow_prepare(c, (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient, &slow_cap)) return RT580_FAILURE;
+        DISPATCH_MODE(mode, launch_shade, c, n0, n1, slow_cap);
+        if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
+        if (n_slow) {
+            k_shade_finish<<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->slow_rays.p, c->slow_res.p, n_slow, c->nodes.p, c->aux.p);
+            c->launches++;
+        }
         if (L == fp.depth) break;
         unsigned q = 0;
         if (read_counter(c, 1, &q)) return RT580_FAILURE;
         if (q == 0) break;
         CU(c->nodes.ensure((size_t)n1 + q, n1, st));
         CU(c->aux.ensure((size_t)n1 + q, n1, st));
-        DISPATCH_MODE(mode, launch_trace, c, false, q, (unsigned)c->nodes.cap);
+        if (slow_prepare(c, q, &slow_cap)) return RT580_FAILURE;
+        DISPATCH_MODE(mode, launch_trace, c, false, q, (unsigned)c->nodes.cap, slow_cap);
+        if (slow_run(c, false, slow_cap, &n_slow)) return RT580_FAILURE;
+        if (n_slow) {
+            k_trace_finish<false><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
+                                                                    c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
+                                                                    (unsigned)c->nodes.cap);
+            c->launches++;
+        }
         if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
         c->level_rays.push_back(q);
         c->level_off.push_back(n_nodes);
@@ -948,7 +1226,14 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     CU(cudaEventRecord(c->ev[3], st));
     const unsigned long long n_ao = n_calls * (unsigned long long)fp.spp;
     if (n_ao > 0xffffffffull * 128ull) FAIL(RT580_FAILURE, "rt580_render_finish: AO ray count exceeds one launch");
-    if (n_ao) DISPATCH_MODE(mode, launch_ao, c, n_ao);
+    if (n_ao) {
+        unsigned slow_cap = 0, n_slow = 0;
+        if (slow_prepare(c, n_ao, &slow_cap)) return RT580_FAILURE;
+        DISPATCH_MODE(mode, launch_ao, c, n_ao, slow_cap);
+        CU(cudaEventRecord(c->ev[7], st));
+        if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
+        if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, c->ao_hits.p); c->launches++; }
+    } else CU(cudaEventRecord(c->ev[7], st));
     CU(cudaEventRecord(c->ev[4], st));
     for (int L = n_levels - 1; L >= 0; L--) {
         const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
@@ -967,7 +1252,8 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.ms_structure = ms;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.ms_order = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[6]); c->stats.ms_order += ms;
-    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.ms_ao = ms; c->stats.ms_ao_kernel = ms;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.ms_ao = ms;
+    cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]); c->stats.ms_ao_kernel = ms;
     cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->stats.ms_resolve = ms;
     c->stats.ms_total = c->stats.ms_structure + c->stats.ms_order + c->stats.ms_ao + c->stats.ms_resolve;
     c->stats.kernel_launches = c->launches;

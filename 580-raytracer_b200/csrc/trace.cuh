@@ -166,6 +166,63 @@ __device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, 
 // the whole warp serves them one at a time: the ray is broadcast, lane l tests records
 // l, l+32, ... (coalesced 512-byte loads), and a lexicographic (t, prim) warp reduction
 // returns what the reference's first-wins loop would.  Must be called by all 32 lanes.
+// One slow ray served by a whole warp (all 32 lanes call with the same ray): returns whether
+// something was accepted; for closest hits `best` holds the lexicographic (t, prim) minimum.
+template <bool ANY>
+__device__ __forceinline__ bool warp_scan_one(const DeviceScene& sc, bool lin, V3 Ob, V3 db, HitRec& best)
+{
+    const int lane = threadIdx.x & 31;
+    const float4* __restrict__ far = sc.far;
+    const int n = sc.n_leaf;
+    best.leaf = -1;
+    bool f = false;
+    if (!lin) {
+        // far scan: 4 filter records per lane in flight (independent loads), exact test on the survivors
+        for (int base = 0; base < n && !(ANY && f); base += 128) {
+            float4 fr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = base + 32 * k + lane;
+                fr[k] = (i < n) ? __ldg(far + i) : make_float4(0.f, 0.f, 0.f, -1.0f);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float nd = __fmaf_rn(fr[k].x, db.x, __fmaf_rn(fr[k].y, db.y, fr[k].z * db.z));   // filter only: FMA is fine
+                if (fabsf(nd) <= fr[k].w) {
+                    const int i = base + 32 * k + lane;
+                    float t; int prim;
+                    if (prim_test<true>(sc.prims + i, Ob, db, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+                        best.t = t; best.leaf = i; best.prim = prim; f = true;
+                    }
+                }
+            }
+        }
+    } else {
+        for (int i = lane; i < n; i += 32) {
+            float t; int prim;
+            if (prim_test<true>(sc.prims + i, Ob, db, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+                best.t = t; best.leaf = i; best.prim = prim; f = true;
+                if (ANY) break;
+            }
+        }
+    }
+    const bool anyf = __any_sync(0xffffffffu, f);
+    if (!ANY) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float t2 = __shfl_xor_sync(0xffffffffu, best.t, o);
+            const int p2 = __shfl_xor_sync(0xffffffffu, best.prim, o);
+            const int l2 = __shfl_xor_sync(0xffffffffu, best.leaf, o);
+            if (t2 < best.t || (t2 == best.t && (p2 < best.prim || (p2 == best.prim && l2 > best.leaf)))) {
+                best.t = t2; best.prim = p2; best.leaf = l2;
+            }
+        }
+    }
+    return anyf;
+}
+
+// In-kernel form: the lanes that need the slow path are served one after the other by the
+// whole warp (used when no deferred queue is available, or it is full).
 template <bool ANY>
 __device__ __forceinline__ bool warp_slow_path(const DeviceScene& sc, bool need, bool linear, V3 O, V3 d,
                                                HitRec& hit, bool found)
@@ -173,8 +230,6 @@ __device__ __forceinline__ bool warp_slow_path(const DeviceScene& sc, bool need,
     unsigned pending = __ballot_sync(0xffffffffu, need);
     if (pending == 0u) return found;
     const int lane = threadIdx.x & 31;
-    const float4* __restrict__ far = sc.far;
-    const int n = sc.n_leaf;
     while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1u;
@@ -184,50 +239,7 @@ __device__ __forceinline__ bool warp_slow_path(const DeviceScene& sc, bool need,
         HitRec best;
         best.t = __shfl_sync(0xffffffffu, hit.t, src);
         best.prim = __shfl_sync(0xffffffffu, hit.prim, src);
-        best.leaf = -1;
-        bool f = false;
-        if (!lin) {
-            // far scan: 4 filter records per lane in flight (independent loads), exact test on the survivors
-            for (int base = 0; base < n && !(ANY && f); base += 128) {
-                float4 fr[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int i = base + 32 * k + lane;
-                    fr[k] = (i < n) ? __ldg(far + i) : make_float4(0.f, 0.f, 0.f, -1.0f);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float nd = __fmaf_rn(fr[k].x, db.x, __fmaf_rn(fr[k].y, db.y, fr[k].z * db.z));   // filter only: FMA is fine
-                    if (fabsf(nd) <= fr[k].w) {
-                        const int i = base + 32 * k + lane;
-                        float t; int prim;
-                        if (prim_test<true>(sc.prims + i, Ob, db, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
-                            best.t = t; best.leaf = i; best.prim = prim; f = true;
-                        }
-                    }
-                }
-            }
-        } else {
-            for (int i = lane; i < n; i += 32) {
-                float t; int prim;
-                if (prim_test<true>(sc.prims + i, Ob, db, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
-                    best.t = t; best.leaf = i; best.prim = prim; f = true;
-                    if (ANY) break;
-                }
-            }
-        }
-        const bool anyf = __any_sync(0xffffffffu, f);
-        if (!ANY) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float t2 = __shfl_xor_sync(0xffffffffu, best.t, o);
-                const int p2 = __shfl_xor_sync(0xffffffffu, best.prim, o);
-                const int l2 = __shfl_xor_sync(0xffffffffu, best.leaf, o);
-                if (t2 < best.t || (t2 == best.t && (p2 < best.prim || (p2 == best.prim && l2 > best.leaf)))) {
-                    best.t = t2; best.prim = p2; best.leaf = l2;
-                }
-            }
-        }
+        const bool anyf = warp_scan_one<ANY>(sc, lin, Ob, db, best);
         if (lane == src && anyf) {
             found = true;
             if (!ANY) hit = best;
