@@ -36,12 +36,22 @@ def _translation_for(p, scale, ry_deg):
     return [c * q[0] - s * q[2], q[1], s * q[0] + c * q[2]]
 
 
-def _mesh_room(half, y0, y1):
-    """Closed room: floor, ceiling and four walls, 12 triangles, all normals facing inward."""
+def _mesh_room(half, y0, y1, shell=1.0):
+    """Closed room with thick walls: an inner box (floor, ceiling, four walls: 12 triangles) and an
+    outer box `shell` units further out (12 more), all geometric normals facing inward.  The outer
+    box catches the rays the reference starts 0.2 units BEHIND an inner wall (its shadow / AO /
+    reflection origins are hit point + 0.2 * direction, cpp:67, cpp:98, cpp:322, so a hit closer
+    than 0.2 to a wall tunnels through it)."""
     def tri(a, b, c, n):
         return {"type": "polygon", "v0": {"v": a, "n": n, "t": [0.0, 0.0]}, "v1": {"v": b, "n": n, "t": [1.0, 0.0]},
                 "v2": {"v": c, "n": n, "t": [1.0, 1.0]}}
-    h = half
+    data = []
+    for h, ya, yb in ((half, y0, y1), (half + shell, y0 - shell, y1 + shell)) if shell > 0 else ((half, y0, y1),):
+        data += _box_inward(h, ya, yb, tri)
+    return {"data": data}
+
+
+def _box_inward(h, y0, y1, tri):
     c = [[-h, y0, -h], [h, y0, -h], [h, y0, h], [-h, y0, h], [-h, y1, -h], [h, y1, -h], [h, y1, h], [-h, y1, h]]
     quads = [((0, 2, 1), (0, 3, 2), [0.0, 1.0, 0.0]),      # floor (normal up)
              ((4, 5, 6), (4, 6, 7), [0.0, -1.0, 0.0]),     # ceiling
@@ -61,7 +71,7 @@ def _mesh_room(half, y0, y1):
         for t in (t0, t1):
             a, b, cc = inward(c[t[0]], c[t[1]], c[t[2]], n)
             data.append(tri(a, b, cc, n))
-    return {"data": data}
+    return data
 
 
 def write_synthetic_scene(out_dir, name, n_teapots, n_spheres, seed=580, spacing=4.5, teapot_mesh="teapot",
@@ -140,7 +150,7 @@ def write_synthetic_scene(out_dir, name, n_teapots, n_spheres, seed=580, spacing
                                   "resolution": [3840, 2160]}}}
     with open(os.path.join(out_dir, name + ".json"), "w") as f:
         json.dump(scene, f)
-    return {"scene": name + ".json", "n_triangles": n_teapots * TEAPOT_TRIS + (12 if room else (2 if with_floor else 0)),
+    return {"scene": name + ".json", "n_triangles": n_teapots * TEAPOT_TRIS + (24 if room else (2 if with_floor else 0)),
             "n_spheres": n_spheres, "n_shapes": len(shapes), "camera_from": cam_from, "half_extent": half}
 
 

@@ -300,7 +300,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "scene": "977 teapot instances (1,000,448 triangles) + 1000 spheres + closed room (12 triangles), seed 580",
+                "config": {"workload": WORKLOAD, "scene": "977 teapot instances (1,000,448 triangles) + 1000 spheres + closed double-walled room (24 triangles), seed 580",
                            "width": W, "height": H, "depth": DEPTH, "ao_spp": SPP, "rng": "reference_lcg", "farfield": args.farfield, "far_scans": st0.far_scans, "linear_fallbacks": st0.linear_fallbacks,
                            "partition": "rows interleaved over %d rank(s)" % world, "l2": "working set > L2: nodes+records %.0f MB, frame data %.0f MB/step" % (
                                info.n_leaf * 144 / 1e6, st0.hit_nodes * 110 / 1e6)},
