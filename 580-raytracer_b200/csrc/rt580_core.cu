@@ -144,6 +144,7 @@ struct rt580_context {
     DBuf<int16_t> fb;              // [n_rows][W][3]
     DBuf<unsigned int> counters;   // [0] node count, [1] queue count, [2] slow-ray count, [4..5] diagnostics
     DBuf<SlowRay> slow_rays; DBuf<SlowRes> slow_res;
+    DBuf<struct ARay> arays;       // one chunk of generated AO rays
     uint64_t slow_total = 0;
     std::vector<size_t> level_off; // node index where each level starts (+ end)
     std::vector<uint64_t> level_rays;
@@ -687,6 +688,147 @@ k_ao(DeviceScene sc, FrameParams fp, unsigned long long n_rays, int n_ambient, c
     }
 }
 
+// ---- occlusion pass, wavefront form -------------------------------------------------------
+// k_ao (above) maps one thread to one AO ray: rays of a warp end after very different numbers of
+// node visits (any-hit), and ncu shows 9.5 of 32 lanes active on average.  The wavefront form
+// splits it: k_ao_gen writes the sample rays (the exact RNG / hemisphere arithmetic of
+// cpp:269-292, 32 bytes per ray), k_anyhit is a persistent kernel in which a lane that finishes
+// its ray immediately fetches the next one (warp-aggregated atomic on the ray counter), so the
+// warps stay full until the queue runs dry.
+struct __align__(16) ARay {
+    float4 a;   // origin.xyz, dir.x
+    float4 b;   // dir.y, dir.z, bits(consumer id: AO call), tmax
+};
+
+__global__ void __launch_bounds__(256)
+k_ao_gen(FrameParams fp, unsigned long long first, unsigned n, int n_ambient, const Node* __restrict__ nodes,
+         const uint32_t* __restrict__ ao_state, ARay* __restrict__ out)
+{
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long i = first + j;
+    const unsigned call = (unsigned)(i / (unsigned)fp.spp);
+    const unsigned k = (unsigned)(i % (unsigned)fp.spp);
+    const unsigned node = call / (unsigned)n_ambient;
+    uint32_t st = lcg_mulmod(__ldg(ao_state + call), lcg_state_at(2ull * k));   // state after the 2k draws before sample k
+    const float4 nP = __ldg(&nodes[node].P), nN = __ldg(&nodes[node].N);
+    const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
+    const V3 dir = random_in_hemisphere(st, N);                                  // cpp:321
+    const V3 org = P + dir * RT_SHADOW_OFFSET;                                   // cpp:322
+    const V3 rd = normalize(dir);                                                // Ray ctor h:431-433
+    ARay r;
+    r.a = make_float4(org.x, org.y, org.z, rd.x);
+    r.b = make_float4(rd.y, rd.z, __uint_as_float(call), __int_as_float(0x7f800000));
+    out[j] = r;
+}
+
+#define AH_STEPS 4    // traversal steps between two refill checks
+#define AH_BATCH 512  // rays a warp reserves per atomic on the queue counter
+__global__ void __launch_bounds__(128)
+k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, unsigned n, unsigned int* __restrict__ next_ray,
+         uint32_t* __restrict__ hit_count, SlowQ sq)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    bool active = false;
+    V3 O = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
+    float tmax = 0.f; unsigned id = 0;
+    int stack[RT_STACK_SIZE];
+    int sp = 0, node = 0;
+    bool last_batch = false;        // warp-uniform: the queue counter has run past n, no further batch exists
+    unsigned wnext = 0, wend = 0;   // warp-uniform: this warp's current batch [wnext, wend) of the ray queue
+    for (;;) {
+        const bool exhausted = last_batch && wnext == wend;
+        if (!exhausted) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            if (idle) {
+                const unsigned want = (unsigned)__popc(idle);
+                if (wend - wnext < want) {
+                    // one atomic per AH_BATCH rays and warp (a single hot counter would serialise the GPU);
+                    // the unused tail of the old batch (< 32 rays) is handed out first
+                    if (wnext == wend && !last_batch) {
+                        unsigned b = 0;
+                        if (lane == 0) b = atomicAdd(next_ray, (unsigned)AH_BATCH);
+                        wnext = __shfl_sync(0xffffffffu, b, 0);
+                        wend = wnext + AH_BATCH;
+                        if (wend >= n) { last_batch = true; if (wend > n) wend = n; if (wnext > n) wnext = n; }
+                    }
+                }
+                const unsigned base = wnext;
+                const unsigned give = min(want, wend - wnext);
+                wnext += give;
+                if (!active) {
+                    const unsigned rank = (unsigned)__popc(idle & lt_mask);
+                    const unsigned idx = base + rank;
+                    if (rank < give) {
+                        const float4 a = __ldg(&rays[idx].a), b = __ldg(&rays[idx].b);
+                        O = mk(a.x, a.y, a.z); d = mk(a.w, b.x, b.y);
+                        id = __float_as_uint(b.z); tmax = b.w;
+                        if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent) {
+                            // child of a far-field hit: the reference's linear loop, deferred (trace.cuh)
+                            if (sc.diag) atomicAdd(sc.diag + 1, 1u);
+                            const unsigned slot = atomicAdd(sq.count, 1u);
+                            if (slot < sq.cap) {
+                                SlowRay r; r.o = make_float4(O.x, O.y, O.z, tmax); r.d = make_float4(d.x, d.y, d.z, __int_as_float(0x7fffffff));
+                                r.c = make_int4(1, (int)id, 0, -1);
+                                sq.rays[slot] = r;
+                                SlowRes z; z.key = 0ull; z.found = 0; z.pad = 0; sq.res[slot] = z;
+                            }
+                        } else if (sc.n_leaf > 0) {
+                            inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                            node = 0; sp = 0; active = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) { if (last_batch && wnext == wend) break; continue; }
+#pragma unroll 1
+        for (int step = 0; step < AH_STEPS; step++) {
+            if (!active) continue;
+            const BvhNode* __restrict__ nd = sc.nodes + node;
+            const float4 xy0 = __ldg(&nd->xy0), xy1 = __ldg(&nd->xy1), z01 = __ldg(&nd->z01);
+            const int4 kids = __ldg(&nd->kids);
+            float tn0, tn1;
+            const bool h0 = slab(xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, O, inv, tmax, tn0);
+            const bool h1 = slab(xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, O, inv, tmax, tn1);
+            int next; bool done = false, found = false;
+            if (h0 && h1) {
+                int nearc = kids.x, farc = kids.y;
+                if (tn1 < tn0) { nearc = kids.y; farc = kids.x; }
+                if (sp < RT_STACK_SIZE) stack[sp++] = farc;
+                next = nearc;
+            } else if (h0) next = kids.x;
+            else if (h1) next = kids.y;
+            else { if (sp == 0) { done = true; next = 0; } else next = stack[--sp]; }
+            while (!done && next < 0) {
+                float t; int prim;
+                if (prim_test<true>(sc.prims + (~next), O, d, tmax, 0x7fffffff, t, prim)) { found = true; done = true; break; }
+                if (sp == 0) done = true; else next = stack[--sp];
+            }
+            if (done) {
+                active = false;
+                if (!found && sc.farfield) {
+                    HitRec h; h.t = tmax; h.leaf = -1; h.prim = 0x7fffffff;
+                    if (sc.n_always) found = always_scan<true>(sc, O, d, h, false);
+                    if (!found && tmax >= sc.far_tmin) {
+                        // found nothing nearer than far_tmin: deferred far-field scan (trace.cuh)
+                        if (sc.diag) atomicAdd(sc.diag, 1u);
+                        const unsigned slot = atomicAdd(sq.count, 1u);
+                        if (slot < sq.cap) {
+                            SlowRay r; r.o = make_float4(O.x, O.y, O.z, tmax); r.d = make_float4(d.x, d.y, d.z, __int_as_float(0x7fffffff));
+                            r.c = make_int4(0, (int)id, 0, -1);
+                            sq.rays[slot] = r;
+                            SlowRes z; z.key = 0ull; z.found = 0; z.pad = 0; sq.res[slot] = z;
+                        }
+                    }
+                }
+                if (found) atomicAdd(hit_count + id, 1u);
+            } else node = next;
+        }
+    }
+}
+
 // bottom-up per level: cpp:39-51 (ambient term), cpp:85-128 (Fresnel blend in Pixel algebra)
 __global__ void k_resolve(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __restrict__ nodes,
                           NodeAux* __restrict__ aux, const uint32_t* __restrict__ ao_hits, int n_ambient,
@@ -833,7 +975,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     c->ndc.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
-    c->slow_rays.release(); c->slow_res.release();
+    c->slow_rays.release(); c->slow_res.release(); c->arays.release();
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1228,12 +1370,36 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     if (n_ao > 0xffffffffull * 128ull) FAIL(RT580_FAILURE, "rt580_render_finish: AO ray count exceeds one launch");
     if (n_ao) {
         unsigned slow_cap = 0, n_slow = 0;
-        if (slow_prepare(c, n_ao, &slow_cap)) return RT580_FAILURE;
-        DISPATCH_MODE(mode, launch_ao, c, n_ao, slow_cap);
-        CU(cudaEventRecord(c->ev[7], st));
-        if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
-        if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, c->ao_hits.p); c->launches++; }
-    } else CU(cudaEventRecord(c->ev[7], st));
+        float kernel_ms = 0.f;
+        if (mode == 0) {
+            // wavefront form: chunks of at most SLOW_CAP_MAX rays (the deferred queue can then hold
+            // every ray of a chunk, so it cannot overflow): generate, trace persistently, finish
+            CU(c->arays.ensure((size_t)(n_ao < SLOW_CAP_MAX ? n_ao : SLOW_CAP_MAX), 0, st));
+            const unsigned blocks = (unsigned)c->prop.multiProcessorCount * 8u;
+            for (unsigned long long first = 0; first < n_ao; first += SLOW_CAP_MAX) {
+                const unsigned n = (unsigned)((n_ao - first) < SLOW_CAP_MAX ? (n_ao - first) : SLOW_CAP_MAX);
+                if (slow_prepare(c, n, &slow_cap)) return RT580_FAILURE;
+                CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), st));
+                CU(cudaEventRecord(c->ev[8], st));
+                k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p); c->launches++;
+                k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, n, c->counters.p + 3, c->ao_hits.p, slowq(c, slow_cap ? slow_cap : 0u));
+                c->launches++;
+                CU(cudaEventRecord(c->ev[9], st));
+                if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
+                if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, c->ao_hits.p); c->launches++; }
+                CU(cudaStreamSynchronize(st));
+                float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); kernel_ms += ms;
+            }
+        } else {
+            if (slow_prepare(c, n_ao, &slow_cap)) return RT580_FAILURE;
+            CU(cudaEventRecord(c->ev[8], st));
+            DISPATCH_MODE(mode, launch_ao, c, n_ao, slow_cap);
+            CU(cudaEventRecord(c->ev[9], st));
+            CU(cudaStreamSynchronize(st));
+            cudaEventElapsedTime(&kernel_ms, c->ev[8], c->ev[9]);
+        }
+        c->stats.ms_ao_kernel = kernel_ms;
+    }
     CU(cudaEventRecord(c->ev[4], st));
     for (int L = n_levels - 1; L >= 0; L--) {
         const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
@@ -1253,7 +1419,6 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.ms_order = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[6]); c->stats.ms_order += ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.ms_ao = ms;
-    cudaEventElapsedTime(&ms, c->ev[3], c->ev[7]); c->stats.ms_ao_kernel = ms;
     cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->stats.ms_resolve = ms;
     c->stats.ms_total = c->stats.ms_structure + c->stats.ms_order + c->stats.ms_ao + c->stats.ms_resolve;
     c->stats.kernel_launches = c->launches;
