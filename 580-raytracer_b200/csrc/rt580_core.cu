@@ -26,6 +26,7 @@
 #include "shade.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <vector>
@@ -90,6 +91,12 @@ __host__ __device__ __forceinline__ unsigned long long slow_key(float t, int pri
 }
 #define SLOW_CAP_MAX (16u << 20)
 
+// k_anyhit (persistent any-hit traversal) constants
+#define AH_STEPS 48        // at most this many inner-node steps between two leaf / refill phases
+#define AH_MIN_SEARCH 12   // leave the inner-node phase when fewer lanes than this still have an inner node
+#define AH_NONE 0x7fffffff // traversal cursor: nothing left
+#define AH_BATCH 512  // rays a warp reserves per atomic on the queue counter
+
 struct FrameParams {
     int W, H;
     int row_first, row_step, n_rows;
@@ -146,6 +153,7 @@ struct rt580_context {
     DBuf<SlowRay> slow_rays; DBuf<SlowRes> slow_res;
     DBuf<struct ARay> arays;       // one chunk of generated AO rays
     uint64_t slow_total = 0;
+    int ah_steps = AH_STEPS, ah_min_search = AH_MIN_SEARCH, ah_blocks_per_sm = 12;  // k_anyhit tuning (env RT580_AH_*)
     std::vector<size_t> level_off; // node index where each level starts (+ end)
     std::vector<uint64_t> level_rays;
     bool frame_begun = false;
@@ -722,11 +730,9 @@ k_ao_gen(FrameParams fp, unsigned long long first, unsigned n, int n_ambient, co
     out[j] = r;
 }
 
-#define AH_STEPS 4    // traversal steps between two refill checks
-#define AH_BATCH 512  // rays a warp reserves per atomic on the queue counter
 __global__ void __launch_bounds__(128)
 k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, unsigned n, unsigned int* __restrict__ next_ray,
-         uint32_t* __restrict__ hit_count, SlowQ sq)
+         uint32_t* __restrict__ hit_count, SlowQ sq, int ah_steps, int ah_min_search)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -734,7 +740,7 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, unsigned n, unsigned int
     V3 O = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
     float tmax = 0.f; unsigned id = 0;
     int stack[RT_STACK_SIZE];
-    int sp = 0, node = 0;
+    int sp = 0, cur = AH_NONE;      // cursor: >= 0 inner node, < 0 leaf (~index), AH_NONE nothing left
     bool last_batch = false;        // warp-uniform: the queue counter has run past n, no further batch exists
     unsigned wnext = 0, wend = 0;   // warp-uniform: this warp's current batch [wnext, wend) of the ray queue
     for (;;) {
@@ -776,35 +782,49 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, unsigned n, unsigned int
                             }
                         } else if (sc.n_leaf > 0) {
                             inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                            node = 0; sp = 0; active = true;
+                            cur = 0; sp = 0; active = true;
                         }
                     }
                 }
             }
         }
         if (!__any_sync(0xffffffffu, active)) { if (last_batch && wnext == wend) break; continue; }
+        // phase 1: inner nodes.  A lane whose next item is a leaf waits here, so that the (long) leaf
+        // tests below run with many lanes at once instead of one or two (ncu, profiles/: with leaf
+        // tests inline only ~10 of 32 lanes were active per issued instruction).
 #pragma unroll 1
-        for (int step = 0; step < AH_STEPS; step++) {
-            if (!active) continue;
-            const BvhNode* __restrict__ nd = sc.nodes + node;
-            const float4 xy0 = __ldg(&nd->xy0), xy1 = __ldg(&nd->xy1), z01 = __ldg(&nd->z01);
-            const int4 kids = __ldg(&nd->kids);
-            float tn0, tn1;
-            const bool h0 = slab(xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, O, inv, tmax, tn0);
-            const bool h1 = slab(xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, O, inv, tmax, tn1);
-            int next; bool done = false, found = false;
-            if (h0 && h1) {
-                int nearc = kids.x, farc = kids.y;
-                if (tn1 < tn0) { nearc = kids.y; farc = kids.x; }
-                if (sp < RT_STACK_SIZE) stack[sp++] = farc;
-                next = nearc;
-            } else if (h0) next = kids.x;
-            else if (h1) next = kids.y;
-            else { if (sp == 0) { done = true; next = 0; } else next = stack[--sp]; }
-            while (!done && next < 0) {
+        for (int it = 0; it < ah_steps; it++) {
+            const bool searching = active && cur >= 0 && cur != AH_NONE;
+            const int n_search = __popc(__ballot_sync(0xffffffffu, searching));
+            const bool leaf_work = __any_sync(0xffffffffu, active && !searching);
+            if (n_search == 0 || (n_search < ah_min_search && leaf_work)) break;
+            if (searching) {
+                const BvhNode* __restrict__ nd = sc.nodes + cur;
+                const float4 xy0 = __ldg(&nd->xy0), xy1 = __ldg(&nd->xy1), z01 = __ldg(&nd->z01);
+                const int4 kids = __ldg(&nd->kids);
+                float tn0, tn1;
+                const bool h0 = slab(xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, O, inv, tmax, tn0);
+                const bool h1 = slab(xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, O, inv, tmax, tn1);
+                if (h0 && h1) {
+                    int nearc = kids.x, farc = kids.y;
+                    if (tn1 < tn0) { nearc = kids.y; farc = kids.x; }
+                    if (sp < RT_STACK_SIZE) stack[sp++] = farc;
+                    cur = nearc;
+                } else if (h0) cur = kids.x;
+                else if (h1) cur = kids.y;
+                else if (sp > 0) cur = stack[--sp];
+                else cur = AH_NONE;
+            }
+        }
+        // phase 2: leaves, and rays that ran out of nodes
+        if (active) {
+            bool found = false, done = false;
+            if (cur == AH_NONE) done = true;
+            else if (cur < 0) {
                 float t; int prim;
-                if (prim_test<true>(sc.prims + (~next), O, d, tmax, 0x7fffffff, t, prim)) { found = true; done = true; break; }
-                if (sp == 0) done = true; else next = stack[--sp];
+                if (prim_test<true>(sc.prims + (~cur), O, d, tmax, 0x7fffffff, t, prim)) { found = true; done = true; }
+                else if (sp > 0) cur = stack[--sp];
+                else done = true;
             }
             if (done) {
                 active = false;
@@ -824,7 +844,7 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, unsigned n, unsigned int
                     }
                 }
                 if (found) atomicAdd(hit_count + id, 1u);
-            } else node = next;
+            }
         }
     }
 }
@@ -954,6 +974,9 @@ extern "C" int rt580_create(int device, rt580_context** out)
     CU(cudaGetDeviceProperties(&c->prop, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+    if (const char* e = getenv("RT580_AH_STEPS")) c->ah_steps = atoi(e) > 0 ? atoi(e) : c->ah_steps;
+    if (const char* e = getenv("RT580_AH_MIN_SEARCH")) c->ah_min_search = atoi(e) > 0 ? atoi(e) : c->ah_min_search;
+    if (const char* e = getenv("RT580_AH_BLOCKS_PER_SM")) c->ah_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ah_blocks_per_sm;
     *out = c;
     return RT580_SUCCESS;
 }
@@ -1375,14 +1398,15 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
             // wavefront form: chunks of at most SLOW_CAP_MAX rays (the deferred queue can then hold
             // every ray of a chunk, so it cannot overflow): generate, trace persistently, finish
             CU(c->arays.ensure((size_t)(n_ao < SLOW_CAP_MAX ? n_ao : SLOW_CAP_MAX), 0, st));
-            const unsigned blocks = (unsigned)c->prop.multiProcessorCount * 8u;
+            const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ah_blocks_per_sm;
             for (unsigned long long first = 0; first < n_ao; first += SLOW_CAP_MAX) {
                 const unsigned n = (unsigned)((n_ao - first) < SLOW_CAP_MAX ? (n_ao - first) : SLOW_CAP_MAX);
                 if (slow_prepare(c, n, &slow_cap)) return RT580_FAILURE;
                 CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), st));
                 CU(cudaEventRecord(c->ev[8], st));
                 k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p); c->launches++;
-                k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, n, c->counters.p + 3, c->ao_hits.p, slowq(c, slow_cap ? slow_cap : 0u));
+                k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, n, c->counters.p + 3, c->ao_hits.p, slowq(c, slow_cap ? slow_cap : 0u),
+                                                    c->ah_steps, c->ah_min_search);
                 c->launches++;
                 CU(cudaEventRecord(c->ev[9], st));
                 if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
