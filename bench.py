@@ -256,9 +256,15 @@ def run_ours(args):
     e0 = time.perf_counter()
     e_steps = max(1, min(args.steps, 3))
     for _ in range(e_steps):
+        _t0 = time.perf_counter()
         ctx.upload_scene(flat)
+        _t1 = time.perf_counter()
+        if os.environ.get("RT580_BENCH_DEBUG"):
+            print("e2e upload %.1f ms" % ((_t1 - _t0) * 1e3), file=sys.stderr)
         if world == 1:
             ctx.render(p)
+            if os.environ.get("RT580_BENCH_DEBUG"):
+                print("e2e render %.1f ms" % ((time.perf_counter() - _t1) * 1e3), file=sys.stderr)
         else:
             counts = ctx.render_begin(p)
             mine = torch.zeros(max_rows, dtype=torch.int64, device="cuda")
