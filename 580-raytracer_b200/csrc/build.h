@@ -5,6 +5,29 @@
 
 namespace rt580 {
 
+// Bump allocator over one device block that only ever grows.  The scene build used to cudaMalloc /
+// cudaFree ~25 buffers per upload; inside a process that also hosts another CUDA allocator
+// (PyTorch in bench.py) those calls took 0.2 - 3 s per upload.  Two arenas owned by the context
+// (temporaries, scene) make a re-upload allocation-free.
+struct DevArena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    void reset() { off = 0; }
+    template <typename T> T* take(size_t n) {
+        const size_t bytes = ((n ? n : 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (off + bytes > cap) return nullptr;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+// make sure the arena holds at least `bytes` (contents are lost when it has to grow) and reset it
+bool arena_reserve(DevArena& a, size_t bytes, char* err, size_t errlen);
+void arena_release(DevArena& a);
+// upper bounds of what build_bvh takes from the two arenas for n_in input primitives
+size_t build_tmp_bytes(int64_t n_in);
+size_t build_out_bytes(int64_t n_in, int64_t n_prims);
+
 struct BuildInput {            // device pointers (already uploaded)
     const float4* tri_v0; const float4* tri_v1; const float4* tri_v2;
     const int32_t* tri_prim; int64_t n_tris;
@@ -14,7 +37,7 @@ struct BuildInput {            // device pointers (already uploaded)
 };
 
 struct BuildOutput {
-    PrimRec* prims;            // [n_leaf] Morton order (cudaMalloc'ed, caller frees)
+    PrimRec* prims;            // [n_leaf] Morton order (all outputs live in the `out` arena)
     BvhNode* nodes;            // [max(n_leaf-1,1)]
     float4* far;               // [n_leaf] far-field filter records
     float far_tmin;            // min over triangles of T_far
@@ -29,6 +52,7 @@ struct BuildOutput {
     int launches;
 };
 
-bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char* err, size_t errlen);
+bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmp, DevArena& outa, cudaStream_t stream, char* err,
+               size_t errlen);
 
 }  // namespace rt580

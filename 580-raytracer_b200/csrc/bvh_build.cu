@@ -303,14 +303,42 @@ __global__ void k_depth(int n, const int* __restrict__ parent, unsigned int* __r
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return false; } } while (0)
 
-template <typename T> static bool dalloc(T** p, size_t n, char* err, size_t errlen) {
-    *p = nullptr;
-    if (n == 0) n = 1;
-    CK(cudaMalloc((void**)p, n * sizeof(T)));
+#define TAKE(ptr, arena, T, n) do { (ptr) = (arena).take<T>(n); if (!(ptr)) { snprintf(err, errlen, "%s:%d arena too small for %s", __FILE__, __LINE__, #ptr); return false; } } while (0)
+
+bool arena_reserve(DevArena& a, size_t bytes, char* err, size_t errlen)
+{
+    a.off = 0;
+    if (bytes <= a.cap) return true;
+    if (a.base) cudaFree(a.base);
+    a.base = nullptr; a.cap = 0;
+    const size_t want = bytes + bytes / 8 + (1u << 20);
+    CK(cudaMalloc((void**)&a.base, want));
+    a.cap = want;
     return true;
 }
+void arena_release(DevArena& a) { if (a.base) cudaFree(a.base); a.base = nullptr; a.cap = 0; a.off = 0; }
 
-bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char* err, size_t errlen)
+static size_t sort_tmp_bytes(int64_t n_in)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n_in, 0, 64, (cudaStream_t)0);
+    return bytes;
+}
+size_t build_tmp_bytes(int64_t n_in)
+{
+    const size_t n = (size_t)(n_in > 0 ? n_in : 1);
+    // rec 64, boxes 32, far 16, keys 16, ids 8 | node boxes 64, kids 8, parent 8, arrive 4 | 32 buffers x 256 B rounding
+    return n * (64 + 32 + 16 + 16 + 8 + 64 + 8 + 8 + 4) + sort_tmp_bytes(n_in) + 64 * 256 + 4096;
+}
+size_t build_out_bytes(int64_t n_in, int64_t n_prims)
+{
+    const size_t n = (size_t)(n_in > 0 ? n_in : 1), np = (size_t)(n_prims > 0 ? n_prims : 1);
+    return n * (64 + 64 + 16 + 4) + np * 4 + 16 * 256 + 4096;   // prims, nodes, far, always_idx | leaf_of_prim
+}
+
+bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena& outa, cudaStream_t stream, char* err,
+               size_t errlen)
 {
     const int64_t n_in = in.n_tris + in.n_spheres;
     out->prims = nullptr; out->nodes = nullptr; out->far = nullptr; out->far_tmin = 0.f; out->n_always = 0; out->always_idx = nullptr; out->leaf_of_prim = nullptr;
@@ -318,7 +346,7 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
     if (n_in > 0x7ffffff0ll) { snprintf(err, errlen, "too many primitives (%lld)", (long long)n_in); return false; }
 
     int* d_bounds = nullptr; unsigned int* d_counters = nullptr;
-    if (!dalloc(&d_bounds, 6, err, errlen) || !dalloc(&d_counters, 4, err, errlen)) return false;
+    TAKE(d_bounds, tmpa, int, 6); TAKE(d_counters, tmpa, unsigned int, 4);
     CK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), stream));   // dropped, depth, max thr bits, always-candidates
     {
         const int init[6] = { 0x7f7fffff, 0x7f7fffff, 0x7f7fffff,                     // +FLT_MAX, ordered encoding
@@ -352,14 +380,12 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
     }
     out->pad = sp.pad; out->extent = E;
     for (int k = 0; k < 3; k++) { out->bounds_lo[k] = lo[k]; out->bounds_hi[k] = hi[k]; }
-    if (n_in == 0) { cudaFree(d_bounds); cudaFree(d_counters); return true; }
+    if (n_in == 0) return true;
 
     PrimRec* rec = nullptr; float4 *blo = nullptr, *bhi = nullptr, *far_in = nullptr;
     uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *ids = nullptr, *ids2 = nullptr;
-    if (!dalloc(&rec, n_in, err, errlen) || !dalloc(&blo, n_in, err, errlen) || !dalloc(&bhi, n_in, err, errlen) ||
-        !dalloc(&far_in, n_in, err, errlen) ||
-        !dalloc(&keys, n_in, err, errlen) || !dalloc(&keys2, n_in, err, errlen) || !dalloc(&ids, n_in, err, errlen) ||
-        !dalloc(&ids2, n_in, err, errlen)) return false;
+    TAKE(rec, tmpa, PrimRec, n_in); TAKE(blo, tmpa, float4, n_in); TAKE(bhi, tmpa, float4, n_in); TAKE(far_in, tmpa, float4, n_in);
+    TAKE(keys, tmpa, uint64_t, n_in); TAKE(keys2, tmpa, uint64_t, n_in); TAKE(ids, tmpa, uint32_t, n_in); TAKE(ids2, tmpa, uint32_t, n_in);
     {
         int blocks = (int)((n_in + 255) / 256);
         k_prim_setup<<<blocks, 256, 0, stream>>>(in.tri_v0, in.tri_v1, in.tri_v2, in.tri_prim, in.n_tris, in.sph,
@@ -368,8 +394,8 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
     }
     size_t tmp_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ids, ids2, (int)n_in, 0, 64, stream));
-    void* tmp = nullptr;
-    CK(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    char* tmp = nullptr;
+    TAKE(tmp, tmpa, char, tmp_bytes);
     CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, ids2, (int)n_in, 0, 64, stream));
     out->launches += 4;   // cub onesweep: histogram + scan + passes (approximate, library)
     unsigned int hc[4];
@@ -388,10 +414,9 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
     if (n > 0) {
         PrimRec* prims = nullptr; BvhNode* nodes = nullptr; float4* far = nullptr;
         float4 *nlo = nullptr, *nhi = nullptr; int2* kids = nullptr; int* parent = nullptr; unsigned int* arrive = nullptr;
-        if (!dalloc(&prims, n, err, errlen) || !dalloc(&nodes, n > 1 ? n - 1 : 1, err, errlen) || !dalloc(&far, n, err, errlen) ||
-            !dalloc(&nlo, 2 * (size_t)n, err, errlen) || !dalloc(&nhi, 2 * (size_t)n, err, errlen) ||
-            !dalloc(&kids, n, err, errlen) || !dalloc(&parent, 2 * (size_t)n, err, errlen) ||
-            !dalloc(&arrive, n, err, errlen)) return false;
+        TAKE(prims, outa, PrimRec, n); TAKE(nodes, outa, BvhNode, n > 1 ? n - 1 : 1); TAKE(far, outa, float4, n);
+        TAKE(nlo, tmpa, float4, 2 * (size_t)n); TAKE(nhi, tmpa, float4, 2 * (size_t)n);
+        TAKE(kids, tmpa, int2, n); TAKE(parent, tmpa, int, 2 * (size_t)n); TAKE(arrive, tmpa, unsigned int, n);
         int blocks = (n + 255) / 256;
         k_gather<<<blocks, 256, 0, stream>>>(rec, blo, bhi, far_in, ids2, n, prims, far, nlo, nhi); out->launches++;
         if (n > 1) {
@@ -419,18 +444,17 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
             out->max_depth = 1;
         }
         CK(cudaGetLastError());
-        cudaFree(nlo); cudaFree(nhi); cudaFree(kids); cudaFree(parent); cudaFree(arrive);
         out->prims = prims; out->nodes = nodes; out->far = far;
         {
             int32_t* lop = nullptr;
-            if (!dalloc(&lop, (size_t)in.n_prims, err, errlen)) return false;
+            TAKE(lop, outa, int32_t, (size_t)in.n_prims);
             CK(cudaMemsetAsync(lop, 0xff, sizeof(int32_t) * (size_t)(in.n_prims ? in.n_prims : 1), stream));
             k_leaf_of_prim<<<blocks, 256, 0, stream>>>(prims, n, lop); out->launches++;
             out->leaf_of_prim = lop;
         }
         if (out->n_always > 0) {
             int32_t* idx = nullptr;
-            if (!dalloc(&idx, out->n_always, err, errlen)) return false;
+            TAKE(idx, outa, int32_t, out->n_always);
             CK(cudaMemsetAsync(d_counters, 0, sizeof(unsigned int), stream));
             k_collect_always<<<blocks, 256, 0, stream>>>(far, n, idx, d_counters); out->launches++;
             CK(cudaStreamSynchronize(stream));
@@ -439,8 +463,6 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, cudaStream_t stream, char
     }
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
-    cudaFree(tmp); cudaFree(rec); cudaFree(blo); cudaFree(bhi); cudaFree(far_in); cudaFree(keys); cudaFree(keys2); cudaFree(ids); cudaFree(ids2);
-    cudaFree(d_bounds); cudaFree(d_counters);
     return true;
 }
 

@@ -134,6 +134,7 @@ struct rt580_context {
     int n_always = 0, n_dropped = 0; int32_t* d_always = nullptr; int32_t* d_leaf_of_prim = nullptr;
     float4* d_vn = nullptr; int32_t* d_prim_material = nullptr; float* d_materials = nullptr;
     int32_t* d_light_type = nullptr; float* d_light_f = nullptr;
+    DevArena scene_arena, build_arena;   // scene buffers / upload + build temporaries (grow-only)
     bool have_scene = false;
     float build_ms = 0.f; unsigned bvh_depth = 0; float pad_extent = 0.f;
     // frame
@@ -982,10 +983,9 @@ extern "C" int rt580_create(int device, rt580_context** out)
 }
 
 static void free_scene(rt580_context* c) {
-    cudaFree(c->d_prims); cudaFree(c->d_nodes); cudaFree(c->d_far); cudaFree(c->d_always); cudaFree(c->d_leaf_of_prim); cudaFree(c->d_vn); cudaFree(c->d_prim_material);
-    cudaFree(c->d_materials); cudaFree(c->d_light_type); cudaFree(c->d_light_f);
-    c->d_prims = nullptr; c->d_nodes = nullptr; c->d_far = nullptr; c->d_always = nullptr; c->d_leaf_of_prim = nullptr; c->d_vn = nullptr; c->d_prim_material = nullptr;
-    c->d_materials = nullptr; c->d_light_type = nullptr; c->d_light_f = nullptr;
+    // every scene pointer lives in c->scene_arena, which is kept for the next upload
+    c->d_prims = nullptr; c->d_nodes = nullptr; c->d_far = nullptr; c->d_always = nullptr; c->d_leaf_of_prim = nullptr;
+    c->d_vn = nullptr; c->d_prim_material = nullptr; c->d_materials = nullptr; c->d_light_type = nullptr; c->d_light_f = nullptr;
     c->have_scene = false;
 }
 
@@ -995,6 +995,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c);
+    arena_release(c->scene_arena); arena_release(c->build_arena);
     c->ndc.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
@@ -1020,12 +1021,11 @@ extern "C" int rt580_get_stream(rt580_context* c, void** cuda_stream)
     return RT580_SUCCESS;
 }
 
-template <typename T> static cudaError_t upload(T** dst, const void* src, size_t count, cudaStream_t s) {
-    *dst = nullptr;
-    cudaError_t e = cudaMalloc((void**)dst, (count ? count : 1) * sizeof(T));
-    if (e != cudaSuccess) return e;
-    if (count) e = cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
-    return e;
+template <typename T> static cudaError_t upload(DevArena& a, T** dst, const void* src, size_t count, cudaStream_t s) {
+    *dst = a.take<T>(count);
+    if (!*dst) return cudaErrorMemoryAllocation;
+    if (count) return cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    return cudaSuccess;
 }
 
 extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
@@ -1037,13 +1037,23 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     CU(cudaSetDevice(c->device));
     free_scene(c);
     cudaStream_t st = c->stream;
+    CU(cudaStreamSynchronize(st));
+    {
+        char aerr[256] = "";
+        const size_t in_bytes = (size_t)s->n_tris * (3 * 16 + 4) + (size_t)s->n_spheres * (16 + 4) + 16 * 256;
+        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 44 + 16 * 256;
+        if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
+            !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
+            FAIL(RT580_FAILURE, "rt580_upload_scene: %s", aerr);
+    }
+    DevArena& ta = c->build_arena; DevArena& sa = c->scene_arena;
     float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr, *sph = nullptr; int32_t *tprim = nullptr, *sprim = nullptr;
-    CU(upload(&v0, s->tri_v0, (size_t)s->n_tris, st));
-    CU(upload(&v1, s->tri_v1, (size_t)s->n_tris, st));
-    CU(upload(&v2, s->tri_v2, (size_t)s->n_tris, st));
-    CU(upload(&tprim, s->tri_prim, (size_t)s->n_tris, st));
-    CU(upload(&sph, s->sph_center_r, (size_t)s->n_spheres, st));
-    CU(upload(&sprim, s->sph_prim, (size_t)s->n_spheres, st));
+    CU(upload(ta, &v0, s->tri_v0, (size_t)s->n_tris, st));
+    CU(upload(ta, &v1, s->tri_v1, (size_t)s->n_tris, st));
+    CU(upload(ta, &v2, s->tri_v2, (size_t)s->n_tris, st));
+    CU(upload(ta, &tprim, s->tri_prim, (size_t)s->n_tris, st));
+    CU(upload(ta, &sph, s->sph_center_r, (size_t)s->n_spheres, st));
+    CU(upload(ta, &sprim, s->sph_prim, (size_t)s->n_spheres, st));
     // shading tables addressed by primitive order index
     std::vector<float> vn((size_t)s->n_prims * 12, 0.f);
     std::vector<int32_t> pm((size_t)s->n_prims, 0);
@@ -1061,11 +1071,11 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         pm[p] = s->sph_material[k];
     }
     for (auto m : pm) if (m < 0 || m >= s->n_materials) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: material index out of range");
-    CU(upload(&c->d_vn, vn.data(), (size_t)s->n_prims * 3, st));
-    CU(upload(&c->d_prim_material, pm.data(), (size_t)s->n_prims, st));
-    CU(upload(&c->d_materials, s->materials, (size_t)s->n_materials * 8, st));
-    CU(upload(&c->d_light_type, s->light_type, (size_t)s->n_lights, st));
-    CU(upload(&c->d_light_f, s->light_f, (size_t)s->n_lights * 10, st));
+    CU(upload(sa, &c->d_vn, vn.data(), (size_t)s->n_prims * 3, st));
+    CU(upload(sa, &c->d_prim_material, pm.data(), (size_t)s->n_prims, st));
+    CU(upload(sa, &c->d_materials, s->materials, (size_t)s->n_materials * 8, st));
+    CU(upload(sa, &c->d_light_type, s->light_type, (size_t)s->n_lights, st));
+    CU(upload(sa, &c->d_light_f, s->light_f, (size_t)s->n_lights * 10, st));
 
     BuildInput in{};
     in.tri_v0 = v0; in.tri_v1 = v1; in.tri_v2 = v2; in.tri_prim = tprim; in.n_tris = s->n_tris;
@@ -1075,11 +1085,10 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     BuildOutput bo{};
     CU(cudaEventRecord(c->ev[10], st));
     char err[256] = "";
-    if (!build_bvh(in, &bo, st, err, sizeof err)) FAIL(RT580_FAILURE, "rt580_upload_scene: %s", err);
+    if (!build_bvh(in, &bo, ta, sa, st, err, sizeof err)) FAIL(RT580_FAILURE, "rt580_upload_scene: %s", err);
     CU(cudaEventRecord(c->ev[11], st));
     CU(cudaStreamSynchronize(st));
     CU(cudaEventElapsedTime(&c->build_ms, c->ev[10], c->ev[11]));
-    cudaFree(v0); cudaFree(v1); cudaFree(v2); cudaFree(tprim); cudaFree(sph); cudaFree(sprim);
     if (bo.max_depth > RT_STACK_SIZE)
         FAIL(RT580_FAILURE, "rt580_upload_scene: LBVH depth %u exceeds the traversal stack (%d)", bo.max_depth, RT_STACK_SIZE);
     c->d_prims = bo.prims; c->d_nodes = bo.nodes; c->d_far = bo.far; c->bvh_depth = bo.max_depth; c->pad_extent = bo.extent;
