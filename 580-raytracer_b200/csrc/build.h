@@ -44,7 +44,8 @@ struct BuildOutput {
     int n_always;              // triangles that are far-field candidates for every ray (slivers)
     int32_t* always_idx;       // [n_always] their indices into prims
     int32_t* leaf_of_prim;     // [n_prims] inverse of the Morton permutation (-1 for dropped triangles)
-    int n_leaf;
+    int n_leaf;                // primitives in the tree
+    int n_big;                 // large primitives after them in `prims` / `far`
     int n_dropped;             // zero-area triangles
     unsigned int max_depth;
     float pad, extent;

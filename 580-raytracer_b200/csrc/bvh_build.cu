@@ -106,7 +106,11 @@ struct SetupParams {
     float pad;          // box padding (see file header)
     float sph_extra;    // added to r^2 for sphere boxes
     float E;            // bound on |coordinate| of ray origins and hit points
+    float big_diam;     // primitives with a larger diameter stay out of the tree (RT_MAX_BIG of them at most)
 };
+#define RT_MAX_BIG 64
+#define KEY_DROPPED (~0ull)
+#define KEY_BIG (~0ull - 1ull)
 
 __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __restrict__ v1,
                              const float4* __restrict__ v2, const int32_t* __restrict__ tri_prim, int64_t n_tris,
@@ -119,7 +123,7 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
     if (i >= n_tris + n_sph) return;
     PrimRec r;
     float lo[3], hi[3];
-    bool drop = false;
+    bool drop = false, big = false;
     if (i < n_tris) {
         float4 a = v0[i], b = v1[i], c = v2[i];
         V3 p0 = mk(a.x, a.y, a.z), p1 = mk(b.x, b.y, b.z), p2 = mk(c.x, c.y, c.z);
@@ -154,9 +158,10 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
         if (!(l_near >= 0.0f)) l_near = diam;                                    // NaN guard
         const float pad = sp.pad + l_near;
         far[i] = make_float4(N.x, N.y, N.z, drop ? -1.0f : thr);
+        big = !drop && diam > sp.big_diam;
         if (!drop) {
             if (thr < 4.0f) atomicMax(n_dropped + 2, (unsigned)__float_as_int(thr));   // positive floats order like ints
-            else atomicAdd(n_dropped + 3, 1u);
+            else if (!big) atomicAdd(n_dropped + 3, 1u);
         }
         lo[0] = fminf(p0.x, fminf(p1.x, p2.x)) - pad; hi[0] = fmaxf(p0.x, fmaxf(p1.x, p2.x)) + pad;
         lo[1] = fminf(p0.y, fminf(p1.y, p2.y)) - pad; hi[1] = fmaxf(p0.y, fmaxf(p1.y, p2.y)) + pad;
@@ -164,6 +169,7 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
     } else {
         far[i] = make_float4(0.f, 0.f, 0.f, -1.0f);                              // spheres have no far field
         float4 s = sph[i - n_tris];
+        big = 2.0f * fabsf(s.w) > sp.big_diam;
         r.a = s;
         r.b = make_float4(s.w * s.w, 0.f, 0.f, 0.f);          // cpp:423 radius*radius
         r.c = make_float4(0.f, 0.f, 0.f, __int_as_float(sph_prim[i - n_tris]));
@@ -175,7 +181,8 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
     box_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
     box_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
     uint64_t key;
-    if (drop) { key = ~0ull; atomicAdd(n_dropped, 1u); }
+    if (drop) { key = KEY_DROPPED; atomicAdd(n_dropped, 1u); }
+    else if (big) { key = KEY_BIG; atomicAdd(n_dropped + 4, 1u); }
     else {
         uint32_t q[3];
         for (int k = 0; k < 3; k++) {
@@ -192,15 +199,16 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
 
 __global__ void k_gather(const PrimRec* __restrict__ rec, const float4* __restrict__ box_lo,
                          const float4* __restrict__ box_hi, const float4* __restrict__ far_in,
-                         const uint32_t* __restrict__ ids, int n_leaf,
+                         const uint32_t* __restrict__ ids, int n_leaf, int n_all,
                          PrimRec* __restrict__ out, float4* __restrict__ far_out, float4* __restrict__ nb_lo,
                          float4* __restrict__ nb_hi)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_leaf) return;
+    if (j >= n_all) return;
     uint32_t i = ids[j];
     out[j] = rec[i];
     far_out[j] = far_in[i];
+    if (j >= n_leaf) return;      // large primitives: record only, no place in the tree
     // node boxes: inner nodes [0, n_leaf-1), leaves [n_leaf-1, 2 n_leaf-1)
     nb_lo[n_leaf - 1 + j] = box_lo[i];
     nb_hi[n_leaf - 1 + j] = box_hi[i];
@@ -342,12 +350,12 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
 {
     const int64_t n_in = in.n_tris + in.n_spheres;
     out->prims = nullptr; out->nodes = nullptr; out->far = nullptr; out->far_tmin = 0.f; out->n_always = 0; out->always_idx = nullptr; out->leaf_of_prim = nullptr;
-    out->n_leaf = 0; out->max_depth = 0; out->launches = 0;
+    out->n_leaf = 0; out->n_big = 0; out->max_depth = 0; out->launches = 0;
     if (n_in > 0x7ffffff0ll) { snprintf(err, errlen, "too many primitives (%lld)", (long long)n_in); return false; }
 
     int* d_bounds = nullptr; unsigned int* d_counters = nullptr;
-    TAKE(d_bounds, tmpa, int, 6); TAKE(d_counters, tmpa, unsigned int, 4);
-    CK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned int), stream));   // dropped, depth, max thr bits, always-candidates
+    TAKE(d_bounds, tmpa, int, 6); TAKE(d_counters, tmpa, unsigned int, 8);
+    CK(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned int), stream));   // dropped, depth, max thr bits, always-candidates, big
     {
         const int init[6] = { 0x7f7fffff, 0x7f7fffff, 0x7f7fffff,                     // +FLT_MAX, ordered encoding
                               (int)0x80800000, (int)0x80800000, (int)0x80800000 };    // -FLT_MAX, ordered encoding
@@ -373,6 +381,11 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
     sp.pad = E * (1.0f / 262144.0f);                                   // 2^-18 E
     sp.E = E;
     sp.sph_extra = (2.f * E + 1.f) * (2.f * E + 1.f) * (1.0f / 262144.0f);   // 2^-18 (2E+1)^2
+    {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        sp.big_diam = 0.125f * sqrtf(dx * dx + dy * dy + dz * dz);
+        if (!(sp.big_diam > 0.f) || n_in <= RT_MAX_BIG) sp.big_diam = 3.0e38f;   // tiny scenes: nothing to separate
+    }
     for (int k = 0; k < 3; k++) {
         float l = lo[k] - 2.f * sp.pad, h = hi[k] + 2.f * sp.pad;
         sp.blo[k] = l;
@@ -398,11 +411,24 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
     TAKE(tmp, tmpa, char, tmp_bytes);
     CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, ids2, (int)n_in, 0, 64, stream));
     out->launches += 4;   // cub onesweep: histogram + scan + passes (approximate, library)
-    unsigned int hc[4];
+    unsigned int hc[8];
     CK(cudaMemcpyAsync(hc, d_counters, sizeof hc, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    const int n = (int)(n_in - hc[0]);
-    out->n_leaf = n;
+    if (hc[4] > RT_MAX_BIG) {
+        // too many "large" primitives for a list that every ray walks: keep them all in the tree
+        sp.big_diam = 3.0e38f;
+        CK(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned int), stream));
+        k_prim_setup<<<(int)((n_in + 255) / 256), 256, 0, stream>>>(in.tri_v0, in.tri_v1, in.tri_v2, in.tri_prim, in.n_tris, in.sph,
+                                                                    in.sph_prim, in.n_spheres, sp, rec, blo, bhi, keys, ids, far_in, d_counters);
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, ids2, (int)n_in, 0, 64, stream));
+        out->launches += 5;
+        CK(cudaMemcpyAsync(hc, d_counters, sizeof hc, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    const int n_big = (int)hc[4];
+    const int n = (int)(n_in - hc[0]) - n_big;
+    const int n_all = n + n_big;
+    out->n_leaf = n; out->n_big = n_big;
     out->n_dropped = (int)hc[0];
     out->n_always = (int)hc[3];
     {
@@ -411,14 +437,14 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
         // every ray) there is no lower bound
         out->far_tmin = max_thr > 0.f ? 4.0f * E / max_thr : 3.0e38f;
     }
-    if (n > 0) {
+    if (n_all > 0) {
         PrimRec* prims = nullptr; BvhNode* nodes = nullptr; float4* far = nullptr;
         float4 *nlo = nullptr, *nhi = nullptr; int2* kids = nullptr; int* parent = nullptr; unsigned int* arrive = nullptr;
-        TAKE(prims, outa, PrimRec, n); TAKE(nodes, outa, BvhNode, n > 1 ? n - 1 : 1); TAKE(far, outa, float4, n);
-        TAKE(nlo, tmpa, float4, 2 * (size_t)n); TAKE(nhi, tmpa, float4, 2 * (size_t)n);
-        TAKE(kids, tmpa, int2, n); TAKE(parent, tmpa, int, 2 * (size_t)n); TAKE(arrive, tmpa, unsigned int, n);
-        int blocks = (n + 255) / 256;
-        k_gather<<<blocks, 256, 0, stream>>>(rec, blo, bhi, far_in, ids2, n, prims, far, nlo, nhi); out->launches++;
+        TAKE(prims, outa, PrimRec, n_all); TAKE(nodes, outa, BvhNode, n > 1 ? n - 1 : 1); TAKE(far, outa, float4, n_all);
+        TAKE(nlo, tmpa, float4, 2 * (size_t)n + 2); TAKE(nhi, tmpa, float4, 2 * (size_t)n + 2);
+        TAKE(kids, tmpa, int2, n + 1); TAKE(parent, tmpa, int, 2 * (size_t)n + 2); TAKE(arrive, tmpa, unsigned int, n + 1);
+        int blocks = (n_all + 255) / 256;
+        k_gather<<<blocks, 256, 0, stream>>>(rec, blo, bhi, far_in, ids2, n, n_all, prims, far, nlo, nhi); out->launches++;
         if (n > 1) {
             CK(cudaMemsetAsync(arrive, 0, sizeof(unsigned int) * n, stream));
             k_hierarchy<<<blocks, 256, 0, stream>>>(keys2, n, kids, parent); out->launches++;
@@ -428,7 +454,7 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
             CK(cudaMemcpyAsync(hc, d_counters, sizeof hc, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             out->max_depth = hc[1];
-        } else {
+        } else if (n == 1) {
             // single primitive: one node, child1 = empty box that no ray can enter
             float4 l, h;
             CK(cudaMemcpyAsync(&l, nlo + (n - 1), sizeof l, cudaMemcpyDeviceToHost, stream));
@@ -449,7 +475,7 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
             int32_t* lop = nullptr;
             TAKE(lop, outa, int32_t, (size_t)in.n_prims);
             CK(cudaMemsetAsync(lop, 0xff, sizeof(int32_t) * (size_t)(in.n_prims ? in.n_prims : 1), stream));
-            k_leaf_of_prim<<<blocks, 256, 0, stream>>>(prims, n, lop); out->launches++;
+            k_leaf_of_prim<<<blocks, 256, 0, stream>>>(prims, n_all, lop); out->launches++;
             out->leaf_of_prim = lop;
         }
         if (out->n_always > 0) {

@@ -43,7 +43,11 @@ struct DeviceScene {
     float extent;              // E: the boxes and far-field records are valid for ray origins with |coordinate| <= E
     unsigned int* diag;        // [2] device counters: far-field scans, linear fallbacks (rare events)
     int32_t farfield;          // 1: replay the reference's far-field acceptances (exact), 0: skip
-    int32_t n_leaf;            // primitives in the BVH
+    int32_t n_leaf;            // primitives in the BVH: prims[0, n_leaf)
+    int32_t n_big;             // very large primitives kept out of the tree: prims[n_leaf, n_leaf + n_big), tested
+                               // first for every ray (they would bloat every ancestor box of an LBVH, and as
+                               // the likeliest occluders they end most any-hit rays at once)
+    int32_t n_all;             // n_leaf + n_big: what the linear loops and the far-field scan walk
     int32_t n_prims;           // primitives in reference order (incl. dropped ones)
     const float4* vn;          // [n_prims][3] object-space vertex normals (Q10); unused for spheres
     const int32_t* prim_material;   // [n_prims]

@@ -191,8 +191,8 @@ __device__ __forceinline__ unsigned warp_alloc(unsigned int* counter, bool want)
 template <int MODE /*0 bvh, 1 linear from smem, 2 linear from global*/, bool ANY>
 __device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* smem_prims, bool active, V3 O, V3 d,
                                          float tmax, HitRec& hit, SlowQ q, int ca, int cb, unsigned* cnt = nullptr) {
-    if (MODE == 1) return (active && traverse_linear<ANY, false>(smem_prims, sc.n_leaf, O, d, tmax, hit)) ? TR_HIT : TR_MISS;
-    if (MODE == 2) return (active && traverse_linear<ANY, true>(sc.prims, sc.n_leaf, O, d, tmax, hit)) ? TR_HIT : TR_MISS;
+    if (MODE == 1) return (active && traverse_linear<ANY, false>(smem_prims, sc.n_all, O, d, tmax, hit)) ? TR_HIT : TR_MISS;
+    if (MODE == 2) return (active && traverse_linear<ANY, true>(sc.prims, sc.n_all, O, d, tmax, hit)) ? TR_HIT : TR_MISS;
     bool found = false, need = false, linear = false, pending = false;
     hit.t = ANY ? tmax : __int_as_float(0x7f800000); hit.leaf = -1; hit.prim = 0x7fffffff;
     if (active) {
@@ -203,7 +203,8 @@ __device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* s
             if (cnt) cnt[3]++;
             if (sc.diag) atomicAdd(sc.diag + 1, 1u);
         } else {
-            found = traverse_bvh<ANY>(sc, O, d, tmax, hit, cnt);
+            found = big_scan<ANY>(sc, O, d, hit);
+            if (!(ANY && found)) found = traverse_bvh<ANY>(sc, O, d, tmax, hit, cnt) || found;
             // a zero direction (total internal reflection, cpp:197-199, Q20) fails |N.d| >= EPSILON for
             // every triangle (cpp:371): only spheres can "hit" it, and those are all in the tree
             const bool zero_dir = (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f);
@@ -264,7 +265,7 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
         }
     }
     // blockIdx.y selects a slice of the records (few slow rays -> more slices, so the GPU stays busy)
-    const int nl = min(sc.n_leaf, ((int)blockIdx.y + 1) * chunk);
+    const int nl = min(sc.n_all, ((int)blockIdx.y + 1) * chunk);
     for (int base = (int)blockIdx.y * chunk; base < nl; base += SLOW_TILE) {
         {   // stage one tile: thread t brings record base + t
             const int i = base + (int)threadIdx.x;
@@ -326,7 +327,7 @@ __device__ __forceinline__ const PrimRec* stage_prims(const DeviceScene& sc, Pri
     if (MODE == 1) {
         const float4* src = reinterpret_cast<const float4*>(sc.prims);
         float4* dst = reinterpret_cast<float4*>(smem);
-        for (int i = threadIdx.x; i < sc.n_leaf * 4; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < sc.n_all * 4; i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
     return smem;
@@ -710,31 +711,55 @@ struct __align__(16) ARay {
 };
 
 __global__ void __launch_bounds__(256)
-k_ao_gen(FrameParams fp, unsigned long long first, unsigned n, int n_ambient, const Node* __restrict__ nodes,
-         const uint32_t* __restrict__ ao_state, ARay* __restrict__ out)
+k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, int n_ambient, const Node* __restrict__ nodes,
+         const uint32_t* __restrict__ ao_state, ARay* __restrict__ out, unsigned int* __restrict__ n_out,
+         uint32_t* __restrict__ ao_hits)
 {
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const unsigned long long i = first + j;
-    const unsigned call = (unsigned)(i / (unsigned)fp.spp);
-    const unsigned k = (unsigned)(i % (unsigned)fp.spp);
-    const unsigned node = call / (unsigned)n_ambient;
-    uint32_t st = lcg_mulmod(__ldg(ao_state + call), lcg_state_at(2ull * k));   // state after the 2k draws before sample k
-    const float4 nP = __ldg(&nodes[node].P), nN = __ldg(&nodes[node].N);
-    const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
-    const V3 dir = random_in_hemisphere(st, N);                                  // cpp:321
-    const V3 org = P + dir * RT_SHADOW_OFFSET;                                   // cpp:322
-    const V3 rd = normalize(dir);                                                // Ray ctor h:431-433
+    const bool active = j < n;
+    unsigned call = 0xffffffffu;
+    bool emit = false, hit = false;
     ARay r;
-    r.a = make_float4(org.x, org.y, org.z, rd.x);
-    r.b = make_float4(rd.y, rd.z, __uint_as_float(call), __int_as_float(0x7f800000));
-    out[j] = r;
+    r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a;
+    if (active) {
+        const unsigned long long i = first + j;
+        call = (unsigned)(i / (unsigned)fp.spp);
+        const unsigned k = (unsigned)(i % (unsigned)fp.spp);
+        const unsigned node = call / (unsigned)n_ambient;
+        uint32_t st = lcg_mulmod(__ldg(ao_state + call), lcg_state_at(2ull * k));   // state after the 2k draws before sample k
+        const float4 nP = __ldg(&nodes[node].P), nN = __ldg(&nodes[node].N);
+        const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
+        const V3 dir = random_in_hemisphere(st, N);                                  // cpp:321
+        const V3 org = P + dir * RT_SHADOW_OFFSET;                                   // cpp:322
+        const V3 rd = normalize(dir);                                                // Ray ctor h:431-433
+        r.a = make_float4(org.x, org.y, org.z, rd.x);
+        r.b = make_float4(rd.y, rd.z, __uint_as_float(call), __int_as_float(0x7f800000));
+        emit = true;
+        // the large primitives first: most likely occluders, and the ray is not queued at all if one is hit
+        const bool far_origin = sc.farfield && fmaxf(fabsf(org.x), fmaxf(fabsf(org.y), fabsf(org.z))) > sc.extent;
+        if (!far_origin && sc.n_big > 0) {
+            HitRec h; h.t = __int_as_float(0x7f800000); h.leaf = -1; h.prim = 0x7fffffff;
+            hit = big_scan<true>(sc, org, rd, h);
+            emit = !hit;
+        }
+    }
+    // occluded samples of one AO call inside the warp: one atomic per (warp, call)
+    const unsigned peers = __match_any_sync(0xffffffffu, call);
+    const unsigned votes = __ballot_sync(0xffffffffu, hit);
+    if (active && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
+        const unsigned c = __popc(votes & peers);
+        if (c) atomicAdd(ao_hits + call, c);
+    }
+    const unsigned slot = warp_alloc(n_out, emit);
+    if (emit) out[slot] = r;
 }
 
+#define AH_DUMMY 0
 __global__ void __launch_bounds__(128)
-k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, unsigned n, unsigned int* __restrict__ next_ray,
-         uint32_t* __restrict__ hit_count, SlowQ sq, int ah_steps, int ah_min_search)
+k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __restrict__ n_ptr,
+         unsigned int* __restrict__ next_ray, uint32_t* __restrict__ hit_count, SlowQ sq, int ah_steps, int ah_min_search)
 {
+    const unsigned n = __ldg(n_ptr);
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     bool active = false;
@@ -955,8 +980,8 @@ __global__ void k_powf(long long n, const float* __restrict__ x, const float* __
 // ---------------------------------------------------------------------------------------
 static int pick_mode(const rt580_context* c, int traversal) {
     if (traversal == RT580_TRAVERSAL_BVH) return 0;
-    if (traversal == RT580_TRAVERSAL_BRUTE_FORCE) return c->sc.n_leaf <= RT_SMEM_PRIMS ? 1 : 2;
-    return c->sc.n_leaf <= RT_SMEM_PRIMS ? 1 : 0;     // AUTO
+    if (traversal == RT580_TRAVERSAL_BRUTE_FORCE) return c->sc.n_all <= RT_SMEM_PRIMS ? 1 : 2;
+    return c->sc.n_all <= RT_SMEM_PRIMS ? 1 : 0;     // AUTO
 }
 
 extern "C" int rt580_create(int device, rt580_context** out)
@@ -1096,7 +1121,8 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->n_always = bo.n_always; c->n_dropped = bo.n_dropped;
     c->d_always = bo.always_idx; c->sc.always_idx = bo.always_idx; c->sc.n_always = bo.n_always;
     c->d_leaf_of_prim = bo.leaf_of_prim; c->sc.leaf_of_prim = bo.leaf_of_prim;
-    c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_prims = (int32_t)s->n_prims;
+    c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_big = bo.n_big; c->sc.n_all = bo.n_leaf + bo.n_big;
+    c->sc.n_prims = (int32_t)s->n_prims;
     c->sc.vn = c->d_vn; c->sc.prim_material = c->d_prim_material; c->sc.materials = c->d_materials;
     c->sc.n_materials = s->n_materials; c->sc.light_type = c->d_light_type; c->sc.light_f = c->d_light_f;
     c->sc.n_lights = s->n_lights;
@@ -1112,7 +1138,7 @@ extern "C" int rt580_scene_info_get(rt580_context* c, rt580_scene_info* out) {
     if (!c || !out) FAIL(RT580_INVALID_ARG, "rt580_scene_info_get: NULL argument");
     if (!c->have_scene) FAIL(RT580_FAILURE, "rt580_scene_info_get: no scene uploaded");
     memset(out, 0, sizeof *out);
-    out->n_leaf = c->sc.n_leaf; out->n_dropped = c->n_dropped; out->n_always = c->n_always;
+    out->n_leaf = c->sc.n_all; out->n_dropped = c->n_dropped; out->n_always = c->n_always;
     out->far_tmin = c->sc.far_tmin; out->pad = c->pad_extent / 262144.0f; out->extent = c->pad_extent;
     out->build_ms = c->build_ms; out->bvh_max_depth = c->bvh_depth;
     return RT580_SUCCESS;
@@ -1189,7 +1215,7 @@ static int read_counter(rt580_context* c, int which, unsigned* out) {
 static int slow_prepare(rt580_context* c, unsigned long long max_rays, unsigned* cap_out)
 {
     unsigned cap = (unsigned)(max_rays < (unsigned long long)SLOW_CAP_MAX ? max_rays : (unsigned long long)SLOW_CAP_MAX);
-    if (!c->sc.farfield || c->sc.n_leaf <= RT_SMEM_PRIMS) cap = 0;       // linear modes never defer
+    if (!c->sc.farfield || c->sc.n_all <= RT_SMEM_PRIMS) cap = 0;        // linear modes never defer
     if (cap) {
         CU(c->slow_rays.ensure(cap, 0, c->stream));
         CU(c->slow_res.ensure(cap, 0, c->stream));
@@ -1209,11 +1235,11 @@ static int slow_run(rt580_context* c, bool any, unsigned cap, unsigned* n_out)
     if (n) {
         const unsigned batches = nblk(n, SLOW_RPB);
         unsigned slices = nblk(4u * (unsigned)c->prop.multiProcessorCount, batches);
-        const unsigned max_slices = nblk((unsigned)c->sc.n_leaf, SLOW_TILE);
+        const unsigned max_slices = nblk((unsigned)c->sc.n_all, SLOW_TILE);
         if (slices > max_slices) slices = max_slices;
         if (slices > 256u) slices = 256u;
         if (slices < 1u) slices = 1u;
-        const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_leaf, slices), SLOW_TILE) * SLOW_TILE);
+        const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_all, slices), SLOW_TILE) * SLOW_TILE);
         const dim3 grid(batches, slices);
         if (any) k_slow<true><<<grid, 256, 0, c->stream>>>(c->sc, c->slow_rays.p, n, c->slow_res.p, chunk);
         else k_slow<false><<<grid, 256, 0, c->stream>>>(c->sc, c->slow_rays.p, n, c->slow_res.p, chunk);
@@ -1411,11 +1437,13 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
             for (unsigned long long first = 0; first < n_ao; first += SLOW_CAP_MAX) {
                 const unsigned n = (unsigned)((n_ao - first) < SLOW_CAP_MAX ? (n_ao - first) : SLOW_CAP_MAX);
                 if (slow_prepare(c, n, &slow_cap)) return RT580_FAILURE;
-                CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), st));
+                CU(cudaMemsetAsync(c->counters.p + 6, 0, 2 * sizeof(unsigned), st));   // [6] rays emitted, [7] rays fetched
                 CU(cudaEventRecord(c->ev[8], st));
-                k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p); c->launches++;
-                k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, n, c->counters.p + 3, c->ao_hits.p, slowq(c, slow_cap ? slow_cap : 0u),
-                                                    c->ah_steps, c->ah_min_search);
+                k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,
+                                                       c->counters.p + 6, c->ao_hits.p);
+                c->launches++;
+                k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, c->counters.p + 6, c->counters.p + 7, c->ao_hits.p,
+                                                 slowq(c, slow_cap ? slow_cap : 0u), c->ah_steps, c->ah_min_search);
                 c->launches++;
                 CU(cudaEventRecord(c->ev[9], st));
                 if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;

@@ -105,13 +105,11 @@ __device__ __forceinline__ bool slab(float lox, float hix, float loy, float hiy,
 // Closest hit (ANY == false): best = lexicographic min (t, prim) over accepted primitives.
 // Any hit     (ANY == true) : true as soon as one primitive is accepted with t <= tmax
 //                             (cpp:75 and cpp:325 use only that boolean).
+// `best` comes in initialised (t = tmax or +inf / the best of the large-primitive list).
 template <bool ANY>
 __device__ __forceinline__ bool traverse_bvh(const DeviceScene& sc, V3 O, V3 d, float tmax, HitRec& best,
                                              unsigned* cnt = nullptr)
 {
-    best.t = ANY ? tmax : __int_as_float(0x7f800000);
-    best.leaf = -1;
-    best.prim = 0x7fffffff;
     if (sc.n_leaf <= 0) return false;
     const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     int stack[RT_STACK_SIZE];
@@ -173,7 +171,7 @@ __device__ __forceinline__ bool warp_scan_one(const DeviceScene& sc, bool lin, V
 {
     const int lane = threadIdx.x & 31;
     const float4* __restrict__ far = sc.far;
-    const int n = sc.n_leaf;
+    const int n = sc.n_all;
     best.leaf = -1;
     bool f = false;
     if (!lin) {
@@ -243,6 +241,22 @@ __device__ __forceinline__ bool warp_slow_path(const DeviceScene& sc, bool need,
         if (lane == src && anyf) {
             found = true;
             if (!ANY) hit = best;
+        }
+    }
+    return found;
+}
+
+// The large primitives kept out of the tree (DeviceScene::n_big): exact test, first, for every ray.
+template <bool ANY>
+__device__ __forceinline__ bool big_scan(const DeviceScene& sc, V3 O, V3 d, HitRec& best)
+{
+    bool found = false;
+    for (int k = 0; k < sc.n_big; k++) {
+        const int i = sc.n_leaf + k;
+        float t; int prim;
+        if (prim_test<true>(sc.prims + i, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+            if (ANY) return true;
+            best.t = t; best.leaf = i; best.prim = prim; found = true;
         }
     }
     return found;
