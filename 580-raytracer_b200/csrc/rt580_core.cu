@@ -203,8 +203,13 @@ __device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* s
             if (cnt) cnt[3]++;
             if (sc.diag) atomicAdd(sc.diag + 1, 1u);
         } else {
-            found = big_scan<ANY>(sc, O, d, hit);
+            // large-primitive list: first for closest hits (it bounds t for the tree) and for unbounded
+            // any-hit rays (the likeliest occluders); last for bounded shadow rays, whose occluder, if
+            // any, is usually a small object between the surface and the light
+            const bool big_first = !ANY || !(tmax < 3.0e38f);
+            if (big_first) found = big_scan<ANY>(sc, O, d, hit);
             if (!(ANY && found)) found = traverse_bvh<ANY>(sc, O, d, tmax, hit, cnt) || found;
+            if (!big_first && !found) found = big_scan<ANY>(sc, O, d, hit);
             // a zero direction (total internal reflection, cpp:197-199, Q20) fails |N.d| >= EPSILON for
             // every triangle (cpp:371): only spheres can "hit" it, and those are all in the tree
             const bool zero_dir = (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f);
@@ -715,6 +720,14 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
          const uint32_t* __restrict__ ao_state, ARay* __restrict__ out, unsigned int* __restrict__ n_out,
          uint32_t* __restrict__ ao_hits)
 {
+    // the large-primitive list (<= 64 records) is walked by every ray: keep it in shared memory
+    __shared__ PrimRec s_big[64];
+    {
+        const float4* src = reinterpret_cast<const float4*>(sc.prims + sc.n_leaf);
+        float4* dst = reinterpret_cast<float4*>(s_big);
+        for (int i = threadIdx.x; i < sc.n_big * 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < n;
     unsigned call = 0xffffffffu;
@@ -738,8 +751,10 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
         // the large primitives first: most likely occluders, and the ray is not queued at all if one is hit
         const bool far_origin = sc.farfield && fmaxf(fabsf(org.x), fmaxf(fabsf(org.y), fabsf(org.z))) > sc.extent;
         if (!far_origin && sc.n_big > 0) {
-            HitRec h; h.t = __int_as_float(0x7f800000); h.leaf = -1; h.prim = 0x7fffffff;
-            hit = big_scan<true>(sc, org, rd, h);
+            for (int k = 0; k < sc.n_big && !hit; k++) {
+                float t; int prim;
+                hit = prim_test<false>(&s_big[k], org, rd, __int_as_float(0x7f800000), 0x7fffffff, t, prim);
+            }
             emit = !hit;
         }
     }
@@ -1434,9 +1449,10 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
             // every ray of a chunk, so it cannot overflow): generate, trace persistently, finish
             CU(c->arays.ensure((size_t)(n_ao < SLOW_CAP_MAX ? n_ao : SLOW_CAP_MAX), 0, st));
             const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ah_blocks_per_sm;
+            if (slow_prepare(c, SLOW_CAP_MAX, &slow_cap)) return RT580_FAILURE;     // queue shared by all chunks of the frame
+            unsigned queued = 0;
             for (unsigned long long first = 0; first < n_ao; first += SLOW_CAP_MAX) {
                 const unsigned n = (unsigned)((n_ao - first) < SLOW_CAP_MAX ? (n_ao - first) : SLOW_CAP_MAX);
-                if (slow_prepare(c, n, &slow_cap)) return RT580_FAILURE;
                 CU(cudaMemsetAsync(c->counters.p + 6, 0, 2 * sizeof(unsigned), st));   // [6] rays emitted, [7] rays fetched
                 CU(cudaEventRecord(c->ev[8], st));
                 k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,
@@ -1446,8 +1462,16 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
                                                  slowq(c, slow_cap ? slow_cap : 0u), c->ah_steps, c->ah_min_search);
                 c->launches++;
                 CU(cudaEventRecord(c->ev[9], st));
-                if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
-                if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, c->ao_hits.p); c->launches++; }
+                // deferred rays pile up over the chunks; answer them when the next chunk could overflow the
+                // queue (it can add at most its own size) or after the last chunk
+                if (slow_cap && read_counter(c, 2, &queued)) return RT580_FAILURE;
+                { unsigned emitted = 0; if (read_counter(c, 6, &emitted)) return RT580_FAILURE; c->stats.ao_rays_traversed += emitted; }
+                const unsigned long long next_n = (first + SLOW_CAP_MAX < n_ao) ? ((n_ao - first - SLOW_CAP_MAX) < SLOW_CAP_MAX ? (n_ao - first - SLOW_CAP_MAX) : SLOW_CAP_MAX) : 0ull;
+                if (slow_cap && queued && (next_n == 0 || (unsigned long long)queued + next_n > slow_cap)) {
+                    if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
+                    if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, c->ao_hits.p); c->launches++; }
+                    CU(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned), st));
+                }
                 CU(cudaStreamSynchronize(st));
                 float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); kernel_ms += ms;
             }
@@ -1455,6 +1479,7 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
             if (slow_prepare(c, n_ao, &slow_cap)) return RT580_FAILURE;
             CU(cudaEventRecord(c->ev[8], st));
             DISPATCH_MODE(mode, launch_ao, c, n_ao, slow_cap);
+            c->stats.ao_rays_traversed = n_ao;
             CU(cudaEventRecord(c->ev[9], st));
             CU(cudaStreamSynchronize(st));
             cudaEventElapsedTime(&kernel_ms, c->ev[8], c->ev[9]);

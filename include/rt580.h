@@ -133,6 +133,8 @@ typedef struct rt580_stats {
     uint32_t bvh_max_depth;
     uint32_t far_scans;            /* rays that needed the far-field scan (found nothing nearer) */
     uint32_t linear_fallbacks;     /* rays that started outside the padded extent (children of far hits) */
+    uint64_t ao_rays_traversed;    /* AO rays that went through the tree; the others were already occluded by
+                                      one of the scene's few very large primitives (tested first) */
 } rt580_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

@@ -275,3 +275,54 @@ def test_empty_scene_and_single_primitive(pkg, oracle, tmp_path):
         assert rt.Render("") == pkg.RT_SUCCESS
         assert rt.stats().rays == rays
         assert np.array_equal(rt.frame_buffer(), ref)
+
+
+def _scenegen():
+    import importlib.util
+    import __graft_entry__ as ge
+    spec = importlib.util.spec_from_file_location("scenegen", os.path.join(ge.PKG_DIR, "scenegen.py"))
+    sg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sg)
+    return sg
+
+
+def test_closed_room_scene(pkg, oracle, tmp_path):
+    """The benchmark's scene family at a size the oracle renders whole: teapots + spheres in the
+    closed double-walled room.  Exercises the large-primitive list (the 24 wall triangles stay out
+    of the tree), the persistent any-hit kernel and a frame without a single escaping ray."""
+    import shutil
+    d = str(tmp_path)
+    shutil.copy(os.path.join(ASSETS, "teapot.json"), d)
+    _scenegen().write_synthetic_scene(d, "room", n_teapots=3, n_spheres=6, seed=11, room=True)
+    W, H, spp, depth = 200, 112, 4, 4
+    orc = oracle.Oracle(oracle.load_scene_json(d, "room.json"))
+    ref, rays, hits = orc.render(W, H, spp, depth, nthreads=NT)
+    for trav in (pkg.TRAVERSAL_AUTO, pkg.TRAVERSAL_BRUTE_FORCE):
+        rt = pkg.Raytracer(W, H)
+        rt.SetAssetsPath(d)
+        rt.SetOptions(depth=depth, ao_spp=spp, traversal=trav)
+        assert rt.LoadSceneJSON("room.json") == pkg.RT_SUCCESS
+        assert rt.Render("") == pkg.RT_SUCCESS
+        st = rt.stats()
+        assert st.rays == rays and st.hit_nodes == int(hits.sum())
+        assert np.array_equal(rt.frame_buffer(), ref)
+    assert (hits > 0).all()          # closed room: every primary ray hits something
+
+
+def test_every_ray_of_a_frame_matches_the_oracle(pkg, oracle, oracle_scene):
+    """Ray-level parity: every IntersectScene call the oracle makes for a frame (primary, secondary,
+    shadow, AO - including the rays that start at far-field hits 10^6 units away) is re-traced
+    through the LBVH path: same primitive, same t bits."""
+    scene, W, H, spp, depth = "scene.json", 192, 108, 2, 4
+    log = oracle_scene(scene).render_log(W, H, spp, depth)
+    rt = make_rt(pkg, scene, W, H, spp, depth)
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    p, t = ctx.trace_closest(log["org"], log["dir"], pkg.TRAVERSAL_BVH)
+    assert np.array_equal(p.astype(np.int64), log["prim"])
+    hit = log["prim"] >= 0
+    assert np.array_equal(t[hit].view(np.uint32), log["t"][hit].view(np.uint32))
+    assert len(log["t"]) > 20000 and set(np.unique(log["kind"])) == {0, 1, 2}
+    far = np.abs(log["org"]).max(axis=1) > 1e4
+    assert far.sum() > 0, "this frame is known to contain rays that start at far-field hits"
+    ctx.close()
