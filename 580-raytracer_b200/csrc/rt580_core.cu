@@ -152,7 +152,8 @@ struct rt580_context {
     DBuf<int16_t> fb;              // [n_rows][W][3]
     DBuf<unsigned int> counters;   // [0] node count, [1] queue count, [2] slow-ray count, [4..5] diagnostics
     DBuf<SlowRay> slow_rays; DBuf<SlowRes> slow_res;
-    DBuf<struct ARay> arays;       // one chunk of generated AO rays
+    DBuf<struct ARay> arays;       // one chunk of generated any-hit rays (AO samples / shadow rays)
+    DBuf<uint32_t> occl;           // per shadow ray of the current level: occluders found
     uint64_t slow_total = 0;
     int ah_steps = AH_STEPS, ah_min_search = AH_MIN_SEARCH, ah_blocks_per_sm = 12;  // k_anyhit tuning (env RT580_AH_*)
     std::vector<size_t> level_off; // node index where each level starts (+ end)
@@ -474,11 +475,27 @@ __device__ __forceinline__ V3 shading_normal(const DeviceScene& sc, const Node& 
     return normalize((mk(a.x, a.y, a.z) * nd.B.x + mk(b.x, b.y, b.z) * nd.B.y) + mk(c.x, c.y, c.z) * nd.B.z);   // cpp:334-336
 }
 
+// the shadow ray of cpp:55-71 for one light: origin, direction (normalised twice, Ray ctor), and the
+// distance beyond which a hit no longer shadows (point light: |light - P|, cpp:71-75; else unbounded)
+__device__ __forceinline__ void shadow_ray(const Light& L, V3 P, V3& so, V3& sd, float& tmax) {
+    V3 lightDir = mk(0, 0, 0);
+    if (L.type == RT580_LIGHT_DIRECTIONAL) lightDir = -L.direction;          // cpp:56-60
+    else if (L.type == RT580_LIGHT_POINT) lightDir = L.position - P;         // cpp:62-64
+    lightDir = normalize(lightDir);                                          // cpp:65
+    so = P + lightDir * RT_SHADOW_OFFSET;                                    // cpp:67
+    sd = normalize(lightDir);                                                // Ray ctor h:431-433
+    const float distToLight = length(L.position - P);                        // cpp:71
+    tmax = (L.type == RT580_LIGHT_POINT) ? distToLight : __int_as_float(0x7f800000);
+}
+
 // Per hit node of one level: direct lighting with shadow rays, then spawn the children.
-template <int MODE>
+// PRETRACED: the shadow rays went through k_shade_gen + k_anyhit already (occl[(node - n0) * n_nonambient + j]
+// counts their occluders in the tree); only the large-primitive list is left to test here.
+template <int MODE, bool PRETRACED>
 __global__ void __launch_bounds__(128)
 k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __restrict__ nodes,
-        NodeAux* __restrict__ aux, QRay* __restrict__ queue, unsigned int* __restrict__ counters, SlowQ sq)
+        NodeAux* __restrict__ aux, QRay* __restrict__ queue, unsigned int* __restrict__ counters, SlowQ sq,
+        const uint32_t* __restrict__ occl)
 {
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
@@ -500,22 +517,30 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
     Pix local = mkpix(0, 0, 0);                                       // SHADOW_COLOR h:598
     const V3 cam = mk(fp.cam[0], fp.cam[1], fp.cam[2]);
     // the light loop is uniform over the warp (trace_ray is warp-collective)
+    int j = 0;                                                        // index among the non-ambient lights
     for (int li = 0; li < sc.n_lights; li++) {                        // cpp:39
         const Light L = load_light(sc.light_type, sc.light_f, li);
         if (L.type == RT580_LIGHT_AMBIENT) continue;                  // handled by k_ao / k_resolve
-        V3 lightDir = mk(0, 0, 0);
-        if (L.type == RT580_LIGHT_DIRECTIONAL) lightDir = -L.direction;          // cpp:56-60
-        else if (L.type == RT580_LIGHT_POINT) lightDir = L.position - P;         // cpp:62-64
-        lightDir = normalize(lightDir);                                          // cpp:65
-        const V3 so = P + lightDir * RT_SHADOW_OFFSET;                           // cpp:67
-        const V3 sd = normalize(lightDir);                                       // Ray ctor h:431-433
-        const float distToLight = length(L.position - P);                        // cpp:71
-        HitRec sh;
-        // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
-        const float tmax = (L.type == RT580_LIGHT_POINT) ? distToLight : __int_as_float(0x7f800000);
-        const int tr = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh, sq, (int)i, li);
+        V3 so, sd; float tmax;
+        shadow_ray(L, P, so, sd, tmax);
+        int tr;
+        if (PRETRACED) {
+            tr = TR_MISS;
+            if (active) {
+                if (__ldg(occl + (size_t)(i - n0) * sc.n_nonambient + j) != 0u) tr = TR_HIT;
+                else if (sc.n_big > 0 && !(sc.farfield && fmaxf(fabsf(so.x), fmaxf(fabsf(so.y), fabsf(so.z))) > sc.extent)) {
+                    HitRec sh; sh.t = tmax; sh.leaf = -1; sh.prim = 0x7fffffff;
+                    if (big_scan<true>(sc, so, sd, sh)) tr = TR_HIT;
+                }
+            }
+        } else {
+            HitRec sh;
+            // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
+            tr = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh, sq, (int)i, li);
+        }
         // TR_PENDING: k_shade_finish adds this light's term once the deferred ray is answered
         if (active && tr == TR_MISS) local = pix_add(local, calculate_local_color(P, sn, L, M, cam));   // cpp:77
+        j++;
     }
     if (active) {
         NodeAux a;
@@ -573,6 +598,11 @@ k_shade_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays,
     atomicAdd(w, (unsigned)(unsigned short)c.r | ((unsigned)(unsigned short)c.g << 16));
     atomicAdd(w + 1, (unsigned)(unsigned short)c.b);
 }
+
+// shadow rays of one level as a ray queue for k_anyhit: ray id = (node - n0) * n_nonambient + j
+__global__ void __launch_bounds__(256)
+k_shade_gen(DeviceScene sc, unsigned n0, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
+            struct ARay* __restrict__ out, unsigned int* __restrict__ n_out);
 
 // deferred AO rays of k_ao: a hit is one more occluded sample of its AO call (cpp:325-326)
 __global__ void k_ao_finish(const SlowRay* __restrict__ rays, const SlowRes* __restrict__ res, unsigned n_slow,
@@ -769,7 +799,27 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
     if (emit) out[slot] = r;
 }
 
-#define AH_DUMMY 0
+__global__ void __launch_bounds__(256)
+k_shade_gen(DeviceScene sc, unsigned n0, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
+            ARay* __restrict__ out, unsigned int* __restrict__ n_out)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *n_out = n;
+    if (t >= n) return;
+    const unsigned long long id = first + t;
+    const unsigned node = n0 + (unsigned)(id / (unsigned)sc.n_nonambient);
+    int j = (int)(id % (unsigned)sc.n_nonambient), li = 0;
+    for (;; li++) { if (__ldg(sc.light_type + li) != RT580_LIGHT_AMBIENT) { if (j == 0) break; j--; } }
+    const Light L = load_light(sc.light_type, sc.light_f, li);
+    const float4 nP = __ldg(&nodes[node].P);
+    V3 so, sd; float tmax;
+    shadow_ray(L, mk(nP.x, nP.y, nP.z), so, sd, tmax);
+    ARay r;
+    r.a = make_float4(so.x, so.y, so.z, sd.x);
+    r.b = make_float4(sd.y, sd.z, __uint_as_float((unsigned)id), tmax);
+    out[t] = r;
+}
+
 __global__ void __launch_bounds__(128)
 k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __restrict__ n_ptr,
          unsigned int* __restrict__ next_ray, uint32_t* __restrict__ hit_count, SlowQ sq, int ah_steps, int ah_min_search)
@@ -1039,7 +1089,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     c->ndc.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
-    c->slow_rays.release(); c->slow_res.release(); c->arays.release();
+    c->slow_rays.release(); c->slow_res.release(); c->arays.release(); c->occl.release();
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1181,8 +1231,8 @@ template <int MODE> static void launch_trace(rt580_context* c, bool primary, uns
     c->launches++;
 }
 template <int MODE> static void launch_shade(rt580_context* c, unsigned n0, unsigned n1, unsigned slow_cap) {
-    k_shade<MODE><<<nblk(n1 - n0, 128), 128, 0, c->stream>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p,
-                                                             slowq(c, slow_cap));
+    k_shade<MODE, false><<<nblk(n1 - n0, 128), 128, 0, c->stream>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p,
+                                                                    c->counters.p, slowq(c, slow_cap), nullptr);
     c->launches++;
 }
 template <int MODE> static void launch_ao(rt580_context* c, unsigned long long n_rays, unsigned slow_cap) {
@@ -1262,6 +1312,47 @@ static int slow_run(rt580_context* c, bool any, unsigned cap, unsigned* n_out)
         c->slow_total += n;
     }
     *n_out = n;
+    return RT580_SUCCESS;
+}
+
+// Any-hit pass in wavefront form over `total` rays: in chunks of at most SLOW_CAP_MAX rays (so the
+// deferred queue can hold every ray of a chunk), `gen(first, n)` launches a kernel that writes the
+// chunk's rays into c->arays and their number into counters[6]; k_anyhit (persistent, lanes refill)
+// adds 1 to hits[ray id] for every occluded ray; deferred rays pile up over the chunks and are
+// answered by k_slow when the queue could overflow or after the last chunk.
+template <typename Gen>
+static int anyhit_queue_pass(rt580_context* c, unsigned long long total, uint32_t* hits, float* kernel_ms,
+                             unsigned long long* traversed, Gen gen)
+{
+    cudaStream_t st = c->stream;
+    unsigned slow_cap = 0, n_slow = 0, queued = 0;
+    CU(c->arays.ensure((size_t)(total < SLOW_CAP_MAX ? total : SLOW_CAP_MAX), 0, st));
+    const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ah_blocks_per_sm;
+    if (slow_prepare(c, SLOW_CAP_MAX, &slow_cap)) return RT580_FAILURE;     // queue shared by all chunks of the pass
+    for (unsigned long long first = 0; first < total; first += SLOW_CAP_MAX) {
+        const unsigned n = (unsigned)((total - first) < SLOW_CAP_MAX ? (total - first) : SLOW_CAP_MAX);
+        CU(cudaMemsetAsync(c->counters.p + 6, 0, 2 * sizeof(unsigned), st));   // [6] rays emitted, [7] rays fetched
+        CU(cudaEventRecord(c->ev[8], st));
+        gen(first, n);
+        c->launches++;
+        k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, c->counters.p + 6, c->counters.p + 7, hits,
+                                         slowq(c, slow_cap ? slow_cap : 0u), c->ah_steps, c->ah_min_search);
+        c->launches++;
+        CU(cudaEventRecord(c->ev[9], st));
+        if (slow_cap && read_counter(c, 2, &queued)) return RT580_FAILURE;
+        { unsigned emitted = 0; if (read_counter(c, 6, &emitted)) return RT580_FAILURE; if (traversed) *traversed += emitted; }
+        const unsigned long long rest = total - first - n;
+        const unsigned long long next_n = rest < SLOW_CAP_MAX ? rest : SLOW_CAP_MAX;
+        if (slow_cap && queued && (next_n == 0 || (unsigned long long)queued + next_n > slow_cap)) {
+            if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
+            if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, hits); c->launches++; }
+            CU(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned), st));
+        }
+        CU(cudaStreamSynchronize(st));
+        float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]);
+        if (kernel_ms) *kernel_ms += ms;
+    }
+    CU(cudaGetLastError());
     return RT580_SUCCESS;
 }
 
@@ -1351,12 +1442,30 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
         CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
         if (L < fp.depth) CU(c->queue.ensure(2 * (size_t)(n1 - n0), 0, st));
         else CU(c->queue.ensure(1, 0, st));
-        if (slow_prepare(c, (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient, &slow_cap)) return RT580_FAILURE;
-        DISPATCH_MODE(mode, launch_shade, c, n0, n1, slow_cap);
-        if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
-        if (n_slow) {
-            k_shade_finish<<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->slow_rays.p, c->slow_res.p, n_slow, c->nodes.p, c->aux.p);
+        if (mode == 0) {
+            // shadow rays in wavefront form (k_shade_gen -> k_anyhit), then shading with their answers
+            const unsigned long long n_sh = (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient;
+            CU(c->occl.ensure((size_t)n_sh + 1, 0, st));
+            CU(cudaMemsetAsync(c->occl.p, 0, sizeof(uint32_t) * ((size_t)n_sh + 1), st));
+            if (n_sh) {
+                const int rc = anyhit_queue_pass(c, n_sh, c->occl.p, nullptr, nullptr,
+                    [&](unsigned long long first, unsigned n) {
+                        k_shade_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6);
+                    });
+                if (rc) return rc;
+            }
+            CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
+            k_shade<0, true><<<nblk(n1 - n0, 128), 128, 0, st>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p,
+                                                                 slowq(c, 0u), c->occl.p);
             c->launches++;
+        } else {
+            if (slow_prepare(c, (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient, &slow_cap)) return RT580_FAILURE;
+            DISPATCH_MODE(mode, launch_shade, c, n0, n1, slow_cap);
+            if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
+            if (n_slow) {
+                k_shade_finish<<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->slow_rays.p, c->slow_res.p, n_slow, c->nodes.p, c->aux.p);
+                c->launches++;
+            }
         }
         if (L == fp.depth) break;
         unsigned q = 0;
@@ -1445,36 +1554,14 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
         unsigned slow_cap = 0, n_slow = 0;
         float kernel_ms = 0.f;
         if (mode == 0) {
-            // wavefront form: chunks of at most SLOW_CAP_MAX rays (the deferred queue can then hold
-            // every ray of a chunk, so it cannot overflow): generate, trace persistently, finish
-            CU(c->arays.ensure((size_t)(n_ao < SLOW_CAP_MAX ? n_ao : SLOW_CAP_MAX), 0, st));
-            const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ah_blocks_per_sm;
-            if (slow_prepare(c, SLOW_CAP_MAX, &slow_cap)) return RT580_FAILURE;     // queue shared by all chunks of the frame
-            unsigned queued = 0;
-            for (unsigned long long first = 0; first < n_ao; first += SLOW_CAP_MAX) {
-                const unsigned n = (unsigned)((n_ao - first) < SLOW_CAP_MAX ? (n_ao - first) : SLOW_CAP_MAX);
-                CU(cudaMemsetAsync(c->counters.p + 6, 0, 2 * sizeof(unsigned), st));   // [6] rays emitted, [7] rays fetched
-                CU(cudaEventRecord(c->ev[8], st));
-                k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,
-                                                       c->counters.p + 6, c->ao_hits.p);
-                c->launches++;
-                k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, c->counters.p + 6, c->counters.p + 7, c->ao_hits.p,
-                                                 slowq(c, slow_cap ? slow_cap : 0u), c->ah_steps, c->ah_min_search);
-                c->launches++;
-                CU(cudaEventRecord(c->ev[9], st));
-                // deferred rays pile up over the chunks; answer them when the next chunk could overflow the
-                // queue (it can add at most its own size) or after the last chunk
-                if (slow_cap && read_counter(c, 2, &queued)) return RT580_FAILURE;
-                { unsigned emitted = 0; if (read_counter(c, 6, &emitted)) return RT580_FAILURE; c->stats.ao_rays_traversed += emitted; }
-                const unsigned long long next_n = (first + SLOW_CAP_MAX < n_ao) ? ((n_ao - first - SLOW_CAP_MAX) < SLOW_CAP_MAX ? (n_ao - first - SLOW_CAP_MAX) : SLOW_CAP_MAX) : 0ull;
-                if (slow_cap && queued && (next_n == 0 || (unsigned long long)queued + next_n > slow_cap)) {
-                    if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
-                    if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, c->ao_hits.p); c->launches++; }
-                    CU(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned), st));
-                }
-                CU(cudaStreamSynchronize(st));
-                float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); kernel_ms += ms;
-            }
+            unsigned long long traversed = 0;
+            const int rc = anyhit_queue_pass(c, n_ao, c->ao_hits.p, &kernel_ms, &traversed,
+                [&](unsigned long long first, unsigned n) {
+                    k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,
+                                                           c->counters.p + 6, c->ao_hits.p);
+                });
+            if (rc) return rc;
+            c->stats.ao_rays_traversed = traversed;
         } else {
             if (slow_prepare(c, n_ao, &slow_cap)) return RT580_FAILURE;
             CU(cudaEventRecord(c->ev[8], st));
