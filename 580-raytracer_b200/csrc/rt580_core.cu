@@ -781,6 +781,8 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
         // the large primitives first: most likely occluders, and the ray is not queued at all if one is hit
         const bool far_origin = sc.farfield && fmaxf(fabsf(org.x), fmaxf(fabsf(org.y), fabsf(org.z))) > sc.extent;
         if (!far_origin && sc.n_big > 0) {
+            // any hit is an OR over the list: plain list order (reordering passes by N.d were tried and
+            // cost more in divergence than they saved in tests)
             for (int k = 0; k < sc.n_big && !hit; k++) {
                 float t; int prim;
                 hit = prim_test<false>(&s_big[k], org, rd, __int_as_float(0x7f800000), 0x7fffffff, t, prim);
