@@ -1272,6 +1272,13 @@ static int exclusive_scan_u32(rt580_context* c, const uint32_t* in, uint32_t* ou
     return RT580_SUCCESS;
 }
 
+// all eight counters in one 32-byte copy + one stream sync (every host round trip idles the GPU for
+// ~10-20 us; with 8 ranks a frame is only ~10 ms long)
+static int read_counters(rt580_context* c, unsigned out[8]) {
+    CU(cudaMemcpyAsync(out, c->counters.p, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return RT580_SUCCESS;
+}
 static int read_counter(rt580_context* c, int which, unsigned* out) {
     CU(cudaMemcpyAsync(out, c->counters.p + which, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1292,12 +1299,12 @@ static int slow_prepare(rt580_context* c, unsigned long long max_rays, unsigned*
     return RT580_SUCCESS;
 }
 // Answer the recorded slow rays (one warp each); returns how many there were.
-static int slow_run(rt580_context* c, bool any, unsigned cap, unsigned* n_out)
+static int slow_run(rt580_context* c, bool any, unsigned cap, unsigned* n_out, int known = -1)
 {
     *n_out = 0;
     if (!cap) return RT580_SUCCESS;
-    unsigned n = 0;
-    if (read_counter(c, 2, &n)) return RT580_FAILURE;
+    unsigned n = (unsigned)known;
+    if (known < 0 && read_counter(c, 2, &n)) return RT580_FAILURE;
     if (n > cap) n = cap;
     if (n) {
         const unsigned batches = nblk(n, SLOW_RPB);
@@ -1341,16 +1348,17 @@ static int anyhit_queue_pass(rt580_context* c, unsigned long long total, uint32_
                                          slowq(c, slow_cap ? slow_cap : 0u), c->ah_steps, c->ah_min_search);
         c->launches++;
         CU(cudaEventRecord(c->ev[9], st));
-        if (slow_cap && read_counter(c, 2, &queued)) return RT580_FAILURE;
-        { unsigned emitted = 0; if (read_counter(c, 6, &emitted)) return RT580_FAILURE; if (traversed) *traversed += emitted; }
+        unsigned cnt[8];
+        if (read_counters(c, cnt)) return RT580_FAILURE;
+        queued = slow_cap ? cnt[2] : 0u;
+        if (traversed) *traversed += cnt[6];
         const unsigned long long rest = total - first - n;
         const unsigned long long next_n = rest < SLOW_CAP_MAX ? rest : SLOW_CAP_MAX;
         if (slow_cap && queued && (next_n == 0 || (unsigned long long)queued + next_n > slow_cap)) {
-            if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
+            if (slow_run(c, true, slow_cap, &n_slow, (int)(queued > slow_cap ? slow_cap : queued))) return RT580_FAILURE;
             if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, hits); c->launches++; }
             CU(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned), st));
         }
-        CU(cudaStreamSynchronize(st));
         float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]);
         if (kernel_ms) *kernel_ms += ms;
     }
@@ -1427,14 +1435,17 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
     if (npix) {
         if (slow_prepare(c, npix, &slow_cap)) return RT580_FAILURE;
         DISPATCH_MODE(mode, launch_trace, c, true, npix, (unsigned)c->nodes.cap, slow_cap);
-        if (slow_run(c, false, slow_cap, &n_slow)) return RT580_FAILURE;
+        unsigned cnt[8];
+        if (read_counters(c, cnt)) return RT580_FAILURE;
+        n_nodes = cnt[0];
+        if (slow_run(c, false, slow_cap, &n_slow, (int)(cnt[2] > slow_cap ? slow_cap : cnt[2]))) return RT580_FAILURE;
         if (n_slow) {
             k_trace_finish<true><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
                                                                    c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
                                                                    (unsigned)c->nodes.cap);
             c->launches++;
+            if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
         }
-        if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
     }
     c->level_rays.push_back(npix);
     c->level_off.push_back(n_nodes);
@@ -1477,14 +1488,17 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
         CU(c->aux.ensure((size_t)n1 + q, n1, st));
         if (slow_prepare(c, q, &slow_cap)) return RT580_FAILURE;
         DISPATCH_MODE(mode, launch_trace, c, false, q, (unsigned)c->nodes.cap, slow_cap);
-        if (slow_run(c, false, slow_cap, &n_slow)) return RT580_FAILURE;
+        unsigned cnt[8];
+        if (read_counters(c, cnt)) return RT580_FAILURE;
+        n_nodes = cnt[0];
+        if (slow_run(c, false, slow_cap, &n_slow, (int)(cnt[2] > slow_cap ? slow_cap : cnt[2]))) return RT580_FAILURE;
         if (n_slow) {
             k_trace_finish<false><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
                                                                     c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
                                                                     (unsigned)c->nodes.cap);
             c->launches++;
+            if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
         }
-        if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
         c->level_rays.push_back(q);
         c->level_off.push_back(n_nodes);
     }

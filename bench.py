@@ -185,16 +185,21 @@ def run_ours(args):
     # int16 is not an NCCL dtype: the bands are gathered as bytes
     gather_list = [torch.empty((max_rows, W, 6), dtype=torch.uint8, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
     padded = torch.zeros((max_rows, W, 3), dtype=torch.int16, device="cuda") if world > 1 else None
+    if world > 1:
+        mine_h = torch.zeros(max_rows, dtype=torch.int64).pin_memory()
+        mine_d = torch.zeros(max_rows, dtype=torch.int64, device="cuda")
+        all_d = torch.zeros((world, max_rows), dtype=torch.int64, device="cuda")
+        all_h = torch.zeros((world, max_rows), dtype=torch.int64).pin_memory()
 
     def frame():
         """one step: this rank's rows; returns (stats, frame on rank 0 or None)"""
         counts = ctx.render_begin(p)
         if world > 1:
-            mine = torch.zeros(max_rows, dtype=torch.int64, device="cuda")
-            mine[:p.n_rows] = torch.from_numpy(counts.astype(np.int64)).cuda()
-            allc = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(allc, mine)                                   # the one exchange of the LCG mode
-            per_rank = [c.cpu().numpy().astype(np.uint64) for c in allc]
+            mine_h[:p.n_rows] = torch.from_numpy(counts.astype(np.int64))
+            mine_d.copy_(mine_h, non_blocking=True)
+            dist.all_gather_into_tensor(all_d, mine_d)                    # the one exchange of the LCG mode
+            all_h.copy_(all_d)                                            # one D2H for all ranks' counts
+            per_rank = [all_h[r].numpy().astype(np.uint64) for r in range(world)]
             bases = pkg.row_bases_from_counts(H, world, per_rank)[rank]
         else:
             bases = pkg.row_bases_from_counts(H, 1, [counts])[0]
@@ -267,11 +272,11 @@ def run_ours(args):
                 print("e2e render %.1f ms" % ((time.perf_counter() - _t1) * 1e3), file=sys.stderr)
         else:
             counts = ctx.render_begin(p)
-            mine = torch.zeros(max_rows, dtype=torch.int64, device="cuda")
-            mine[:p.n_rows] = torch.from_numpy(counts.astype(np.int64)).cuda()
-            allc = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(allc, mine)
-            bases = pkg.row_bases_from_counts(H, world, [c.cpu().numpy().astype(np.uint64) for c in allc])[rank]
+            mine_h[:p.n_rows] = torch.from_numpy(counts.astype(np.int64))
+            mine_d.copy_(mine_h, non_blocking=True)
+            dist.all_gather_into_tensor(all_d, mine_d)
+            all_h.copy_(all_d)
+            bases = pkg.row_bases_from_counts(H, world, [all_h[r].numpy().astype(np.uint64) for r in range(world)])[rank]
             ctx.render_finish(p, bases)                                   # host band
     sync()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / e_steps
