@@ -26,6 +26,7 @@
 #include "shade.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -1380,6 +1381,9 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
             FAIL(RT580_INVALID_ARG, "rt580_render_begin: camera_from[%d]=%g lies outside the extent (%g) the BVH boxes were padded for; "
                  "pass the camera as rt580_flat_scene::origin_hint", k, p->camera_from[k], c->pad_extent);
     CU(cudaSetDevice(c->device));
+    const bool dbg_t = getenv("RT580_DEBUG_TIMING") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_enter = now_ms();
     FrameParams& fp = c->fp;
     fp.W = p->width; fp.H = p->height;
     if (p->n_rows == 0) { fp.row_first = 0; fp.row_step = 1; fp.n_rows = p->height; }
@@ -1427,6 +1431,7 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
     CU(c->aux.ensure(npix + 1, 0, st));
     CU(c->row_vals.ensure((size_t)fp.n_rows + 1, 0, st));
 
+    const double t_setup = now_ms();
     CU(cudaEventRecord(c->ev[0], st));
     c->level_off.clear(); c->level_rays.clear();
     c->level_off.push_back(0);
@@ -1502,6 +1507,7 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
         c->level_rays.push_back(q);
         c->level_off.push_back(n_nodes);
     }
+    const double t_struct = now_ms();
     CU(cudaEventRecord(c->ev[1], st));
     // order: subtree sizes bottom-up, per-pixel exclusive scan, per-row totals
     const int n_levels = (int)c->level_off.size() - 1;
@@ -1521,6 +1527,8 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
     CU(cudaGetLastError());
     if (row_hit_nodes) for (int r = 0; r < fp.n_rows; r++) row_hit_nodes[r] = rows[r];
     c->frame_begun = true;
+    if (dbg_t) fprintf(stderr, "[rt580] render_begin host ms: setup %.2f structure %.2f order %.2f (levels %d, launches %u)\n",
+                       t_setup - t_enter, t_struct - t_setup, now_ms() - t_struct, (int)c->level_off.size() - 1, c->launches);
     // ray accounting: one ray == one IntersectScene call of the reference (cpp:30, cpp:75, cpp:325)
     c->stats.rays_primary = npix;
     for (size_t l = 1; l < c->level_rays.size(); l++) c->stats.rays_secondary += c->level_rays[l];

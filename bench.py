@@ -191,9 +191,14 @@ def run_ours(args):
         all_d = torch.zeros((world, max_rows), dtype=torch.int64, device="cuda")
         all_h = torch.zeros((world, max_rows), dtype=torch.int64).pin_memory()
 
+    dbg = bool(os.environ.get("RT580_BENCH_DEBUG")) and rank == 0
+    tparts = [0.0, 0.0, 0.0, 0.0]
+
     def frame():
         """one step: this rank's rows; returns (stats, frame on rank 0 or None)"""
+        _a = time.perf_counter()
         counts = ctx.render_begin(p)
+        _b = time.perf_counter()
         if world > 1:
             mine_h[:p.n_rows] = torch.from_numpy(counts.astype(np.int64))
             mine_d.copy_(mine_h, non_blocking=True)
@@ -203,10 +208,17 @@ def run_ours(args):
             bases = pkg.row_bases_from_counts(H, world, per_rank)[rank]
         else:
             bases = pkg.row_bases_from_counts(H, 1, [counts])[0]
+        _c = time.perf_counter()
         _, st = ctx.render_finish(p, bases, device_ptr=band.data_ptr())
+        _d = time.perf_counter()
         if world > 1:
             padded[:p.n_rows].copy_(band[:p.n_rows])
             dist.gather(padded.view(torch.uint8), gather_list, dst=0)     # int16 bands (as bytes) to rank 0 over NVLink
+        if dbg:
+            torch.cuda.synchronize()
+            _e = time.perf_counter()
+            for k, v in enumerate([_b - _a, _c - _b, _d - _c, _e - _d]):
+                tparts[k] += v * 1e3
         return st
 
     def sync():
@@ -236,6 +248,9 @@ def run_ours(args):
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
+    if dbg:
+        n_fr = args.steps + args.warmup
+        print("rank0 wall ms/frame: begin %.2f  exchange %.2f  finish %.2f  gather %.2f" % tuple(t / n_fr for t in tparts), file=sys.stderr)
     step_ms = max(dev_ms, 0.0) / args.steps
     rays_rank = float(np.mean([s.rays for s in stats]))
     ao_ms = float(np.mean([s.ms_ao_kernel for s in stats]))
