@@ -90,13 +90,17 @@ __host__ __device__ __forceinline__ unsigned long long slow_key(float t, int pri
     unsigned u; memcpy(&u, &t, 4); return ((unsigned long long)u << 32) | (unsigned)prim;
 #endif
 }
-#define SLOW_CAP_MAX (16u << 20)
+#define SLOW_CAP_MAX (16u << 20)   // deferred closest-hit rays / any-hit rays of a leaky scene: one entry per ray of a chunk
+#define SLOW_ANY_CAP (4u << 20)    // deferred any-hit rays of a scene that hardly leaks (on overflow the pass is repeated "leaky")
+#define RT580_INTERNAL_OVERFLOW 100
+#define AH_CHUNK_TIGHT (32u << 20) // any-hit rays generated per chunk when the scene hardly leaks
+#define OCCL_PENDING 0x40000000u   // shadow ray deferred to the end of the structure pass (k_shadow_finish decides)
 
 // k_anyhit (persistent any-hit traversal) constants
 #define AH_STEPS 48        // at most this many inner-node steps between two leaf / refill phases
 #define AH_MIN_SEARCH 12   // leave the inner-node phase when fewer lanes than this still have an inner node
 #define AH_NONE 0x7fffffff // traversal cursor: nothing left
-#define AH_BATCH 512  // rays a warp reserves per atomic on the queue counter
+#define AH_BATCH 512  // most rays a warp reserves per atomic on the queue counter (fewer when the queue is short)
 
 struct FrameParams {
     int W, H;
@@ -106,6 +110,7 @@ struct FrameParams {
     float inv[9];
     const float* ndc_x;   // [W]  (float)(NDCX * aspect * tan(fov/2))   cpp:834-839, 846
     const float* ndc_y;   // [H]  (float)(NDCY * tan(fov/2))            cpp:835, 840, 846
+    const uint32_t* lcg_pow;   // [spp] 16807^(2k) mod (2^31-1): advances an AO call's engine state to its sample k
 };
 
 template <typename T> struct DBuf {
@@ -151,8 +156,16 @@ struct rt580_context {
     DBuf<uint32_t> scan_tmp;
     DBuf<uint64_t> row_vals;       // per local row: hit nodes / base
     DBuf<int16_t> fb;              // [n_rows][W][3]
-    DBuf<unsigned int> counters;   // [0] node count, [1] queue count, [2] slow-ray count, [4..5] diagnostics
-    DBuf<SlowRay> slow_rays; DBuf<SlowRes> slow_res;
+    DBuf<unsigned int> counters;   // see read_counters
+    DBuf<SlowRay> slow_rays; DBuf<SlowRes> slow_res;   // deferred closest-hit rays (answered level by level)
+    DBuf<SlowRay> any_rays; DBuf<SlowRes> any_res;     // deferred any-hit rays (flushed once per pass when the scene hardly leaks)
+    unsigned any_cap = 0;
+    unsigned long long slow_seen = 0;                  // slow rays of the frame so far (host copy of counters[4] + [5])
+    unsigned long long rays_structure = 0;
+    unsigned syncs = 0;                                // host round trips of the frame
+    bool force_leaky = false;                          // the small any-hit queue overflowed once for this scene
+    int ndc_w = 0, ndc_h = 0; float ndc_fov = 0.f;     // what the primary-ray tables were built for
+    DBuf<uint32_t> lcg_pow; int lcg_pow_spp = 0;
     DBuf<struct ARay> arays;       // one chunk of generated any-hit rays (AO samples / shadow rays)
     DBuf<uint32_t> occl;           // per shadow ray of the current level: occluders found
     uint64_t slow_total = 0;
@@ -403,11 +416,14 @@ __device__ __forceinline__ void commit_closest(const PrimRec* __restrict__ prims
 template <int MODE, bool PRIMARY>
 __global__ void __launch_bounds__(128)
 k_trace(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, unsigned n_items,
-        Node* __restrict__ nodes, NodeAux* __restrict__ aux, unsigned int* __restrict__ counters,
-        uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap, SlowQ sq)
+        const unsigned int* __restrict__ n_items_dev, Node* __restrict__ nodes, NodeAux* __restrict__ aux,
+        unsigned int* __restrict__ counters, uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap, SlowQ sq)
 {
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
+    // the queue length is still on the device when the launch is issued (no host round trip between
+    // k_shade and this kernel): the grid covers the upper bound n_items, the count trims it
+    if (n_items_dev) n_items = min(n_items, __ldg(n_items_dev));
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n_items;
     V3 O = mk(0, 0, 0), d = mk(0, 0, 0);
@@ -600,6 +616,38 @@ k_shade_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays,
     atomicAdd(w + 1, (unsigned)(unsigned short)c.b);
 }
 
+// Deferred shadow rays of the wavefront path (k_shade_gen -> k_anyhit), answered by k_slow after
+// k_shade has run: c.y = node * n_nonambient + j.  k_shade saw OCCL_PENDING and left the light's
+// term out; an unoccluded ray adds it now (what is left to test is the large-primitive list).
+__global__ void __launch_bounds__(128)
+k_shadow_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays, const SlowRes* __restrict__ res,
+                unsigned n_slow, const Node* __restrict__ nodes, NodeAux* __restrict__ aux)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_slow) return;
+    if (res[e].found) return;                                          // occluded: + SHADOW_COLOR (cpp:80)
+    const SlowRay r = rays[e];
+    const unsigned gid = (unsigned)r.c.y;
+    const unsigned i = gid / (unsigned)sc.n_nonambient;
+    int j = (int)(gid % (unsigned)sc.n_nonambient), li = 0;
+    for (;; li++) { if (__ldg(sc.light_type + li) != RT580_LIGHT_AMBIENT) { if (j == 0) break; j--; } }
+    const V3 so = mk(r.o.x, r.o.y, r.o.z), sd = mk(r.d.x, r.d.y, r.d.z);
+    if (sc.n_big > 0 && !(r.c.x & 1)) {                                // the linear fallback saw every record already
+        HitRec sh; sh.t = r.o.w; sh.leaf = -1; sh.prim = 0x7fffffff;
+        if (big_scan<true>(sc, so, sd, sh)) return;
+    }
+    const Node nd = nodes[i];
+    const unsigned flags = __float_as_uint(nd.B.w);
+    const int prim = __float_as_int(nd.P.w);
+    const Material M = load_material(sc.materials, __ldg(sc.prim_material + prim));
+    const V3 sn = shading_normal(sc, nd, flags, prim);
+    const Light L = load_light(sc.light_type, sc.light_f, li);
+    const Pix c = calculate_local_color(mk(nd.P.x, nd.P.y, nd.P.z), sn, L, M, mk(fp.cam[0], fp.cam[1], fp.cam[2]));
+    unsigned int* w = reinterpret_cast<unsigned int*>(aux[i].local);
+    atomicAdd(w, (unsigned)(unsigned short)c.r | ((unsigned)(unsigned short)c.g << 16));
+    atomicAdd(w + 1, (unsigned)(unsigned short)c.b);
+}
+
 // shadow rays of one level as a ray queue for k_anyhit: ray id = (node - n0) * n_nonambient + j
 __global__ void __launch_bounds__(256)
 k_shade_gen(DeviceScene sc, unsigned n0, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
@@ -716,7 +764,7 @@ k_ao(DeviceScene sc, FrameParams fp, unsigned long long n_rays, int n_ambient, c
         const unsigned k = (unsigned)(i % (unsigned)fp.spp);
         const unsigned node = call / (unsigned)n_ambient;
         // state after the 2k draws of the preceding samples of this call: s0 * 16807^(2k)
-        uint32_t st = lcg_mulmod(__ldg(ao_state + call), lcg_state_at(2ull * k));
+        uint32_t st = lcg_mulmod(__ldg(ao_state + call), __ldg(fp.lcg_pow + k));
         const float4 nP = __ldg(&nodes[node].P), nN = __ldg(&nodes[node].N);
         const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
         const V3 dir = random_in_hemisphere(st, N);                            // cpp:321
@@ -746,6 +794,37 @@ struct __align__(16) ARay {
     float4 b;   // dir.y, dir.z, bits(consumer id: AO call), tmax
 };
 
+// Any hit of an unbounded ray against the large-primitive list (staged in shared memory).  "Any hit" is
+// an OR over the list, so the order of the exact tests is free: a first pass finds the two nearest
+// planes ahead of the ray with approximate arithmetic (FMA, fast reciprocal: it only ORDERS the
+// tests), which in a closed room are the two triangles of the wall the ray leaves through; the
+// exact test (the reference's, prim_test) runs on those two and only walks the rest of the list
+// if both miss.  With the tests in list order the lanes of a warp left the loop after 1..n_big
+// iterations and ncu showed 6-14 of 32 lanes active over 74 % of k_ao_gen's instructions.
+__device__ __forceinline__ bool big_any_nearest_first(const PrimRec* __restrict__ s_big, int n_big, V3 O, V3 d)
+{
+    const float inf = __int_as_float(0x7f800000);
+    float t1 = inf, t2 = inf; int k1 = -1, k2 = -1;
+    for (int k = 0; k < n_big; k++) {
+        const float4 rd = s_big[k].d, ra = s_big[k].a;
+        float ta = 0.0f;                                              // spheres: always a candidate
+        if (!(__float_as_int(rd.w) & RT_PRIM_SPHERE)) {
+            const float nd = __fmaf_rn(rd.x, d.x, __fmaf_rn(rd.y, d.y, rd.z * d.z));
+            const float num = -__fmaf_rn(rd.x, O.x, __fmaf_rn(rd.y, O.y, __fmaf_rn(rd.z, O.z, ra.w)));
+            ta = __fdividef(num, nd);
+            if (!(ta > 0.0f)) ta = inf;                               // behind the ray, parallel, NaN
+        }
+        if (ta < t1) { t2 = t1; k2 = k1; t1 = ta; k1 = k; }
+        else if (ta < t2) { t2 = ta; k2 = k; }
+    }
+    float t; int prim;
+    if (k1 >= 0 && prim_test<false>(&s_big[k1], O, d, inf, 0x7fffffff, t, prim)) return true;
+    if (k2 >= 0 && prim_test<false>(&s_big[k2], O, d, inf, 0x7fffffff, t, prim)) return true;
+    for (int k = 0; k < n_big; k++)
+        if (k != k1 && k != k2 && prim_test<false>(&s_big[k], O, d, inf, 0x7fffffff, t, prim)) return true;
+    return false;
+}
+
 __global__ void __launch_bounds__(256)
 k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, int n_ambient, const Node* __restrict__ nodes,
          const uint32_t* __restrict__ ao_state, ARay* __restrict__ out, unsigned int* __restrict__ n_out,
@@ -770,7 +849,7 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
         call = (unsigned)(i / (unsigned)fp.spp);
         const unsigned k = (unsigned)(i % (unsigned)fp.spp);
         const unsigned node = call / (unsigned)n_ambient;
-        uint32_t st = lcg_mulmod(__ldg(ao_state + call), lcg_state_at(2ull * k));   // state after the 2k draws before sample k
+        uint32_t st = lcg_mulmod(__ldg(ao_state + call), __ldg(fp.lcg_pow + k));    // state after the 2k draws before sample k
         const float4 nP = __ldg(&nodes[node].P), nN = __ldg(&nodes[node].N);
         const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
         const V3 dir = random_in_hemisphere(st, N);                                  // cpp:321
@@ -782,12 +861,7 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
         // the large primitives first: most likely occluders, and the ray is not queued at all if one is hit
         const bool far_origin = sc.farfield && fmaxf(fabsf(org.x), fmaxf(fabsf(org.y), fabsf(org.z))) > sc.extent;
         if (!far_origin && sc.n_big > 0) {
-            // any hit is an OR over the list: plain list order (reordering passes by N.d were tried and
-            // cost more in divergence than they saved in tests)
-            for (int k = 0; k < sc.n_big && !hit; k++) {
-                float t; int prim;
-                hit = prim_test<false>(&s_big[k], org, rd, __int_as_float(0x7f800000), 0x7fffffff, t, prim);
-            }
+            hit = big_any_nearest_first(s_big, sc.n_big, org, rd);
             emit = !hit;
         }
     }
@@ -823,13 +897,37 @@ k_shade_gen(DeviceScene sc, unsigned n0, unsigned long long first, unsigned n, c
     out[t] = r;
 }
 
+// Put an any-hit ray on the deferred queue (far-field scan or, `linear`, the reference's own loop,
+// trace.cuh).  A full queue drops the ray but still counts it: the host sees count > cap when it
+// flushes and repeats the pass with a queue that takes every ray (it never happens in scenes
+// that do not leak; keeping the in-place service out of this kernel keeps it at 51 registers).
+__device__ __forceinline__ bool defer_any(const SlowQ& sq, V3 O, V3 d, float tmax, bool linear, unsigned gid) {
+    if (!sq.rays) return false;
+    const unsigned slot = atomicAdd(sq.count, 1u);
+    if (slot >= sq.cap) return false;
+    SlowRay r; r.o = make_float4(O.x, O.y, O.z, tmax); r.d = make_float4(d.x, d.y, d.z, __int_as_float(0x7fffffff));
+    r.c = make_int4(linear ? 1 : 0, (int)gid, 0, -1);
+    sq.rays[slot] = r;
+    SlowRes z; z.key = 0ull; z.found = 0; z.pad = 0; sq.res[slot] = z;
+    return true;
+}
+
+// Persistent any-hit traversal.  hit_count[id] += 1 for every ray that is occluded.  A ray the tree
+// cannot answer alone goes to the deferred queue `sq` under the id `id + id_offset`; with
+// `pending_mark` its hit_count entry is flagged so that the consumer knows the answer comes later.
 __global__ void __launch_bounds__(128)
 k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __restrict__ n_ptr,
-         unsigned int* __restrict__ next_ray, uint32_t* __restrict__ hit_count, SlowQ sq, int ah_steps, int ah_min_search)
+         unsigned int* __restrict__ next_ray, uint32_t* __restrict__ hit_count, SlowQ sq, unsigned id_offset,
+         unsigned pending_mark, unsigned long long* __restrict__ traversed_acc, int ah_steps, int ah_min_search)
 {
     const unsigned n = __ldg(n_ptr);
+    if (traversed_acc && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(traversed_acc, (unsigned long long)n);
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    // rays a warp reserves per atomic on the queue counter: large for long queues (a single hot counter
+    // would serialise the GPU), small for short ones (the last batches are the tail of the kernel)
+    unsigned batch = n / (gridDim.x * (blockDim.x >> 5) * 4u);
+    batch = batch > (unsigned)AH_BATCH ? (unsigned)AH_BATCH : (batch < 32u ? 32u : (batch & ~31u));
     bool active = false;
     V3 O = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
     float tmax = 0.f; unsigned id = 0;
@@ -844,13 +942,12 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
             if (idle) {
                 const unsigned want = (unsigned)__popc(idle);
                 if (wend - wnext < want) {
-                    // one atomic per AH_BATCH rays and warp (a single hot counter would serialise the GPU);
                     // the unused tail of the old batch (< 32 rays) is handed out first
                     if (wnext == wend && !last_batch) {
                         unsigned b = 0;
-                        if (lane == 0) b = atomicAdd(next_ray, (unsigned)AH_BATCH);
+                        if (lane == 0) b = atomicAdd(next_ray, batch);
                         wnext = __shfl_sync(0xffffffffu, b, 0);
-                        wend = wnext + AH_BATCH;
+                        wend = wnext + batch;
                         if (wend >= n) { last_batch = true; if (wend > n) wend = n; if (wnext > n) wnext = n; }
                     }
                 }
@@ -867,13 +964,7 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
                         if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent) {
                             // child of a far-field hit: the reference's linear loop, deferred (trace.cuh)
                             if (sc.diag) atomicAdd(sc.diag + 1, 1u);
-                            const unsigned slot = atomicAdd(sq.count, 1u);
-                            if (slot < sq.cap) {
-                                SlowRay r; r.o = make_float4(O.x, O.y, O.z, tmax); r.d = make_float4(d.x, d.y, d.z, __int_as_float(0x7fffffff));
-                                r.c = make_int4(1, (int)id, 0, -1);
-                                sq.rays[slot] = r;
-                                SlowRes z; z.key = 0ull; z.found = 0; z.pad = 0; sq.res[slot] = z;
-                            }
+                            if (defer_any(sq, O, d, tmax, true, id + id_offset) && pending_mark) atomicOr(hit_count + id, pending_mark);
                         } else if (sc.n_leaf > 0) {
                             inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
                             cur = 0; sp = 0; active = true;
@@ -928,13 +1019,7 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
                     if (!found && tmax >= sc.far_tmin) {
                         // found nothing nearer than far_tmin: deferred far-field scan (trace.cuh)
                         if (sc.diag) atomicAdd(sc.diag, 1u);
-                        const unsigned slot = atomicAdd(sq.count, 1u);
-                        if (slot < sq.cap) {
-                            SlowRay r; r.o = make_float4(O.x, O.y, O.z, tmax); r.d = make_float4(d.x, d.y, d.z, __int_as_float(0x7fffffff));
-                            r.c = make_int4(0, (int)id, 0, -1);
-                            sq.rays[slot] = r;
-                            SlowRes z; z.key = 0ull; z.found = 0; z.pad = 0; sq.res[slot] = z;
-                        }
+                        if (defer_any(sq, O, d, tmax, false, id + id_offset) && pending_mark) atomicOr(hit_count + id, pending_mark);
                     }
                 }
                 if (found) atomicAdd(hit_count + id, 1u);
@@ -1089,10 +1174,10 @@ extern "C" void rt580_destroy(rt580_context* c)
     cudaStreamSynchronize(c->stream);
     free_scene(c);
     arena_release(c->scene_arena); arena_release(c->build_arena);
-    c->ndc.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
+    c->ndc.release(); c->lcg_pow.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
-    c->slow_rays.release(); c->slow_res.release(); c->arays.release(); c->occl.release();
+    c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release();
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1199,6 +1284,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->sc.n_nonambient = s->n_lights - c->sc.n_ambient;
     c->have_scene = true;
     c->frame_begun = false;
+    c->force_leaky = false;
     return RT580_SUCCESS;
 }
 
@@ -1224,12 +1310,18 @@ static SlowQ slowq(rt580_context* c, unsigned cap) {
     SlowQ q; q.rays = c->slow_rays.p; q.res = c->slow_res.p; q.count = c->counters.p + 2; q.cap = cap;
     return q;
 }
-template <int MODE> static void launch_trace(rt580_context* c, bool primary, unsigned n_items, unsigned node_cap, unsigned slow_cap) {
+// the second deferred queue: any-hit rays (shadow rays of all levels of a frame, then its AO rays)
+static SlowQ slowq_any(rt580_context* c) {
+    SlowQ q; q.rays = c->any_cap ? c->any_rays.p : nullptr; q.res = c->any_res.p; q.count = c->counters.p + 3; q.cap = c->any_cap;
+    return q;
+}
+template <int MODE> static void launch_trace(rt580_context* c, bool primary, unsigned n_items, const unsigned* n_items_dev,
+                                             unsigned node_cap, unsigned slow_cap) {
     if (primary)
-        k_trace<MODE, true><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, c->nodes.p, c->aux.p,
+        k_trace<MODE, true><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, n_items_dev, c->nodes.p, c->aux.p,
                                                                       c->counters.p, c->pix_hits.p, c->fb.p, node_cap, slowq(c, slow_cap));
     else
-        k_trace<MODE, false><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, c->nodes.p, c->aux.p,
+        k_trace<MODE, false><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, n_items_dev, c->nodes.p, c->aux.p,
                                                                        c->counters.p, c->pix_hits.p, c->fb.p, node_cap, slowq(c, slow_cap));
     c->launches++;
 }
@@ -1273,20 +1365,21 @@ static int exclusive_scan_u32(rt580_context* c, const uint32_t* in, uint32_t* ou
     return RT580_SUCCESS;
 }
 
-// all eight counters in one 32-byte copy + one stream sync (every host round trip idles the GPU for
-// ~10-20 us; with 8 ranks a frame is only ~10 ms long)
-static int read_counters(rt580_context* c, unsigned out[8]) {
-    CU(cudaMemcpyAsync(out, c->counters.p, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+// Device counters (uint32[N_COUNTERS]): [0] hit nodes, [1] queued secondary rays, [2] deferred closest-hit
+// rays, [3] deferred any-hit rays, [4] far-field scans, [5] linear fallbacks (diagnostics, whole frame),
+// [6] any-hit rays generated for the running chunk, [7] any-hit rays fetched, [8..9] uint64: AO rays that
+// went through the tree.  All of them come back in one 64-byte copy + one stream sync (every host round
+// trip idles the GPU for ~10-20 us; with 8 ranks a frame is only ~10 ms long).
+#define N_COUNTERS 16
+static int read_counters(rt580_context* c, unsigned out[N_COUNTERS]) {
+    CU(cudaMemcpyAsync(out, c->counters.p, N_COUNTERS * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    return RT580_SUCCESS;
-}
-static int read_counter(rt580_context* c, int which, unsigned* out) {
-    CU(cudaMemcpyAsync(out, c->counters.p + which, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    c->slow_seen = (unsigned long long)out[4] + out[5];
+    c->syncs++;
     return RT580_SUCCESS;
 }
 
-// Reserve the deferred-ray queue for a launch that may record up to `max_rays` slow rays.
+// Reserve the deferred closest-hit queue for a launch that may record up to `max_rays` slow rays.
 static int slow_prepare(rt580_context* c, unsigned long long max_rays, unsigned* cap_out)
 {
     unsigned cap = (unsigned)(max_rays < (unsigned long long)SLOW_CAP_MAX ? max_rays : (unsigned long long)SLOW_CAP_MAX);
@@ -1299,75 +1392,124 @@ static int slow_prepare(rt580_context* c, unsigned long long max_rays, unsigned*
     *cap_out = cap;
     return RT580_SUCCESS;
 }
-// Answer the recorded slow rays (one warp each); returns how many there were.
-static int slow_run(rt580_context* c, bool any, unsigned cap, unsigned* n_out, int known = -1)
+// Same for the any-hit queue, which lives across launches until it is flushed.
+static int any_prepare(rt580_context* c, unsigned long long max_rays)
 {
-    *n_out = 0;
-    if (!cap) return RT580_SUCCESS;
-    unsigned n = (unsigned)known;
-    if (known < 0 && read_counter(c, 2, &n)) return RT580_FAILURE;
-    if (n > cap) n = cap;
-    if (n) {
-        const unsigned batches = nblk(n, SLOW_RPB);
-        unsigned slices = nblk(4u * (unsigned)c->prop.multiProcessorCount, batches);
-        const unsigned max_slices = nblk((unsigned)c->sc.n_all, SLOW_TILE);
-        if (slices > max_slices) slices = max_slices;
-        if (slices > 256u) slices = 256u;
-        if (slices < 1u) slices = 1u;
-        const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_all, slices), SLOW_TILE) * SLOW_TILE);
-        const dim3 grid(batches, slices);
-        if (any) k_slow<true><<<grid, 256, 0, c->stream>>>(c->sc, c->slow_rays.p, n, c->slow_res.p, chunk);
-        else k_slow<false><<<grid, 256, 0, c->stream>>>(c->sc, c->slow_rays.p, n, c->slow_res.p, chunk);
-        c->launches++;
-        c->slow_total += n;
+    unsigned cap = (unsigned)(max_rays < 0xfffffff0ull ? max_rays : 0xfffffff0ull);
+    if (!c->sc.farfield || c->sc.n_all <= RT_SMEM_PRIMS) cap = 0;
+    if (cap) {
+        CU(c->any_rays.ensure(cap, 0, c->stream));
+        CU(c->any_res.ensure(cap, 0, c->stream));
     }
+    CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), c->stream));
+    c->any_cap = cap;
+    return RT580_SUCCESS;
+}
+// Answer n recorded slow rays: 32 rays per block, the records sliced over blockIdx.y (k_slow).
+static void slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes* res, unsigned n)
+{
+    if (!n) return;
+    const unsigned batches = nblk(n, SLOW_RPB);
+    unsigned slices = nblk(4u * (unsigned)c->prop.multiProcessorCount, batches);
+    const unsigned max_slices = nblk((unsigned)c->sc.n_all, SLOW_TILE);
+    if (slices > max_slices) slices = max_slices;
+    if (slices > 256u) slices = 256u;
+    if (slices < 1u) slices = 1u;
+    const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_all, slices), SLOW_TILE) * SLOW_TILE);
+    const dim3 grid(batches, slices);
+    if (any) k_slow<true><<<grid, 256, 0, c->stream>>>(c->sc, rays, n, res, chunk);
+    else k_slow<false><<<grid, 256, 0, c->stream>>>(c->sc, rays, n, res, chunk);
+    c->launches++;
+    c->slow_total += n;
+}
+// Closest-hit queue: `n` rays were recorded (counter [2], read by the caller).
+static void slow_run(rt580_context* c, bool any, unsigned cap, unsigned n, unsigned* n_out)
+{
+    if (n > cap) n = cap;
+    slow_launch(c, any, c->slow_rays.p, c->slow_res.p, n);
     *n_out = n;
+}
+
+// A scene "leaks" when a noticeable share of its rays needs the slow path (open scenes: every ray that
+// escapes).  Then the deferred queue must be able to take every ray of a launch; otherwise a small
+// queue, flushed once, is enough (should it overflow, the pass is repeated in the leaky form).
+static bool is_leaky(const rt580_context* c, unsigned long long rays_so_far) {
+    if (c->force_leaky) return true;
+    const unsigned long long thr = rays_so_far / 10000ull;
+    return c->slow_seen > (thr > 4096ull ? thr : 4096ull);
+}
+
+// Flush the any-hit queue: answer its rays (k_slow) and hand the answers to `finish(n)`.
+template <typename Fin>
+static int any_flush(rt580_context* c, Fin finish)
+{
+    if (!c->any_cap) return RT580_SUCCESS;
+    unsigned cnt[N_COUNTERS];
+    if (read_counters(c, cnt)) return RT580_FAILURE;
+    if (cnt[3] > c->any_cap) return RT580_INTERNAL_OVERFLOW;      // rays were dropped: the caller repeats the pass
+    const unsigned n = cnt[3];
+    if (n) {
+        slow_launch(c, true, c->any_rays.p, c->any_res.p, n);
+        finish(n);
+        c->launches++;
+        CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), c->stream));
+    }
     return RT580_SUCCESS;
 }
 
-// Any-hit pass in wavefront form over `total` rays: in chunks of at most SLOW_CAP_MAX rays (so the
-// deferred queue can hold every ray of a chunk), `gen(first, n)` launches a kernel that writes the
-// chunk's rays into c->arays and their number into counters[6]; k_anyhit (persistent, lanes refill)
-// adds 1 to hits[ray id] for every occluded ray; deferred rays pile up over the chunks and are
-// answered by k_slow when the queue could overflow or after the last chunk.
+// Any-hit pass in wavefront form over `total` rays, in chunks: `gen(first, n)` launches a kernel that
+// writes the chunk's rays into c->arays and their number into counters[6]; k_anyhit (persistent, lanes
+// refill) adds 1 to hits[ray id] for every occluded ray and defers what the tree cannot answer to the
+// any-hit queue (prepared by the caller).  No host round trip between the chunks unless the scene leaks
+// and the pass may flush (`ao`: the answers only add to hits[], k_ao_finish).
 template <typename Gen>
-static int anyhit_queue_pass(rt580_context* c, unsigned long long total, uint32_t* hits, float* kernel_ms,
-                             unsigned long long* traversed, Gen gen)
+static int anyhit_queue_pass(rt580_context* c, unsigned long long total, uint32_t* hits, unsigned id_offset,
+                             unsigned pending_mark, bool leaky, bool ao, Gen gen)
 {
     cudaStream_t st = c->stream;
-    unsigned slow_cap = 0, n_slow = 0, queued = 0;
-    CU(c->arays.ensure((size_t)(total < SLOW_CAP_MAX ? total : SLOW_CAP_MAX), 0, st));
+    const unsigned long long chunk = leaky ? (unsigned long long)SLOW_CAP_MAX : (unsigned long long)AH_CHUNK_TIGHT;
+    CU(c->arays.ensure((size_t)(total < chunk ? total : chunk), 0, st));
     const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ah_blocks_per_sm;
-    if (slow_prepare(c, SLOW_CAP_MAX, &slow_cap)) return RT580_FAILURE;     // queue shared by all chunks of the pass
-    for (unsigned long long first = 0; first < total; first += SLOW_CAP_MAX) {
-        const unsigned n = (unsigned)((total - first) < SLOW_CAP_MAX ? (total - first) : SLOW_CAP_MAX);
+    for (unsigned long long first = 0; first < total; first += chunk) {
+        const unsigned n = (unsigned)((total - first) < chunk ? (total - first) : chunk);
         CU(cudaMemsetAsync(c->counters.p + 6, 0, 2 * sizeof(unsigned), st));   // [6] rays emitted, [7] rays fetched
-        CU(cudaEventRecord(c->ev[8], st));
         gen(first, n);
         c->launches++;
-        k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, c->counters.p + 6, c->counters.p + 7, hits,
-                                         slowq(c, slow_cap ? slow_cap : 0u), c->ah_steps, c->ah_min_search);
+        k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, c->counters.p + 6, c->counters.p + 7, hits, slowq_any(c), id_offset,
+                                         pending_mark, ao ? reinterpret_cast<unsigned long long*>(c->counters.p + 8) : nullptr,
+                                         c->ah_steps, c->ah_min_search);
         c->launches++;
-        CU(cudaEventRecord(c->ev[9], st));
-        unsigned cnt[8];
-        if (read_counters(c, cnt)) return RT580_FAILURE;
-        queued = slow_cap ? cnt[2] : 0u;
-        if (traversed) *traversed += cnt[6];
         const unsigned long long rest = total - first - n;
-        const unsigned long long next_n = rest < SLOW_CAP_MAX ? rest : SLOW_CAP_MAX;
-        if (slow_cap && queued && (next_n == 0 || (unsigned long long)queued + next_n > slow_cap)) {
-            if (slow_run(c, true, slow_cap, &n_slow, (int)(queued > slow_cap ? slow_cap : queued))) return RT580_FAILURE;
-            if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, hits); c->launches++; }
-            CU(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(unsigned), st));
+        if (leaky && ao && c->any_cap && rest) {
+            // the queue must be able to take every ray of the next chunk
+            unsigned cnt[N_COUNTERS];
+            if (read_counters(c, cnt)) return RT580_FAILURE;
+            const unsigned long long next_n = rest < chunk ? rest : chunk;
+            if (cnt[3] && (unsigned long long)cnt[3] + next_n > c->any_cap) {
+                const unsigned q = cnt[3] > c->any_cap ? c->any_cap : cnt[3];
+                slow_launch(c, true, c->any_rays.p, c->any_res.p, q);
+                k_ao_finish<<<nblk(q, 256), 256, 0, st>>>(c->any_rays.p, c->any_res.p, q, hits); c->launches++;
+                CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), st));
+            }
         }
-        float ms = 0.f; cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]);
-        if (kernel_ms) *kernel_ms += ms;
     }
     CU(cudaGetLastError());
     return RT580_SUCCESS;
 }
 
+static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uint64_t* row_hit_nodes);
 extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p, uint64_t* row_hit_nodes)
+{
+    int rc = render_begin_impl(c, p, row_hit_nodes);
+    if (rc == RT580_INTERNAL_OVERFLOW) {
+        // the scene leaks after all: once more, with a deferred queue that takes every shadow ray of a level
+        c->force_leaky = true;
+        rc = render_begin_impl(c, p, row_hit_nodes);
+        if (rc == RT580_INTERNAL_OVERFLOW) FAIL(RT580_FAILURE, "rt580_render_begin: deferred-ray queue overflow");
+    }
+    return rc;
+}
+static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uint64_t* row_hit_nodes)
 {
     if (!c || !p) FAIL(RT580_INVALID_ARG, "rt580_render_begin: NULL argument");
     if (!c->have_scene) FAIL(RT580_FAILURE, "rt580_render_begin: no scene uploaded");
@@ -1401,12 +1543,13 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
     c->sc.farfield = (p->farfield == RT580_FARFIELD_EXACT) ? 1 : 0;
     const int mode = pick_mode(c, p->traversal);
     cudaStream_t st = c->stream;
-    c->launches = 0;
+    c->launches = 0; c->syncs = 0;
     memset(&c->stats, 0, sizeof c->stats);
 
     // primary-ray tables: cpp:834-846 evaluated in double on the host, exactly as the reference
-    // does per pixel (tan is libm's; hoisting is bit-exact because it is a pure function of x / y)
-    {
+    // does per pixel (tan is libm's; hoisting is bit-exact because it is a pure function of x / y);
+    // kept across frames of the same resolution
+    if (c->ndc_w != fp.W || c->ndc_h != fp.H || c->ndc_fov != p->fov_degrees) {
         std::vector<float> t((size_t)fp.W + fp.H);
         const float half = p->fov_degrees / 2;
         const float rad = (float)(half * (3.14159265 / 180));                 // ToRadian h:581-583
@@ -1419,11 +1562,25 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
         CU(c->ndc.ensure(t.size(), 0, st));
         CU(cudaMemcpyAsync(c->ndc.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         CU(cudaStreamSynchronize(st));
-        fp.ndc_x = c->ndc.p; fp.ndc_y = c->ndc.p + fp.W;
+        c->ndc_w = fp.W; c->ndc_h = fp.H; c->ndc_fov = p->fov_degrees;
     }
-    CU(c->counters.ensure(8, 0, st));
-    CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned), st));
+    fp.ndc_x = c->ndc.p; fp.ndc_y = c->ndc.p + fp.W;
+    if (c->lcg_pow_spp != fp.spp) {
+        // 16807^(2k) mod (2^31-1), k < spp: sample k of an AO call starts 2k engine steps after the call (cpp:320-321)
+        std::vector<uint32_t> t((size_t)fp.spp);
+        const uint64_t m = 2147483647ull, a2 = (16807ull * 16807ull) % m;
+        uint64_t v = 1;
+        for (int k = 0; k < fp.spp; k++) { t[k] = (uint32_t)v; v = (v * a2) % m; }
+        CU(c->lcg_pow.ensure(t.size(), 0, st));
+        CU(cudaMemcpyAsync(c->lcg_pow.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        c->lcg_pow_spp = fp.spp;
+    }
+    fp.lcg_pow = c->lcg_pow.p;
+    CU(c->counters.ensure(N_COUNTERS, 0, st));
+    CU(cudaMemsetAsync(c->counters.p, 0, N_COUNTERS * sizeof(unsigned), st));
     c->sc.diag = c->counters.p + 4;
+    c->slow_seen = 0; c->any_cap = 0;
     CU(c->pix_hits.ensure(npix + 1, 0, st));
     CU(c->pix_scan.ensure(npix + 1, 0, st));
     CU(c->fb.ensure((size_t)npix * 3 + 1, 0, st));
@@ -1436,77 +1593,104 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
     c->level_off.clear(); c->level_rays.clear();
     c->level_off.push_back(0);
     unsigned n_nodes = 0, slow_cap = 0, n_slow = 0;
+    unsigned cnt[N_COUNTERS];
     c->slow_total = 0;
     if (npix) {
         if (slow_prepare(c, npix, &slow_cap)) return RT580_FAILURE;
-        DISPATCH_MODE(mode, launch_trace, c, true, npix, (unsigned)c->nodes.cap, slow_cap);
-        unsigned cnt[8];
+        DISPATCH_MODE(mode, launch_trace, c, true, npix, nullptr, (unsigned)c->nodes.cap, slow_cap);
         if (read_counters(c, cnt)) return RT580_FAILURE;
         n_nodes = cnt[0];
-        if (slow_run(c, false, slow_cap, &n_slow, (int)(cnt[2] > slow_cap ? slow_cap : cnt[2]))) return RT580_FAILURE;
+        slow_run(c, false, slow_cap, cnt[2], &n_slow);
         if (n_slow) {
             k_trace_finish<true><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
                                                                    c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
                                                                    (unsigned)c->nodes.cap);
             c->launches++;
-            if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
+            if (read_counters(c, cnt)) return RT580_FAILURE;
+            n_nodes = cnt[0];
         }
     }
     c->level_rays.push_back(npix);
     c->level_off.push_back(n_nodes);
+    unsigned long long rays_so_far = npix;
+    bool any_open = false;      // shadow rays of earlier levels wait in the any-hit queue
+    auto shadow_finish = [&](unsigned n) {
+        k_shadow_finish<<<nblk(n, 128), 128, 0, st>>>(c->sc, c->fp, c->any_rays.p, c->any_res.p, n, c->nodes.p, c->aux.p);
+    };
     for (int L = 0; L <= fp.depth; L++) {
         const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
         if (n1 == n0) break;
+        const unsigned q_max = (L < fp.depth) ? 2u * (n1 - n0) : 0u;       // every node spawns at most two rays
+        CU(c->queue.ensure((size_t)q_max + 1, 0, st));
+        if (q_max) {
+            // room for the next level before anything is launched: its size is only known on the device
+            CU(c->nodes.ensure((size_t)n1 + q_max, n1, st));
+            CU(c->aux.ensure((size_t)n1 + q_max, n1, st));
+        }
         CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
-        if (L < fp.depth) CU(c->queue.ensure(2 * (size_t)(n1 - n0), 0, st));
-        else CU(c->queue.ensure(1, 0, st));
+        const unsigned long long n_sh = (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient;
         if (mode == 0) {
             // shadow rays in wavefront form (k_shade_gen -> k_anyhit), then shading with their answers
-            const unsigned long long n_sh = (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient;
+            if (n_sh > 0xfffffff0ull) FAIL(RT580_FAILURE, "rt580_render_begin: too many shadow rays in one level");
             CU(c->occl.ensure((size_t)n_sh + 1, 0, st));
             CU(cudaMemsetAsync(c->occl.p, 0, sizeof(uint32_t) * ((size_t)n_sh + 1), st));
+            const bool leaky = is_leaky(c, rays_so_far);
             if (n_sh) {
-                const int rc = anyhit_queue_pass(c, n_sh, c->occl.p, nullptr, nullptr,
+                if (leaky) {
+                    // the queue takes every shadow ray of the level and is flushed right after k_shade
+                    if (any_open) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; any_open = false; }
+                    if (any_prepare(c, n_sh)) return RT580_FAILURE;
+                } else if (!any_open) {
+                    if (any_prepare(c, SLOW_ANY_CAP)) return RT580_FAILURE;
+                    any_open = c->any_cap != 0;
+                }
+                const int rc = anyhit_queue_pass(c, n_sh, c->occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
                     [&](unsigned long long first, unsigned n) {
                         k_shade_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6);
                     });
                 if (rc) return rc;
             }
-            CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
             k_shade<0, true><<<nblk(n1 - n0, 128), 128, 0, st>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p,
                                                                  slowq(c, 0u), c->occl.p);
             c->launches++;
+            if (leaky && n_sh) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
         } else {
-            if (slow_prepare(c, (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient, &slow_cap)) return RT580_FAILURE;
+            if (slow_prepare(c, n_sh, &slow_cap)) return RT580_FAILURE;
             DISPATCH_MODE(mode, launch_shade, c, n0, n1, slow_cap);
-            if (slow_run(c, true, slow_cap, &n_slow)) return RT580_FAILURE;
-            if (n_slow) {
-                k_shade_finish<<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->slow_rays.p, c->slow_res.p, n_slow, c->nodes.p, c->aux.p);
-                c->launches++;
+            if (slow_cap) {
+                if (read_counters(c, cnt)) return RT580_FAILURE;
+                slow_run(c, true, slow_cap, cnt[2], &n_slow);
+                if (n_slow) {
+                    k_shade_finish<<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->slow_rays.p, c->slow_res.p, n_slow, c->nodes.p, c->aux.p);
+                    c->launches++;
+                }
             }
         }
+        rays_so_far += n_sh;
         if (L == fp.depth) break;
-        unsigned q = 0;
-        if (read_counter(c, 1, &q)) return RT580_FAILURE;
-        if (q == 0) break;
-        CU(c->nodes.ensure((size_t)n1 + q, n1, st));
-        CU(c->aux.ensure((size_t)n1 + q, n1, st));
-        if (slow_prepare(c, q, &slow_cap)) return RT580_FAILURE;
-        DISPATCH_MODE(mode, launch_trace, c, false, q, (unsigned)c->nodes.cap, slow_cap);
-        unsigned cnt[8];
+        // the queued reflection / refraction rays: their number stays on the device (counters[1])
+        if (slow_prepare(c, q_max, &slow_cap)) return RT580_FAILURE;
+        DISPATCH_MODE(mode, launch_trace, c, false, q_max, c->counters.p + 1, (unsigned)c->nodes.cap, slow_cap);
         if (read_counters(c, cnt)) return RT580_FAILURE;
+        const unsigned q = cnt[1];
+        if (q == 0) break;
         n_nodes = cnt[0];
-        if (slow_run(c, false, slow_cap, &n_slow, (int)(cnt[2] > slow_cap ? slow_cap : cnt[2]))) return RT580_FAILURE;
+        slow_run(c, false, slow_cap, cnt[2], &n_slow);
         if (n_slow) {
             k_trace_finish<false><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
                                                                     c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
                                                                     (unsigned)c->nodes.cap);
             c->launches++;
-            if (read_counter(c, 0, &n_nodes)) return RT580_FAILURE;
+            if (read_counters(c, cnt)) return RT580_FAILURE;
+            n_nodes = cnt[0];
         }
         c->level_rays.push_back(q);
         c->level_off.push_back(n_nodes);
+        rays_so_far += q;
     }
+    if (any_open) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
+    c->any_cap = 0;
+    c->rays_structure = rays_so_far;
     const double t_struct = now_ms();
     CU(cudaEventRecord(c->ev[1], st));
     // order: subtree sizes bottom-up, per-pixel exclusive scan, per-row totals
@@ -1521,14 +1705,17 @@ extern "C" int rt580_render_begin(rt580_context* c, const rt580_render_params* p
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev[6], st));
-    std::vector<uint64_t> rows((size_t)fp.n_rows);
-    if (fp.n_rows) CU(cudaMemcpyAsync(rows.data(), c->row_vals.p, sizeof(uint64_t) * fp.n_rows, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    if (row_hit_nodes) for (int r = 0; r < fp.n_rows; r++) row_hit_nodes[r] = rows[r];
+    if (row_hit_nodes) {
+        std::vector<uint64_t> rows((size_t)fp.n_rows);
+        if (fp.n_rows) CU(cudaMemcpyAsync(rows.data(), c->row_vals.p, sizeof(uint64_t) * fp.n_rows, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        c->syncs++;
+        CU(cudaGetLastError());
+        for (int r = 0; r < fp.n_rows; r++) row_hit_nodes[r] = rows[r];
+    }
     c->frame_begun = true;
-    if (dbg_t) fprintf(stderr, "[rt580] render_begin host ms: setup %.2f structure %.2f order %.2f (levels %d, launches %u)\n",
-                       t_setup - t_enter, t_struct - t_setup, now_ms() - t_struct, (int)c->level_off.size() - 1, c->launches);
+    if (dbg_t) fprintf(stderr, "[rt580] render_begin host ms: setup %.2f structure %.2f order %.2f (levels %d, launches %u, host syncs %u)\n",
+                       t_setup - t_enter, t_struct - t_setup, now_ms() - t_struct, (int)c->level_off.size() - 1, c->launches, c->syncs);
     // ray accounting: one ray == one IntersectScene call of the reference (cpp:30, cpp:75, cpp:325)
     c->stats.rays_primary = npix;
     for (size_t l = 1; l < c->level_rays.size(); l++) c->stats.rays_secondary += c->level_rays[l];
@@ -1576,26 +1763,42 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     if (n_ao > 0xffffffffull * 128ull) FAIL(RT580_FAILURE, "rt580_render_finish: AO ray count exceeds one launch");
     if (n_ao) {
         unsigned slow_cap = 0, n_slow = 0;
-        float kernel_ms = 0.f;
+        CU(cudaEventRecord(c->ev[8], st));
         if (mode == 0) {
-            unsigned long long traversed = 0;
-            const int rc = anyhit_queue_pass(c, n_ao, c->ao_hits.p, &kernel_ms, &traversed,
-                [&](unsigned long long first, unsigned n) {
-                    k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,
-                                                           c->counters.p + 6, c->ao_hits.p);
-                });
-            if (rc) return rc;
-            c->stats.ao_rays_traversed = traversed;
+            for (int attempt = 0; ; attempt++) {
+                const bool leaky = is_leaky(c, c->rays_structure);
+                if (any_prepare(c, leaky ? SLOW_CAP_MAX : SLOW_ANY_CAP)) return RT580_FAILURE;
+                const int rc = anyhit_queue_pass(c, n_ao, c->ao_hits.p, 0u, 0u, leaky, true,
+                    [&](unsigned long long first, unsigned n) {
+                        k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,
+                                                               c->counters.p + 6, c->ao_hits.p);
+                    });
+                if (rc) return rc;
+                CU(cudaEventRecord(c->ev[9], st));
+                const int fr = any_flush(c, [&](unsigned n) { k_ao_finish<<<nblk(n, 256), 256, 0, st>>>(c->any_rays.p, c->any_res.p, n, c->ao_hits.p); });
+                if (fr == RT580_INTERNAL_OVERFLOW && attempt == 0) {
+                    // the scene leaks after all: once more with a queue that takes every ray of a chunk
+                    c->force_leaky = true;
+                    CU(cudaMemsetAsync(c->ao_hits.p, 0, sizeof(uint32_t) * (n_calls + 1), st));
+                    CU(cudaMemsetAsync(c->counters.p + 8, 0, 2 * sizeof(unsigned), st));
+                    continue;
+                }
+                if (fr) FAIL(RT580_FAILURE, "rt580_render_finish: deferred-ray queue overflow");
+                break;
+            }
+            c->any_cap = 0;
         } else {
             if (slow_prepare(c, n_ao, &slow_cap)) return RT580_FAILURE;
-            CU(cudaEventRecord(c->ev[8], st));
             DISPATCH_MODE(mode, launch_ao, c, n_ao, slow_cap);
             c->stats.ao_rays_traversed = n_ao;
             CU(cudaEventRecord(c->ev[9], st));
-            CU(cudaStreamSynchronize(st));
-            cudaEventElapsedTime(&kernel_ms, c->ev[8], c->ev[9]);
+            if (slow_cap) {
+                unsigned cnt[N_COUNTERS];
+                if (read_counters(c, cnt)) return RT580_FAILURE;
+                slow_run(c, true, slow_cap, cnt[2], &n_slow);
+                if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, c->ao_hits.p); c->launches++; }
+            }
         }
-        c->stats.ms_ao_kernel = kernel_ms;
     }
     CU(cudaEventRecord(c->ev[4], st));
     for (int L = n_levels - 1; L >= 0; L--) {
@@ -1609,7 +1812,8 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     if (fb_out && npix)
         CU(cudaMemcpyAsync(fb_out, c->fb.p, sizeof(int16_t) * 3 * (size_t)npix,
                            fb_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    unsigned cnt[N_COUNTERS];
+    if (read_counters(c, cnt)) return RT580_FAILURE;
     CU(cudaGetLastError());
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.ms_structure = ms;
@@ -1617,13 +1821,11 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[6]); c->stats.ms_order += ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.ms_ao = ms;
     cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->stats.ms_resolve = ms;
+    if (n_ao) { cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); c->stats.ms_ao_kernel = ms; }
     c->stats.ms_total = c->stats.ms_structure + c->stats.ms_order + c->stats.ms_ao + c->stats.ms_resolve;
     c->stats.kernel_launches = c->launches;
-    {
-        unsigned dg[2] = { 0, 0 };
-        cudaMemcpy(dg, c->counters.p + 4, sizeof dg, cudaMemcpyDeviceToHost);
-        c->stats.far_scans = dg[0]; c->stats.linear_fallbacks = dg[1];
-    }
+    c->stats.far_scans = cnt[4]; c->stats.linear_fallbacks = cnt[5];
+    if (mode == 0) c->stats.ao_rays_traversed = (uint64_t)cnt[8] | ((uint64_t)cnt[9] << 32);
     if (stats) *stats = c->stats;
     c->frame_begun = false;
     return RT580_SUCCESS;

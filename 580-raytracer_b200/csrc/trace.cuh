@@ -51,7 +51,13 @@ __device__ __forceinline__ bool prim_test(const PrimRec* __restrict__ p, V3 O, V
         const V3 N = mk(rd.x, rd.y, rd.z);
         const float nd = dot(N, d);                               // cpp:367
         if (fabsf(nd - 0.0f) <= RT_EPS_F) return false;           // cpp:371
-        const float t = -(dot(N, O) + ra.w) / nd;                 // cpp:381
+        const float num = -(dot(N, O) + ra.w);
+        // two rejections that need no division (an IEEE division keeps the sign, and is within half an
+        // ulp of the quotient): the plane lies behind the ray, t <= 0 <= EPSILON (cpp:382); or so far
+        // beyond t_limit that the rounded t exceeds it as well (the caller would discard the hit)
+        if (num == 0.0f || ((num < 0.0f) != (nd < 0.0f))) return false;
+        if (fabsf(num) > (t_limit * fabsf(nd)) * 1.000001f) return false;
+        const float t = num / nd;                                 // cpp:381
         if (t <= RT_EPS_F) return false;                          // cpp:382
         if (!(t < t_limit || (t == t_limit && prim < prim_limit))) return false;
         const float4 rb = ld4<GLOBAL>(&p->b);
