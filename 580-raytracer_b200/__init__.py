@@ -28,7 +28,8 @@ LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AMBIENT = 0, 1, 2
 EXPORTS = [
     "rt580_create", "rt580_destroy", "rt580_last_error", "rt580_device_info", "rt580_upload_scene", "rt580_build_ms",
     "rt580_scene_info_get", "rt580_get_stream",
-    "rt580_render", "rt580_render_begin", "rt580_render_finish", "rt580_trace_closest", "rt580_trace_any", "rt580_trace_profile",
+    "rt580_render", "rt580_render_begin", "rt580_render_finish", "rt580_row_counts_to_device", "rt580_render_finish_interleaved",
+    "rt580_frame_export", "rt580_frame_import", "rt580_frame_release", "rt580_frame_read", "rt580_trace_closest", "rt580_trace_any", "rt580_trace_profile",
     "rt580_last_frame_ao_base", "rt580_hemisphere_stream", "rt580_powf",
     "rt580_raytracer_new", "rt580_raytracer_delete", "rt580_raytracer_set_assets_path", "rt580_raytracer_set_options", "rt580_raytracer_set_quiet",
     "rt580_raytracer_load_scene_json", "rt580_raytracer_render", "rt580_raytracer_flush_ppm",
@@ -132,6 +133,12 @@ def lib():
         L.rt580_render.argtypes = [vp, ctypes.POINTER(RenderParams), vp, ctypes.POINTER(Stats)]
         L.rt580_render_begin.argtypes = [vp, ctypes.POINTER(RenderParams), vp]
         L.rt580_render_finish.argtypes = [vp, vp, vp, i32, ctypes.POINTER(Stats)]
+        L.rt580_row_counts_to_device.argtypes = [vp, vp, i32]
+        L.rt580_render_finish_interleaved.argtypes = [vp, vp, i32, i32, i32, vp, i32, ctypes.POINTER(Stats)]
+        L.rt580_frame_export.argtypes = [vp, i32, i32, vp]
+        L.rt580_frame_import.argtypes = [vp, vp, i32, i32]
+        L.rt580_frame_release.argtypes = [vp]
+        L.rt580_frame_read.argtypes = [vp, vp]
         L.rt580_trace_closest.argtypes = [vp, i64, vp, vp, i32, vp, vp]
         L.rt580_trace_any.argtypes = [vp, i64, vp, vp, vp, i32, vp]
         L.rt580_trace_profile.argtypes = [vp, i64, vp, vp, vp, vp]
@@ -212,11 +219,44 @@ class Context:
         _check(lib().rt580_render(self._h, ctypes.byref(params), fb.ctypes.data, ctypes.byref(st)))
         return fb, st
 
-    def render_begin(self, params: RenderParams):
+    def render_begin(self, params: RenderParams, want_counts=True):
+        """Structure pass.  Returns the per-row hit-node counts, or None with want_counts=False
+        (they then stay on the device for row_counts_to_device)."""
         n_rows = params.n_rows or params.height
+        if not want_counts:
+            _check(lib().rt580_render_begin(self._h, ctypes.byref(params), None))
+            return None
         rows = np.zeros(max(n_rows, 1), np.uint64)
         _check(lib().rt580_render_begin(self._h, ctypes.byref(params), rows.ctypes.data))
         return rows[:n_rows]
+
+    def row_counts_to_device(self, dst_device_ptr, max_rows):
+        _check(lib().rt580_row_counts_to_device(self._h, dst_device_ptr, max_rows))
+
+    def render_finish_interleaved(self, all_counts_device_ptr, world, rank, max_rows, device_ptr=None):
+        """Finish with the all-gathered row counts on the device (no host round trip)."""
+        st = Stats()
+        _check(lib().rt580_render_finish_interleaved(self._h, all_counts_device_ptr, world, rank, max_rows, device_ptr,
+                                                      1 if device_ptr else 0, ctypes.byref(st)))
+        return st
+
+    def frame_export(self, width, height):
+        """Rank 0: allocate the whole frame; returns the 64-byte CUDA IPC handle for the other ranks."""
+        h = ctypes.create_string_buffer(64)
+        _check(lib().rt580_frame_export(self._h, width, height, h))
+        return h.raw
+
+    def frame_import(self, handle, width, height):
+        buf = ctypes.create_string_buffer(bytes(handle), 64)
+        _check(lib().rt580_frame_import(self._h, buf, width, height))
+
+    def frame_release(self):
+        _check(lib().rt580_frame_release(self._h))
+
+    def frame_read(self, width, height):
+        fb = np.empty((height, width, 3), np.int16)
+        _check(lib().rt580_frame_read(self._h, fb.ctypes.data))
+        return fb
 
     def render_finish(self, params: RenderParams, row_ao_base=None, out=None, device_ptr=None):
         """out: host int16 array, or device_ptr: raw CUDA pointer (e.g. torch tensor data_ptr())."""

@@ -47,6 +47,13 @@ struct DeviceScene {
     int32_t n_big;             // very large primitives kept out of the tree: prims[n_leaf, n_leaf + n_big), tested
                                // first for every ray (they would bloat every ancestor box of an LBVH, and as
                                // the likeliest occluders they end most any-hit rays at once)
+    // the distinct planes of the large triangles (a wall is two coplanar triangles): the plane part of the
+    // reference's triangle test (cpp:367-382) is the same arithmetic for every triangle of a plane, so
+    // it is done once per plane and rejects all its triangles at once
+    const float4* big_planes;               // [n_big_planes] (N.xyz, D), bit-identical in all member records
+    const unsigned long long* big_masks;    // [n_big_planes] members: bit k = prims[n_leaf + k]
+    unsigned long long big_sphere_mask;     // large spheres (no plane): bit k = prims[n_leaf + k]
+    int32_t n_big_planes;
     int32_t n_all;             // n_leaf + n_big: what the linear loops and the far-field scan walk
     int32_t n_prims;           // primitives in reference order (incl. dropped ones)
     const float4* vn;          // [n_prims][3] object-space vertex normals (Q10); unused for spheres

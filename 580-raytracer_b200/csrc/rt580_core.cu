@@ -166,6 +166,9 @@ struct rt580_context {
     bool force_leaky = false;                          // the small any-hit queue overflowed once for this scene
     int ndc_w = 0, ndc_h = 0; float ndc_fov = 0.f;     // what the primary-ray tables were built for
     DBuf<uint32_t> lcg_pow; int lcg_pow_spp = 0;
+    // the whole W x H frame of a multi-GPU render: rank 0's own allocation, or that allocation mapped
+    // into this process over NVLink (cudaIpc); every rank stores its rows there after the resolve pass
+    int16_t* frame = nullptr; bool frame_imported = false; int frame_w = 0, frame_h = 0;
     DBuf<struct ARay> arays;       // one chunk of generated any-hit rays (AO samples / shadow rays)
     DBuf<uint32_t> occl;           // per shadow ray of the current level: occluders found
     uint64_t slow_total = 0;
@@ -178,6 +181,8 @@ struct rt580_context {
     uint32_t launches = 0;
     std::vector<uint64_t> last_ao_base;   // host copy for the checker
 };
+
+static void frame_release(rt580_context* c);
 
 // ---------------------------------------------------------------------------------------
 // device helpers
@@ -795,33 +800,50 @@ struct __align__(16) ARay {
 };
 
 // Any hit of an unbounded ray against the large-primitive list (staged in shared memory).  "Any hit" is
-// an OR over the list, so the order of the exact tests is free: a first pass finds the two nearest
-// planes ahead of the ray with approximate arithmetic (FMA, fast reciprocal: it only ORDERS the
-// tests), which in a closed room are the two triangles of the wall the ray leaves through; the
-// exact test (the reference's, prim_test) runs on those two and only walks the rest of the list
-// if both miss.  With the tests in list order the lanes of a warp left the loop after 1..n_big
-// iterations and ncu showed 6-14 of 32 lanes active over 74 % of k_ao_gen's instructions.
-__device__ __forceinline__ bool big_any_nearest_first(const PrimRec* __restrict__ s_big, int n_big, V3 O, V3 d)
+// an OR over the list, so the order of the exact tests is free: a first pass over the distinct PLANES
+// of the list finds the two nearest ahead of the ray with approximate arithmetic (FMA, approximate
+// reciprocal: it only ORDERS the tests), which in a closed room is the wall the ray leaves through;
+// the exact tests (the reference's, prim_test) run on the triangles of those two planes and only walk
+// the rest of the list if all of them miss.  With the tests in list order the lanes of a warp left
+// the loop after 1..n_big iterations and ncu showed 6-14 of 32 lanes active over 74 % of k_ao_gen's
+// instructions.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ bool big_any_nearest_first(const PrimRec* __restrict__ s_big, int n_big, const float4* __restrict__ s_plane,
+                                                      const unsigned long long* __restrict__ s_mask, int n_planes,
+                                                      unsigned long long sphere_mask, V3 O, V3 d)
 {
     const float inf = __int_as_float(0x7f800000);
-    float t1 = inf, t2 = inf; int k1 = -1, k2 = -1;
-    for (int k = 0; k < n_big; k++) {
-        const float4 rd = s_big[k].d, ra = s_big[k].a;
-        float ta = 0.0f;                                              // spheres: always a candidate
-        if (!(__float_as_int(rd.w) & RT_PRIM_SPHERE)) {
-            const float nd = __fmaf_rn(rd.x, d.x, __fmaf_rn(rd.y, d.y, rd.z * d.z));
-            const float num = -__fmaf_rn(rd.x, O.x, __fmaf_rn(rd.y, O.y, __fmaf_rn(rd.z, O.z, ra.w)));
-            ta = __fdividef(num, nd);
-            if (!(ta > 0.0f)) ta = inf;                               // behind the ray, parallel, NaN
-        }
-        if (ta < t1) { t2 = t1; k2 = k1; t1 = ta; k1 = k; }
-        else if (ta < t2) { t2 = ta; k2 = k; }
-    }
     float t; int prim;
-    if (k1 >= 0 && prim_test<false>(&s_big[k1], O, d, inf, 0x7fffffff, t, prim)) return true;
-    if (k2 >= 0 && prim_test<false>(&s_big[k2], O, d, inf, 0x7fffffff, t, prim)) return true;
+    for (unsigned long long m = sphere_mask; m; m &= m - 1ull)
+        if (prim_test<false>(&s_big[__ffsll((long long)m) - 1], O, d, inf, 0x7fffffff, t, prim)) return true;
+    // keys: approximate t (a positive float orders like its bits) with the plane index in the low 6 bits
+    unsigned m1 = 0xffffffffu, m2 = 0xffffffffu;
+#pragma unroll 4
+    for (int j = 0; j < n_planes; j++) {
+        const float4 pl = s_plane[j];
+        const float nd = __fmaf_rn(pl.x, d.x, __fmaf_rn(pl.y, d.y, pl.z * d.z));
+        const float num = -__fmaf_rn(pl.x, O.x, __fmaf_rn(pl.y, O.y, __fmaf_rn(pl.z, O.z, pl.w)));
+        const float ta = num * rcp_approx(nd);
+        const unsigned key = (ta > 0.0f) ? ((__float_as_uint(ta) & ~63u) | (unsigned)j) : 0xffffffffu;   // behind, parallel, NaN: last
+        const unsigned hi = max(key, m1);
+        m1 = min(key, m1);
+        m2 = min(m2, hi);
+    }
+    unsigned long long tested = sphere_mask;
+    if (m1 != 0xffffffffu) {
+        const unsigned long long mm = s_mask[m1 & 63u];
+        for (unsigned long long m = mm; m; m &= m - 1ull)
+            if (prim_test<false>(&s_big[__ffsll((long long)m) - 1], O, d, inf, 0x7fffffff, t, prim)) return true;
+        tested |= mm;
+    }
+    if (m2 != 0xffffffffu) {
+        const unsigned long long mm = s_mask[m2 & 63u];
+        for (unsigned long long m = mm; m; m &= m - 1ull)
+            if (prim_test<false>(&s_big[__ffsll((long long)m) - 1], O, d, inf, 0x7fffffff, t, prim)) return true;
+        tested |= mm;
+    }
     for (int k = 0; k < n_big; k++)
-        if (k != k1 && k != k2 && prim_test<false>(&s_big[k], O, d, inf, 0x7fffffff, t, prim)) return true;
+        if (!((tested >> k) & 1ull) && prim_test<false>(&s_big[k], O, d, inf, 0x7fffffff, t, prim)) return true;
     return false;
 }
 
@@ -832,10 +854,13 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
 {
     // the large-primitive list (<= 64 records) is walked by every ray: keep it in shared memory
     __shared__ PrimRec s_big[64];
+    __shared__ float4 s_plane[64];
+    __shared__ unsigned long long s_mask[64];
     {
         const float4* src = reinterpret_cast<const float4*>(sc.prims + sc.n_leaf);
         float4* dst = reinterpret_cast<float4*>(s_big);
         for (int i = threadIdx.x; i < sc.n_big * 4; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < sc.n_big_planes; i += blockDim.x) { s_plane[i] = __ldg(sc.big_planes + i); s_mask[i] = __ldg(sc.big_masks + i); }
         __syncthreads();
     }
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -861,7 +886,7 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
         // the large primitives first: most likely occluders, and the ray is not queued at all if one is hit
         const bool far_origin = sc.farfield && fmaxf(fabsf(org.x), fmaxf(fabsf(org.y), fabsf(org.z))) > sc.extent;
         if (!far_origin && sc.n_big > 0) {
-            hit = big_any_nearest_first(s_big, sc.n_big, org, rd);
+            hit = big_any_nearest_first(s_big, sc.n_big, s_plane, s_mask, sc.n_big_planes, sc.big_sphere_mask, org, rd);
             emit = !hit;
         }
     }
@@ -1075,6 +1100,56 @@ __global__ void k_resolve(DeviceScene sc, FrameParams fp, unsigned n0, unsigned 
     }
 }
 
+// ---- multi-GPU, device side ---------------------------------------------------------------
+// AO-stream prefix of this rank's rows from the all-gathered per-row hit-node counts of every rank
+// (rows interleaved: row y belongs to rank y % world, where it is row y / world).  One block; the
+// frame has a few thousand rows.  Replaces a D2H copy, a host prefix sum and an H2D copy per frame.
+__global__ void __launch_bounds__(1024)
+k_row_bases_interleaved(const uint64_t* __restrict__ all_counts, int world, int rank, int max_rows, int H,
+                        uint64_t* __restrict__ row_base)
+{
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0ull;
+    __syncthreads();
+    for (int y0 = 0; y0 < H; y0 += 1024) {
+        const int y = y0 + (int)threadIdx.x;
+        const uint64_t v = (y < H) ? all_counts[(size_t)(y % world) * max_rows + y / world] : 0ull;
+        uint64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        const uint64_t excl = carry + incl - v + (warp ? warp_sums[warp - 1] : 0ull);
+        if (y < H && y % world == rank) row_base[y / world] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+}
+
+// This rank's rows -> the whole frame (rank 0's memory; for the other ranks a peer mapping, so these
+// are stores over NVLink: whole rows, 16 bytes per lane, no NCCL gather and no staging buffer).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_store_band(const T* __restrict__ band, T* __restrict__ frame, unsigned row_units, int n_rows, int row_first, int row_step)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long total = (unsigned long long)row_units * (unsigned)n_rows;
+    if (i >= total) return;
+    const unsigned row = (unsigned)(i / row_units), u = (unsigned)(i % row_units);
+    frame[(size_t)(row_first + (int)row * row_step) * row_units + u] = band[i];
+}
+
 // checker kernels: arbitrary rays
 template <int MODE, bool ANY>
 __global__ void __launch_bounds__(128)
@@ -1173,6 +1248,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c);
+    frame_release(c);
     arena_release(c->scene_arena); arena_release(c->build_arena);
     c->ndc.release(); c->lcg_pow.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
@@ -1219,7 +1295,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     {
         char aerr[256] = "";
         const size_t in_bytes = (size_t)s->n_tris * (3 * 16 + 4) + (size_t)s->n_spheres * (16 + 4) + 16 * 256;
-        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 44 + 16 * 256;
+        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 44 + 24 * 256;
         if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
             !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
             FAIL(RT580_FAILURE, "rt580_upload_scene: %s", aerr);
@@ -1275,6 +1351,32 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->d_always = bo.always_idx; c->sc.always_idx = bo.always_idx; c->sc.n_always = bo.n_always;
     c->d_leaf_of_prim = bo.leaf_of_prim; c->sc.leaf_of_prim = bo.leaf_of_prim;
     c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_big = bo.n_big; c->sc.n_all = bo.n_leaf + bo.n_big;
+    {
+        // distinct planes of the large triangles (device_scene.h); at most 64 records, grouped on the host
+        c->sc.big_planes = nullptr; c->sc.big_masks = nullptr; c->sc.big_sphere_mask = 0ull; c->sc.n_big_planes = 0;
+        if (bo.n_big > 64) FAIL(RT580_FAILURE, "rt580_upload_scene: %d large primitives (at most 64)", bo.n_big);
+        if (bo.n_big > 0) {
+            std::vector<PrimRec> big((size_t)bo.n_big);
+            CU(cudaMemcpy(big.data(), bo.prims + bo.n_leaf, sizeof(PrimRec) * bo.n_big, cudaMemcpyDeviceToHost));
+            std::vector<float4> planes; std::vector<unsigned long long> masks;
+            for (int k = 0; k < bo.n_big; k++) {
+                int flags; memcpy(&flags, &big[k].d.w, 4);
+                if (flags & RT_PRIM_SPHERE) { c->sc.big_sphere_mask |= 1ull << k; continue; }
+                const float4 pl = make_float4(big[k].d.x, big[k].d.y, big[k].d.z, big[k].a.w);
+                size_t j = 0;
+                for (; j < planes.size(); j++) if (memcmp(&planes[j], &pl, sizeof pl) == 0) break;
+                if (j == planes.size()) { planes.push_back(pl); masks.push_back(0ull); }
+                masks[j] |= 1ull << k;
+            }
+            if (!planes.empty()) {
+                float4* dp = nullptr; unsigned long long* dm = nullptr;
+                CU(upload(sa, &dp, planes.data(), planes.size(), st));
+                CU(upload(sa, &dm, masks.data(), masks.size(), st));
+                CU(cudaStreamSynchronize(st));
+                c->sc.big_planes = dp; c->sc.big_masks = dm; c->sc.n_big_planes = (int)planes.size();
+            }
+        }
+    }
     c->sc.n_prims = (int32_t)s->n_prims;
     c->sc.vn = c->d_vn; c->sc.prim_material = c->d_prim_material; c->sc.materials = c->d_materials;
     c->sc.n_materials = s->n_materials; c->sc.light_type = c->d_light_type; c->sc.light_f = c->d_light_f;
@@ -1727,11 +1829,51 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
     return RT580_SUCCESS;
 }
 
+static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, bool bases_on_device, int16_t* fb_out,
+                              int fb_on_device, rt580_stats* stats);
 extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base, int16_t* fb_out, int fb_on_device,
                                    rt580_stats* stats)
 {
     if (!c) FAIL(RT580_INVALID_ARG, "rt580_render_finish: ctx is NULL");
     if (!c->frame_begun) FAIL(RT580_FAILURE, "rt580_render_finish: no frame begun");
+    if (c->fp.rng_mode == RT580_RNG_REFERENCE_LCG && !row_ao_base && c->fp.n_rows)
+        FAIL(RT580_INVALID_ARG, "rt580_render_finish: row_ao_base required in RT580_RNG_REFERENCE_LCG mode");
+    return render_finish_impl(c, row_ao_base, false, fb_out, fb_on_device, stats);
+}
+
+extern "C" int rt580_row_counts_to_device(rt580_context* c, uint64_t* dst_device, int32_t max_rows)
+{
+    if (!c || !dst_device) FAIL(RT580_INVALID_ARG, "rt580_row_counts_to_device: NULL argument");
+    if (!c->frame_begun) FAIL(RT580_FAILURE, "rt580_row_counts_to_device: no frame begun");
+    if (max_rows < c->fp.n_rows) FAIL(RT580_INVALID_ARG, "rt580_row_counts_to_device: max_rows %d < %d rows of this context", max_rows, c->fp.n_rows);
+    CU(cudaSetDevice(c->device));
+    if (c->fp.n_rows)
+        CU(cudaMemcpyAsync(dst_device, c->row_vals.p, sizeof(uint64_t) * c->fp.n_rows, cudaMemcpyDeviceToDevice, c->stream));
+    if (max_rows > c->fp.n_rows)
+        CU(cudaMemsetAsync(dst_device + c->fp.n_rows, 0, sizeof(uint64_t) * (size_t)(max_rows - c->fp.n_rows), c->stream));
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_render_finish_interleaved(rt580_context* c, const uint64_t* all_counts_device, int32_t world, int32_t rank,
+                                               int32_t max_rows, int16_t* fb_out, int fb_on_device, rt580_stats* stats)
+{
+    if (!c || !all_counts_device) FAIL(RT580_INVALID_ARG, "rt580_render_finish_interleaved: NULL argument");
+    if (!c->frame_begun) FAIL(RT580_FAILURE, "rt580_render_finish_interleaved: no frame begun");
+    const FrameParams& fp = c->fp;
+    if (world < 1 || rank < 0 || rank >= world || fp.row_step != world || (fp.n_rows && fp.row_first != rank) ||
+        max_rows < (fp.H + world - 1) / world)
+        FAIL(RT580_INVALID_ARG, "rt580_render_finish_interleaved: the frame begun is not rank %d's share of rows interleaved over %d ranks", rank, world);
+    CU(cudaSetDevice(c->device));
+    if (fp.n_rows) {
+        k_row_bases_interleaved<<<1, 1024, 0, c->stream>>>(all_counts_device, world, rank, max_rows, fp.H, c->row_vals.p);
+        c->launches++;
+    }
+    return render_finish_impl(c, nullptr, true, fb_out, fb_on_device, stats);
+}
+
+static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, bool bases_on_device, int16_t* fb_out,
+                              int fb_on_device, rt580_stats* stats)
+{
     CU(cudaSetDevice(c->device));
     FrameParams& fp = c->fp;
     cudaStream_t st = c->stream;
@@ -1740,9 +1882,7 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     const unsigned n_nodes = (unsigned)c->level_off.back();
     const int n_amb = c->sc.n_ambient;
     const int n_levels = (int)c->level_off.size() - 1;
-    if (fp.rng_mode == RT580_RNG_REFERENCE_LCG && !row_ao_base && fp.n_rows)
-        FAIL(RT580_INVALID_ARG, "rt580_render_finish: row_ao_base required in RT580_RNG_REFERENCE_LCG mode");
-    if (row_ao_base && fp.n_rows)
+    if (!bases_on_device && row_ao_base && fp.n_rows)
         CU(cudaMemcpyAsync(c->row_vals.p, row_ao_base, sizeof(uint64_t) * fp.n_rows, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(c->ev[2], st));
     const unsigned long long n_calls = (unsigned long long)n_nodes * n_amb;
@@ -1809,6 +1949,22 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
         }
     }
     CU(cudaEventRecord(c->ev[5], st));
+    if (c->frame && npix) {
+        // multi-GPU: this rank's rows straight into the whole frame on rank 0 (own memory or peer mapping)
+        if (c->frame_w != fp.W || c->frame_h != fp.H)
+            FAIL(RT580_FAILURE, "rt580_render_finish: the shared frame is %dx%d, the render %dx%d", c->frame_w, c->frame_h, fp.W, fp.H);
+        const size_t row_bytes = (size_t)fp.W * 6;
+        if (row_bytes % 16 == 0) {
+            const unsigned units = (unsigned)(row_bytes / 16);
+            k_store_band<uint4><<<nblk((unsigned long long)units * fp.n_rows, 256), 256, 0, st>>>(
+                reinterpret_cast<const uint4*>(c->fb.p), reinterpret_cast<uint4*>(c->frame), units, fp.n_rows, fp.row_first, fp.row_step);
+        } else {
+            const unsigned units = (unsigned)(row_bytes / 2);
+            k_store_band<uint16_t><<<nblk((unsigned long long)units * fp.n_rows, 256), 256, 0, st>>>(
+                reinterpret_cast<const uint16_t*>(c->fb.p), reinterpret_cast<uint16_t*>(c->frame), units, fp.n_rows, fp.row_first, fp.row_step);
+        }
+        c->launches++;
+    }
     if (fb_out && npix)
         CU(cudaMemcpyAsync(fb_out, c->fb.p, sizeof(int16_t) * 3 * (size_t)npix,
                            fb_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
@@ -1828,6 +1984,58 @@ extern "C" int rt580_render_finish(rt580_context* c, const uint64_t* row_ao_base
     if (mode == 0) c->stats.ao_rays_traversed = (uint64_t)cnt[8] | ((uint64_t)cnt[9] << 32);
     if (stats) *stats = c->stats;
     c->frame_begun = false;
+    return RT580_SUCCESS;
+}
+
+// ---- the shared frame of a multi-GPU render ------------------------------------------------
+static void frame_release(rt580_context* c) {
+    if (!c->frame) return;
+    cudaStreamSynchronize(c->stream);
+    if (c->frame_imported) cudaIpcCloseMemHandle(c->frame); else cudaFree(c->frame);
+    c->frame = nullptr; c->frame_imported = false; c->frame_w = c->frame_h = 0;
+}
+extern "C" int rt580_frame_export(rt580_context* c, int32_t width, int32_t height, void* ipc_handle64)
+{
+    if (!c || width <= 0 || height <= 0) FAIL(RT580_INVALID_ARG, "rt580_frame_export: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU(cudaSetDevice(c->device));
+    frame_release(c);
+    // a dedicated cudaMalloc (not the arena): IPC handles export whole allocations
+    CU(cudaMalloc((void**)&c->frame, (size_t)width * height * 3 * sizeof(int16_t)));
+    c->frame_w = width; c->frame_h = height; c->frame_imported = false;
+    if (ipc_handle64) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, c->frame));
+        memcpy(ipc_handle64, &h, sizeof h);
+    }
+    return RT580_SUCCESS;
+}
+extern "C" int rt580_frame_import(rt580_context* c, const void* ipc_handle64, int32_t width, int32_t height)
+{
+    if (!c || !ipc_handle64 || width <= 0 || height <= 0) FAIL(RT580_INVALID_ARG, "rt580_frame_import: bad argument");
+    CU(cudaSetDevice(c->device));
+    frame_release(c);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->frame = (int16_t*)p; c->frame_imported = true; c->frame_w = width; c->frame_h = height;
+    return RT580_SUCCESS;
+}
+extern "C" int rt580_frame_release(rt580_context* c)
+{
+    if (!c) FAIL(RT580_INVALID_ARG, "rt580_frame_release: ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    frame_release(c);
+    return RT580_SUCCESS;
+}
+extern "C" int rt580_frame_read(rt580_context* c, int16_t* fb_out)
+{
+    if (!c || !fb_out) FAIL(RT580_INVALID_ARG, "rt580_frame_read: NULL argument");
+    if (!c->frame || c->frame_imported) FAIL(RT580_FAILURE, "rt580_frame_read: this context does not own a shared frame (rt580_frame_export)");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(fb_out, c->frame, (size_t)c->frame_w * c->frame_h * 3 * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return RT580_SUCCESS;
 }
 

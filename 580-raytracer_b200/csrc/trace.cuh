@@ -252,17 +252,42 @@ __device__ __forceinline__ bool warp_slow_path(const DeviceScene& sc, bool need,
     return found;
 }
 
-// The large primitives kept out of the tree (DeviceScene::n_big): exact test, first, for every ray.
+// The plane part of the reference's triangle test (cpp:367-382) for one plane record (N.xyz, D), with
+// the two division-free rejections of prim_test: can a triangle in this plane still be accepted with
+// t within t_limit?  Same operations on the same values as prim_test, hence the same answer for
+// every triangle of the plane.
+__device__ __forceinline__ bool plane_ahead(float4 pl, V3 O, V3 d, float t_limit) {
+    const V3 N = mk(pl.x, pl.y, pl.z);
+    const float nd = dot(N, d);                                   // cpp:367
+    if (fabsf(nd - 0.0f) <= RT_EPS_F) return false;               // cpp:371
+    const float num = -(dot(N, O) + pl.w);
+    if (num == 0.0f || ((num < 0.0f) != (nd < 0.0f))) return false;
+    return !(fabsf(num) > (t_limit * fabsf(nd)) * 1.000001f);
+}
+
+// The large primitives kept out of the tree (DeviceScene::n_big): exact test, first, for every ray,
+// plane by plane (device_scene.h).
 template <bool ANY>
 __device__ __forceinline__ bool big_scan(const DeviceScene& sc, V3 O, V3 d, HitRec& best)
 {
     bool found = false;
-    for (int k = 0; k < sc.n_big; k++) {
-        const int i = sc.n_leaf + k;
+    for (unsigned long long m = sc.big_sphere_mask; m; m &= m - 1ull) {
+        const int i = sc.n_leaf + (__ffsll((long long)m) - 1);
         float t; int prim;
         if (prim_test<true>(sc.prims + i, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
             if (ANY) return true;
             best.t = t; best.leaf = i; best.prim = prim; found = true;
+        }
+    }
+    for (int j = 0; j < sc.n_big_planes; j++) {
+        if (!plane_ahead(__ldg(sc.big_planes + j), O, d, best.t)) continue;
+        for (unsigned long long m = __ldg(sc.big_masks + j); m; m &= m - 1ull) {
+            const int i = sc.n_leaf + (__ffsll((long long)m) - 1);
+            float t; int prim;
+            if (prim_test<true>(sc.prims + i, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+                if (ANY) return true;
+                best.t = t; best.leaf = i; best.prim = prim; found = true;
+            }
         }
     }
     return found;

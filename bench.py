@@ -182,38 +182,59 @@ def run_ours(args):
     p.row_first, p.row_step, p.n_rows = pkg.rows_for_rank(H, rank, world)
     band = torch.empty((max(p.n_rows, 1), W, 3), dtype=torch.int16, device="cuda")
     max_rows = (H + world - 1) // world
-    # int16 is not an NCCL dtype: the bands are gathered as bytes
-    gather_list = [torch.empty((max_rows, W, 6), dtype=torch.uint8, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
-    padded = torch.zeros((max_rows, W, 3), dtype=torch.int16, device="cuda") if world > 1 else None
+    peer_frame = False
     if world > 1:
-        mine_h = torch.zeros(max_rows, dtype=torch.int64).pin_memory()
+        # the exchange stays on the device: per-row counts all-gathered on the context's stream ...
         mine_d = torch.zeros(max_rows, dtype=torch.int64, device="cuda")
         all_d = torch.zeros((world, max_rows), dtype=torch.int64, device="cuda")
-        all_h = torch.zeros((world, max_rows), dtype=torch.int64).pin_memory()
+        done = torch.zeros(1, dtype=torch.int32, device="cuda")
+        # ... and so does the gather: rank 0 owns the whole frame, the other ranks map it (CUDA IPC) and
+        # store their rows into it over NVLink at the end of rt580_render_finish_interleaved
+        handle = [ctx.frame_export(W, H) if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        if rank != 0:
+            try:
+                ctx.frame_import(handle[0], W, H)
+            except pkg.Rt580Error as e:
+                print("rank %d: cannot map rank 0's frame (%s); falling back to an NCCL gather" % (rank, e), file=sys.stderr)
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        peer_frame = bool(int(ok.item()))
+        if not peer_frame:
+            ctx.frame_release()
+            # int16 is not an NCCL dtype: the bands are gathered as bytes
+            gather_list = [torch.empty((max_rows, W, 6), dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+            padded = torch.zeros((max_rows, W, 3), dtype=torch.int16, device="cuda")
 
     dbg = bool(os.environ.get("RT580_BENCH_DEBUG")) and rank == 0
     tparts = [0.0, 0.0, 0.0, 0.0]
 
     def frame():
-        """one step: this rank's rows; returns (stats, frame on rank 0 or None)"""
+        """one step: this rank's rows; the frame ends up on rank 0 (device memory)"""
         _a = time.perf_counter()
-        counts = ctx.render_begin(p)
-        _b = time.perf_counter()
-        if world > 1:
-            mine_h[:p.n_rows] = torch.from_numpy(counts.astype(np.int64))
-            mine_d.copy_(mine_h, non_blocking=True)
-            dist.all_gather_into_tensor(all_d, mine_d)                    # the one exchange of the LCG mode
-            all_h.copy_(all_d)                                            # one D2H for all ranks' counts
-            per_rank = [all_h[r].numpy().astype(np.uint64) for r in range(world)]
-            bases = pkg.row_bases_from_counts(H, world, per_rank)[rank]
-        else:
+        if world == 1:
+            counts = ctx.render_begin(p)
+            _b = time.perf_counter()
             bases = pkg.row_bases_from_counts(H, 1, [counts])[0]
-        _c = time.perf_counter()
-        _, st = ctx.render_finish(p, bases, device_ptr=band.data_ptr())
-        _d = time.perf_counter()
-        if world > 1:
-            padded[:p.n_rows].copy_(band[:p.n_rows])
-            dist.gather(padded.view(torch.uint8), gather_list, dst=0)     # int16 bands (as bytes) to rank 0 over NVLink
+            _c = time.perf_counter()
+            _, st = ctx.render_finish(p, bases, device_ptr=band.data_ptr())
+            _d = time.perf_counter()
+        else:
+            ctx.render_begin(p, want_counts=False)
+            _b = time.perf_counter()
+            ctx.row_counts_to_device(mine_d.data_ptr(), max_rows)
+            with torch.cuda.stream(ext_stream):
+                dist.all_gather_into_tensor(all_d, mine_d)                # the one exchange of the LCG mode
+            _c = time.perf_counter()
+            st = ctx.render_finish_interleaved(all_d.data_ptr(), world, rank, max_rows,
+                                               device_ptr=None if peer_frame else padded.data_ptr())
+            _d = time.perf_counter()
+            with torch.cuda.stream(ext_stream):
+                if peer_frame:
+                    dist.all_reduce(done)                                  # every rank's rows have landed in rank 0's frame
+                else:
+                    dist.gather(padded.view(torch.uint8), gather_list, dst=0)
         if dbg:
             torch.cuda.synchronize()
             _e = time.perf_counter()
@@ -267,9 +288,34 @@ def run_ours(args):
         wall_step_ms, rays_total, ao_rays_total = wall_ms / args.steps, rays_rank, ao_rays
     value = rays_total / (step_ms * 1e-3) / 1e6
 
+    verify = None
+    if args.verify and world > 1:
+        # the frame the ranks assembled on rank 0 against the same frame rendered by rank 0 alone
+        sync()
+        if rank == 0:
+            if peer_frame:
+                got = ctx.frame_read(W, H)
+                ctx.frame_release()
+            else:
+                got = pkg.interleave_rows(H, W, world, [g.view(torch.int16).reshape(max_rows, W, 3).cpu().numpy() for g in gather_list])
+            want, _ = ctx.render(params)
+            verify = {"multi_gpu_frame_equals_single_gpu_frame": bool(np.array_equal(got, want)), "pixels": int(W * H)}
+            if peer_frame:
+                handle = [ctx.frame_export(W, H)]
+        if peer_frame:
+            # rank 0 released its frame for the check: map the new one
+            if rank != 0:
+                ctx.frame_release()
+                handle = [None]
+            dist.broadcast_object_list(handle, src=0)
+            if rank != 0:
+                ctx.frame_import(handle[0], W, H)
+        sync()
+
     # e2e: the reference-facing call with host buffers, every step: upload (H2D + LBVH build) + render (D2H)
     h2d = int(flat.n_tris * (6 * 16 + 8) + flat.n_spheres * (16 + 8) + flat.n_materials * 32 + flat.n_lights * 44)
-    d2h = int(p.n_rows * W * 6)
+    d2h = int(p.n_rows * W * 6) if world == 1 else int(W * H * 6)
+    host_frame = None
     for _ in range(1):
         ctx.upload_scene(flat); ctx.render(p) if world == 1 else None
     sync()
@@ -286,13 +332,13 @@ def run_ours(args):
             if os.environ.get("RT580_BENCH_DEBUG"):
                 print("e2e render %.1f ms" % ((time.perf_counter() - _t1) * 1e3), file=sys.stderr)
         else:
-            counts = ctx.render_begin(p)
-            mine_h[:p.n_rows] = torch.from_numpy(counts.astype(np.int64))
-            mine_d.copy_(mine_h, non_blocking=True)
-            dist.all_gather_into_tensor(all_d, mine_d)
-            all_h.copy_(all_d)
-            bases = pkg.row_bases_from_counts(H, world, [all_h[r].numpy().astype(np.uint64) for r in range(world)])[rank]
-            ctx.render_finish(p, bases)                                   # host band
+            frame()
+            if rank == 0:
+                torch.cuda.synchronize()
+                if peer_frame:
+                    host_frame = ctx.frame_read(W, H)                     # the whole frame -> host memory on rank 0
+                else:
+                    host_frame = torch.stack(gather_list).cpu()
     sync()
     e2e_ms = (time.perf_counter() - e0) * 1e3 / e_steps
     te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
@@ -328,7 +374,9 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "scene": "977 teapot instances (1,000,448 triangles) + 1000 spheres + closed double-walled room (24 triangles), seed 580",
                            "width": W, "height": H, "depth": DEPTH, "ao_spp": SPP, "rng": "reference_lcg", "farfield": args.farfield, "far_scans": st0.far_scans, "linear_fallbacks": st0.linear_fallbacks,
-                           "partition": "rows interleaved over %d rank(s)" % world, "l2": "working set > L2: nodes+records %.0f MB, frame data %.0f MB/step" % (
+                           "partition": "rows interleaved over %d rank(s)" % world,
+                           "gather": ("none" if world == 1 else ("peer stores into rank 0's frame over NVLink (CUDA IPC), row counts all-gathered on the device"
+                                                                  if peer_frame else "NCCL gather of int16 bands")), "l2": "working set > L2: nodes+records %.0f MB, frame data %.0f MB/step" % (
                                info.n_leaf * 144 / 1e6, st0.hit_nodes * 110 / 1e6)},
                 "rays_per_frame": rays_total, "ms_per_frame_4k": step_ms, "wall_ms_per_step": wall_step_ms,
                 "phases_ms": {"structure": st0.ms_structure, "order": st0.ms_order, "ao": st0.ms_ao, "resolve": st0.ms_resolve},
@@ -341,7 +389,7 @@ def run_ours(args):
                 "scene_info": info.as_dict(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": float(te[0]), "includes": "rt580_upload_scene (H2D + LBVH build) + rt580_render (D2H int16 frame)"},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "verify": verify, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "clocks": sampler.summary() if sampler else None}
         print(json.dumps(line))
     if world > 1:
@@ -357,6 +405,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="N > 1: compare the assembled frame with rank 0's own single-GPU frame")
     ap.add_argument("--farfield", default="exact", choices=["exact", "off"], help="debug only")
     ap.add_argument("--workload", default=WORKLOAD, help="debug only")
     ap.add_argument("--width", type=int, default=0, help="debug only: override the frame width")

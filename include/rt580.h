@@ -168,6 +168,33 @@ int  rt580_render_begin(rt580_context* ctx, const rt580_render_params* params, u
 int  rt580_render_finish(rt580_context* ctx, const uint64_t* row_ao_base, int16_t* fb_out, int fb_on_device,
                          rt580_stats* stats);
 
+/* ---- several GPUs, one frame: the exchange and the gather without leaving the device -----
+ * The reference renders its rows in one loop (cpp:921-922) and shares one random stream between
+ * them (h:592).  With rows interleaved over `world` contexts (row y -> rank y % world), what the
+ * ranks must exchange is the per-row hit-node count (for the stream position of every row) and,
+ * at the end, the rows themselves.  Both stay on the device:
+ *   rt580_row_counts_to_device     after rt580_render_begin (row_hit_nodes may then be NULL): the
+ *                                  counts of this context's rows -> dst_device[max_rows] (zero padded),
+ *                                  on the context's stream; the caller all-gathers them (NCCL) into
+ *                                  all_counts_device[world][max_rows] on the same stream;
+ *   rt580_render_finish_interleaved computes this rank's row_ao_base from all_counts_device on the
+ *                                  device and finishes the frame like rt580_render_finish;
+ *   rt580_frame_export / _import   rank 0 allocates the whole width x height frame and exports a
+ *                                  64-byte CUDA IPC handle; the other ranks' contexts map it.  While
+ *                                  a context has a shared frame, every finish stores its rows into
+ *                                  it (for the importing ranks these are stores over NVLink to rank
+ *                                  0's memory): no NCCL gather, no staging.  The caller orders rank
+ *                                  0's read after the other ranks' stores (one tiny collective on
+ *                                  the contexts' streams);
+ *   rt580_frame_read               rank 0: the whole frame -> host [height][width][3] int16. */
+int  rt580_row_counts_to_device(rt580_context* ctx, uint64_t* dst_device, int32_t max_rows);
+int  rt580_render_finish_interleaved(rt580_context* ctx, const uint64_t* all_counts_device, int32_t world, int32_t rank,
+                                     int32_t max_rows, int16_t* fb_out, int fb_on_device, rt580_stats* stats);
+int  rt580_frame_export(rt580_context* ctx, int32_t width, int32_t height, void* ipc_handle64);
+int  rt580_frame_import(rt580_context* ctx, const void* ipc_handle64, int32_t width, int32_t height);
+int  rt580_frame_release(rt580_context* ctx);
+int  rt580_frame_read(rt580_context* ctx, int16_t* fb_out);
+
 /* ---- checkers (used by the parity tests; same kernels as the frame path) ---------------- */
 /* Closest hit of n arbitrary rays: prim_out = primitive order index or -1, t_out = distance. */
 int  rt580_trace_closest(rt580_context* ctx, int64_t n, const float* org3, const float* dir3, int traversal,
