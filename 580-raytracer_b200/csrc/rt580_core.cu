@@ -171,6 +171,8 @@ struct rt580_context {
     int16_t* frame = nullptr; bool frame_imported = false; int frame_w = 0, frame_h = 0;
     DBuf<struct ARay> arays;       // one chunk of generated any-hit rays (AO samples / shadow rays)
     DBuf<uint32_t> occl;           // per shadow ray of the current level: occluders found
+    DBuf<struct CHit> chits;       // per queued secondary ray: what the tree answered (k_closest -> k_commit)
+    int ch_blocks_per_sm = 10; bool one_thread_per_ray = false;   // RT580_CH_BLOCKS_PER_SM, RT580_ONE_THREAD_PER_RAY (A/B)
     uint64_t slow_total = 0;
     int ah_steps = AH_STEPS, ah_min_search = AH_MIN_SEARCH, ah_blocks_per_sm = 12;  // k_anyhit tuning (env RT580_AH_*)
     std::vector<size_t> level_off; // node index where each level starts (+ end)
@@ -255,6 +257,46 @@ __device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* s
         }
     }
     if (sc.farfield) found = warp_slow_path<ANY>(sc, need, linear, O, d, hit, found);
+    return pending ? TR_PENDING : (found ? TR_HIT : TR_MISS);
+}
+
+// Closest hit, second half, for rays whose tree traversal ran elsewhere (k_closest): `hit` comes in
+// with the tree's answer (leaf -1: nothing, leaf -2: the ray starts outside the padded extent and was
+// not traversed) and leaves with the closest hit over the tree, the large-primitive list, the sliver
+// list and - deferred or in place, as in trace_ray - the far field.  Called by all 32 lanes.
+__device__ __forceinline__ int finish_closest(const DeviceScene& sc, bool active, V3 O, V3 d, HitRec& hit, SlowQ q, int ca)
+{
+    bool found = false, need = false, linear = false, pending = false;
+    if (active) {
+        if (hit.leaf == -2) {
+            need = true; linear = true;
+            hit.t = __int_as_float(0x7f800000); hit.leaf = -1; hit.prim = 0x7fffffff;
+            if (sc.diag) atomicAdd(sc.diag + 1, 1u);
+        } else {
+            found = hit.leaf >= 0;
+            found = big_scan<false>(sc, O, d, hit) || found;
+            const bool zero_dir = (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f);
+            if (sc.farfield && !zero_dir) {
+                if (sc.n_always) found = always_scan<false>(sc, O, d, hit, found);
+                need = !found || hit.t >= sc.far_tmin;
+                if (need && sc.diag) atomicAdd(sc.diag, 1u);
+            }
+        }
+        if (need && q.rays) {
+            const unsigned slot = atomicAdd(q.count, 1u);
+            if (slot < q.cap) {
+                SlowRay r;
+                r.o = make_float4(O.x, O.y, O.z, hit.t);
+                r.d = make_float4(d.x, d.y, d.z, __int_as_float(hit.prim));
+                r.c = make_int4(linear ? 1 : 0, ca, 0, found ? hit.leaf : -1);
+                q.rays[slot] = r;
+                SlowRes a; a.key = slow_key(hit.t, hit.prim); a.found = 0; a.pad = 0;
+                q.res[slot] = a;
+                pending = true; need = false;
+            }
+        }
+    }
+    if (sc.farfield) found = warp_slow_path<false>(sc, need, linear, O, d, hit, found);
     return pending ? TR_PENDING : (found ? TR_HIT : TR_MISS);
 }
 
@@ -488,6 +530,137 @@ k_trace_finish(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, c
     commit_closest<PRIMARY>(sc.prims, hit, h, O, d, parent, pixel, flags, slot, node_cap, nodes, aux, pix_hits, fb);
 }
 
+// ---- closest hit of the queued reflection / refraction rays, wavefront form ----------------
+// k_trace<secondary> maps one thread to one ray: the rays of a warp scatter over the scene and end
+// after very different numbers of node visits (ncu: 13-17 of 32 lanes active, the leaf tests at 9).
+// As in k_anyhit the traversal becomes a persistent kernel whose lanes fetch the next ray when theirs
+// is done and which runs inner nodes and leaf tests as two phases; it only walks the tree and leaves
+// (t, leaf, prim) per ray.  k_commit (one thread per ray, convergent) then adds the large-primitive
+// list, the sliver list and the far field, and creates the nodes exactly as k_trace does.
+struct __align__(16) CHit { float t; int leaf; int prim; int pad; };
+
+__global__ void __launch_bounds__(128)
+k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __restrict__ n_ptr, unsigned n_bound,
+          unsigned int* __restrict__ next_ray, CHit* __restrict__ out, int ah_steps, int ah_min_search)
+{
+    const unsigned n = min(__ldg(n_ptr), n_bound);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned batch = n / (gridDim.x * (blockDim.x >> 5) * 4u);
+    batch = batch > (unsigned)AH_BATCH ? (unsigned)AH_BATCH : (batch < 32u ? 32u : (batch & ~31u));
+    bool active = false;
+    V3 O = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
+    float best_t = 0.f; int best_leaf = -1, best_prim = 0x7fffffff; unsigned idx = 0;
+    int stack[RT_STACK_SIZE];
+    int sp = 0, cur = AH_NONE;
+    bool last_batch = false;
+    unsigned wnext = 0, wend = 0;
+    for (;;) {
+        const bool exhausted = last_batch && wnext == wend;
+        if (!exhausted) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            if (idle) {
+                const unsigned want = (unsigned)__popc(idle);
+                if (wend - wnext < want) {
+                    if (wnext == wend && !last_batch) {
+                        unsigned b = 0;
+                        if (lane == 0) b = atomicAdd(next_ray, batch);
+                        wnext = __shfl_sync(0xffffffffu, b, 0);
+                        wend = wnext + batch;
+                        if (wend >= n) { last_batch = true; if (wend > n) wend = n; if (wnext > n) wnext = n; }
+                    }
+                }
+                const unsigned base = wnext;
+                const unsigned give = min(want, wend - wnext);
+                wnext += give;
+                if (!active) {
+                    const unsigned rank = (unsigned)__popc(idle & lt_mask);
+                    if (rank < give) {
+                        idx = base + rank;
+                        const float4 qo = __ldg(&queue[idx].o), qd = __ldg(&queue[idx].d);
+                        O = mk(qo.x, qo.y, qo.z); d = mk(qd.x, qd.y, qd.z);
+                        best_t = __int_as_float(0x7f800000); best_leaf = -1; best_prim = 0x7fffffff;
+                        if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent) {
+                            CHit h; h.t = best_t; h.leaf = -2; h.prim = best_prim; h.pad = 0;   // not traversed: k_commit takes the linear loop
+                            out[idx] = h;
+                        } else if (sc.n_leaf > 0) {
+                            inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                            cur = 0; sp = 0; active = true;
+                        } else {
+                            CHit h; h.t = best_t; h.leaf = -1; h.prim = best_prim; h.pad = 0;
+                            out[idx] = h;
+                        }
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) { if (last_batch && wnext == wend) break; continue; }
+        // phase 1: inner nodes
+#pragma unroll 1
+        for (int it = 0; it < ah_steps; it++) {
+            const bool searching = active && cur >= 0 && cur != AH_NONE;
+            const int n_search = __popc(__ballot_sync(0xffffffffu, searching));
+            const bool leaf_work = __any_sync(0xffffffffu, active && !searching);
+            if (n_search == 0 || (n_search < ah_min_search && leaf_work)) break;
+            if (searching) {
+                const BvhNode* __restrict__ nd = sc.nodes + cur;
+                const float4 xy0 = __ldg(&nd->xy0), xy1 = __ldg(&nd->xy1), z01 = __ldg(&nd->z01);
+                const int4 kids = __ldg(&nd->kids);
+                float tn0, tn1;
+                const bool h0 = slab(xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, O, inv, best_t, tn0);
+                const bool h1 = slab(xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, O, inv, best_t, tn1);
+                if (h0 && h1) {
+                    int nearc = kids.x, farc = kids.y;
+                    if (tn1 < tn0) { nearc = kids.y; farc = kids.x; }
+                    if (sp < RT_STACK_SIZE) stack[sp++] = farc;
+                    cur = nearc;
+                } else if (h0) cur = kids.x;
+                else if (h1) cur = kids.y;
+                else if (sp > 0) cur = stack[--sp];
+                else cur = AH_NONE;
+            }
+        }
+        // phase 2: one leaf per lane, or the end of the ray
+        if (active) {
+            if (cur != AH_NONE && cur < 0) {
+                float t; int prim;
+                if (prim_test<true>(sc.prims + (~cur), O, d, best_t, best_prim, t, prim)) { best_t = t; best_leaf = ~cur; best_prim = prim; }
+                cur = (sp > 0) ? stack[--sp] : AH_NONE;
+            }
+            if (cur == AH_NONE) {
+                CHit h; h.t = best_t; h.leaf = best_leaf; h.prim = best_prim; h.pad = 0;
+                out[idx] = h;
+                active = false;
+            }
+        }
+    }
+}
+
+// one thread per queued ray: the rest of the closest-hit search and what cpp:30-32 does with the answer
+__global__ void __launch_bounds__(128)
+k_commit(DeviceScene sc, const QRay* __restrict__ queue, unsigned n_items, const unsigned int* __restrict__ n_items_dev,
+         const CHit* __restrict__ chits, Node* __restrict__ nodes, NodeAux* __restrict__ aux, unsigned int* __restrict__ counters,
+         uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap, SlowQ sq)
+{
+    if (n_items_dev) n_items = min(n_items, __ldg(n_items_dev));
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n_items;
+    V3 O = mk(0, 0, 0), d = mk(0, 0, 0);
+    int parent = -1; unsigned flags = 0;
+    HitRec h; h.t = __int_as_float(0x7f800000); h.leaf = -1; h.prim = 0x7fffffff;
+    if (active) {
+        const float4 qo = queue[i].o, qd = queue[i].d;
+        O = mk(qo.x, qo.y, qo.z); d = mk(qd.x, qd.y, qd.z);
+        parent = __float_as_int(qo.w); flags = __float_as_uint(qd.w);
+        const CHit c = chits[i];
+        h.t = c.t; h.leaf = c.leaf; h.prim = c.prim;
+    }
+    const int tr = finish_closest(sc, active, O, d, h, sq, (int)i);
+    const unsigned slot = warp_alloc(&counters[0], tr == TR_HIT);
+    if (!active || tr == TR_PENDING) return;
+    commit_closest<false>(sc.prims, tr == TR_HIT, h, O, d, parent, 0, flags, slot, node_cap, nodes, aux, pix_hits, fb);
+}
+
 // shading normal of a node (cpp:225-236): interpolated object-space vertex normals for a triangle
 // (InterpolateVector3 cpp:333-338, normalised once there), the geometric hit normal for a sphere
 __device__ __forceinline__ V3 shading_normal(const DeviceScene& sc, const Node& nd, unsigned flags, int prim) {
@@ -655,7 +828,7 @@ k_shadow_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays
 
 // shadow rays of one level as a ray queue for k_anyhit: ray id = (node - n0) * n_nonambient + j
 __global__ void __launch_bounds__(256)
-k_shade_gen(DeviceScene sc, unsigned n0, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
+k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
             struct ARay* __restrict__ out, unsigned int* __restrict__ n_out);
 
 // deferred AO rays of k_ao: a hit is one more occluded sample of its AO call (cpp:325-326)
@@ -902,23 +1075,27 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
 }
 
 __global__ void __launch_bounds__(256)
-k_shade_gen(DeviceScene sc, unsigned n0, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
+k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
             ARay* __restrict__ out, unsigned int* __restrict__ n_out)
 {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) *n_out = n;
     if (t >= n) return;
-    const unsigned long long id = first + t;
-    const unsigned node = n0 + (unsigned)(id / (unsigned)sc.n_nonambient);
-    int j = (int)(id % (unsigned)sc.n_nonambient), li = 0;
+    // queue order = light-major: the lanes of a warp take neighbouring nodes and the SAME light, so their
+    // rays run to one point and walk the tree together (node-major order put three lights in adjacent lanes)
+    const unsigned long long q = first + t;
+    int j = (int)(q / n_level);
+    const unsigned m = (unsigned)(q % n_level);
+    const unsigned id = m * (unsigned)sc.n_nonambient + (unsigned)j;      // ray id = (node - n0) * n_nonambient + j
+    int li = 0;
     for (;; li++) { if (__ldg(sc.light_type + li) != RT580_LIGHT_AMBIENT) { if (j == 0) break; j--; } }
     const Light L = load_light(sc.light_type, sc.light_f, li);
-    const float4 nP = __ldg(&nodes[node].P);
+    const float4 nP = __ldg(&nodes[n0 + m].P);
     V3 so, sd; float tmax;
     shadow_ray(L, mk(nP.x, nP.y, nP.z), so, sd, tmax);
     ARay r;
     r.a = make_float4(so.x, so.y, so.z, sd.x);
-    r.b = make_float4(sd.y, sd.z, __uint_as_float((unsigned)id), tmax);
+    r.b = make_float4(sd.y, sd.z, __uint_as_float(id), tmax);
     out[t] = r;
 }
 
@@ -1231,6 +1408,8 @@ extern "C" int rt580_create(int device, rt580_context** out)
     if (const char* e = getenv("RT580_AH_STEPS")) c->ah_steps = atoi(e) > 0 ? atoi(e) : c->ah_steps;
     if (const char* e = getenv("RT580_AH_MIN_SEARCH")) c->ah_min_search = atoi(e) > 0 ? atoi(e) : c->ah_min_search;
     if (const char* e = getenv("RT580_AH_BLOCKS_PER_SM")) c->ah_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ah_blocks_per_sm;
+    if (const char* e = getenv("RT580_CH_BLOCKS_PER_SM")) c->ch_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ch_blocks_per_sm;
+    if (const char* e = getenv("RT580_ONE_THREAD_PER_RAY")) c->one_thread_per_ray = atoi(e) != 0;
     *out = c;
     return RT580_SUCCESS;
 }
@@ -1253,7 +1432,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     c->ndc.release(); c->lcg_pow.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
-    c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release();
+    c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release(); c->chits.release();
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1748,7 +1927,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                 }
                 const int rc = anyhit_queue_pass(c, n_sh, c->occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
                     [&](unsigned long long first, unsigned n) {
-                        k_shade_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6);
+                        k_shade_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6);
                     });
                 if (rc) return rc;
             }
@@ -1772,7 +1951,18 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         if (L == fp.depth) break;
         // the queued reflection / refraction rays: their number stays on the device (counters[1])
         if (slow_prepare(c, q_max, &slow_cap)) return RT580_FAILURE;
-        DISPATCH_MODE(mode, launch_trace, c, false, q_max, c->counters.p + 1, (unsigned)c->nodes.cap, slow_cap);
+        if (mode == 0 && !c->one_thread_per_ray) {
+            CU(c->chits.ensure((size_t)q_max + 1, 0, st));
+            CU(cudaMemsetAsync(c->counters.p + 7, 0, sizeof(unsigned), st));
+            const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ch_blocks_per_sm;
+            k_closest<<<blocks, 128, 0, st>>>(c->sc, c->queue.p, c->counters.p + 1, q_max, c->counters.p + 7, c->chits.p,
+                                              c->ah_steps, c->ah_min_search);
+            k_commit<<<nblk(q_max, 128), 128, 0, st>>>(c->sc, c->queue.p, q_max, c->counters.p + 1, c->chits.p, c->nodes.p, c->aux.p,
+                                                       c->counters.p, c->pix_hits.p, c->fb.p, (unsigned)c->nodes.cap, slowq(c, slow_cap));
+            c->launches += 2;
+        } else {
+            DISPATCH_MODE(mode, launch_trace, c, false, q_max, c->counters.p + 1, (unsigned)c->nodes.cap, slow_cap);
+        }
         if (read_counters(c, cnt)) return RT580_FAILURE;
         const unsigned q = cnt[1];
         if (q == 0) break;

@@ -207,8 +207,8 @@ def run_ours(args):
             gather_list = [torch.empty((max_rows, W, 6), dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
             padded = torch.zeros((max_rows, W, 3), dtype=torch.int16, device="cuda")
 
-    dbg = bool(os.environ.get("RT580_BENCH_DEBUG")) and rank == 0
-    tparts = [0.0, 0.0, 0.0, 0.0]
+    dbg = bool(os.environ.get("RT580_BENCH_DEBUG")) and (rank == 0 or os.environ.get("RT580_BENCH_DEBUG") == "2")
+    tparts = [0.0] * 8
 
     def frame():
         """one step: this rank's rows; the frame ends up on rank 0 (device memory)"""
@@ -240,6 +240,7 @@ def run_ours(args):
             _e = time.perf_counter()
             for k, v in enumerate([_b - _a, _c - _b, _d - _c, _e - _d]):
                 tparts[k] += v * 1e3
+            tparts[4] += st.ms_structure; tparts[5] += st.ms_order; tparts[6] += st.ms_ao; tparts[7] += st.ms_resolve
         return st
 
     def sync():
@@ -271,7 +272,8 @@ def run_ours(args):
         sampler.join(timeout=2)
     if dbg:
         n_fr = args.steps + args.warmup
-        print("rank0 wall ms/frame: begin %.2f  exchange %.2f  finish %.2f  gather %.2f" % tuple(t / n_fr for t in tparts), file=sys.stderr)
+        print("rank %d wall ms/frame: begin %.3f  exchange %.3f  finish %.3f  gather %.3f | device: structure %.3f order %.3f ao %.3f resolve %.3f" % (
+            (rank,) + tuple(t / n_fr for t in tparts)), file=sys.stderr)
     step_ms = max(dev_ms, 0.0) / args.steps
     rays_rank = float(np.mean([s.rays for s in stats]))
     ao_ms = float(np.mean([s.ms_ao_kernel for s in stats]))
