@@ -26,7 +26,7 @@ LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AMBIENT = 0, 1, 2
 
 # every symbol include/rt580.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
-    "rt580_create", "rt580_destroy", "rt580_last_error", "rt580_device_info", "rt580_upload_scene", "rt580_build_ms",
+    "rt580_create", "rt580_destroy", "rt580_last_error", "rt580_device_info", "rt580_host_alloc", "rt580_host_free", "rt580_upload_scene", "rt580_build_ms",
     "rt580_scene_info_get", "rt580_get_stream",
     "rt580_render", "rt580_render_begin", "rt580_render_finish", "rt580_row_counts_to_device", "rt580_render_finish_interleaved",
     "rt580_frame_export", "rt580_frame_import", "rt580_frame_release", "rt580_frame_read", "rt580_trace_closest", "rt580_trace_any", "rt580_trace_profile",
@@ -127,6 +127,10 @@ def lib():
         L.rt580_destroy.restype = None
         L.rt580_device_info.argtypes = [vp, vp, vp, vp]
         L.rt580_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
+        L.rt580_host_alloc.restype = vp
+        L.rt580_host_alloc.argtypes = [ctypes.c_uint64]
+        L.rt580_host_free.restype = None
+        L.rt580_host_free.argtypes = [vp]
         L.rt580_upload_scene.argtypes = [vp, ctypes.POINTER(FlatScene)]
         L.rt580_build_ms.argtypes = [vp, vp]
         L.rt580_scene_info_get.argtypes = [vp, ctypes.POINTER(SceneInfo)]
@@ -212,9 +216,12 @@ class Context:
         _check(lib().rt580_build_ms(self._h, ctypes.addressof(ms)))
         return ms.value
 
-    def render(self, params: RenderParams):
+    def render(self, params: RenderParams, out=None):
+        """Whole frame (or the rows in params) -> host int16 [n_rows][width][3]; `out`: a preallocated
+        array to fill (e.g. over page-locked memory, host_array())."""
         n_rows = params.n_rows or params.height
-        fb = np.empty((n_rows, params.width, 3), np.int16)
+        fb = np.empty((n_rows, params.width, 3), np.int16) if out is None else out
+        assert fb.dtype == np.int16 and fb.size == n_rows * params.width * 3 and fb.flags["C_CONTIGUOUS"]
         st = Stats()
         _check(lib().rt580_render(self._h, ctypes.byref(params), fb.ctypes.data, ctypes.byref(st)))
         return fb, st
@@ -410,6 +417,31 @@ def flat_scene_arrays(fs: FlatScene):
         "light_type": arr(fs.light_type, fs.n_lights, 1, np.int32),
         "light_f": arr(fs.light_f, fs.n_lights, 10, np.float32),
     }
+
+
+class HostArray:
+    """numpy array over rt580_host_alloc memory (page-locked when a GPU is present)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * self.dtype.itemsize
+        self._p = lib().rt580_host_alloc(max(n, 1))
+        if not self._p:
+            raise MemoryError("rt580_host_alloc(%d)" % n)
+        buf = (ctypes.c_char * max(n, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, self.dtype, int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            lib().rt580_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- multi-GPU host logic (pure index arithmetic; the collectives live in bench.py / callers) ----

@@ -276,7 +276,7 @@ int Raytracer::FlattenScene() {
     mTriPrim.reserve(nt); mTriMaterial.reserve(nt);
     int64_t prim = 0;
     int32_t shapeIdx = 0;
-    auto push4 = [](std::vector<float>& v, V3 p) { v.push_back(p.x); v.push_back(p.y); v.push_back(p.z); v.push_back(0.0f); };
+    auto push4 = [](Rt580HostVector<float>& v, V3 p) { v.push_back(p.x); v.push_back(p.y); v.push_back(p.z); v.push_back(0.0f); };
     for (const Shape& sh : mScene->shapes) {
         const Mesh& mesh = mScene->meshMap.find(sh.geometryId)->second;
         const Material& m = sh.material;

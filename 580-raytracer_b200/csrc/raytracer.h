@@ -17,9 +17,23 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <new>
 #include <string>
 #include <vector>
 #include "../../include/rt580.h"
+
+// std::vector over rt580_host_alloc (page-locked when a GPU is present): the flattened scene and the
+// frame buffer cross PCIe at full speed
+template <class T> struct Rt580HostAlloc {
+    using value_type = T;
+    Rt580HostAlloc() = default;
+    template <class U> Rt580HostAlloc(const Rt580HostAlloc<U>&) {}
+    T* allocate(size_t n) { void* p = rt580_host_alloc((uint64_t)n * sizeof(T)); if (!p) throw std::bad_alloc(); return static_cast<T*>(p); }
+    void deallocate(T* p, size_t) { rt580_host_free(p); }
+    template <class U> bool operator==(const Rt580HostAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const Rt580HostAlloc<U>&) const { return false; }
+};
+template <class T> using Rt580HostVector = std::vector<T, Rt580HostAlloc<T>>;
 
 #define RT_SUCCESS      0
 #define RT_FAILURE      1
@@ -93,7 +107,7 @@ private:
     std::string mAssetsPath = "Assets/";
     int mWidth, mHeight;
     float mFov = 60.0f;                                                // cpp:786
-    std::vector<Pixel> mFrameBuffer;                                   // Display::frameBuffer h:423
+    Rt580HostVector<Pixel> mFrameBuffer;                               // Display::frameBuffer h:423
     Scene* mScene = nullptr;
     int mSceneStatus = RT_SUCCESS;
     int mDepth = 4, mAoSpp = 128, mRngMode = RT580_RNG_REFERENCE_LCG, mTraversal = RT580_TRAVERSAL_AUTO, mDevice = 0,
@@ -103,8 +117,10 @@ private:
     bool mQuiet = false;
 
     // flattened scene (host SoA, float4 records) handed to rt580_upload_scene
-    std::vector<float> mTriV0, mTriV1, mTriV2, mTriN0, mTriN1, mTriN2, mSphere, mMaterials, mLightF;
-    std::vector<int32_t> mTriPrim, mTriMaterial, mSphPrim, mSphMaterial, mLightType;
+    Rt580HostVector<float> mTriV0, mTriV1, mTriV2, mTriN0, mTriN1, mTriN2;
+    std::vector<float> mSphere, mMaterials, mLightF;
+    Rt580HostVector<int32_t> mTriPrim, mTriMaterial;
+    std::vector<int32_t> mSphPrim, mSphMaterial, mLightType;
     int64_t mNumPrims = 0;
 
     rt580_context* mCtx = nullptr;

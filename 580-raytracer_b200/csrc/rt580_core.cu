@@ -174,6 +174,7 @@ struct rt580_context {
     DBuf<struct CHit> chits;       // per queued secondary ray: what the tree answered (k_closest -> k_commit)
     int ch_blocks_per_sm = 10; bool one_thread_per_ray = false;   // RT580_CH_BLOCKS_PER_SM, RT580_ONE_THREAD_PER_RAY (A/B)
     uint64_t slow_total = 0;
+    int ah_batch_div = 4;
     int ah_steps = AH_STEPS, ah_min_search = AH_MIN_SEARCH, ah_blocks_per_sm = 12;  // k_anyhit tuning (env RT580_AH_*)
     std::vector<size_t> level_off; // node index where each level starts (+ end)
     std::vector<uint64_t> level_rays;
@@ -541,12 +542,12 @@ struct __align__(16) CHit { float t; int leaf; int prim; int pad; };
 
 __global__ void __launch_bounds__(128)
 k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __restrict__ n_ptr, unsigned n_bound,
-          unsigned int* __restrict__ next_ray, CHit* __restrict__ out, int ah_steps, int ah_min_search)
+          unsigned int* __restrict__ next_ray, CHit* __restrict__ out, int ah_steps, int ah_min_search, int batch_div)
 {
     const unsigned n = min(__ldg(n_ptr), n_bound);
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned batch = n / (gridDim.x * (blockDim.x >> 5) * 4u);
+    unsigned batch = n / (gridDim.x * (blockDim.x >> 5) * (unsigned)batch_div);
     batch = batch > (unsigned)AH_BATCH ? (unsigned)AH_BATCH : (batch < 32u ? 32u : (batch & ~31u));
     bool active = false;
     V3 O = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
@@ -1120,7 +1121,7 @@ __device__ __forceinline__ bool defer_any(const SlowQ& sq, V3 O, V3 d, float tma
 __global__ void __launch_bounds__(128)
 k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __restrict__ n_ptr,
          unsigned int* __restrict__ next_ray, uint32_t* __restrict__ hit_count, SlowQ sq, unsigned id_offset,
-         unsigned pending_mark, unsigned long long* __restrict__ traversed_acc, int ah_steps, int ah_min_search)
+         unsigned pending_mark, unsigned long long* __restrict__ traversed_acc, int ah_steps, int ah_min_search, int batch_div)
 {
     const unsigned n = __ldg(n_ptr);
     if (traversed_acc && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(traversed_acc, (unsigned long long)n);
@@ -1128,7 +1129,7 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
     const unsigned lt_mask = (1u << lane) - 1u;
     // rays a warp reserves per atomic on the queue counter: large for long queues (a single hot counter
     // would serialise the GPU), small for short ones (the last batches are the tail of the kernel)
-    unsigned batch = n / (gridDim.x * (blockDim.x >> 5) * 4u);
+    unsigned batch = n / (gridDim.x * (blockDim.x >> 5) * (unsigned)batch_div);
     batch = batch > (unsigned)AH_BATCH ? (unsigned)AH_BATCH : (batch < 32u ? 32u : (batch & ~31u));
     bool active = false;
     V3 O = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
@@ -1383,10 +1384,56 @@ __global__ void k_powf(long long n, const float* __restrict__ x, const float* __
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+// Shading tables addressed by primitive order index (vertex normals, material index), scattered on the
+// device from the flat arrays as they were uploaded: the host used to assemble them (a 48 MB loop per upload).
+__global__ void __launch_bounds__(256)
+k_scatter_shading(long long n_tris, const float4* __restrict__ n0, const float4* __restrict__ n1, const float4* __restrict__ n2,
+                  const int32_t* __restrict__ tri_prim, const int32_t* __restrict__ tri_material, long long n_spheres,
+                  const int32_t* __restrict__ sph_prim, const int32_t* __restrict__ sph_material, long long n_prims,
+                  int n_materials, float4* __restrict__ vn, int32_t* __restrict__ prim_material, unsigned int* __restrict__ bad)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tris) {
+        const int32_t p = tri_prim[i], m = tri_material[i];
+        if (p < 0 || p >= n_prims) { atomicOr(bad, 1u); return; }
+        if (m < 0 || m >= n_materials) { atomicOr(bad, 2u); return; }
+        vn[3 * (size_t)p] = n0[i]; vn[3 * (size_t)p + 1] = n1[i]; vn[3 * (size_t)p + 2] = n2[i];
+        prim_material[p] = m;
+    } else if (i < n_tris + n_spheres) {
+        const long long k = i - n_tris;
+        const int32_t p = sph_prim[k], m = sph_material[k];
+        if (p < 0 || p >= n_prims) { atomicOr(bad, 4u); return; }
+        if (m < 0 || m >= n_materials) { atomicOr(bad, 2u); return; }
+        prim_material[p] = m;
+    }
+}
+
 static int pick_mode(const rt580_context* c, int traversal) {
     if (traversal == RT580_TRAVERSAL_BVH) return 0;
     if (traversal == RT580_TRAVERSAL_BRUTE_FORCE) return c->sc.n_all <= RT_SMEM_PRIMS ? 1 : 2;
     return c->sc.n_all <= RT_SMEM_PRIMS ? 1 : 0;     // AUTO
+}
+
+// Host staging memory (rt580.h): a 64-byte header in front of the block remembers how it was obtained.
+extern "C" void* rt580_host_alloc(uint64_t bytes)
+{
+    static const bool have_gpu = [] { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess && n > 0; }();
+    void* base = nullptr;
+    uint64_t pinned = 0;
+    if (have_gpu && cudaHostAlloc(&base, (size_t)bytes + 64, cudaHostAllocPortable) == cudaSuccess) pinned = 1;
+    else { cudaGetLastError(); base = malloc((size_t)bytes + 64); }
+    if (!base) return nullptr;
+    uint64_t* h = static_cast<uint64_t*>(base);
+    h[0] = 0x52543538304d454dull; h[1] = pinned;
+    return static_cast<char*>(base) + 64;
+}
+extern "C" void rt580_host_free(void* p)
+{
+    if (!p) return;
+    uint64_t* h = reinterpret_cast<uint64_t*>(static_cast<char*>(p) - 64);
+    if (h[0] != 0x52543538304d454dull) return;          // not ours
+    h[0] = 0;
+    if (h[1]) cudaFreeHost(h); else free(h);
 }
 
 extern "C" int rt580_create(int device, rt580_context** out)
@@ -1408,6 +1455,7 @@ extern "C" int rt580_create(int device, rt580_context** out)
     if (const char* e = getenv("RT580_AH_STEPS")) c->ah_steps = atoi(e) > 0 ? atoi(e) : c->ah_steps;
     if (const char* e = getenv("RT580_AH_MIN_SEARCH")) c->ah_min_search = atoi(e) > 0 ? atoi(e) : c->ah_min_search;
     if (const char* e = getenv("RT580_AH_BLOCKS_PER_SM")) c->ah_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ah_blocks_per_sm;
+    if (const char* e = getenv("RT580_AH_BATCH_DIV")) c->ah_batch_div = atoi(e) > 0 ? atoi(e) : c->ah_batch_div;
     if (const char* e = getenv("RT580_CH_BLOCKS_PER_SM")) c->ch_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ch_blocks_per_sm;
     if (const char* e = getenv("RT580_ONE_THREAD_PER_RAY")) c->one_thread_per_ray = atoi(e) != 0;
     *out = c;
@@ -1454,6 +1502,7 @@ extern "C" int rt580_get_stream(rt580_context* c, void** cuda_stream)
     return RT580_SUCCESS;
 }
 
+static inline unsigned nblk_ll(long long n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 template <typename T> static cudaError_t upload(DevArena& a, T** dst, const void* src, size_t count, cudaStream_t s) {
     *dst = a.take<T>(count);
     if (!*dst) return cudaErrorMemoryAllocation;
@@ -1473,7 +1522,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     CU(cudaStreamSynchronize(st));
     {
         char aerr[256] = "";
-        const size_t in_bytes = (size_t)s->n_tris * (3 * 16 + 4) + (size_t)s->n_spheres * (16 + 4) + 16 * 256;
+        const size_t in_bytes = (size_t)s->n_tris * (6 * 16 + 8) + (size_t)s->n_spheres * (16 + 8) + 24 * 256;
         const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 44 + 24 * 256;
         if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
             !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
@@ -1487,25 +1536,30 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     CU(upload(ta, &tprim, s->tri_prim, (size_t)s->n_tris, st));
     CU(upload(ta, &sph, s->sph_center_r, (size_t)s->n_spheres, st));
     CU(upload(ta, &sprim, s->sph_prim, (size_t)s->n_spheres, st));
-    // shading tables addressed by primitive order index
-    std::vector<float> vn((size_t)s->n_prims * 12, 0.f);
-    std::vector<int32_t> pm((size_t)s->n_prims, 0);
-    for (int64_t t = 0; t < s->n_tris; t++) {
-        const int32_t p = s->tri_prim[t];
-        if (p < 0 || p >= s->n_prims) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: tri_prim[%lld] out of range", (long long)t);
-        memcpy(&vn[(size_t)p * 12 + 0], s->tri_n0 + 4 * t, 16);
-        memcpy(&vn[(size_t)p * 12 + 4], s->tri_n1 + 4 * t, 16);
-        memcpy(&vn[(size_t)p * 12 + 8], s->tri_n2 + 4 * t, 16);
-        pm[p] = s->tri_material[t];
+    // shading tables addressed by primitive order index: scattered on the device (k_scatter_shading)
+    float4 *tn0 = nullptr, *tn1 = nullptr, *tn2 = nullptr; int32_t *tmat = nullptr, *smat = nullptr; unsigned int* d_bad = nullptr;
+    CU(upload(ta, &tn0, s->tri_n0, (size_t)s->n_tris, st));
+    CU(upload(ta, &tn1, s->tri_n1, (size_t)s->n_tris, st));
+    CU(upload(ta, &tn2, s->tri_n2, (size_t)s->n_tris, st));
+    CU(upload(ta, &tmat, s->tri_material, (size_t)s->n_tris, st));
+    CU(upload(ta, &smat, s->sph_material, (size_t)s->n_spheres, st));
+    d_bad = ta.take<unsigned int>(1);
+    c->d_vn = sa.take<float4>((size_t)s->n_prims * 3);
+    c->d_prim_material = sa.take<int32_t>((size_t)s->n_prims);
+    if (!d_bad || !c->d_vn || !c->d_prim_material) FAIL(RT580_FAILURE, "rt580_upload_scene: arena exhausted");
+    CU(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(c->d_vn, 0, sizeof(float4) * 3 * (size_t)(s->n_prims ? s->n_prims : 1), st));
+    CU(cudaMemsetAsync(c->d_prim_material, 0, sizeof(int32_t) * (size_t)(s->n_prims ? s->n_prims : 1), st));
+    if (s->n_prims > 0) {
+        k_scatter_shading<<<nblk_ll(s->n_tris + s->n_spheres, 256), 256, 0, st>>>(s->n_tris, tn0, tn1, tn2, tprim, tmat, s->n_spheres, sprim, smat,
+                                                                                s->n_prims, s->n_materials, c->d_vn, c->d_prim_material, d_bad);
+        unsigned int bad = 0;
+        CU(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (bad & 1u) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: tri_prim out of range");
+        if (bad & 4u) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: sph_prim out of range");
+        if (bad & 2u) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: material index out of range");
     }
-    for (int64_t k = 0; k < s->n_spheres; k++) {
-        const int32_t p = s->sph_prim[k];
-        if (p < 0 || p >= s->n_prims) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: sph_prim[%lld] out of range", (long long)k);
-        pm[p] = s->sph_material[k];
-    }
-    for (auto m : pm) if (m < 0 || m >= s->n_materials) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: material index out of range");
-    CU(upload(sa, &c->d_vn, vn.data(), (size_t)s->n_prims * 3, st));
-    CU(upload(sa, &c->d_prim_material, pm.data(), (size_t)s->n_prims, st));
     CU(upload(sa, &c->d_materials, s->materials, (size_t)s->n_materials * 8, st));
     CU(upload(sa, &c->d_light_type, s->light_type, (size_t)s->n_lights, st));
     CU(upload(sa, &c->d_light_f, s->light_f, (size_t)s->n_lights * 10, st));
@@ -1758,7 +1812,7 @@ static int anyhit_queue_pass(rt580_context* c, unsigned long long total, uint32_
         c->launches++;
         k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, c->counters.p + 6, c->counters.p + 7, hits, slowq_any(c), id_offset,
                                          pending_mark, ao ? reinterpret_cast<unsigned long long*>(c->counters.p + 8) : nullptr,
-                                         c->ah_steps, c->ah_min_search);
+                                         c->ah_steps, c->ah_min_search, c->ah_batch_div);
         c->launches++;
         const unsigned long long rest = total - first - n;
         if (leaky && ao && c->any_cap && rest) {
@@ -1956,7 +2010,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             CU(cudaMemsetAsync(c->counters.p + 7, 0, sizeof(unsigned), st));
             const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ch_blocks_per_sm;
             k_closest<<<blocks, 128, 0, st>>>(c->sc, c->queue.p, c->counters.p + 1, q_max, c->counters.p + 7, c->chits.p,
-                                              c->ah_steps, c->ah_min_search);
+                                              c->ah_steps, c->ah_min_search, c->ah_batch_div);
             k_commit<<<nblk(q_max, 128), 128, 0, st>>>(c->sc, c->queue.p, q_max, c->counters.p + 1, c->chits.p, c->nodes.p, c->aux.p,
                                                        c->counters.p, c->pix_hits.p, c->fb.p, (unsigned)c->nodes.cap, slowq(c, slow_cap));
             c->launches += 2;

@@ -146,6 +146,13 @@ int  rt580_device_info(rt580_context* ctx, int32_t* sm_count, int32_t* sm_clock_
 /* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
 int  rt580_get_stream(rt580_context* ctx, void** cuda_stream);
 
+/* Host staging memory: page-locked when a CUDA device is present (copies to / from the device then run
+ * at PCIe speed instead of through the driver's bounce buffers), plain malloc otherwise.  The host
+ * class keeps the flattened scene and the frame buffer in it; any host pointer works with the calls
+ * below, this is only faster. */
+void* rt580_host_alloc(uint64_t bytes);
+void  rt580_host_free(void* p);
+
 /* ---- scene: H2D + per-triangle constants (cpp:362-365, 377, 389) + LBVH build ----------- */
 int  rt580_upload_scene(rt580_context* ctx, const rt580_flat_scene* scene);
 /* device ms of the last upload's build kernels (setup, morton, sort, hierarchy, refit, pack) */

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--contiguous", action="store_true", help="one band of H/world consecutive rows instead of interleaved rows")
     args = ap.parse_args()
     pkg = load_package()
     d = bench.scene_dir(args.workload)
@@ -41,6 +42,9 @@ def main():
     ctx.upload_scene(rt.flat_scene())
     p = rt.render_params().copy()
     p.row_first, p.row_step, p.n_rows = pkg.rows_for_rank(args.height, args.rank, args.world)
+    if args.contiguous:
+        n = args.height // args.world
+        p.row_first, p.row_step, p.n_rows = args.rank * n, 1, n
     import torch
     band = torch.empty((max(p.n_rows, 1), args.width, 3), dtype=torch.int16, device="cuda")
     walls, sts = [], []
