@@ -279,7 +279,26 @@ __device__ __forceinline__ bool big_scan(const DeviceScene& sc, V3 O, V3 d, HitR
             best.t = t; best.leaf = i; best.prim = prim; found = true;
         }
     }
-    for (int j = 0; j < sc.n_big_planes; j++) {
+    // Closest hit: the plane the ray reaches first goes first (found with approximate arithmetic, it only
+    // orders the exact tests); a hit there bounds t, and plane_ahead then turns away the planes behind it
+    // without a triangle test.  In list order a ray met several walls "ahead" and tested all their triangles.
+    int first = -1;
+    if (!ANY && sc.n_big_planes > 2) {
+        unsigned m1 = 0xffffffffu;
+        for (int j = 0; j < sc.n_big_planes; j++) {
+            const float4 pl = __ldg(sc.big_planes + j);
+            const float nd = __fmaf_rn(pl.x, d.x, __fmaf_rn(pl.y, d.y, pl.z * d.z));
+            const float num = -__fmaf_rn(pl.x, O.x, __fmaf_rn(pl.y, O.y, __fmaf_rn(pl.z, O.z, pl.w)));
+            float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(nd));
+            const float ta = num * r;
+            const unsigned key = (ta > 0.0f) ? ((__float_as_uint(ta) & ~63u) | (unsigned)j) : 0xffffffffu;
+            m1 = min(m1, key);
+        }
+        if (m1 != 0xffffffffu) first = (int)(m1 & 63u);
+    }
+    for (int jj = (first >= 0 ? -1 : 0); jj < sc.n_big_planes; jj++) {
+        const int j = jj < 0 ? first : jj;
+        if (jj >= 0 && j == first) continue;
         if (!plane_ahead(__ldg(sc.big_planes + j), O, d, best.t)) continue;
         for (unsigned long long m = __ldg(sc.big_masks + j); m; m &= m - 1ull) {
             const int i = sc.n_leaf + (__ffsll((long long)m) - 1);
