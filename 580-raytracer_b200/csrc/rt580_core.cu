@@ -175,6 +175,7 @@ struct rt580_context {
     int ch_blocks_per_sm = 10; bool one_thread_per_ray = false;   // RT580_CH_BLOCKS_PER_SM, RT580_ONE_THREAD_PER_RAY (A/B)
     uint64_t slow_total = 0;
     int ah_batch_div = 4;
+    unsigned slow_any_cap = SLOW_ANY_CAP;   // RT580_SLOW_ANY_CAP: shrink it to exercise the overflow -> repeat path
     int ah_steps = AH_STEPS, ah_min_search = AH_MIN_SEARCH, ah_blocks_per_sm = 12;  // k_anyhit tuning (env RT580_AH_*)
     std::vector<size_t> level_off; // node index where each level starts (+ end)
     std::vector<uint64_t> level_rays;
@@ -1455,6 +1456,7 @@ extern "C" int rt580_create(int device, rt580_context** out)
     if (const char* e = getenv("RT580_AH_STEPS")) c->ah_steps = atoi(e) > 0 ? atoi(e) : c->ah_steps;
     if (const char* e = getenv("RT580_AH_MIN_SEARCH")) c->ah_min_search = atoi(e) > 0 ? atoi(e) : c->ah_min_search;
     if (const char* e = getenv("RT580_AH_BLOCKS_PER_SM")) c->ah_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ah_blocks_per_sm;
+    if (const char* e = getenv("RT580_SLOW_ANY_CAP")) c->slow_any_cap = atoi(e) > 0 ? (unsigned)atoi(e) : c->slow_any_cap;
     if (const char* e = getenv("RT580_AH_BATCH_DIV")) c->ah_batch_div = atoi(e) > 0 ? atoi(e) : c->ah_batch_div;
     if (const char* e = getenv("RT580_CH_BLOCKS_PER_SM")) c->ch_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ch_blocks_per_sm;
     if (const char* e = getenv("RT580_ONE_THREAD_PER_RAY")) c->one_thread_per_ray = atoi(e) != 0;
@@ -1976,7 +1978,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                     if (any_open) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; any_open = false; }
                     if (any_prepare(c, n_sh)) return RT580_FAILURE;
                 } else if (!any_open) {
-                    if (any_prepare(c, SLOW_ANY_CAP)) return RT580_FAILURE;
+                    if (any_prepare(c, c->slow_any_cap)) return RT580_FAILURE;
                     any_open = c->any_cap != 0;
                 }
                 const int rc = anyhit_queue_pass(c, n_sh, c->occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
@@ -2151,7 +2153,7 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
         if (mode == 0) {
             for (int attempt = 0; ; attempt++) {
                 const bool leaky = is_leaky(c, c->rays_structure);
-                if (any_prepare(c, leaky ? SLOW_CAP_MAX : SLOW_ANY_CAP)) return RT580_FAILURE;
+                if (any_prepare(c, leaky ? SLOW_CAP_MAX : c->slow_any_cap)) return RT580_FAILURE;
                 const int rc = anyhit_queue_pass(c, n_ao, c->ao_hits.p, 0u, 0u, leaky, true,
                     [&](unsigned long long first, unsigned n) {
                         k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,

@@ -5,6 +5,8 @@ import os
 import re
 import subprocess
 
+import numpy as np
+
 import pytest
 
 from conftest import ROOT
@@ -80,3 +82,12 @@ def test_product_never_touches_the_oracle():
                     txt = f.read()
                 assert "oracle580" not in txt and "liboracle" not in txt and "libref580" not in txt, fn
                 assert not re.search(r"^\s*(import|from)\s+oracle", txt, flags=re.M), fn
+
+
+def test_host_alloc_without_a_gpu_is_plain_memory(pkg):
+    """rt580_host_alloc / rt580_host_free work on a box without a GPU (malloc), and HostArray wraps them."""
+    ha = pkg.HostArray((7, 5, 3), np.int16)
+    ha.array[:] = 3
+    assert ha.array.sum() == 7 * 5 * 3 * 3
+    ha.close()
+    pkg.lib().rt580_host_free(None)

@@ -326,3 +326,72 @@ def test_every_ray_of_a_frame_matches_the_oracle(pkg, oracle, oracle_scene):
     far = np.abs(log["org"]).max(axis=1) > 1e4
     assert far.sum() > 0, "this frame is known to contain rays that start at far-field hits"
     ctx.close()
+
+
+def test_device_side_exchange_equals_host_exchange(pkg):
+    """The multi-GPU path of bench.py on one GPU: contexts play the ranks, the per-row counts stay on
+    the device (rt580_row_counts_to_device -> [world][max_rows], what the NCCL all-gather produces),
+    rt580_render_finish_interleaved derives every rank's stream offsets there, and each context
+    stores its rows into a whole frame (rt580_frame_export; the other ranks of a real run map that
+    allocation over CUDA IPC).  Result == the single-context frame, bit for bit."""
+    import torch
+    scene, W, H, spp, depth = "mix_small.json", 160, 90, 4, 4
+    whole, st_whole = render(pkg, scene, W, H, spp, depth)
+    rt = make_rt(pkg, scene, W, H, spp, depth)
+    base_params = rt.render_params()
+    for world in (1, 2, 4):
+        max_rows = (H + world - 1) // world
+        all_d = torch.zeros((world, max_rows), dtype=torch.int64, device="cuda")
+        ctxs, params = [], []
+        for r in range(world):
+            c = pkg.Context(0)
+            c.upload_scene(rt.flat_scene())
+            c.frame_export(W, H)                      # every context its own whole frame in this single-process test
+            p = base_params.copy()
+            p.row_first, p.row_step, p.n_rows = pkg.rows_for_rank(H, r, world)
+            assert c.render_begin(p, want_counts=False) is None
+            c.row_counts_to_device(all_d[r].data_ptr(), max_rows)
+            ctxs.append(c); params.append(p)
+        torch.cuda.synchronize()
+        got = np.zeros((H, W, 3), np.int16)
+        rays = 0
+        for r in range(world):
+            st = ctxs[r].render_finish_interleaved(all_d.data_ptr(), world, r, max_rows)
+            rays += st.rays
+            full = ctxs[r].frame_read(W, H)
+            first, step, n = pkg.rows_for_rank(H, r, world)
+            got[first:first + n * step:step] = full[first:first + n * step:step]
+        assert rays == st_whole.rays
+        assert np.array_equal(got, whole)
+        # a finish that does not match the partition is refused
+        ctxs[0].render_begin(params[0], want_counts=False)
+        with pytest.raises(pkg.Rt580Error):
+            ctxs[0].render_finish_interleaved(all_d.data_ptr(), world + 1, 0, max_rows)
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.parametrize("tag", ["teapots_96_spp1", "mix_small_128x72_spp4", "teapots_point_96x64_spp4"])
+def test_deferred_queue_overflow_repeats_the_pass(pkg, tag, monkeypatch):
+    """A frame that "hardly leaks" (few slow rays so far) gets a small deferred any-hit queue; if it
+    overflows after all, the pass is repeated with a queue that takes every ray.  RT580_SLOW_ANY_CAP=1
+    forces that on open scenes at a low resolution: still the reference's frame, bit for bit."""
+    g = load_golden(tag)
+    monkeypatch.setenv("RT580_SLOW_ANY_CAP", "1")
+    fb, st = render(pkg, g["scene"], g["W"], g["H"], g["spp"], g["depth"], traversal=pkg.TRAVERSAL_BVH)
+    assert st.far_scans + st.linear_fallbacks > 1, "the frame has no slow rays: nothing overflowed"
+    assert st.rays == g["rays"]
+    assert np.array_equal(fb, g["fb"])
+
+
+def test_page_locked_host_arrays(pkg):
+    """rt580_host_alloc memory as the destination of rt580_render (what the host class uses)."""
+    scene, W, H, spp, depth = "simpleSphereScene.json", 96, 64, 4, 4
+    rt = make_rt(pkg, scene, W, H, spp, depth)
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    ha = pkg.HostArray((H, W, 3), np.int16)
+    fb, _ = ctx.render(rt.render_params(), out=ha.array)
+    ref, _ = ctx.render(rt.render_params())
+    assert fb is ha.array and np.array_equal(fb, ref)
+    ha.close(); ctx.close()
