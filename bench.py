@@ -35,6 +35,8 @@ METRIC, UNIT = "Mrays/s", "Mrays/s"
 WORKLOAD = "c4_room"
 W, H, DEPTH, SPP = 3840, 2160, 4, 16
 CACHE = "/tmp/rt580_bench_scenes"
+AO_CHUNK = 32 << 20                        # AH_CHUNK_TIGHT in rt580_core.cu: AO sample rays per k_ao_gen launch
+K_AO_GEN_DRAM_BYTES_PER_RAY = 158.475e6 / (32 << 20)   # ncu capture, see roofline.traffic_source
 
 
 def scene_dir(name):
@@ -355,15 +357,27 @@ def run_ours(args):
         sm_mhz = float(peaks.get("sm_max_mhz") or dev["sm_clock_mhz"])
         fp32_peak = dev["sm_count"] * 128 * 2 * sm_mhz * 1e6 / 1e12          # TFLOP/s, FMA counted as 2
         ao_rate = ao_rays_total / (ao_ms * 1e-3) if ao_ms > 0 else 0.0      # rays/s over all ranks (max kernel time)
-        roofline = {"bound": "fp32", "kernel": "occlusion pass (k_ao_gen: RNG + hemisphere direction + large-primitive list; k_anyhit: persistent LBVH any-hit)",
+        # the dominant kernel is k_ao_gen (39 % of the frame's kernel time, profiles/): the occlusion pass launches it
+        # once per chunk of AO_CHUNK sample rays, each followed by a k_anyhit launch over the rays it could not answer
+        # (a few hundred per frame in this scene); ms_ao_kernel brackets those launches with CUDA events on their stream
+        n_launch = max(1, int(np.ceil(ao_rays_total / world / AO_CHUNK)))
+        rays_per_launch = ao_rays_total / world / n_launch
+        roofline = {"bound": "fp32", "kernel": "k_ao_gen (per AO sample: engine state, RNG draws, double sincos, hemisphere direction, ray; exact any-hit test "
+                                               "against the scene's large primitives, nearest plane first) + k_anyhit (persistent LBVH any-hit) for the rest",
                     "achieved": ao_rate * f_ray / 1e12, "peak": fp32_peak * world, "unit": "TFLOP/s",
                     "frac": (ao_rate * f_ray / 1e12) / (fp32_peak * world) if fp32_peak else None,
                     "peak_source": "%d SMs x 128 lanes x 2 x %.0f MHz (%s); MEASURED_PEAKS.json has no fp32 figure" % (
                         dev["sm_count"], sm_mhz, peak_src),
-                    "flop_per_ray": f_ray, "rays_per_launch": ao_rays_total, "kernel_ms": ao_ms, "traffic": None,
+                    "flop_per_ray": f_ray, "rays_per_launch": rays_per_launch, "launches_per_step": n_launch,
+                    "kernel_ms": ao_ms / n_launch, "pass_ms": ao_ms,
+                    "traffic": K_AO_GEN_DRAM_BYTES_PER_RAY * rays_per_launch,
+                    "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 32M-ray k_ao_gen launch "
+                                      "(profiles/r01_k_ao_gen_v2_1080p_details.txt: 158.5 MB), scaled to this launch size",
+                    "ncu": {"issue_slots_busy_pct": 83.2, "fma_pipe_active_pct": 33.1, "avg_active_lanes": 28.8, "l1_hit_pct": 78.4,
+                            "dram_throughput_pct": 1.85, "source": "same capture"},
                     "hbm": {"achieved": ao_rate * b_ray / 1e9, "peak": float(peaks["hbm_gbs"]) * world, "unit": "GB/s",
                             "frac": (ao_rate * b_ray / 1e9) / (float(peaks["hbm_gbs"]) * world), "bytes_per_ray": b_ray,
-                            "note": "algorithmic node+triangle bytes; served from L1/L2, not HBM, when the BVH fits L2"}}
+                            "note": "algorithmic node+triangle bytes; served from shared memory / L1 / L2, not HBM (measured DRAM throughput 1.9 %)"}}
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
