@@ -92,7 +92,7 @@ class Stats(ctypes.Structure):
         ("ms_resolve", ctypes.c_float), ("ms_total", ctypes.c_float), ("ms_ao_kernel", ctypes.c_float),
         ("kernel_launches", ctypes.c_uint32), ("bvh_max_depth", ctypes.c_uint32),
         ("far_scans", ctypes.c_uint32), ("linear_fallbacks", ctypes.c_uint32),
-        ("ao_rays_traversed", ctypes.c_uint64),
+        ("ao_rays_traversed", ctypes.c_uint64), ("shadow_rays_traversed", ctypes.c_uint64),
     ]
 
     @property

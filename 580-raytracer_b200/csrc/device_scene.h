@@ -65,6 +65,13 @@ struct DeviceScene {
     int32_t n_lights;
     int32_t n_ambient;
     int32_t n_nonambient;
+    // Point-light clearance maps (smap.cuh): per point light a cube map of a LOWER bound of the distance
+    // from the light to the nearest padded leaf box in each direction.  A shadow ray whose far end
+    // (its origin, seen from the light) is nearer than that bound cannot meet a tree primitive: it
+    // skips the traversal.  Pure culling, like the boxes of the tree itself.
+    const float* smap;             // [n_smap][6][SMAP_RES][SMAP_RES]
+    const int32_t* smap_of_light;  // [n_lights] map index, -1: none (not a point light, or a primitive too close to it)
+    int32_t n_smap;
 };
 
 }  // namespace rt580

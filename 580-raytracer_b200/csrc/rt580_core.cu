@@ -24,6 +24,7 @@
 #include "build.h"
 #include "trace.cuh"
 #include "shade.cuh"
+#include "smap.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <ctime>
@@ -829,7 +830,7 @@ k_shadow_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays
 }
 
 // shadow rays of one level as a ray queue for k_anyhit: ray id = (node - n0) * n_nonambient + j
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
             struct ARay* __restrict__ out, unsigned int* __restrict__ n_out);
 
@@ -1076,29 +1077,57 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
     if (emit) out[slot] = r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
             ARay* __restrict__ out, unsigned int* __restrict__ n_out)
 {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) *n_out = n;
-    if (t >= n) return;
-    // queue order = light-major: the lanes of a warp take neighbouring nodes and the SAME light, so their
-    // rays run to one point and walk the tree together (node-major order put three lights in adjacent lanes)
-    const unsigned long long q = first + t;
-    int j = (int)(q / n_level);
-    const unsigned m = (unsigned)(q % n_level);
-    const unsigned id = m * (unsigned)sc.n_nonambient + (unsigned)j;      // ray id = (node - n0) * n_nonambient + j
-    int li = 0;
-    for (;; li++) { if (__ldg(sc.light_type + li) != RT580_LIGHT_AMBIENT) { if (j == 0) break; j--; } }
-    const Light L = load_light(sc.light_type, sc.light_f, li);
-    const float4 nP = __ldg(&nodes[n0 + m].P);
-    V3 so, sd; float tmax;
-    shadow_ray(L, mk(nP.x, nP.y, nP.z), so, sd, tmax);
+    bool emit = false;
     ARay r;
-    r.a = make_float4(so.x, so.y, so.z, sd.x);
-    r.b = make_float4(sd.y, sd.z, __uint_as_float(id), tmax);
-    out[t] = r;
+    r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a;
+    if (t < n) {
+        // queue order = light-major: the lanes of a warp take neighbouring nodes and the SAME light, so their
+        // rays run to one point and walk the tree together (node-major order put three lights in adjacent lanes)
+        const unsigned long long q = first + t;
+        int j = (int)(q / n_level);
+        const unsigned m = (unsigned)(q % n_level);
+        const unsigned id = m * (unsigned)sc.n_nonambient + (unsigned)j;      // ray id = (node - n0) * n_nonambient + j
+        int li = 0;
+        for (;; li++) { if (__ldg(sc.light_type + li) != RT580_LIGHT_AMBIENT) { if (j == 0) break; j--; } }
+        const Light L = load_light(sc.light_type, sc.light_f, li);
+        const float4 nP = __ldg(&nodes[n0 + m].P);
+        V3 so, sd; float tmax;
+        shadow_ray(L, mk(nP.x, nP.y, nP.z), so, sd, tmax);
+        r.a = make_float4(so.x, so.y, so.z, sd.x);
+        r.b = make_float4(sd.y, sd.z, __uint_as_float(id), tmax);
+        emit = true;
+        // the light's clearance map may prove that no tree primitive lies between the ray origin and the
+        // light (smap.cuh): such a ray is not queued, its occluder count stays 0, and k_shade goes on with
+        // the large-primitive test as for any ray the tree did not stop
+        // (not for rays whose hit / miss the tree does not decide alone: a far origin, a light beyond far_tmin)
+        const int mi = sc.n_smap ? __ldg(sc.smap_of_light + li) : -1;
+        if (mi >= 0 && !(sc.farfield && (tmax >= sc.far_tmin || fmaxf(fabsf(so.x), fmaxf(fabsf(so.y), fabsf(so.z))) > sc.extent)) &&
+            smap_clear(sc.smap + (size_t)mi * 6 * SMAP_RES * SMAP_RES, L.position, so)) emit = false;
+    }
+    // order-preserving compaction with ONE global atomic per block (one per warp, 3.7 M on the same
+    // address for a 4K level, cost as much as the traversal they saved)
+    __shared__ unsigned s_cnt[32];
+    __shared__ unsigned s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const unsigned mask = __ballot_sync(0xffffffffu, emit);
+    if (lane == 0) s_cnt[warp] = (unsigned)__popc(mask);
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned v = lane < n_warps ? s_cnt[lane] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        s_cnt[lane] = incl - v;
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) s_base = total ? atomicAdd(n_out, total) : 0u;
+    }
+    __syncthreads();
+    if (emit) out[s_base + s_cnt[warp] + (unsigned)__popc(mask & ((1u << lane) - 1u))] = r;
 }
 
 // Put an any-hit ray on the deferred queue (far-field scan or, `linear`, the reference's own loop,
@@ -1525,7 +1554,11 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     {
         char aerr[256] = "";
         const size_t in_bytes = (size_t)s->n_tris * (6 * 16 + 8) + (size_t)s->n_spheres * (16 + 8) + 24 * 256;
-        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 44 + 24 * 256;
+        int n_point = 0;
+        for (int i = 0; i < s->n_lights; i++) if (s->light_type && s->light_type[i] == RT580_LIGHT_POINT) n_point++;
+        if (n_point > SMAP_MAX) n_point = SMAP_MAX;
+        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 48 + 32 * 256 +
+                                   (size_t)n_point * 6 * SMAP_RES * SMAP_RES * sizeof(float);
         if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
             !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
             FAIL(RT580_FAILURE, "rt580_upload_scene: %s", aerr);
@@ -1610,6 +1643,40 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
                 CU(cudaStreamSynchronize(st));
                 c->sc.big_planes = dp; c->sc.big_masks = dm; c->sc.n_big_planes = (int)planes.size();
             }
+        }
+    }
+    {
+        // clearance maps of the point lights (smap.cuh)
+        c->sc.smap = nullptr; c->sc.smap_of_light = nullptr; c->sc.n_smap = 0;
+        std::vector<int32_t> of_light((size_t)s->n_lights, -1);
+        int n_maps = 0;
+        // (sliver triangles are tested for every ray whatever the tree says: a scene that has them gets no maps)
+        const bool use_maps = bo.n_leaf > RT_SMEM_PRIMS && bo.n_always == 0 && !getenv("RT580_NO_SMAP");
+        if (use_maps) for (int i = 0; i < s->n_lights && n_maps < SMAP_MAX; i++) if (s->light_type[i] == RT580_LIGHT_POINT) of_light[i] = n_maps++;
+        if (n_maps) {
+            const size_t per = (size_t)6 * SMAP_RES * SMAP_RES;
+            float* maps = sa.take<float>(per * n_maps);
+            unsigned int* clear = ta.take<unsigned int>(SMAP_MAX);
+            if (!maps || !clear) FAIL(RT580_FAILURE, "rt580_upload_scene: arena exhausted (clearance maps)");
+            CU(cudaMemsetAsync(maps, 0x7f, sizeof(float) * per * n_maps, st));        // 0x7f7f7f7f = 3.4e38: nothing there
+            CU(cudaMemsetAsync(clear, 0x7f, sizeof(unsigned int) * SMAP_MAX, st));
+            const int n_nodes = bo.n_leaf > 1 ? bo.n_leaf - 1 : 1;
+            for (int i = 0; i < s->n_lights; i++) {
+                if (of_light[i] < 0) continue;
+                const float* lf = s->light_f + 10 * (size_t)i;
+                k_smap_raster<<<nblk_ll(2ll * n_nodes, 256), 256, 0, st>>>(bo.nodes, n_nodes, lf[4], lf[5], lf[6], maps + per * of_light[i],
+                                                                        clear + of_light[i]);
+            }
+            float hclear[SMAP_MAX];
+            CU(cudaMemcpyAsync(hclear, clear, sizeof hclear, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            CU(cudaGetLastError());
+            // a primitive within reach of the 0.2 units by which the reference's shadow ray overshoots the light: no map
+            for (int i = 0; i < s->n_lights; i++) if (of_light[i] >= 0 && !(hclear[of_light[i]] >= SMAP_CLEARANCE)) of_light[i] = -1;
+            int32_t* dl = nullptr;
+            CU(upload(sa, &dl, of_light.data(), of_light.size(), st));
+            CU(cudaStreamSynchronize(st));
+            c->sc.smap = maps; c->sc.smap_of_light = dl; c->sc.n_smap = n_maps;
         }
     }
     c->sc.n_prims = (int32_t)s->n_prims;
@@ -1813,7 +1880,7 @@ static int anyhit_queue_pass(rt580_context* c, unsigned long long total, uint32_
         gen(first, n);
         c->launches++;
         k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, c->counters.p + 6, c->counters.p + 7, hits, slowq_any(c), id_offset,
-                                         pending_mark, ao ? reinterpret_cast<unsigned long long*>(c->counters.p + 8) : nullptr,
+                                         pending_mark, reinterpret_cast<unsigned long long*>(c->counters.p + (ao ? 8 : 10)),
                                          c->ah_steps, c->ah_min_search, c->ah_batch_div);
         c->launches++;
         const unsigned long long rest = total - first - n;
@@ -1983,7 +2050,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                 }
                 const int rc = anyhit_queue_pass(c, n_sh, c->occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
                     [&](unsigned long long first, unsigned n) {
-                        k_shade_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6);
+                        k_shade_gen<<<nblk(n, 512), 512, 0, st>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6);
                     });
                 if (rc) return rc;
             }
@@ -2227,7 +2294,10 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
     c->stats.ms_total = c->stats.ms_structure + c->stats.ms_order + c->stats.ms_ao + c->stats.ms_resolve;
     c->stats.kernel_launches = c->launches;
     c->stats.far_scans = cnt[4]; c->stats.linear_fallbacks = cnt[5];
-    if (mode == 0) c->stats.ao_rays_traversed = (uint64_t)cnt[8] | ((uint64_t)cnt[9] << 32);
+    if (mode == 0) {
+        c->stats.ao_rays_traversed = (uint64_t)cnt[8] | ((uint64_t)cnt[9] << 32);
+        c->stats.shadow_rays_traversed = (uint64_t)cnt[10] | ((uint64_t)cnt[11] << 32);
+    } else c->stats.shadow_rays_traversed = c->stats.rays_shadow;
     if (stats) *stats = c->stats;
     c->frame_begun = false;
     return RT580_SUCCESS;

@@ -135,6 +135,8 @@ typedef struct rt580_stats {
     uint32_t linear_fallbacks;     /* rays that started outside the padded extent (children of far hits) */
     uint64_t ao_rays_traversed;    /* AO rays that went through the tree; the others were already occluded by
                                       one of the scene's few very large primitives (tested first) */
+    uint64_t shadow_rays_traversed;/* shadow rays that went through the tree; for the others the point light's
+                                      clearance map proved that no tree primitive lies before the light */
 } rt580_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

@@ -67,7 +67,8 @@ def main():
     print("  device ms:     structure %.3f  order %.3f  ao %.3f (kernels %.3f)  resolve %.3f  sum %.3f" % (
         dev[0], dev[1], dev[2], dev[4], dev[3], dev[:4].sum()))
     print("  Mrays/s of this slice: %.1f   x world = %.1f" % (st.rays / w[:, 0].mean() / 1e3, st.rays / w[:, 0].mean() / 1e3 * args.world))
-    print("  far scans %d, linear fallbacks %d" % (st.far_scans, st.linear_fallbacks))
+    print("  far scans %d, linear fallbacks %d; through the tree: %d of %d shadow rays, %d of %d AO rays" % (
+        st.far_scans, st.linear_fallbacks, st.shadow_rays_traversed, st.rays_shadow, st.ao_rays_traversed, st.rays_ao))
 
 
 if __name__ == "__main__":
