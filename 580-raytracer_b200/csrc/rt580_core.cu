@@ -98,6 +98,9 @@ __host__ __device__ __forceinline__ unsigned long long slow_key(float t, int pri
 #define OCCL_PENDING 0x40000000u   // shadow ray deferred to the end of the structure pass (k_shadow_finish decides)
 
 // k_anyhit (persistent any-hit traversal) constants
+#ifndef AH_MIN_BLOCKS
+#define AH_MIN_BLOCKS 12
+#endif
 #define AH_STEPS 48        // at most this many inner-node steps between two leaf / refill phases
 #define AH_MIN_SEARCH 12   // leave the inner-node phase when fewer lanes than this still have an inner node
 #define AH_NONE 0x7fffffff // traversal cursor: nothing left
@@ -112,6 +115,7 @@ struct FrameParams {
     const float* ndc_x;   // [W]  (float)(NDCX * aspect * tan(fov/2))   cpp:834-839, 846
     const float* ndc_y;   // [H]  (float)(NDCY * tan(fov/2))            cpp:835, 840, 846
     const uint32_t* lcg_pow;   // [spp] 16807^(2k) mod (2^31-1): advances an AO call's engine state to its sample k
+    const uint32_t* lcg_tab;   // [4][256] 16807^(d * 256^k) mod (2^31-1): engine state at any step in 3 modular products
 };
 
 template <typename T> struct DBuf {
@@ -167,6 +171,7 @@ struct rt580_context {
     bool force_leaky = false;                          // the small any-hit queue overflowed once for this scene
     int ndc_w = 0, ndc_h = 0; float ndc_fov = 0.f;     // what the primary-ray tables were built for
     DBuf<uint32_t> lcg_pow; int lcg_pow_spp = 0;
+    DBuf<uint32_t> lcg_tab;
     // the whole W x H frame of a multi-GPU render: rank 0's own allocation, or that allocation mapped
     // into this process over NVLink (cudaIpc); every rank stores its rows there after the resolve pass
     int16_t* frame = nullptr; bool frame_imported = false; int frame_w = 0, frame_h = 0;
@@ -542,7 +547,7 @@ k_trace_finish(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, c
 // list, the sliver list and the far field, and creates the nodes exactly as k_trace does.
 struct __align__(16) CHit { float t; int leaf; int prim; int pad; };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, AH_MIN_BLOCKS)
 k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __restrict__ n_ptr, unsigned n_bound,
           unsigned int* __restrict__ next_ray, CHit* __restrict__ out, int ah_steps, int ah_min_search, int batch_div)
 {
@@ -714,6 +719,7 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
     }
     Pix local = mkpix(0, 0, 0);                                       // SHADOW_COLOR h:598
     const V3 cam = mk(fp.cam[0], fp.cam[1], fp.cam[2]);
+    const PhongFrame pf = phong_frame(P, sn, cam);
     // the light loop is uniform over the warp (trace_ray is warp-collective)
     int j = 0;                                                        // index among the non-ambient lights
     for (int li = 0; li < sc.n_lights; li++) {                        // cpp:39
@@ -737,7 +743,7 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
             tr = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh, sq, (int)i, li);
         }
         // TR_PENDING: k_shade_finish adds this light's term once the deferred ray is answered
-        if (active && tr == TR_MISS) local = pix_add(local, calculate_local_color(P, sn, L, M, cam));   // cpp:77
+        if (active && tr == TR_MISS) local = pix_add(local, calculate_local_color(P, pf, L, M));   // cpp:77
         j++;
     }
     if (active) {
@@ -924,7 +930,7 @@ __global__ void k_preorder(unsigned n0, unsigned n1, const Node* __restrict__ no
     pre[i] = ord;
     for (int a = 0; a < n_ambient; a++) {
         const uint64_t call = ord * (uint64_t)n_ambient + a;      // one AO call per ambient light (cpp:41-45, Q6)
-        ao_state[(size_t)i * n_ambient + a] = lcg_state_at(2ull * (uint64_t)fp.spp * call);
+        ao_state[(size_t)i * n_ambient + a] = lcg_state_at_tab(2ull * (uint64_t)fp.spp * call, fp.lcg_tab);
     }
 }
 
@@ -1148,7 +1154,7 @@ __device__ __forceinline__ bool defer_any(const SlowQ& sq, V3 O, V3 d, float tma
 // Persistent any-hit traversal.  hit_count[id] += 1 for every ray that is occluded.  A ray the tree
 // cannot answer alone goes to the deferred queue `sq` under the id `id + id_offset`; with
 // `pending_mark` its hit_count entry is flagged so that the consumer knows the answer comes later.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, AH_MIN_BLOCKS)
 k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __restrict__ n_ptr,
          unsigned int* __restrict__ next_ray, uint32_t* __restrict__ hit_count, SlowQ sq, unsigned id_offset,
          unsigned pending_mark, unsigned long long* __restrict__ traversed_acc, int ah_steps, int ah_min_search, int batch_div)
@@ -1508,7 +1514,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     free_scene(c);
     frame_release(c);
     arena_release(c->scene_arena); arena_release(c->build_arena);
-    c->ndc.release(); c->lcg_pow.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
+    c->ndc.release(); c->lcg_pow.release(); c->lcg_tab.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
     c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release(); c->chits.release();
@@ -1981,6 +1987,20 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         c->lcg_pow_spp = fp.spp;
     }
     fp.lcg_pow = c->lcg_pow.p;
+    if (!c->lcg_tab.p) {
+        std::vector<uint32_t> t(1024);
+        const uint64_t m = 2147483647ull;
+        uint64_t base = 16807ull;                                  // 16807^(256^k)
+        for (int k = 0; k < 4; k++) {
+            uint64_t v = 1;
+            for (int d = 0; d < 256; d++) { t[(size_t)k * 256 + d] = (uint32_t)v; v = (v * base) % m; }
+            base = v;                                              // = base^256
+        }
+        CU(c->lcg_tab.ensure(t.size(), 0, st));
+        CU(cudaMemcpyAsync(c->lcg_tab.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    fp.lcg_tab = c->lcg_tab.p;
     CU(c->counters.ensure(N_COUNTERS, 0, st));
     CU(cudaMemsetAsync(c->counters.p, 0, N_COUNTERS * sizeof(unsigned), st));
     c->sc.diag = c->counters.p + 4;

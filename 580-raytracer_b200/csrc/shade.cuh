@@ -60,21 +60,27 @@ __device__ __forceinline__ V3 calculate_refraction(V3 I, V3 N, float indexM2) {
     return I * eta + n * (eta * cosi - sqrtf(k));
 }
 
-// cpp:213-267.  shading_normal: interpolated vertex normal (triangle, normalised once by
-// InterpolateVector3) or the geometric hit normal (sphere); normalised (again) at cpp:237.
-__device__ __forceinline__ Pix calculate_local_color(V3 hitPoint, V3 shading_normal, const Light& L,
-                                                     const Material& M, V3 cam_from) {
+// cpp:213-267.  `normal` = normalize(shading normal) (cpp:237: the interpolated vertex normal of a triangle,
+// normalised once already by InterpolateVector3, or the geometric hit normal of a sphere) and `view` =
+// normalize(camera.from - hitPoint) (cpp:249-250, Q8) do not depend on the light: the caller computes them
+// once per node (phong_frame) instead of once per light.
+struct PhongFrame { V3 normal, view; };
+__device__ __forceinline__ PhongFrame phong_frame(V3 hitPoint, V3 shading_normal, V3 cam_from) {
+    PhongFrame f;
+    f.normal = normalize(shading_normal);                                // cpp:237
+    f.view = normalize(cam_from - hitPoint);                             // cpp:249-250 (Q8)
+    return f;
+}
+__device__ __forceinline__ Pix calculate_local_color(V3 hitPoint, const PhongFrame& f, const Light& L, const Material& M) {
     V3 lightVector;
     if (L.type == 1) lightVector = normalize(L.position - hitPoint);     // cpp:215-218
     else lightVector = normalize(L.direction * -1.0f);                   // cpp:220-221
-    const V3 normal = normalize(shading_normal);                         // cpp:237
-    // fmax(double(x), 0) back to float == x > 0 ? x : +0 (x is never NaN-free-guaranteed: fmax drops NaN)
-    const float ldn = dot(lightVector, normal);
+    // fmax(double(x), 0) back to float == x > 0 ? x : +0 (fmax drops a NaN)
+    const float ldn = dot(lightVector, f.normal);
     const float diffuseStrength = (ldn > 0.0f) ? ldn : 0.0f;             // cpp:242
     const V3 diffuse = (L.color * diffuseStrength) * L.intensity;        // cpp:243
-    const V3 reflection = normalize(reflect(lightVector, normal));       // cpp:246-247 (Q9)
-    const V3 view = normalize(cam_from - hitPoint);                      // cpp:249-250 (Q8)
-    const float vdr = dot(view, reflection);
+    const V3 reflection = normalize(reflect(lightVector, f.normal));     // cpp:246-247 (Q9)
+    const float vdr = dot(f.view, reflection);
     float spec = (vdr > 0.0f) ? vdr : 0.0f;                              // cpp:252
     spec = powf_glibc(spec, M.n);                                        // cpp:253
     const V3 specular = (L.color * spec) * L.intensity;                  // cpp:254
@@ -82,6 +88,10 @@ __device__ __forceinline__ Pix calculate_local_color(V3 hitPoint, V3 shading_nor
     V3 color = M.Cs * lighting;                                          // cpp:258
     color.x = clipf(color.x, 0, 1); color.y = clipf(color.y, 0, 1); color.z = clipf(color.z, 0, 1);
     return pix_from_v3(color);                                           // cpp:264
+}
+__device__ __forceinline__ Pix calculate_local_color(V3 hitPoint, V3 shading_normal, const Light& L,
+                                                     const Material& M, V3 cam_from) {
+    return calculate_local_color(hitPoint, phong_frame(hitPoint, shading_normal, cam_from), L, M);
 }
 
 // ---- the AO sample stream ----------------------------------------------------------------
@@ -99,6 +109,14 @@ __device__ __forceinline__ uint32_t lcg_state_at(uint64_t steps) {
     uint32_t base = 16807u, r = 1u;
     while (e) { if (e & 1u) r = lcg_mulmod(r, base); base = lcg_mulmod(base, base); e >>= 1; }
     return r;
+}
+// same through a table of 16807^(d * 256^k), d < 256, k < 4 (tab[k * 256 + d]): 3 modular products instead of ~45
+__device__ __forceinline__ uint32_t lcg_state_at_tab(uint64_t steps, const uint32_t* __restrict__ tab) {
+    const uint32_t e = (uint32_t)(steps % (uint64_t)(RT_LCG_M - 1u));
+    uint32_t r = __ldg(tab + (e & 255u));
+    r = lcg_mulmod(r, __ldg(tab + 256 + ((e >> 8) & 255u)));
+    r = lcg_mulmod(r, __ldg(tab + 512 + ((e >> 16) & 255u)));
+    return lcg_mulmod(r, __ldg(tab + 768 + (e >> 24)));
 }
 __device__ __forceinline__ float lcg_canonical(uint32_t& st) {
     st = lcg_mulmod(st, 16807u);
