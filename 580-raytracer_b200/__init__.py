@@ -29,7 +29,7 @@ EXPORTS = [
     "rt580_create", "rt580_destroy", "rt580_last_error", "rt580_device_info", "rt580_host_alloc", "rt580_host_free", "rt580_upload_scene", "rt580_build_ms",
     "rt580_scene_info_get", "rt580_get_stream",
     "rt580_render", "rt580_render_begin", "rt580_render_finish", "rt580_row_counts_to_device", "rt580_render_finish_interleaved",
-    "rt580_frame_export", "rt580_frame_import", "rt580_frame_release", "rt580_frame_read", "rt580_trace_closest", "rt580_trace_any", "rt580_trace_profile",
+    "rt580_frame_export", "rt580_frame_import", "rt580_frame_release", "rt580_frame_read", "rt580_frame_rgb8", "rt580_trace_closest", "rt580_trace_any", "rt580_trace_profile",
     "rt580_last_frame_ao_base", "rt580_hemisphere_stream", "rt580_powf",
     "rt580_raytracer_new", "rt580_raytracer_delete", "rt580_raytracer_set_assets_path", "rt580_raytracer_set_options", "rt580_raytracer_set_quiet",
     "rt580_raytracer_load_scene_json", "rt580_raytracer_render", "rt580_raytracer_flush_ppm",
@@ -143,6 +143,7 @@ def lib():
         L.rt580_frame_import.argtypes = [vp, vp, i32, i32]
         L.rt580_frame_release.argtypes = [vp]
         L.rt580_frame_read.argtypes = [vp, vp]
+        L.rt580_frame_rgb8.argtypes = [vp, vp, vp, i32]
         L.rt580_trace_closest.argtypes = [vp, i64, vp, vp, i32, vp, vp]
         L.rt580_trace_any.argtypes = [vp, i64, vp, vp, vp, i32, vp]
         L.rt580_trace_profile.argtypes = [vp, i64, vp, vp, vp, vp]
@@ -246,6 +247,14 @@ class Context:
         _check(lib().rt580_render_finish_interleaved(self._h, all_counts_device_ptr, world, rank, max_rows, device_ptr,
                                                       1 if device_ptr else 0, ctypes.byref(st)))
         return st
+
+    def frame_rgb8(self, lut256, n_rows, width):
+        """The last finished frame as the PPM's 8-bit RGB body (gamma table applied on the device)."""
+        lut = np.ascontiguousarray(lut256, np.uint8)
+        assert lut.size == 256
+        out = np.empty((n_rows, width, 3), np.uint8)
+        _check(lib().rt580_frame_rgb8(self._h, lut.ctypes.data, out.ctypes.data, 0))
+        return out
 
     def frame_export(self, width, height):
         """Rank 0: allocate the whole frame; returns the 64-byte CUDA IPC handle for the other ranks."""

@@ -408,7 +408,26 @@ int Raytracer::RenderToFrameBuffer() {
 int Raytracer::Render(const std::string outputName) {
     const int st = RenderToFrameBuffer();
     if (st != RT_SUCCESS) return st;
-    return FlushFrameBufferToPPM(outputName);                        // cpp:934
+    // cpp:934 FlushFrameBufferToPPM: the gamma table is applied on the device and the PPM body comes back
+    // as 3 bytes per pixel (rt580_frame_rgb8); the host restatement below is the fallback and the
+    // public method (it writes whatever the frame buffer holds, like the reference's)
+    if (mCtx && mWidth > 0 && mHeight > 0) {
+        unsigned char lut[256];
+        for (int c = 0; c < 256; c++) lut[c] = static_cast<unsigned char>(std::pow(c / 255.0f, 1.0f / 2.2f) * 255.0f);   // cpp:816-818
+        Rt580HostVector<unsigned char> body((size_t)mWidth * mHeight * 3);
+        if (rt580_frame_rgb8(mCtx, lut, body.data(), 0) == RT580_SUCCESS) {
+            std::ofstream outfile(outputName, std::ios::binary);
+            if (!outfile.is_open()) {
+                std::cerr << "Failed to create output file: " << outputName << std::endl;
+                return RT_FAILURE;
+            }
+            outfile << "P6\n" << mWidth << " " << mHeight << "\n255\n";
+            outfile.write(reinterpret_cast<const char*>(body.data()), (std::streamsize)body.size());
+            outfile.close();
+            return RT_SUCCESS;
+        }
+    }
+    return FlushFrameBufferToPPM(outputName);
 }
 
 // cpp:796-830: gamma 1/2.2 through libm powf, truncation to 8 bit (Q24)

@@ -172,6 +172,7 @@ struct rt580_context {
     int ndc_w = 0, ndc_h = 0; float ndc_fov = 0.f;     // what the primary-ray tables were built for
     DBuf<uint32_t> lcg_pow; int lcg_pow_spp = 0;
     DBuf<uint32_t> lcg_tab;
+    DBuf<uint8_t> rgb8; unsigned long long fb_pixels = 0;   // gamma-encoded copy of the last frame (rt580_frame_rgb8)
     // the whole W x H frame of a multi-GPU render: rank 0's own allocation, or that allocation mapped
     // into this process over NVLink (cudaIpc); every rank stores its rows there after the resolve pass
     int16_t* frame = nullptr; bool frame_imported = false; int frame_w = 0, frame_h = 0;
@@ -1314,6 +1315,28 @@ __global__ void k_resolve(DeviceScene sc, FrameParams fp, unsigned n0, unsigned 
     }
 }
 
+// FlushFrameBufferToPPM's per-channel work (cpp:809-823) on the device: out = lut[value], where lut is the
+// caller's table of the reference expression u8(powf(c / 255.0f, 1 / 2.2f) * 255.0f), c = 0..255 (built on
+// the host with the host's powf, so the bytes are the reference's by construction; the path only emits
+// values in [0,255]: cpp:128 clamps, the background is a constant).  3 B per pixel leave the device, not 6.
+__global__ void __launch_bounds__(256)
+k_gamma_rgb8(const int16_t* __restrict__ fb, unsigned long long n, const uint8_t* __restrict__ lut_g, uint8_t* __restrict__ out)
+{
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = lut_g[threadIdx.x];
+    __syncthreads();
+    const unsigned long long i4 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 4ull;
+    if (i4 + 4ull <= n) {
+        const short4 v = *reinterpret_cast<const short4*>(fb + i4);
+        uchar4 o;
+        o.x = lut[min(max((int)v.x, 0), 255)]; o.y = lut[min(max((int)v.y, 0), 255)];
+        o.z = lut[min(max((int)v.z, 0), 255)]; o.w = lut[min(max((int)v.w, 0), 255)];
+        *reinterpret_cast<uchar4*>(out + i4) = o;
+    } else {
+        for (unsigned long long i = i4; i < n; i++) out[i] = lut[min(max((int)fb[i], 0), 255)];
+    }
+}
+
 // ---- multi-GPU, device side ---------------------------------------------------------------
 // AO-stream prefix of this rank's rows from the all-gathered per-row hit-node counts of every rank
 // (rows interleaved: row y belongs to rank y % world, where it is row y / world).  One block; the
@@ -1514,7 +1537,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     free_scene(c);
     frame_release(c);
     arena_release(c->scene_arena); arena_release(c->build_arena);
-    c->ndc.release(); c->lcg_pow.release(); c->lcg_tab.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
+    c->ndc.release(); c->lcg_pow.release(); c->lcg_tab.release(); c->rgb8.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
     c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release(); c->chits.release();
@@ -2148,7 +2171,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         CU(cudaGetLastError());
         for (int r = 0; r < fp.n_rows; r++) row_hit_nodes[r] = rows[r];
     }
-    c->frame_begun = true;
+    c->frame_begun = true; c->fb_pixels = 0;
     if (dbg_t) fprintf(stderr, "[rt580] render_begin host ms: setup %.2f structure %.2f order %.2f (levels %d, launches %u, host syncs %u)\n",
                        t_setup - t_enter, t_struct - t_setup, now_ms() - t_struct, (int)c->level_off.size() - 1, c->launches, c->syncs);
     // ray accounting: one ray == one IntersectScene call of the reference (cpp:30, cpp:75, cpp:325)
@@ -2320,6 +2343,24 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
     } else c->stats.shadow_rays_traversed = c->stats.rays_shadow;
     if (stats) *stats = c->stats;
     c->frame_begun = false;
+    c->fb_pixels = npix;
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_frame_rgb8(rt580_context* c, const uint8_t* lut256, uint8_t* rgb_out, int out_on_device)
+{
+    if (!c || !lut256 || !rgb_out) FAIL(RT580_INVALID_ARG, "rt580_frame_rgb8: NULL argument");
+    if (c->frame_begun || !c->fb_pixels) FAIL(RT580_FAILURE, "rt580_frame_rgb8: no finished frame on the device");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const unsigned long long n = 3ull * c->fb_pixels;
+    CU(c->rgb8.ensure((size_t)n + 256, 0, st));
+    CU(cudaMemcpyAsync(c->rgb8.p + n, lut256, 256, cudaMemcpyHostToDevice, st));
+    uint8_t* dst = out_on_device ? rgb_out : c->rgb8.p;
+    k_gamma_rgb8<<<nblk((n + 3ull) / 4ull, 256), 256, 0, st>>>(c->fb.p, n, c->rgb8.p + n, dst);
+    if (!out_on_device) CU(cudaMemcpyAsync(rgb_out, c->rgb8.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
     return RT580_SUCCESS;
 }
 

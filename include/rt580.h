@@ -166,6 +166,11 @@ int  rt580_scene_info_get(rt580_context* ctx, rt580_scene_info* out);
  * fb_out: [n_rows][width][3] int16 raw Pixel{short r,g,b} (h:373-374), host memory. */
 int  rt580_render(rt580_context* ctx, const rt580_render_params* params, int16_t* fb_out, rt580_stats* stats);
 
+/* The last finished frame (its rows on this context) as 8-bit RGB, the body of the reference's PPM
+ * (cpp:809-823): rgb = lut256[value] with the caller's table of u8(powf(c / 255.0f, 1 / 2.2f) * 255.0f),
+ * c = 0..255, evaluated with the host's powf.  rgb_out: [n_rows][width][3] bytes, host or device. */
+int  rt580_frame_rgb8(rt580_context* ctx, const uint8_t* lut256, uint8_t* rgb_out, int out_on_device);
+
 /* Split form for several ranks (one context per GPU, rows partitioned):
  *   begin  : structure pass; row_hit_nodes[n_rows] = AO-relevant hit nodes per owned row
  *   finish : row_ao_base[n_rows] = for each owned row the number of hit nodes in ALL rows

@@ -395,3 +395,26 @@ def test_page_locked_host_arrays(pkg):
     ref, _ = ctx.render(rt.render_params())
     assert fb is ha.array and np.array_equal(fb, ref)
     ha.close(); ctx.close()
+
+
+def test_ppm_body_from_the_device(pkg, oracle):
+    """rt580_frame_rgb8 (FlushFrameBufferToPPM's gamma + truncation on the device): the bytes
+    equal the host restatement of cpp:809-823 applied to the int16 frame, for a whole frame and for a
+    band of rows whose element count is not a multiple of four."""
+    scene, W, H, spp, depth = "simpleSphereScene.json", 123, 77, 4, 4
+    rt = make_rt(pkg, scene, W, H, spp, depth)
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    lut = oracle.gamma_encode(np.arange(256, dtype=np.int16))
+    p = rt.render_params()
+    fb, _ = ctx.render(p)
+    assert np.array_equal(ctx.frame_rgb8(lut, H, W), oracle.gamma_encode(fb))
+    q = p.copy()
+    q.row_first, q.row_step, q.n_rows = 1, 3, 25
+    ctx.render_begin(q)
+    band, _ = ctx.render_finish(q, np.zeros(25, np.uint64))
+    assert np.array_equal(ctx.frame_rgb8(lut, 25, W), oracle.gamma_encode(band))
+    with pytest.raises(pkg.Rt580Error):
+        ctx.render_begin(q)
+        ctx.frame_rgb8(lut, 25, W)          # no finished frame
+    ctx.close()
