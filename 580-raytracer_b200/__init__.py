@@ -269,8 +269,9 @@ class Context:
     def frame_release(self):
         _check(lib().rt580_frame_release(self._h))
 
-    def frame_read(self, width, height):
-        fb = np.empty((height, width, 3), np.int16)
+    def frame_read(self, width, height, out=None):
+        fb = np.empty((height, width, 3), np.int16) if out is None else out
+        assert fb.dtype == np.int16 and fb.size == height * width * 3 and fb.flags["C_CONTIGUOUS"]
         _check(lib().rt580_frame_read(self._h, fb.ctypes.data))
         return fb
 

@@ -209,6 +209,7 @@ def run_ours(args):
             gather_list = [torch.empty((max_rows, W, 6), dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
             padded = torch.zeros((max_rows, W, 3), dtype=torch.int16, device="cuda")
 
+    side_stream = torch.cuda.Stream() if world > 1 else None
     dbg = bool(os.environ.get("RT580_BENCH_DEBUG")) and (rank == 0 or os.environ.get("RT580_BENCH_DEBUG") == "2")
     tparts = [0.0] * 8
 
@@ -232,10 +233,15 @@ def run_ours(args):
             st = ctx.render_finish_interleaved(all_d.data_ptr(), world, rank, max_rows,
                                                device_ptr=None if peer_frame else padded.data_ptr())
             _d = time.perf_counter()
-            with torch.cuda.stream(ext_stream):
-                if peer_frame:
-                    dist.all_reduce(done)                                  # every rank's rows have landed in rank 0's frame
-                else:
+            if peer_frame:
+                # "every rank's rows have landed in rank 0's frame": a 4-byte all-reduce ordered after this rank's
+                # stores, on a side stream - whoever consumes the frame on rank 0 waits for it, the next frame's
+                # structure pass does not (ranks drift by a few % per frame: the GPUs of a box are not equally fast)
+                side_stream.wait_stream(ext_stream)
+                with torch.cuda.stream(side_stream):
+                    dist.all_reduce(done)
+            else:
+                with torch.cuda.stream(ext_stream):
                     dist.gather(padded.view(torch.uint8), gather_list, dst=0)
         if dbg:
             torch.cuda.synchronize()
@@ -265,6 +271,8 @@ def run_ours(args):
         st = frame()
         stats.append(st)
         launches += st.kernel_launches
+    if side_stream is not None:
+        ext_stream.wait_stream(side_stream)      # the timed region ends when the last frame is complete on rank 0
     ev1.record(ext_stream)
     sync()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -320,7 +328,8 @@ def run_ours(args):
     h2d = int(flat.n_tris * (6 * 16 + 8) + flat.n_spheres * (16 + 8) + flat.n_materials * 32 + flat.n_lights * 44)
     d2h = int(p.n_rows * W * 6) if world == 1 else int(W * H * 6)
     host_frame = None
-    host_out = pkg.HostArray((p.n_rows, W, 3), np.int16) if world == 1 else None     # page-locked, like the host class's frame buffer
+    # page-locked, like the host class's frame buffer
+    host_out = pkg.HostArray((p.n_rows, W, 3), np.int16) if world == 1 else (pkg.HostArray((H, W, 3), np.int16) if rank == 0 else None)
     for _ in range(1):
         ctx.upload_scene(flat); ctx.render(p, out=host_out.array) if world == 1 else None
     sync()
@@ -339,9 +348,9 @@ def run_ours(args):
         else:
             frame()
             if rank == 0:
-                torch.cuda.synchronize()
+                torch.cuda.synchronize()                                  # includes the side stream's "all rows landed"
                 if peer_frame:
-                    host_frame = ctx.frame_read(W, H)                     # the whole frame -> host memory on rank 0
+                    host_frame = ctx.frame_read(W, H, out=host_out.array)  # the whole frame -> host memory on rank 0
                 else:
                     host_frame = torch.stack(gather_list).cpu()
     sync()
