@@ -69,7 +69,8 @@ struct DeviceScene {
     // from the light to the nearest padded leaf box in each direction.  A shadow ray whose far end
     // (its origin, seen from the light) is nearer than that bound cannot meet a tree primitive: it
     // skips the traversal.  Pure culling, like the boxes of the tree itself.
-    const float* smap;             // [n_smap][6][SMAP_RES][SMAP_RES]
+    const float* smap;             // [n_smap][6][smap_res][smap_res]
+    int32_t smap_res;
     const int32_t* smap_of_light;  // [n_lights] map index, -1: none (not a point light, or a primitive too close to it)
     int32_t n_smap;
 };

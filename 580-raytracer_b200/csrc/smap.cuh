@@ -17,7 +17,7 @@
 
 namespace rt580 {
 
-#define SMAP_RES 512
+#define SMAP_RES_DEFAULT 512   // texels per cube-face edge (RT580_SMAP_RES overrides): 0.18 degrees per texel
 #define SMAP_CLEARANCE 0.25f
 #define SMAP_MAX 8           // point lights that get a map
 
@@ -26,7 +26,7 @@ __device__ __forceinline__ float smap_axis(const V3& v, int a) { return a == 0 ?
 // one thread per (inner node, child slot): leaf children rasterise their box into the six faces
 __global__ void __launch_bounds__(256)
 k_smap_raster(const BvhNode* __restrict__ nodes, int n_nodes, float lx, float ly, float lz, float* __restrict__ map,
-              unsigned int* __restrict__ min_clear_bits)
+              unsigned int* __restrict__ min_clear_bits, int SMAP_RES)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = tid >> 1, c = tid & 1;
@@ -66,7 +66,7 @@ k_smap_raster(const BvhNode* __restrict__ nodes, int n_nodes, float lx, float ly
 }
 
 // Does the map prove that no tree primitive lies between `origin` (the shadow ray's start) and the light?
-__device__ __forceinline__ bool smap_clear(const float* __restrict__ map, V3 light, V3 origin)
+__device__ __forceinline__ bool smap_clear(const float* __restrict__ map, int SMAP_RES, V3 light, V3 origin)
 {
     const V3 v = origin - light;
     const float ax = fabsf(v.x), ay = fabsf(v.y), az = fabsf(v.z);
