@@ -182,6 +182,7 @@ struct rt580_context {
     int ch_blocks_per_sm = 10; bool one_thread_per_ray = false;   // RT580_CH_BLOCKS_PER_SM, RT580_ONE_THREAD_PER_RAY (A/B)
     uint64_t slow_total = 0;
     int ah_batch_div = 4;
+    int smap_res = SMAP_RES_DEFAULT;        // RT580_SMAP_RES
     unsigned slow_any_cap = SLOW_ANY_CAP;   // RT580_SLOW_ANY_CAP: shrink it to exercise the overflow -> repeat path
     int ah_steps = AH_STEPS, ah_min_search = AH_MIN_SEARCH, ah_blocks_per_sm = 12;  // k_anyhit tuning (env RT580_AH_*)
     std::vector<size_t> level_off; // node index where each level starts (+ end)
@@ -1114,7 +1115,7 @@ k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long fi
         // (not for rays whose hit / miss the tree does not decide alone: a far origin, a light beyond far_tmin)
         const int mi = sc.n_smap ? __ldg(sc.smap_of_light + li) : -1;
         if (mi >= 0 && !(sc.farfield && (tmax >= sc.far_tmin || fmaxf(fabsf(so.x), fmaxf(fabsf(so.y), fabsf(so.z))) > sc.extent)) &&
-            smap_clear(sc.smap + (size_t)mi * 6 * SMAP_RES * SMAP_RES, L.position, so)) emit = false;
+            smap_clear(sc.smap + (size_t)mi * 6 * sc.smap_res * sc.smap_res, sc.smap_res, L.position, so)) emit = false;
     }
     // order-preserving compaction with ONE global atomic per block (one per warp, 3.7 M on the same
     // address for a 4K level, cost as much as the traversal they saved)
@@ -1514,6 +1515,7 @@ extern "C" int rt580_create(int device, rt580_context** out)
     if (const char* e = getenv("RT580_AH_STEPS")) c->ah_steps = atoi(e) > 0 ? atoi(e) : c->ah_steps;
     if (const char* e = getenv("RT580_AH_MIN_SEARCH")) c->ah_min_search = atoi(e) > 0 ? atoi(e) : c->ah_min_search;
     if (const char* e = getenv("RT580_AH_BLOCKS_PER_SM")) c->ah_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ah_blocks_per_sm;
+    if (const char* e = getenv("RT580_SMAP_RES")) c->smap_res = (atoi(e) >= 16 && atoi(e) <= 4096) ? atoi(e) : c->smap_res;
     if (const char* e = getenv("RT580_SLOW_ANY_CAP")) c->slow_any_cap = atoi(e) > 0 ? (unsigned)atoi(e) : c->slow_any_cap;
     if (const char* e = getenv("RT580_AH_BATCH_DIV")) c->ah_batch_div = atoi(e) > 0 ? atoi(e) : c->ah_batch_div;
     if (const char* e = getenv("RT580_CH_BLOCKS_PER_SM")) c->ch_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ch_blocks_per_sm;
@@ -1587,7 +1589,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         for (int i = 0; i < s->n_lights; i++) if (s->light_type && s->light_type[i] == RT580_LIGHT_POINT) n_point++;
         if (n_point > SMAP_MAX) n_point = SMAP_MAX;
         const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 48 + 32 * 256 +
-                                   (size_t)n_point * 6 * SMAP_RES * SMAP_RES * sizeof(float);
+                                   (size_t)n_point * 6 * c->smap_res * c->smap_res * sizeof(float);
         if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
             !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
             FAIL(RT580_FAILURE, "rt580_upload_scene: %s", aerr);
@@ -1683,7 +1685,8 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         const bool use_maps = bo.n_leaf > RT_SMEM_PRIMS && bo.n_always == 0 && !getenv("RT580_NO_SMAP");
         if (use_maps) for (int i = 0; i < s->n_lights && n_maps < SMAP_MAX; i++) if (s->light_type[i] == RT580_LIGHT_POINT) of_light[i] = n_maps++;
         if (n_maps) {
-            const size_t per = (size_t)6 * SMAP_RES * SMAP_RES;
+            const size_t per = (size_t)6 * c->smap_res * c->smap_res;
+            c->sc.smap_res = c->smap_res;
             float* maps = sa.take<float>(per * n_maps);
             unsigned int* clear = ta.take<unsigned int>(SMAP_MAX);
             if (!maps || !clear) FAIL(RT580_FAILURE, "rt580_upload_scene: arena exhausted (clearance maps)");
@@ -1694,7 +1697,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
                 if (of_light[i] < 0) continue;
                 const float* lf = s->light_f + 10 * (size_t)i;
                 k_smap_raster<<<nblk_ll(2ll * n_nodes, 256), 256, 0, st>>>(bo.nodes, n_nodes, lf[4], lf[5], lf[6], maps + per * of_light[i],
-                                                                        clear + of_light[i]);
+                                                                        clear + of_light[i], c->smap_res);
             }
             float hclear[SMAP_MAX];
             CU(cudaMemcpyAsync(hclear, clear, sizeof hclear, cudaMemcpyDeviceToHost, st));
