@@ -52,6 +52,8 @@ struct DeviceScene {
     // it is done once per plane and rejects all its triangles at once
     const float4* big_planes;               // [n_big_planes] (N.xyz, D), bit-identical in all member records
     const unsigned long long* big_masks;    // [n_big_planes] members: bit k = prims[n_leaf + k]
+    const int32_t* big_plane_newn;          // [n_big_planes] 1: another normal than the plane before (planes are sorted
+                                            //                by normal: parallel walls share N.d and N.O in the ordering pass)
     unsigned long long big_sphere_mask;     // large spheres (no plane): bit k = prims[n_leaf + k]
     int32_t n_big_planes;
     int32_t n_all;             // n_leaf + n_big: what the linear loops and the far-field scan walk

@@ -110,6 +110,7 @@ struct FrameParams {
     int W, H;
     int row_first, row_step, n_rows;
     int depth, spp, rng_mode;
+    int spp_shift;        // log2(spp) when spp is a power of two, else -1
     float cam[3];
     float inv[9];
     const float* ndc_x;   // [W]  (float)(NDCX * aspect * tan(fov/2))   cpp:834-839, 846
@@ -992,22 +993,34 @@ struct __align__(16) ARay {
 // the loop after 1..n_big iterations and ncu showed 6-14 of 32 lanes active over 74 % of k_ao_gen's
 // instructions.
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ bool plane_members_any(const PrimRec* __restrict__ s_big, float4 pl, unsigned long long members, V3 O, V3 d)
+{
+    V3 P;
+    if (!plane_point_any(pl, O, d, __int_as_float(0x7f800000), P)) return false;     // t and P are the same for every triangle of the plane
+    for (unsigned long long m = members; m; m &= m - 1ull)
+        if (tri_bary_accept<false>(&s_big[__ffsll((long long)m) - 1], P)) return true;
+    return false;
+}
 __device__ __forceinline__ bool big_any_nearest_first(const PrimRec* __restrict__ s_big, int n_big, const float4* __restrict__ s_plane,
-                                                      const unsigned long long* __restrict__ s_mask, int n_planes,
-                                                      unsigned long long sphere_mask, V3 O, V3 d)
+                                                      const unsigned long long* __restrict__ s_mask, const unsigned char* __restrict__ s_newn,
+                                                      int n_planes, unsigned long long sphere_mask, V3 O, V3 d)
 {
     const float inf = __int_as_float(0x7f800000);
     float t; int prim;
     for (unsigned long long m = sphere_mask; m; m &= m - 1ull)
         if (prim_test<false>(&s_big[__ffsll((long long)m) - 1], O, d, inf, 0x7fffffff, t, prim)) return true;
-    // keys: approximate t (a positive float orders like its bits) with the plane index in the low 6 bits
+    // keys: approximate t (a positive float orders like its bits) with the plane index in the low 6 bits;
+    // planes are sorted by normal, parallel ones share N.d, N.O and the reciprocal (the branch is warp-uniform)
     unsigned m1 = 0xffffffffu, m2 = 0xffffffffu;
+    float nO = 0.f, r = 0.f;
 #pragma unroll 4
     for (int j = 0; j < n_planes; j++) {
         const float4 pl = s_plane[j];
-        const float nd = __fmaf_rn(pl.x, d.x, __fmaf_rn(pl.y, d.y, pl.z * d.z));
-        const float num = -__fmaf_rn(pl.x, O.x, __fmaf_rn(pl.y, O.y, __fmaf_rn(pl.z, O.z, pl.w)));
-        const float ta = num * rcp_approx(nd);
+        if (s_newn[j]) {
+            nO = __fmaf_rn(pl.x, O.x, __fmaf_rn(pl.y, O.y, pl.z * O.z));
+            r = rcp_approx(__fmaf_rn(pl.x, d.x, __fmaf_rn(pl.y, d.y, pl.z * d.z)));
+        }
+        const float ta = -(nO + pl.w) * r;
         const unsigned key = (ta > 0.0f) ? ((__float_as_uint(ta) & ~63u) | (unsigned)j) : 0xffffffffu;   // behind, parallel, NaN: last
         const unsigned hi = max(key, m1);
         m1 = min(key, m1);
@@ -1016,14 +1029,12 @@ __device__ __forceinline__ bool big_any_nearest_first(const PrimRec* __restrict_
     unsigned long long tested = sphere_mask;
     if (m1 != 0xffffffffu) {
         const unsigned long long mm = s_mask[m1 & 63u];
-        for (unsigned long long m = mm; m; m &= m - 1ull)
-            if (prim_test<false>(&s_big[__ffsll((long long)m) - 1], O, d, inf, 0x7fffffff, t, prim)) return true;
+        if (plane_members_any(s_big, s_plane[m1 & 63u], mm, O, d)) return true;
         tested |= mm;
     }
     if (m2 != 0xffffffffu) {
         const unsigned long long mm = s_mask[m2 & 63u];
-        for (unsigned long long m = mm; m; m &= m - 1ull)
-            if (prim_test<false>(&s_big[__ffsll((long long)m) - 1], O, d, inf, 0x7fffffff, t, prim)) return true;
+        if (plane_members_any(s_big, s_plane[m2 & 63u], mm, O, d)) return true;
         tested |= mm;
     }
     for (int k = 0; k < n_big; k++)
@@ -1040,11 +1051,14 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
     __shared__ PrimRec s_big[64];
     __shared__ float4 s_plane[64];
     __shared__ unsigned long long s_mask[64];
+    __shared__ unsigned char s_newn[64];
     {
         const float4* src = reinterpret_cast<const float4*>(sc.prims + sc.n_leaf);
         float4* dst = reinterpret_cast<float4*>(s_big);
         for (int i = threadIdx.x; i < sc.n_big * 4; i += blockDim.x) dst[i] = __ldg(src + i);
-        for (int i = threadIdx.x; i < sc.n_big_planes; i += blockDim.x) { s_plane[i] = __ldg(sc.big_planes + i); s_mask[i] = __ldg(sc.big_masks + i); }
+        for (int i = threadIdx.x; i < sc.n_big_planes; i += blockDim.x) {
+            s_plane[i] = __ldg(sc.big_planes + i); s_mask[i] = __ldg(sc.big_masks + i); s_newn[i] = (unsigned char)__ldg(sc.big_plane_newn + i);
+        }
         __syncthreads();
     }
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1055,9 +1069,10 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
     r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a;
     if (active) {
         const unsigned long long i = first + j;
-        call = (unsigned)(i / (unsigned)fp.spp);
-        const unsigned k = (unsigned)(i % (unsigned)fp.spp);
-        const unsigned node = call / (unsigned)n_ambient;
+        unsigned k;
+        if (fp.spp_shift >= 0) { call = (unsigned)(i >> fp.spp_shift); k = (unsigned)i & ((unsigned)fp.spp - 1u); }   // spp a power of two: no 64-bit division
+        else { call = (unsigned)(i / (unsigned)fp.spp); k = (unsigned)(i % (unsigned)fp.spp); }
+        const unsigned node = (n_ambient == 1) ? call : call / (unsigned)n_ambient;
         uint32_t st = lcg_mulmod(__ldg(ao_state + call), __ldg(fp.lcg_pow + k));    // state after the 2k draws before sample k
         const float4 nP = __ldg(&nodes[node].P), nN = __ldg(&nodes[node].N);
         const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
@@ -1070,7 +1085,7 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
         // the large primitives first: most likely occluders, and the ray is not queued at all if one is hit
         const bool far_origin = sc.farfield && fmaxf(fabsf(org.x), fmaxf(fabsf(org.y), fabsf(org.z))) > sc.extent;
         if (!far_origin && sc.n_big > 0) {
-            hit = big_any_nearest_first(s_big, sc.n_big, s_plane, s_mask, sc.n_big_planes, sc.big_sphere_mask, org, rd);
+            hit = big_any_nearest_first(s_big, sc.n_big, s_plane, s_mask, s_newn, sc.n_big_planes, sc.big_sphere_mask, org, rd);
             emit = !hit;
         }
     }
@@ -1588,7 +1603,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         int n_point = 0;
         for (int i = 0; i < s->n_lights; i++) if (s->light_type && s->light_type[i] == RT580_LIGHT_POINT) n_point++;
         if (n_point > SMAP_MAX) n_point = SMAP_MAX;
-        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 48 + 32 * 256 +
+        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 48 + 40 * 256 +
                                    (size_t)n_point * 6 * c->smap_res * c->smap_res * sizeof(float);
         if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
             !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
@@ -1652,7 +1667,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_big = bo.n_big; c->sc.n_all = bo.n_leaf + bo.n_big;
     {
         // distinct planes of the large triangles (device_scene.h); at most 64 records, grouped on the host
-        c->sc.big_planes = nullptr; c->sc.big_masks = nullptr; c->sc.big_sphere_mask = 0ull; c->sc.n_big_planes = 0;
+        c->sc.big_planes = nullptr; c->sc.big_masks = nullptr; c->sc.big_plane_newn = nullptr; c->sc.big_sphere_mask = 0ull; c->sc.n_big_planes = 0;
         if (bo.n_big > 64) FAIL(RT580_FAILURE, "rt580_upload_scene: %d large primitives (at most 64)", bo.n_big);
         if (bo.n_big > 0) {
             std::vector<PrimRec> big((size_t)bo.n_big);
@@ -1668,11 +1683,23 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
                 masks[j] |= 1ull << k;
             }
             if (!planes.empty()) {
-                float4* dp = nullptr; unsigned long long* dm = nullptr;
-                CU(upload(sa, &dp, planes.data(), planes.size(), st));
-                CU(upload(sa, &dm, masks.data(), masks.size(), st));
+                // planes with the same normal next to each other (parallel walls), first occurrence order otherwise
+                std::vector<float4> sp; std::vector<unsigned long long> sm; std::vector<int32_t> newn;
+                std::vector<char> used(planes.size(), 0);
+                for (size_t a = 0; a < planes.size(); a++) {
+                    if (used[a]) continue;
+                    for (size_t b = a; b < planes.size(); b++) {
+                        if (used[b] || memcmp(&planes[a], &planes[b], 3 * sizeof(float)) != 0) continue;
+                        used[b] = 1;
+                        sp.push_back(planes[b]); sm.push_back(masks[b]); newn.push_back(b == a ? 1 : 0);
+                    }
+                }
+                float4* dp = nullptr; unsigned long long* dm = nullptr; int32_t* dn = nullptr;
+                CU(upload(sa, &dp, sp.data(), sp.size(), st));
+                CU(upload(sa, &dm, sm.data(), sm.size(), st));
+                CU(upload(sa, &dn, newn.data(), newn.size(), st));
                 CU(cudaStreamSynchronize(st));
-                c->sc.big_planes = dp; c->sc.big_masks = dm; c->sc.n_big_planes = (int)planes.size();
+                c->sc.big_planes = dp; c->sc.big_masks = dm; c->sc.big_plane_newn = dn; c->sc.n_big_planes = (int)sp.size();
             }
         }
     }
@@ -1972,6 +1999,8 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
     if (npix64 > 0x7fffff00ull) FAIL(RT580_INVALID_ARG, "rt580_render_begin: too many pixels for one context");
     const unsigned npix = (unsigned)npix64;
     fp.depth = p->depth; fp.spp = p->ao_spp; fp.rng_mode = p->rng_mode;
+    fp.spp_shift = -1;
+    for (int b = 0; b < 17; b++) if (fp.spp == (1 << b)) fp.spp_shift = b;
     memcpy(fp.cam, p->camera_from, sizeof fp.cam);
     memcpy(fp.inv, p->inv_view3x3, sizeof fp.inv);
     c->traversal = p->traversal;

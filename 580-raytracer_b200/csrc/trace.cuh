@@ -92,6 +92,38 @@ __device__ __forceinline__ bool prim_test(const PrimRec* __restrict__ p, V3 O, V
     }
 }
 
+// The two halves of the triangle branch of prim_test, for callers that test several triangles of ONE plane
+// (bit-identical N and D: device_scene.h big_planes): the plane half gives the same t and P for all of them.
+// Same operations in the same order as prim_test; any-hit form (a hit at t == t_limit counts, cpp:75).
+__device__ __forceinline__ bool plane_point_any(float4 pl, V3 O, V3 d, float t_limit, V3& P_out)
+{
+    const V3 N = mk(pl.x, pl.y, pl.z);
+    const float nd = dot(N, d);                                   // cpp:367
+    if (fabsf(nd - 0.0f) <= RT_EPS_F) return false;               // cpp:371
+    const float num = -(dot(N, O) + pl.w);
+    if (num == 0.0f || ((num < 0.0f) != (nd < 0.0f))) return false;
+    if (fabsf(num) > (t_limit * fabsf(nd)) * 1.000001f) return false;
+    const float t = num / nd;                                     // cpp:381
+    if (t <= RT_EPS_F) return false;                              // cpp:382
+    if (!(t <= t_limit)) return false;
+    P_out = O + d * t;                                            // cpp:387
+    return true;
+}
+template <bool GLOBAL>
+__device__ __forceinline__ bool tri_bary_accept(const PrimRec* __restrict__ p, V3 P)
+{
+    const float4 ra = ld4<GLOBAL>(&p->a), rb = ld4<GLOBAL>(&p->b), rc = ld4<GLOBAL>(&p->c), rd = ld4<GLOBAL>(&p->d);
+    const V3 N = mk(rd.x, rd.y, rd.z);
+    const V3 v0 = mk(ra.x, ra.y, ra.z), v1 = mk(rb.x, rb.y, rb.z), v2 = mk(rc.x, rc.y, rc.z);
+    const bool slow = (__float_as_int(rd.w) & RT_PRIM_SLOWPATH) != 0;
+    const float da = dot(cross(v1 - P, v2 - P), N);               // alpha: (P, v1, v2)   cpp:392
+    if (bary_negative(da, rb.w, slow)) return false;
+    const float db = dot(cross(P - v0, v2 - v0), N);              // beta : (v0, P, v2)   cpp:393
+    if (bary_negative(db, rb.w, slow)) return false;
+    const float dg = dot(cross(v1 - v0, P - v0), N);              // gamma: (v0, v1, P)   cpp:394
+    return !bary_negative(dg, rb.w, slow);                        // cpp:396
+}
+
 // Conservative ray/box slab test.  (plane - o) * inv has <= 3 roundings, so widening the
 // interval by 2^-21 relative makes the float result a superset of the exact one.
 __device__ __forceinline__ bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz,
