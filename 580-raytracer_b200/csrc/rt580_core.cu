@@ -728,19 +728,13 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
     for (int li = 0; li < sc.n_lights; li++) {                        // cpp:39
         const Light L = load_light(sc.light_type, sc.light_f, li);
         if (L.type == RT580_LIGHT_AMBIENT) continue;                  // handled by k_ao / k_resolve
-        V3 so, sd; float tmax;
-        shadow_ray(L, P, so, sd, tmax);
         int tr;
         if (PRETRACED) {
-            tr = TR_MISS;
-            if (active) {
-                if (__ldg(occl + (size_t)(i - n0) * sc.n_nonambient + j) != 0u) tr = TR_HIT;
-                else if (sc.n_big > 0 && !(sc.farfield && fmaxf(fabsf(so.x), fmaxf(fabsf(so.y), fabsf(so.z))) > sc.extent)) {
-                    HitRec sh; sh.t = tmax; sh.leaf = -1; sh.prim = 0x7fffffff;
-                    if (big_scan<true>(sc, so, sd, sh)) tr = TR_HIT;
-                }
-            }
+            // occluders of this ray: tree (k_anyhit), large primitives (k_shade_gen), or still pending (k_shadow_finish)
+            tr = (active && __ldg(occl + (size_t)(i - n0) * sc.n_nonambient + j) != 0u) ? TR_HIT : TR_MISS;
         } else {
+            V3 so, sd; float tmax;
+            shadow_ray(L, P, so, sd, tmax);
             HitRec sh;
             // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
             tr = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh, sq, (int)i, li);
@@ -808,7 +802,7 @@ k_shade_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays,
 
 // Deferred shadow rays of the wavefront path (k_shade_gen -> k_anyhit), answered by k_slow after
 // k_shade has run: c.y = node * n_nonambient + j.  k_shade saw OCCL_PENDING and left the light's
-// term out; an unoccluded ray adds it now (what is left to test is the large-primitive list).
+// term out; an unoccluded ray adds it now.
 __global__ void __launch_bounds__(128)
 k_shadow_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays, const SlowRes* __restrict__ res,
                 unsigned n_slow, const Node* __restrict__ nodes, NodeAux* __restrict__ aux)
@@ -821,11 +815,7 @@ k_shadow_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays
     const unsigned i = gid / (unsigned)sc.n_nonambient;
     int j = (int)(gid % (unsigned)sc.n_nonambient), li = 0;
     for (;; li++) { if (__ldg(sc.light_type + li) != RT580_LIGHT_AMBIENT) { if (j == 0) break; j--; } }
-    const V3 so = mk(r.o.x, r.o.y, r.o.z), sd = mk(r.d.x, r.d.y, r.d.z);
-    if (sc.n_big > 0 && !(r.c.x & 1)) {                                // the linear fallback saw every record already
-        HitRec sh; sh.t = r.o.w; sh.leaf = -1; sh.prim = 0x7fffffff;
-        if (big_scan<true>(sc, so, sd, sh)) return;
-    }
+    // (the large primitives were tested by k_shade_gen before the ray was queued; a linear-fallback ray saw every record)
     const Node nd = nodes[i];
     const unsigned flags = __float_as_uint(nd.B.w);
     const int prim = __float_as_int(nd.P.w);
@@ -841,7 +831,7 @@ k_shadow_finish(DeviceScene sc, FrameParams fp, const SlowRay* __restrict__ rays
 // shadow rays of one level as a ray queue for k_anyhit: ray id = (node - n0) * n_nonambient + j
 __global__ void __launch_bounds__(512)
 k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
-            struct ARay* __restrict__ out, unsigned int* __restrict__ n_out);
+            struct ARay* __restrict__ out, unsigned int* __restrict__ n_out, uint32_t* __restrict__ occl);
 
 // deferred AO rays of k_ao: a hit is one more occluded sample of its AO call (cpp:325-326)
 __global__ void k_ao_finish(const SlowRay* __restrict__ rays, const SlowRes* __restrict__ res, unsigned n_slow,
@@ -1042,7 +1032,7 @@ __device__ __forceinline__ bool big_any_nearest_first(const PrimRec* __restrict_
     return false;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, int n_ambient, const Node* __restrict__ nodes,
          const uint32_t* __restrict__ ao_state, ARay* __restrict__ out, unsigned int* __restrict__ n_out,
          uint32_t* __restrict__ ao_hits)
@@ -1102,7 +1092,7 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
 
 __global__ void __launch_bounds__(512)
 k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long first, unsigned n, const Node* __restrict__ nodes,
-            ARay* __restrict__ out, unsigned int* __restrict__ n_out)
+            ARay* __restrict__ out, unsigned int* __restrict__ n_out, uint32_t* __restrict__ occl)
 {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     bool emit = false;
@@ -1124,12 +1114,18 @@ k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long fi
         r.a = make_float4(so.x, so.y, so.z, sd.x);
         r.b = make_float4(sd.y, sd.z, __uint_as_float(id), tmax);
         emit = true;
+        const bool far_origin = sc.farfield && fmaxf(fabsf(so.x), fmaxf(fabsf(so.y), fabsf(so.z))) > sc.extent;
+        // the large primitives here (plane by plane, exact), so that k_shade only has to read the verdict; a ray one
+        // of them stops is not queued (a far origin takes the reference's linear loop over ALL records instead)
+        if (sc.n_big > 0 && !far_origin) {
+            HitRec sh; sh.t = tmax; sh.leaf = -1; sh.prim = 0x7fffffff;
+            if (big_scan<true>(sc, so, sd, sh)) { occl[id] = 1u; emit = false; }
+        }
         // the light's clearance map may prove that no tree primitive lies between the ray origin and the
-        // light (smap.cuh): such a ray is not queued, its occluder count stays 0, and k_shade goes on with
-        // the large-primitive test as for any ray the tree did not stop
+        // light (smap.cuh): such a ray is not queued and its occluder count stays 0
         // (not for rays whose hit / miss the tree does not decide alone: a far origin, a light beyond far_tmin)
-        const int mi = sc.n_smap ? __ldg(sc.smap_of_light + li) : -1;
-        if (mi >= 0 && !(sc.farfield && (tmax >= sc.far_tmin || fmaxf(fabsf(so.x), fmaxf(fabsf(so.y), fabsf(so.z))) > sc.extent)) &&
+        const int mi = (emit && sc.n_smap) ? __ldg(sc.smap_of_light + li) : -1;
+        if (mi >= 0 && !(sc.farfield && (tmax >= sc.far_tmin || far_origin)) &&
             smap_clear(sc.smap + (size_t)mi * 6 * sc.smap_res * sc.smap_res, sc.smap_res, L.position, so)) emit = false;
     }
     // order-preserving compaction with ONE global atomic per block (one per warp, 3.7 M on the same
@@ -2125,7 +2121,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                 }
                 const int rc = anyhit_queue_pass(c, n_sh, c->occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
                     [&](unsigned long long first, unsigned n) {
-                        k_shade_gen<<<nblk(n, 512), 512, 0, st>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6);
+                        k_shade_gen<<<nblk(n, 512), 512, 0, st>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6, c->occl.p);
                     });
                 if (rc) return rc;
             }
