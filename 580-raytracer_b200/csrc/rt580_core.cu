@@ -311,92 +311,117 @@ __device__ __forceinline__ int finish_closest(const DeviceScene& sc, bool active
     return pending ? TR_PENDING : (found ? TR_HIT : TR_MISS);
 }
 
-// Deferred slow rays.  Every slow ray must see every primitive record (far scan: the 16-byte
-// filter record, and the 64-byte primitive record of the survivors; linear fallback: the
-// primitive record), so the kernel is bound by record traffic unless rays share it: a block takes
-// SLOW_RPB rays, streams the records through shared memory in tiles of SLOW_TILE, and each of
-// its 8 warps tests its 4 rays against the tile (lane l takes records l, l+32, ...).  Record
-// traffic per ray drops by SLOW_RPB; the grid is one block per ray batch over the whole GPU.
+// Deferred slow rays.  Every slow ray must see every primitive's filter record (far scan) or every
+// primitive (linear fallback), so the kernel is bound by record traffic unless rays share it: a block
+// takes SLOW_RPB rays, streams the 16-byte filter records through shared memory in tiles of SLOW_TILE,
+// and each of its 8 warps runs its 4 rays over the tile (lane l takes records l, l+32, ...).  The
+// exact test (the reference's, prim_test, ~100 instructions) is needed for ~0.5 % of the (ray, record)
+// pairs only; run where the filter passes it kept 1-2 lanes of a warp busy and cost more than the
+// filtering itself.  So the survivors go to a per-warp queue of (ray, record) pairs and are tested 32 at
+// a time, one per lane, with the record read from global memory.  blockIdx.y slices the record range
+// (few slow rays -> more slices, so the GPU stays busy); slices combine through atomicMin on the
+// packed (t, prim) key / the found flag.
 #define SLOW_RPB 32
 #define SLOW_TILE 256
 #define SLOW_RPW (SLOW_RPB / 8)
 template <bool ANY>
+__device__ __forceinline__ void slow_exact(const DeviceScene& sc, unsigned long long entry, const float4* __restrict__ s_O,
+                                           const float4* __restrict__ s_D, unsigned long long* s_key, int* s_found)
+{
+    const int j = (int)(entry >> 32);
+    const unsigned i = (unsigned)entry;
+    const float4 o = s_O[j], dd = s_D[j];
+    const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(s_key + j);
+    float t; int prim;
+    if (prim_test<true>(sc.prims + i, mk(o.x, o.y, o.z), mk(dd.x, dd.y, dd.z), __uint_as_float((unsigned)(key >> 32)),
+                        ANY ? 0x7fffffff : (int)(unsigned)(key & 0xffffffffull), t, prim)) {
+        if (ANY) s_found[j] = 1;
+        else atomicMin(s_key + j, slow_key(t, prim));
+    }
+}
+template <bool ANY>
 __global__ void __launch_bounds__(256)
 k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __restrict__ res, int chunk)
 {
-    __shared__ PrimRec s_prim[SLOW_TILE];
     __shared__ float4 s_far[SLOW_TILE];
+    __shared__ float4 s_O[8][SLOW_RPW], s_D[8][SLOW_RPW];
+    __shared__ unsigned long long s_key[8][SLOW_RPW];      // best (t, prim) so far; any hit: (tmax, INT_MAX)
+    __shared__ int s_found[8][SLOW_RPW];
+    __shared__ unsigned long long s_q[8][64];              // survivors of the filter: (ray << 32) | record
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned first = blockIdx.x * SLOW_RPB + warp * SLOW_RPW;
-    V3 O[SLOW_RPW], D[SLOW_RPW]; HitRec best[SLOW_RPW]; bool lin[SLOW_RPW], live[SLOW_RPW], got[SLOW_RPW];
-#pragma unroll
-    for (int j = 0; j < SLOW_RPW; j++) {
-        const unsigned e = first + j;
-        live[j] = e < n; got[j] = false; lin[j] = false;
-        O[j] = mk(0, 0, 0); D[j] = mk(0, 0, 0); best[j].t = 0.f; best[j].prim = 0; best[j].leaf = -1;
-        if (live[j]) {
-            const float4 o = __ldg(&rays[e].o), d = __ldg(&rays[e].d);
-            const int4 c = __ldg(&rays[e].c);
-            O[j] = mk(o.x, o.y, o.z); D[j] = mk(d.x, d.y, d.z);
-            best[j].t = o.w; best[j].prim = __float_as_int(d.w);
-            lin[j] = (c.x & 1) != 0;
+    bool my_live = false, my_lin = false;
+    unsigned long long key0 = 0ull;
+    if (lane < SLOW_RPW) {
+        const unsigned e = first + lane;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
+        if (e < n) {
+            o = __ldg(&rays[e].o); d = __ldg(&rays[e].d);
+            my_lin = (__ldg(&rays[e].c).x & 1) != 0;
+            my_live = true;
         }
+        s_O[warp][lane] = o; s_D[warp][lane] = d;
+        key0 = ((unsigned long long)__float_as_uint(o.w) << 32) | (unsigned)__float_as_int(d.w);
+        s_key[warp][lane] = key0;
+        s_found[warp][lane] = 0;
     }
-    // blockIdx.y selects a slice of the records (few slow rays -> more slices, so the GPU stays busy)
+    unsigned live_mask = __ballot_sync(0xffffffffu, my_live) & ((1u << SLOW_RPW) - 1u);
+    const unsigned lin_mask = __ballot_sync(0xffffffffu, my_lin) & ((1u << SLOW_RPW) - 1u);
+    __syncwarp();
+    float4 dj[SLOW_RPW];
+#pragma unroll
+    for (int j = 0; j < SLOW_RPW; j++) dj[j] = s_D[warp][j];
+    unsigned q_len = 0;
     const int nl = min(sc.n_all, ((int)blockIdx.y + 1) * chunk);
     for (int base = (int)blockIdx.y * chunk; base < nl; base += SLOW_TILE) {
-        {   // stage one tile: thread t brings record base + t
+        {   // stage one tile of filter records: thread t brings record base + t
             const int i = base + (int)threadIdx.x;
-            if (i < nl) {
-                s_far[threadIdx.x] = __ldg(sc.far + i);
-                const float4* src = reinterpret_cast<const float4*>(sc.prims + i);
-                float4* dst = reinterpret_cast<float4*>(&s_prim[threadIdx.x]);
-                dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
-            } else s_far[threadIdx.x] = make_float4(0.f, 0.f, 0.f, -1.0f);
+            s_far[threadIdx.x] = (i < nl) ? __ldg(sc.far + i) : make_float4(0.f, 0.f, 0.f, -1.0f);
         }
         __syncthreads();
-        bool block_live = false;
+        if (ANY) {
 #pragma unroll
-        for (int j = 0; j < SLOW_RPW; j++) {
-            if (!live[j]) continue;
-            block_live = true;
+            for (int j = 0; j < SLOW_RPW; j++)                               // rays that are answered leave
+                if (((live_mask >> j) & 1u) && *reinterpret_cast<volatile int*>(&s_found[warp][j])) live_mask &= ~(1u << j);
+        }
+        // record in the outer loop, the warp's rays in the inner one: one shared-memory load serves four filter tests
 #pragma unroll 2
-            for (int k = 0; k < SLOW_TILE / 32; k++) {
-                const int s = k * 32 + lane, i = base + s;
-                if (i >= nl) break;
-                if (!lin[j]) {
-                    const float4 fr = s_far[s];
-                    const float nd = __fmaf_rn(fr.x, D[j].x, __fmaf_rn(fr.y, D[j].y, fr.z * D[j].z));   // filter only: FMA is fine
-                    if (!(fabsf(nd) <= fr.w)) continue;
-                }
-                float t; int prim;
-                if (prim_test<false>(&s_prim[s], O[j], D[j], best[j].t, ANY ? 0x7fffffff : best[j].prim, t, prim)) {
-                    best[j].t = t; best[j].leaf = i; best[j].prim = prim; got[j] = true;
+        for (int k = 0; k < SLOW_TILE / 32; k++) {
+            const int sl = k * 32 + lane, i = base + sl;
+            const bool in_range = i < nl;
+            const float4 fr = s_far[sl];
+#pragma unroll
+            for (int j = 0; j < SLOW_RPW; j++) {
+                if (!((live_mask >> j) & 1u)) continue;
+                // |N.d| <= thr (filter only: FMA is fine); a linear-fallback ray takes every record
+                const float nd = __fmaf_rn(fr.x, dj[j].x, __fmaf_rn(fr.y, dj[j].y, fr.z * dj[j].z));
+                const bool pass = in_range && (((lin_mask >> j) & 1u) || fabsf(nd) <= fr.w);
+                const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                if (mask == 0u) continue;
+                if (pass) s_q[warp][q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)j << 32) | (unsigned)i;
+                q_len += (unsigned)__popc(mask);
+                if (q_len >= 32u) {
+                    __syncwarp();
+                    slow_exact<ANY>(sc, s_q[warp][lane], s_O[warp], s_D[warp], s_key[warp], s_found[warp]);
+                    __syncwarp();
+                    const unsigned long long tail = (lane + 32u < q_len) ? s_q[warp][lane + 32] : 0ull;
+                    __syncwarp();
+                    if (lane + 32u < q_len) s_q[warp][lane] = tail;
+                    q_len -= 32u;
+                    __syncwarp();
                 }
             }
-            if (ANY && __any_sync(0xffffffffu, got[j])) live[j] = false;     // any hit: this ray is answered
         }
-        if (!__syncthreads_or(block_live ? 1 : 0)) break;                     // also the barrier before the next tile
+        if (!__syncthreads_or(live_mask ? 1 : 0)) break;                     // also the barrier before the next tile
     }
-#pragma unroll
-    for (int j = 0; j < SLOW_RPW; j++) {
-        const unsigned e = first + j;
-        if (e >= n) continue;
-        const bool anyf = __any_sync(0xffffffffu, got[j]);
-        HitRec b = best[j];
-        if (!ANY) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float t2 = __shfl_xor_sync(0xffffffffu, b.t, o);
-                const int p2 = __shfl_xor_sync(0xffffffffu, b.prim, o);
-                const int l2 = __shfl_xor_sync(0xffffffffu, b.leaf, o);
-                if (t2 < b.t || (t2 == b.t && (p2 < b.prim || (p2 == b.prim && l2 > b.leaf)))) { b.t = t2; b.prim = p2; b.leaf = l2; }
-            }
-        }
-        if (lane == 0 && anyf) {
-            if (ANY) res[e].found = 1;
-            else atomicMin(&res[e].key, slow_key(b.t, b.prim));
-        }
+    __syncwarp();
+    if ((unsigned)lane < q_len) slow_exact<ANY>(sc, s_q[warp][lane], s_O[warp], s_D[warp], s_key[warp], s_found[warp]);
+    __syncwarp();
+    if (lane < SLOW_RPW && my_live) {
+        const unsigned e = first + lane;
+        if (ANY) { if (s_found[warp][lane]) res[e].found = 1; }
+        else { const unsigned long long k = s_key[warp][lane]; if (k < key0) atomicMin(&res[e].key, k); }
     }
 }
 
