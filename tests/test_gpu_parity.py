@@ -418,3 +418,62 @@ def test_ppm_body_from_the_device(pkg, oracle):
         ctx.render_begin(q)
         ctx.frame_rgb8(lut, 25, W)          # no finished frame
     ctx.close()
+
+
+def test_benchmark_scene_at_full_size(pkg, oracle):
+    """BASELINE config 4 as bench.py runs it - c4_room: 1,000,448 triangles + 1000 spheres, 3840x2160,
+    depth 4, 16 AO samples, reference stream - checked at full size:
+      * 48 sampled pixels against the T1 oracle (the reference's linear loop over a million primitives),
+        seeded with the AO ordinals of the GPU's structure pass;
+      * ray accounting: rays = primary + secondary + nodes * (shadow lights + spp * ambient lights);
+      * the frame is reproducible (second render bit-identical) and equals the frame assembled from
+        three interleaved row sets with the stream offsets derived on the device."""
+    import bench
+    import torch
+    name, W, H, spp, depth = "c4_room", 3840, 2160, 16, 4
+    d = bench.scene_dir(name)
+    rt = pkg.Raytracer(W, H)
+    rt.SetAssetsPath(d)
+    rt.SetOptions(depth=depth, ao_spp=spp)
+    assert rt.LoadSceneJSON(name + ".json") == pkg.RT_SUCCESS
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    p = rt.render_params()
+    fb, st = ctx.render(p)
+    base = ctx.last_frame_ao_base(W * H)
+    assert st.rays_primary == W * H
+    assert st.rays_shadow == st.hit_nodes * 3 and st.rays_ao == st.hit_nodes * spp
+    assert st.rays == st.rays_primary + st.rays_secondary + st.rays_shadow + st.rays_ao
+    assert st.shadow_rays_traversed < st.rays_shadow      # the clearance maps of the three point lights are in use
+    rng = np.random.default_rng(580)
+    pix = np.sort(rng.choice(W * H, 48, replace=False)).astype(np.int32)
+    orc = oracle.Oracle(oracle.load_scene_json(d, name + ".json"))
+    ref, _, _ = orc.render(W, H, spp, depth, pix=pix, ao_base=base[pix], nthreads=NT)
+    got = fb.reshape(-1, 3)[pix]
+    assert np.array_equal(got, ref), "%d of 48 sampled pixels differ from the oracle" % int((got != ref).any(axis=-1).sum())
+    fb2, st2 = ctx.render(p)
+    assert st2.rays == st.rays and np.array_equal(fb, fb2)
+    # three "ranks" on this one GPU, device-side exchange (the same context, one row set after the other)
+    world = 3
+    max_rows = (H + world - 1) // world
+    all_d = torch.zeros((world, max_rows), dtype=torch.int64, device="cuda")
+    ctxs = [ctx] + [pkg.Context(0) for _ in range(world - 1)]
+    for c in ctxs[1:]:
+        c.upload_scene(rt.flat_scene())
+    qs = []
+    for r in range(world):
+        q = p.copy()
+        q.row_first, q.row_step, q.n_rows = pkg.rows_for_rank(H, r, world)
+        ctxs[r].render_begin(q, want_counts=False)
+        ctxs[r].row_counts_to_device(all_d[r].data_ptr(), max_rows)
+        qs.append(q)
+    torch.cuda.synchronize()
+    got3 = np.empty_like(fb)
+    for r in range(world):
+        band = torch.empty((qs[r].n_rows, W, 3), dtype=torch.int16, device="cuda")
+        ctxs[r].render_finish_interleaved(all_d.data_ptr(), world, r, max_rows, device_ptr=band.data_ptr())
+        first, step, n = pkg.rows_for_rank(H, r, world)
+        got3[first:first + n * step:step] = band.cpu().numpy()
+    assert np.array_equal(got3, fb)
+    for c in ctxs:
+        c.close()
