@@ -639,9 +639,8 @@ k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __
             const bool leaf_work = __any_sync(0xffffffffu, active && !searching);
             if (n_search == 0 || (n_search < ah_min_search && leaf_work)) break;
             if (searching) {
-                const BvhNode* __restrict__ nd = sc.nodes + cur;
-                const float4 xy0 = __ldg(&nd->xy0), xy1 = __ldg(&nd->xy1), z01 = __ldg(&nd->z01);
-                const int4 kids = __ldg(&nd->kids);
+                float4 xy0, xy1, z01; int4 kids;
+                load_node(sc.nodes + cur, xy0, xy1, z01, kids);
                 float tn0, tn1;
                 const bool h0 = slab(xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, O, inv, best_t, tn0);
                 const bool h1 = slab(xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, O, inv, best_t, tn1);
@@ -1261,9 +1260,8 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
             const bool leaf_work = __any_sync(0xffffffffu, active && !searching);
             if (n_search == 0 || (n_search < ah_min_search && leaf_work)) break;
             if (searching) {
-                const BvhNode* __restrict__ nd = sc.nodes + cur;
-                const float4 xy0 = __ldg(&nd->xy0), xy1 = __ldg(&nd->xy1), z01 = __ldg(&nd->z01);
-                const int4 kids = __ldg(&nd->kids);
+                float4 xy0, xy1, z01; int4 kids;
+                load_node(sc.nodes + cur, xy0, xy1, z01, kids);
                 float tn0, tn1;
                 const bool h0 = slab(xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, O, inv, tmax, tn0);
                 const bool h1 = slab(xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, O, inv, tmax, tn1);
