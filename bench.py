@@ -36,7 +36,7 @@ WORKLOAD = "c4_room"
 W, H, DEPTH, SPP = 3840, 2160, 4, 16
 CACHE = "/tmp/rt580_bench_scenes"
 AO_CHUNK = 32 << 20                        # AH_CHUNK_TIGHT in rt580_core.cu: AO sample rays per k_ao_gen launch
-K_AO_GEN_DRAM_BYTES_PER_RAY = 158.475e6 / (32 << 20)   # ncu capture, see roofline.traffic_source
+K_AO_GEN_DRAM_BYTES_PER_RAY = 163.102e6 / (32 << 20)   # ncu capture, see roofline.traffic_source
 
 
 def scene_dir(name):
@@ -381,12 +381,12 @@ def run_ours(args):
                     "kernel_ms": ao_ms / n_launch, "pass_ms": ao_ms,
                     "traffic": K_AO_GEN_DRAM_BYTES_PER_RAY * rays_per_launch,
                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 32M-ray k_ao_gen launch "
-                                      "(profiles/r01_k_ao_gen_v2_1080p_details.txt: 158.5 MB), scaled to this launch size",
-                    "ncu": {"issue_slots_busy_pct": 83.2, "fma_pipe_active_pct": 33.1, "avg_active_lanes": 28.8, "l1_hit_pct": 78.4,
-                            "dram_throughput_pct": 1.85, "source": "same capture"},
+                                      "(profiles/r01_k_ao_gen_v3_1080p_details.txt: 163.1 MB), scaled to this launch size",
+                    "ncu": {"issue_slots_busy_pct": 87.6, "fma_pipe_active_pct": 33.2, "fp64_pipe_pct": 4.1, "avg_active_lanes": 29.5,
+                            "l1_hit_pct": 93.2, "dram_throughput_pct": 2.1, "source": "same capture"},
                     "hbm": {"achieved": ao_rate * b_ray / 1e9, "peak": float(peaks["hbm_gbs"]) * world, "unit": "GB/s",
                             "frac": (ao_rate * b_ray / 1e9) / (float(peaks["hbm_gbs"]) * world), "bytes_per_ray": b_ray,
-                            "note": "algorithmic node+triangle bytes; served from shared memory / L1 / L2, not HBM (measured DRAM throughput 1.9 %)"}}
+                            "note": "algorithmic node+triangle bytes; served from shared memory / L1 / L2, not HBM (measured DRAM throughput 2 %)"}}
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
