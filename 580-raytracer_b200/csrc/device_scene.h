@@ -56,6 +56,13 @@ struct DeviceScene {
                                             //                by normal: parallel walls share N.d and N.O in the ordering pass)
     unsigned long long big_sphere_mask;     // large spheres (no plane): bit k = prims[n_leaf + k]
     int32_t n_big_planes;
+    // A box no large primitive reaches into (the inside of a room, the space above a floor), found at upload.  A
+    // shadow ray that starts inside it and runs to a point light inside it stays inside it (convex): the large
+    // primitives cannot stop it and their plane tests are skipped.  big_free_light: per light, the light and the
+    // 0.2 units by which the reference's ray overshoots it lie inside.  big_free_on = 0: no such box.
+    float big_free_lo[3], big_free_hi[3];
+    const int32_t* big_free_light;          // [n_lights]
+    int32_t big_free_on;
     int32_t n_all;             // n_leaf + n_big: what the linear loops and the far-field scan walk
     int32_t n_prims;           // primitives in reference order (incl. dropped ones)
     const float4* vn;          // [n_prims][3] object-space vertex normals (Q10); unused for spheres

@@ -1125,9 +1125,9 @@ k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long fi
     if (t < n) {
         // queue order = light-major: the lanes of a warp take neighbouring nodes and the SAME light, so their
         // rays run to one point and walk the tree together (node-major order put three lights in adjacent lanes)
-        const unsigned long long q = first + t;
+        const unsigned q = (unsigned)first + t;                                // a level has < 2^32 shadow rays (checked by the host)
         int j = (int)(q / n_level);
-        const unsigned m = (unsigned)(q % n_level);
+        const unsigned m = q - (unsigned)j * n_level;
         const unsigned id = m * (unsigned)sc.n_nonambient + (unsigned)j;      // ray id = (node - n0) * n_nonambient + j
         int li = 0;
         for (;; li++) { if (__ldg(sc.light_type + li) != RT580_LIGHT_AMBIENT) { if (j == 0) break; j--; } }
@@ -1141,7 +1141,10 @@ k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long fi
         const bool far_origin = sc.farfield && fmaxf(fabsf(so.x), fmaxf(fabsf(so.y), fabsf(so.z))) > sc.extent;
         // the large primitives here (plane by plane, exact), so that k_shade only has to read the verdict; a ray one
         // of them stops is not queued (a far origin takes the reference's linear loop over ALL records instead)
-        if (sc.n_big > 0 && !far_origin) {
+        const bool in_free_box = sc.big_free_on && __ldg(sc.big_free_light + li) != 0 &&
+                                 so.x >= sc.big_free_lo[0] && so.x <= sc.big_free_hi[0] && so.y >= sc.big_free_lo[1] && so.y <= sc.big_free_hi[1] &&
+                                 so.z >= sc.big_free_lo[2] && so.z <= sc.big_free_hi[2];
+        if (sc.n_big > 0 && !far_origin && !in_free_box) {
             HitRec sh; sh.t = tmax; sh.leaf = -1; sh.prim = 0x7fffffff;
             if (big_scan<true>(sc, so, sd, sh)) { occl[id] = 1u; emit = false; }
         }
@@ -1622,7 +1625,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         int n_point = 0;
         for (int i = 0; i < s->n_lights; i++) if (s->light_type && s->light_type[i] == RT580_LIGHT_POINT) n_point++;
         if (n_point > SMAP_MAX) n_point = SMAP_MAX;
-        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 48 + 40 * 256 +
+        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 52 + 48 * 256 +
                                    (size_t)n_point * 6 * c->smap_res * c->smap_res * sizeof(float);
         if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
             !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
@@ -1687,6 +1690,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     {
         // distinct planes of the large triangles (device_scene.h); at most 64 records, grouped on the host
         c->sc.big_planes = nullptr; c->sc.big_masks = nullptr; c->sc.big_plane_newn = nullptr; c->sc.big_sphere_mask = 0ull; c->sc.n_big_planes = 0;
+        c->sc.big_free_on = 0; c->sc.big_free_light = nullptr;
         if (bo.n_big > 64) FAIL(RT580_FAILURE, "rt580_upload_scene: %d large primitives (at most 64)", bo.n_big);
         if (bo.n_big > 0) {
             std::vector<PrimRec> big((size_t)bo.n_big);
@@ -1719,6 +1723,71 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
                 CU(upload(sa, &dn, newn.data(), newn.size(), st));
                 CU(cudaStreamSynchronize(st));
                 c->sc.big_planes = dp; c->sc.big_masks = dm; c->sc.big_plane_newn = dn; c->sc.n_big_planes = (int)sp.size();
+            }
+            // the free box (device_scene.h): seeded with the bounds of the tree (its root's two child boxes) and the point
+            // lights, each face then pushed outwards as far as no large triangle is met
+            c->sc.big_free_on = 0; c->sc.big_free_light = nullptr;
+            if (c->sc.big_sphere_mask == 0ull && bo.n_leaf > 1 && !getenv("RT580_NO_FREE_BOX")) {
+                BvhNode root;
+                CU(cudaMemcpy(&root, bo.nodes, sizeof root, cudaMemcpyDeviceToHost));
+                double lo[3] = { fmin(root.xy0.x, root.xy1.x), fmin(root.xy0.z, root.xy1.z), fmin(root.z01.x, root.z01.z) };
+                double hi[3] = { fmax(root.xy0.y, root.xy1.y), fmax(root.xy0.w, root.xy1.w), fmax(root.z01.y, root.z01.w) };
+                for (int i = 0; i < s->n_lights; i++) if (s->light_type[i] == RT580_LIGHT_POINT)
+                    for (int k = 0; k < 3; k++) { lo[k] = fmin(lo[k], (double)s->light_f[10 * i + 4 + k] - 0.3); hi[k] = fmax(hi[k], (double)s->light_f[10 * i + 4 + k] + 0.3); }
+                const double margin = fmax(64.0 * (double)bo.pad, 1e-4 * (double)bo.extent);
+                // a large triangle leaves the box alone if its plane keeps all 8 corners on one side by `margin`,
+                // or if its own bounding box stays `margin` away from the box
+                auto clear_of = [&](const double* blo, const double* bhi) {
+                    for (int k = 0; k < bo.n_big; k++) {
+                        const PrimRec& r = big[k];
+                        const double N[3] = { r.d.x, r.d.y, r.d.z }, D = r.a.w;
+                        double smin = 1e300, smax = -1e300;
+                        for (int cidx = 0; cidx < 8; cidx++) {
+                            const double x = (cidx & 1) ? bhi[0] : blo[0], y = (cidx & 2) ? bhi[1] : blo[1], z = (cidx & 4) ? bhi[2] : blo[2];
+                            const double sd = N[0] * x + N[1] * y + N[2] * z + D;
+                            smin = fmin(smin, sd); smax = fmax(smax, sd);
+                        }
+                        if (smin >= margin || smax <= -margin) continue;
+                        const float* v[3] = { &r.a.x, &r.b.x, &r.c.x };
+                        bool apart = false;
+                        for (int ax = 0; ax < 3; ax++) {
+                            const double tlo = fmin(fmin(v[0][ax], v[1][ax]), v[2][ax]) - margin, thi = fmax(fmax(v[0][ax], v[1][ax]), v[2][ax]) + margin;
+                            if (tlo > bhi[ax] || thi < blo[ax]) apart = true;
+                        }
+                        if (!apart) return false;
+                    }
+                    return true;
+                };
+                if (clear_of(lo, hi)) {
+                    const double E = (double)bo.extent;
+                    for (int face = 0; face < 6; face++) {
+                        const int ax = face >> 1; const bool up = face & 1;
+                        double good = up ? hi[ax] : lo[ax], bad = up ? E : -E;
+                        for (int it = 0; it < 48; it++) {
+                            const double mid = 0.5 * (good + bad);
+                            double tl[3] = { lo[0], lo[1], lo[2] }, th[3] = { hi[0], hi[1], hi[2] };
+                            (up ? th[ax] : tl[ax]) = mid;
+                            if (clear_of(tl, th)) good = mid; else bad = mid;
+                        }
+                        (up ? hi[ax] : lo[ax]) = good;
+                    }
+                    std::vector<int32_t> lin((size_t)s->n_lights, 0);
+                    for (int i = 0; i < s->n_lights; i++) {
+                        if (s->light_type[i] != RT580_LIGHT_POINT) continue;
+                        bool in = true;
+                        for (int k = 0; k < 3; k++) { const double x = s->light_f[10 * i + 4 + k]; if (!(x - 0.25 >= lo[k] && x + 0.25 <= hi[k])) in = false; }
+                        lin[i] = in ? 1 : 0;
+                    }
+                    int32_t* dl = nullptr;
+                    CU(upload(sa, &dl, lin.data(), lin.size(), st));
+                    CU(cudaStreamSynchronize(st));
+                    for (int k = 0; k < 3; k++) {
+                        // inwards by an ulp-scale step: the float box lies inside the double one
+                        c->sc.big_free_lo[k] = (float)lo[k] + 1e-6f * (float)bo.extent;
+                        c->sc.big_free_hi[k] = (float)hi[k] - 1e-6f * (float)bo.extent;
+                    }
+                    c->sc.big_free_light = dl; c->sc.big_free_on = 1;
+                }
             }
         }
     }
