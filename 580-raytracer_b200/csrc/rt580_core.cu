@@ -139,6 +139,9 @@ template <typename T> struct DBuf {
 struct rt580_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;    // the shadow rays of a level run here, beside the spawn -> closest hit -> commit chain
+    cudaEvent_t ev_join = nullptr;
+    bool overlap = true;               // RT580_NO_OVERLAP=1: everything on one stream (A/B)
     cudaDeviceProp prop;
     // scene
     DeviceScene sc{};
@@ -798,6 +801,79 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
         q.d = make_float4(td.x, td.y, td.z, __uint_as_float(child_flags | NF_REFR));
         queue[s1] = q;
     }
+}
+
+// k_shade in two halves for the wavefront path, so that they can run on different streams: spawning the
+// reflection / refraction rays needs nothing from the shadow rays, and the chain spawn -> closest hit ->
+// commit -> next level is the critical path of the structure pass, while the shadow rays of a level and the
+// Phong terms they gate (the bulk of the work) only have to be done before the resolve pass.
+//   k_spawn       per hit node: NodeAux except `local`, children into the ray queue        (cpp:87-112)
+//   k_shade_local per hit node: sum of the unoccluded lights' Phong terms -> NodeAux::local (cpp:53-81)
+// The two write disjoint bytes of NodeAux.
+__global__ void __launch_bounds__(128)
+k_spawn(DeviceScene sc, unsigned n0, unsigned n1, const Node* __restrict__ nodes, NodeAux* __restrict__ aux,
+        QRay* __restrict__ queue, unsigned int* __restrict__ counters)
+{
+    const unsigned i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n1;
+    bool want_refl = false, want_refr = false;
+    V3 P = mk(0, 0, 0), N = mk(0, 0, 0), D = mk(0, 0, 0);
+    int bounces = 0;
+    if (active) {
+        const Node nd = nodes[i];
+        P = mk(nd.P.x, nd.P.y, nd.P.z); N = mk(nd.N.x, nd.N.y, nd.N.z); D = mk(nd.D.x, nd.D.y, nd.D.z);
+        const unsigned flags = __float_as_uint(nd.B.w);
+        bounces = (int)((flags >> NF_BOUNCE_SHIFT) & 0xffu);
+        const Material M = load_material(sc.materials, __ldg(sc.prim_material + __float_as_int(nd.P.w)));
+        uint2* a = reinterpret_cast<uint2*>(aux + i);                 // [0] local (k_shade_local's), [1] refl, [2] refr, [3] subtree sizes
+        a[1] = make_uint2(0u, 0u); a[2] = make_uint2(0u, 0u); a[3] = make_uint2(0u, 0u);   // Pixel() (cpp:91-92)
+        if (bounces > 0) { want_refl = M.Ks > 0; want_refr = M.Kt > 0; }     // cpp:87, 94, 108
+    }
+    const unsigned s0 = warp_alloc(&counters[1], want_refl);
+    const unsigned s1 = warp_alloc(&counters[1], want_refr);
+    if (!active) return;
+    const unsigned child_flags = (unsigned)(bounces - 1) << NF_BOUNCE_SHIFT;
+    if (want_refl) {
+        const V3 rdir = normalize(reflect(D, N));                             // cpp:96-97
+        const V3 ro = P + rdir * RT_SHADOW_OFFSET;                            // cpp:98
+        const V3 rd = normalize(rdir);                                        // Ray ctor
+        QRay q; q.o = make_float4(ro.x, ro.y, ro.z, __int_as_float((int)i));
+        q.d = make_float4(rd.x, rd.y, rd.z, __uint_as_float(child_flags));
+        queue[s0] = q;
+    }
+    if (want_refr) {
+        const V3 tdir = calculate_refraction(D, N, RT_IOR);                   // cpp:109
+        const V3 to = P + tdir * RT_SHADOW_OFFSET;                            // cpp:110
+        const V3 td = normalize(tdir);                                        // Ray ctor (zero stays zero, Q20)
+        QRay q; q.o = make_float4(to.x, to.y, to.z, __int_as_float((int)i));
+        q.d = make_float4(td.x, td.y, td.z, __uint_as_float(child_flags | NF_REFR));
+        queue[s1] = q;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_shade_local(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __restrict__ nodes,
+              NodeAux* __restrict__ aux, const uint32_t* __restrict__ occl)
+{
+    const unsigned i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const Node nd = nodes[i];
+    const V3 P = mk(nd.P.x, nd.P.y, nd.P.z);
+    const unsigned flags = __float_as_uint(nd.B.w);
+    const int prim = __float_as_int(nd.P.w);
+    const Material M = load_material(sc.materials, __ldg(sc.prim_material + prim));
+    const PhongFrame pf = phong_frame(P, shading_normal(sc, nd, flags, prim), mk(fp.cam[0], fp.cam[1], fp.cam[2]));
+    Pix local = mkpix(0, 0, 0);                                       // SHADOW_COLOR h:598
+    int j = 0;                                                        // index among the non-ambient lights
+    for (int li = 0; li < sc.n_lights; li++) {                        // cpp:39
+        if (__ldg(sc.light_type + li) == RT580_LIGHT_AMBIENT) continue;          // handled by the occlusion pass / k_resolve
+        // occluders of this ray: tree (k_anyhit), large primitives (k_shade_gen), or still pending (k_shadow_finish)
+        if (__ldg(occl + (size_t)(i - n0) * sc.n_nonambient + j) == 0u)
+            local = pix_add(local, calculate_local_color(P, pf, load_light(sc.light_type, sc.light_f, li), M));   // cpp:77
+        j++;
+    }
+    *reinterpret_cast<uint2*>(aux + i) = make_uint2((unsigned)(unsigned short)local.r | ((unsigned)(unsigned short)local.g << 16),
+                                                   (unsigned)(unsigned short)local.b);
 }
 
 // deferred shadow rays of k_shade: an unoccluded one adds its light's Phong term (cpp:77).  Pixel
@@ -1548,6 +1624,9 @@ extern "C" int rt580_create(int device, rt580_context** out)
     c->device = device;
     CU(cudaGetDeviceProperties(&c->prop, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    if (getenv("RT580_NO_OVERLAP")) c->overlap = false;
     for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
     if (const char* e = getenv("RT580_AH_STEPS")) c->ah_steps = atoi(e) > 0 ? atoi(e) : c->ah_steps;
     if (const char* e = getenv("RT580_AH_MIN_SEARCH")) c->ah_min_search = atoi(e) > 0 ? atoi(e) : c->ah_min_search;
@@ -1581,6 +1660,9 @@ extern "C" void rt580_destroy(rt580_context* c)
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
     c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release(); c->chits.release();
     for (auto& ev : c->ev) cudaEventDestroy(ev);
+    cudaStreamSynchronize(c->stream2);
+    cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1944,15 +2026,15 @@ static int slow_prepare(rt580_context* c, unsigned long long max_rays, unsigned*
     return RT580_SUCCESS;
 }
 // Same for the any-hit queue, which lives across launches until it is flushed.
-static int any_prepare(rt580_context* c, unsigned long long max_rays)
+static int any_prepare(rt580_context* c, unsigned long long max_rays, cudaStream_t st)
 {
     unsigned cap = (unsigned)(max_rays < 0xfffffff0ull ? max_rays : 0xfffffff0ull);
     if (!c->sc.farfield || c->sc.n_all <= RT_SMEM_PRIMS) cap = 0;
     if (cap) {
-        CU(c->any_rays.ensure(cap, 0, c->stream));
-        CU(c->any_res.ensure(cap, 0, c->stream));
+        CU(c->any_rays.ensure(cap, 0, st));
+        CU(c->any_res.ensure(cap, 0, st));
     }
-    CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), c->stream));
+    CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), st));
     c->any_cap = cap;
     return RT580_SUCCESS;
 }
@@ -2014,10 +2096,9 @@ static int any_flush(rt580_context* c, Fin finish)
 // any-hit queue (prepared by the caller).  No host round trip between the chunks unless the scene leaks
 // and the pass may flush (`ao`: the answers only add to hits[], k_ao_finish).
 template <typename Gen>
-static int anyhit_queue_pass(rt580_context* c, unsigned long long total, uint32_t* hits, unsigned id_offset,
+static int anyhit_queue_pass(rt580_context* c, cudaStream_t st, unsigned long long total, uint32_t* hits, unsigned id_offset,
                              unsigned pending_mark, bool leaky, bool ao, Gen gen)
 {
-    cudaStream_t st = c->stream;
     const unsigned long long chunk = leaky ? (unsigned long long)SLOW_CAP_MAX : (unsigned long long)AH_CHUNK_TIGHT;
     CU(c->arays.ensure((size_t)(total < chunk ? total : chunk), 0, st));
     const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ah_blocks_per_sm;
@@ -2074,6 +2155,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             FAIL(RT580_INVALID_ARG, "rt580_render_begin: camera_from[%d]=%g lies outside the extent (%g) the BVH boxes were padded for; "
                  "pass the camera as rt580_flat_scene::origin_hint", k, p->camera_from[k], c->pad_extent);
     CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream2));         // (idle unless an earlier frame was abandoned on an error)
     const bool dbg_t = getenv("RT580_DEBUG_TIMING") != nullptr;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_enter = now_ms();
@@ -2184,6 +2266,22 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
     auto shadow_finish = [&](unsigned n) {
         k_shadow_finish<<<nblk(n, 128), 128, 0, st>>>(c->sc, c->fp, c->any_rays.p, c->any_res.p, n, c->nodes.p, c->aux.p);
     };
+    // the secondary rays of a level: their number stays on the device (counters[1])
+    auto launch_secondary = [&](unsigned q_max, unsigned slow_cap_) -> int {
+        if (mode == 0 && !c->one_thread_per_ray) {
+            CU(c->chits.ensure((size_t)q_max + 1, 0, st));
+            CU(cudaMemsetAsync(c->counters.p + 12, 0, sizeof(unsigned), st));
+            const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ch_blocks_per_sm;
+            k_closest<<<blocks, 128, 0, st>>>(c->sc, c->queue.p, c->counters.p + 1, q_max, c->counters.p + 12, c->chits.p,
+                                              c->ah_steps, c->ah_min_search, c->ah_batch_div);
+            k_commit<<<nblk(q_max, 128), 128, 0, st>>>(c->sc, c->queue.p, q_max, c->counters.p + 1, c->chits.p, c->nodes.p, c->aux.p,
+                                                       c->counters.p, c->pix_hits.p, c->fb.p, (unsigned)c->nodes.cap, slowq(c, slow_cap_));
+            c->launches += 2;
+        } else {
+            DISPATCH_MODE(mode, launch_trace, c, false, q_max, c->counters.p + 1, (unsigned)c->nodes.cap, slow_cap_);
+        }
+        return RT580_SUCCESS;
+    };
     for (int L = 0; L <= fp.depth; L++) {
         const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
         if (n1 == n0) break;
@@ -2191,34 +2289,53 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         CU(c->queue.ensure((size_t)q_max + 1, 0, st));
         if (q_max) {
             // room for the next level before anything is launched: its size is only known on the device
+            // (a buffer that has to move must not be in use on the second stream)
+            if ((size_t)n1 + q_max > c->nodes.cap || (size_t)n1 + q_max > c->aux.cap) CU(cudaStreamSynchronize(c->stream2));
             CU(c->nodes.ensure((size_t)n1 + q_max, n1, st));
             CU(c->aux.ensure((size_t)n1 + q_max, n1, st));
         }
         CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
         const unsigned long long n_sh = (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient;
         if (mode == 0) {
-            // shadow rays in wavefront form (k_shade_gen -> k_anyhit), then shading with their answers
             if (n_sh > 0xfffffff0ull) FAIL(RT580_FAILURE, "rt580_render_begin: too many shadow rays in one level");
-            CU(c->occl.ensure((size_t)n_sh + 1, 0, st));
-            CU(cudaMemsetAsync(c->occl.p, 0, sizeof(uint32_t) * ((size_t)n_sh + 1), st));
             const bool leaky = is_leaky(c, rays_so_far);
+            // Two chains per level.  Critical path, on the context's stream: spawn the children, find their closest
+            // hits, create the next level's nodes.  Beside it, on the second stream: the level's shadow rays
+            // (k_shade_gen -> k_anyhit) and the Phong terms they gate; nothing needs those before the resolve pass.
+            // Alone, each persistent traversal kernel ends in a tail that leaves most of the GPU idle, which is what
+            // a rank of an 8-GPU run (1/8 of the rays per launch) spent a quarter of its structure pass on.
+            cudaStream_t sb = (c->overlap && !leaky) ? c->stream2 : st;
+            if (sb == st) {
+                // one stream from here on: whatever the second one still does for earlier levels comes first
+                CU(cudaEventRecord(c->ev_join, c->stream2)); CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+            }
+            if (leaky && any_open) {
+                // the small queue of the levels before is flushed before the big one takes over
+                const int fr = any_flush(c, shadow_finish); if (fr) return fr; any_open = false;
+            }
+            k_spawn<<<nblk(n1 - n0, 128), 128, 0, st>>>(c->sc, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p);
+            c->launches++;
+            if (L < fp.depth) {
+                if (slow_prepare(c, q_max, &slow_cap)) return RT580_FAILURE;
+                if (launch_secondary(q_max, slow_cap)) return RT580_FAILURE;
+            }
+            CU(c->occl.ensure((size_t)n_sh + 1, 0, sb));
+            CU(cudaMemsetAsync(c->occl.p, 0, sizeof(uint32_t) * ((size_t)n_sh + 1), sb));
             if (n_sh) {
                 if (leaky) {
-                    // the queue takes every shadow ray of the level and is flushed right after k_shade
-                    if (any_open) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; any_open = false; }
-                    if (any_prepare(c, n_sh)) return RT580_FAILURE;
+                    // the queue takes every shadow ray of the level and is flushed right after the level
+                    if (any_prepare(c, n_sh, sb)) return RT580_FAILURE;
                 } else if (!any_open) {
-                    if (any_prepare(c, c->slow_any_cap)) return RT580_FAILURE;
+                    if (any_prepare(c, c->slow_any_cap, sb)) return RT580_FAILURE;
                     any_open = c->any_cap != 0;
                 }
-                const int rc = anyhit_queue_pass(c, n_sh, c->occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
+                const int rc = anyhit_queue_pass(c, sb, n_sh, c->occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
                     [&](unsigned long long first, unsigned n) {
-                        k_shade_gen<<<nblk(n, 512), 512, 0, st>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6, c->occl.p);
+                        k_shade_gen<<<nblk(n, 512), 512, 0, sb>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6, c->occl.p);
                     });
                 if (rc) return rc;
             }
-            k_shade<0, true><<<nblk(n1 - n0, 128), 128, 0, st>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p,
-                                                                 slowq(c, 0u), c->occl.p);
+            k_shade_local<<<nblk(n1 - n0, 128), 128, 0, sb>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->occl.p);
             c->launches++;
             if (leaky && n_sh) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
         } else {
@@ -2235,19 +2352,9 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         }
         rays_so_far += n_sh;
         if (L == fp.depth) break;
-        // the queued reflection / refraction rays: their number stays on the device (counters[1])
-        if (slow_prepare(c, q_max, &slow_cap)) return RT580_FAILURE;
-        if (mode == 0 && !c->one_thread_per_ray) {
-            CU(c->chits.ensure((size_t)q_max + 1, 0, st));
-            CU(cudaMemsetAsync(c->counters.p + 7, 0, sizeof(unsigned), st));
-            const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ch_blocks_per_sm;
-            k_closest<<<blocks, 128, 0, st>>>(c->sc, c->queue.p, c->counters.p + 1, q_max, c->counters.p + 7, c->chits.p,
-                                              c->ah_steps, c->ah_min_search, c->ah_batch_div);
-            k_commit<<<nblk(q_max, 128), 128, 0, st>>>(c->sc, c->queue.p, q_max, c->counters.p + 1, c->chits.p, c->nodes.p, c->aux.p,
-                                                       c->counters.p, c->pix_hits.p, c->fb.p, (unsigned)c->nodes.cap, slowq(c, slow_cap));
-            c->launches += 2;
-        } else {
-            DISPATCH_MODE(mode, launch_trace, c, false, q_max, c->counters.p + 1, (unsigned)c->nodes.cap, slow_cap);
+        if (mode != 0) {
+            if (slow_prepare(c, q_max, &slow_cap)) return RT580_FAILURE;
+            if (launch_secondary(q_max, slow_cap)) return RT580_FAILURE;
         }
         if (read_counters(c, cnt)) return RT580_FAILURE;
         const unsigned q = cnt[1];
@@ -2266,6 +2373,8 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         c->level_off.push_back(n_nodes);
         rays_so_far += q;
     }
+    // the second stream's work belongs to the structure pass: the context's stream goes on when it is done
+    CU(cudaEventRecord(c->ev_join, c->stream2)); CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     if (any_open) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
     c->any_cap = 0;
     c->rays_structure = rays_so_far;
@@ -2383,8 +2492,8 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
         if (mode == 0) {
             for (int attempt = 0; ; attempt++) {
                 const bool leaky = is_leaky(c, c->rays_structure);
-                if (any_prepare(c, leaky ? SLOW_CAP_MAX : c->slow_any_cap)) return RT580_FAILURE;
-                const int rc = anyhit_queue_pass(c, n_ao, c->ao_hits.p, 0u, 0u, leaky, true,
+                if (any_prepare(c, leaky ? SLOW_CAP_MAX : c->slow_any_cap, st)) return RT580_FAILURE;
+                const int rc = anyhit_queue_pass(c, st, n_ao, c->ao_hits.p, 0u, 0u, leaky, true,
                     [&](unsigned long long first, unsigned n) {
                         k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,
                                                                c->counters.p + 6, c->ao_hits.p);
