@@ -139,8 +139,12 @@ template <typename T> struct DBuf {
 struct rt580_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;    // the shadow rays of a level run here, beside the spawn -> closest hit -> commit chain
-    cudaEvent_t ev_join = nullptr;
+    // the shadow rays of a level run beside the spawn -> closest hit -> commit chain: even levels on side[0], odd
+    // levels on side[1] (each with its own ray chunk, occluder counts and queue counters: lanes 0 and 1)
+    cudaStream_t side[2] = { nullptr, nullptr };
+    cudaEvent_t ev_join[2] = { nullptr, nullptr };
+    cudaEvent_t ev_level = nullptr;    // recorded on the context's stream when a level's nodes exist: the side stream starts after it
+    DBuf<struct ARay> arays2; DBuf<uint32_t> occl2;
     bool overlap = true;               // RT580_NO_OVERLAP=1: everything on one stream (A/B)
     cudaDeviceProp prop;
     // scene
@@ -1624,8 +1628,11 @@ extern "C" int rt580_create(int device, rt580_context** out)
     c->device = device;
     CU(cudaGetDeviceProperties(&c->prop, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_level, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
     if (getenv("RT580_NO_OVERLAP")) c->overlap = false;
     for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
     if (const char* e = getenv("RT580_AH_STEPS")) c->ah_steps = atoi(e) > 0 ? atoi(e) : c->ah_steps;
@@ -1660,9 +1667,9 @@ extern "C" void rt580_destroy(rt580_context* c)
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
     c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release(); c->chits.release();
     for (auto& ev : c->ev) cudaEventDestroy(ev);
-    cudaStreamSynchronize(c->stream2);
-    cudaEventDestroy(c->ev_join);
-    cudaStreamDestroy(c->stream2);
+    for (int k = 0; k < 2; k++) { cudaStreamSynchronize(c->side[k]); cudaEventDestroy(c->ev_join[k]); cudaStreamDestroy(c->side[k]); }
+    c->arays2.release(); c->occl2.release();
+    cudaEventDestroy(c->ev_level);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1939,6 +1946,15 @@ extern "C" int rt580_build_ms(rt580_context* c, float* ms) {
 
 static inline unsigned nblk(unsigned long long n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
+// the context's stream waits for what the side streams have been given so far
+static int join_side(rt580_context* c) {
+    for (int k = 0; k < 2; k++) { CU(cudaEventRecord(c->ev_join[k], c->side[k])); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
+    return RT580_SUCCESS;
+}
+static int sync_side(rt580_context* c) {
+    for (int k = 0; k < 2; k++) CU(cudaStreamSynchronize(c->side[k]));
+    return RT580_SUCCESS;
+}
 static SlowQ slowq(rt580_context* c, unsigned cap) {
     SlowQ q; q.rays = c->slow_rays.p; q.res = c->slow_res.p; q.count = c->counters.p + 2; q.cap = cap;
     return q;
@@ -2096,18 +2112,20 @@ static int any_flush(rt580_context* c, Fin finish)
 // any-hit queue (prepared by the caller).  No host round trip between the chunks unless the scene leaks
 // and the pass may flush (`ao`: the answers only add to hits[], k_ao_finish).
 template <typename Gen>
-static int anyhit_queue_pass(rt580_context* c, cudaStream_t st, unsigned long long total, uint32_t* hits, unsigned id_offset,
+static int anyhit_queue_pass(rt580_context* c, cudaStream_t st, int lane, unsigned long long total, uint32_t* hits, unsigned id_offset,
                              unsigned pending_mark, bool leaky, bool ao, Gen gen)
 {
+    DBuf<ARay>& rays = lane ? c->arays2 : c->arays;
+    unsigned int* ctr = c->counters.p + (lane ? 13 : 6);           // [0] rays emitted, [1] rays fetched
     const unsigned long long chunk = leaky ? (unsigned long long)SLOW_CAP_MAX : (unsigned long long)AH_CHUNK_TIGHT;
-    CU(c->arays.ensure((size_t)(total < chunk ? total : chunk), 0, st));
+    CU(rays.ensure((size_t)(total < chunk ? total : chunk), 0, st));
     const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ah_blocks_per_sm;
     for (unsigned long long first = 0; first < total; first += chunk) {
         const unsigned n = (unsigned)((total - first) < chunk ? (total - first) : chunk);
-        CU(cudaMemsetAsync(c->counters.p + 6, 0, 2 * sizeof(unsigned), st));   // [6] rays emitted, [7] rays fetched
-        gen(first, n);
+        CU(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned), st));
+        gen(first, n, rays.p, ctr);
         c->launches++;
-        k_anyhit<<<blocks, 128, 0, st>>>(c->sc, c->arays.p, c->counters.p + 6, c->counters.p + 7, hits, slowq_any(c), id_offset,
+        k_anyhit<<<blocks, 128, 0, st>>>(c->sc, rays.p, ctr, ctr + 1, hits, slowq_any(c), id_offset,
                                          pending_mark, reinterpret_cast<unsigned long long*>(c->counters.p + (ao ? 8 : 10)),
                                          c->ah_steps, c->ah_min_search, c->ah_batch_div);
         c->launches++;
@@ -2155,7 +2173,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             FAIL(RT580_INVALID_ARG, "rt580_render_begin: camera_from[%d]=%g lies outside the extent (%g) the BVH boxes were padded for; "
                  "pass the camera as rt580_flat_scene::origin_hint", k, p->camera_from[k], c->pad_extent);
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->stream2));         // (idle unless an earlier frame was abandoned on an error)
+    if (sync_side(c)) return RT580_FAILURE;        // (idle unless an earlier frame was abandoned on an error)
     const bool dbg_t = getenv("RT580_DEBUG_TIMING") != nullptr;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_enter = now_ms();
@@ -2290,7 +2308,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         if (q_max) {
             // room for the next level before anything is launched: its size is only known on the device
             // (a buffer that has to move must not be in use on the second stream)
-            if ((size_t)n1 + q_max > c->nodes.cap || (size_t)n1 + q_max > c->aux.cap) CU(cudaStreamSynchronize(c->stream2));
+            if ((size_t)n1 + q_max > c->nodes.cap || (size_t)n1 + q_max > c->aux.cap) { if (sync_side(c)) return RT580_FAILURE; }
             CU(c->nodes.ensure((size_t)n1 + q_max, n1, st));
             CU(c->aux.ensure((size_t)n1 + q_max, n1, st));
         }
@@ -2304,14 +2322,25 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             // (k_shade_gen -> k_anyhit) and the Phong terms they gate; nothing needs those before the resolve pass.
             // Alone, each persistent traversal kernel ends in a tail that leaves most of the GPU idle, which is what
             // a rank of an 8-GPU run (1/8 of the rays per launch) spent a quarter of its structure pass on.
-            cudaStream_t sb = (c->overlap && !leaky) ? c->stream2 : st;
+            const int lane = (c->overlap && !leaky) ? (L & 1) : 0;
+            cudaStream_t sb = (c->overlap && !leaky) ? c->side[lane] : st;
+            DBuf<uint32_t>& occl = lane ? c->occl2 : c->occl;
             if (sb == st) {
-                // one stream from here on: whatever the second one still does for earlier levels comes first
-                CU(cudaEventRecord(c->ev_join, c->stream2)); CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+                // one stream from here on: whatever the side streams still do for earlier levels comes first
+                if (join_side(c)) return RT580_FAILURE;
             }
             if (leaky && any_open) {
                 // the small queue of the levels before is flushed before the big one takes over
                 const int fr = any_flush(c, shadow_finish); if (fr) return fr; any_open = false;
+            }
+            if (!leaky && !any_open) {
+                // the small any-hit queue of the frame, shared by both side streams
+                if (any_prepare(c, c->slow_any_cap, st)) return RT580_FAILURE;
+                any_open = c->any_cap != 0;
+            }
+            if (sb != st) {
+                // everything the context's stream has done so far (the level's nodes, the queue counter) comes first
+                CU(cudaEventRecord(c->ev_level, st)); CU(cudaStreamWaitEvent(sb, c->ev_level, 0));
             }
             k_spawn<<<nblk(n1 - n0, 128), 128, 0, st>>>(c->sc, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p);
             c->launches++;
@@ -2319,23 +2348,20 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                 if (slow_prepare(c, q_max, &slow_cap)) return RT580_FAILURE;
                 if (launch_secondary(q_max, slow_cap)) return RT580_FAILURE;
             }
-            CU(c->occl.ensure((size_t)n_sh + 1, 0, sb));
-            CU(cudaMemsetAsync(c->occl.p, 0, sizeof(uint32_t) * ((size_t)n_sh + 1), sb));
+            CU(occl.ensure((size_t)n_sh + 1, 0, sb));
+            CU(cudaMemsetAsync(occl.p, 0, sizeof(uint32_t) * ((size_t)n_sh + 1), sb));
             if (n_sh) {
                 if (leaky) {
                     // the queue takes every shadow ray of the level and is flushed right after the level
                     if (any_prepare(c, n_sh, sb)) return RT580_FAILURE;
-                } else if (!any_open) {
-                    if (any_prepare(c, c->slow_any_cap, sb)) return RT580_FAILURE;
-                    any_open = c->any_cap != 0;
                 }
-                const int rc = anyhit_queue_pass(c, sb, n_sh, c->occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
-                    [&](unsigned long long first, unsigned n) {
-                        k_shade_gen<<<nblk(n, 512), 512, 0, sb>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, c->arays.p, c->counters.p + 6, c->occl.p);
+                const int rc = anyhit_queue_pass(c, sb, lane, n_sh, occl.p, n0 * (unsigned)c->sc.n_nonambient, OCCL_PENDING, leaky, false,
+                    [&](unsigned long long first, unsigned n, ARay* rays, unsigned int* ctr) {
+                        k_shade_gen<<<nblk(n, 512), 512, 0, sb>>>(c->sc, n0, n1 - n0, first, n, c->nodes.p, rays, ctr, occl.p);
                     });
                 if (rc) return rc;
             }
-            k_shade_local<<<nblk(n1 - n0, 128), 128, 0, sb>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->occl.p);
+            k_shade_local<<<nblk(n1 - n0, 128), 128, 0, sb>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, occl.p);
             c->launches++;
             if (leaky && n_sh) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
         } else {
@@ -2374,7 +2400,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         rays_so_far += q;
     }
     // the second stream's work belongs to the structure pass: the context's stream goes on when it is done
-    CU(cudaEventRecord(c->ev_join, c->stream2)); CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (join_side(c)) return RT580_FAILURE;
     if (any_open) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
     c->any_cap = 0;
     c->rays_structure = rays_so_far;
@@ -2493,10 +2519,9 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
             for (int attempt = 0; ; attempt++) {
                 const bool leaky = is_leaky(c, c->rays_structure);
                 if (any_prepare(c, leaky ? SLOW_CAP_MAX : c->slow_any_cap, st)) return RT580_FAILURE;
-                const int rc = anyhit_queue_pass(c, st, n_ao, c->ao_hits.p, 0u, 0u, leaky, true,
-                    [&](unsigned long long first, unsigned n) {
-                        k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, c->arays.p,
-                                                               c->counters.p + 6, c->ao_hits.p);
+                const int rc = anyhit_queue_pass(c, st, 0, n_ao, c->ao_hits.p, 0u, 0u, leaky, true,
+                    [&](unsigned long long first, unsigned n, ARay* rays, unsigned int* ctr) {
+                        k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, rays, ctr, c->ao_hits.p);
                     });
                 if (rc) return rc;
                 CU(cudaEventRecord(c->ev[9], st));
