@@ -160,7 +160,7 @@ struct rt580_context {
     FrameParams fp{};
     int traversal = 0;
     DBuf<float> ndc;
-    DBuf<Node> nodes; DBuf<NodeAux> aux; DBuf<QRay> queue;
+    DBuf<Node> nodes; DBuf<NodeAux> aux; DBuf<QRay> queue, queue2;   // the ray queues of two consecutive levels (wavefront path)
     DBuf<uint64_t> pre;            // per node: ordinal of its first AO call / n_ambient
     DBuf<uint32_t> ao_state;       // per AO call: engine state at its first draw
     DBuf<uint32_t> ao_hits;        // per AO call: occluded samples
@@ -474,18 +474,56 @@ __device__ __forceinline__ void fill_node(const PrimRec* __restrict__ prims, con
 // What cpp:30-32 / cpp:925 do with the answer of a closest-hit ray: a hit becomes a node of the
 // next level, a miss is the background colour (in the frame for a primary ray, in the parent's
 // child slot otherwise).  `slot` comes from warp_alloc (all lanes).
+// The wavefront path spawns the children of a hit node (cpp:87-112) in the kernel that creates the node: its
+// material decides whether a reflection / a refraction ray exists, the rays go to the NEXT level's queue.
+struct Spawn { QRay* queue; unsigned int* count; };      // queue == nullptr: the caller spawns elsewhere (k_shade)
+// slots in the next queue; called by all 32 lanes
+__device__ __forceinline__ void spawn_slots(const DeviceScene& sc, const Spawn& so, bool hit, unsigned flags, int prim,
+                                            bool& want_refl, bool& want_refr, unsigned& s0, unsigned& s1) {
+    want_refl = want_refr = false; s0 = s1 = 0u;
+    if (!so.queue) return;
+    if (hit && ((flags >> NF_BOUNCE_SHIFT) & 0xffu) > 0u) {                     // cpp:87
+        const Material M = load_material(sc.materials, __ldg(sc.prim_material + prim));
+        want_refl = M.Ks > 0; want_refr = M.Kt > 0;                             // cpp:94, 108
+    }
+    s0 = warp_alloc(so.count, want_refl);
+    s1 = warp_alloc(so.count, want_refr);
+}
+__device__ __forceinline__ void spawn_rays(const Spawn& so, bool want_refl, bool want_refr, unsigned s0, unsigned s1,
+                                           const float4& nP, const float4& nN, V3 D, unsigned flags, unsigned node) {
+    const V3 P = mk(nP.x, nP.y, nP.z), N = mk(nN.x, nN.y, nN.z);
+    const unsigned child_flags = (((flags >> NF_BOUNCE_SHIFT) & 0xffu) - 1u) << NF_BOUNCE_SHIFT;
+    if (want_refl) {
+        const V3 rdir = normalize(reflect(D, N));                             // cpp:96-97
+        const V3 ro = P + rdir * RT_SHADOW_OFFSET;                            // cpp:98
+        const V3 rd = normalize(rdir);                                        // Ray ctor
+        QRay q; q.o = make_float4(ro.x, ro.y, ro.z, __int_as_float((int)node));
+        q.d = make_float4(rd.x, rd.y, rd.z, __uint_as_float(child_flags));
+        so.queue[s0] = q;
+    }
+    if (want_refr) {
+        const V3 tdir = calculate_refraction(D, N, RT_IOR);                   // cpp:109
+        const V3 to = P + tdir * RT_SHADOW_OFFSET;                            // cpp:110
+        const V3 td = normalize(tdir);                                        // Ray ctor (zero stays zero, Q20)
+        QRay q; q.o = make_float4(to.x, to.y, to.z, __int_as_float((int)node));
+        q.d = make_float4(td.x, td.y, td.z, __uint_as_float(child_flags | NF_REFR));
+        so.queue[s1] = q;
+    }
+}
+
 template <bool PRIMARY>
 __device__ __forceinline__ void commit_closest(const PrimRec* __restrict__ prims, bool hit, const HitRec& h, V3 O, V3 d,
                                                int parent, int pixel, unsigned flags, unsigned slot, unsigned node_cap,
                                                Node* __restrict__ nodes, NodeAux* __restrict__ aux,
-                                               uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb)
+                                               uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, Node& nd)
 {
     if (hit) {
         if (slot >= node_cap) return;   // cannot happen: capacity is ensured before the launch
         if (!PRIMARY) pixel = __float_as_int(nodes[parent].D.w);
-        Node nd;
         fill_node(prims, h, O, d, parent, pixel, flags, nd);
         nodes[slot] = nd;
+        uint2* a = reinterpret_cast<uint2*>(aux + slot);          // [0] local (the shading kernel's), [1] refl, [2] refr, [3] subtree sizes
+        a[1] = make_uint2(0u, 0u); a[2] = make_uint2(0u, 0u); a[3] = make_uint2(0u, 0u);   // Pixel() (cpp:91-92)
         if (!PRIMARY) {
             short* s = (flags & NF_REFR) ? aux[parent].refr : aux[parent].refl;
             s[3] = 2;
@@ -507,7 +545,8 @@ template <int MODE, bool PRIMARY>
 __global__ void __launch_bounds__(128)
 k_trace(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, unsigned n_items,
         const unsigned int* __restrict__ n_items_dev, Node* __restrict__ nodes, NodeAux* __restrict__ aux,
-        unsigned int* __restrict__ counters, uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap, SlowQ sq)
+        unsigned int* __restrict__ counters, uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap, SlowQ sq,
+        Spawn spawn)
 {
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
@@ -540,9 +579,13 @@ k_trace(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, unsigned
     HitRec h;
     const int tr = trace_ray<MODE, false>(sc, sp, active, O, d, 0.f, h, sq, (int)i, 0);
     const unsigned slot = warp_alloc(&counters[0], tr == TR_HIT);
+    bool wr, wt; unsigned s0, s1;
+    spawn_slots(sc, spawn, active && tr == TR_HIT, flags, h.prim, wr, wt, s0, s1);
     if (!active || tr == TR_PENDING) return;
+    Node nd;
     commit_closest<PRIMARY>(MODE == 1 ? sp : sc.prims, tr == TR_HIT, h, O, d, parent, pixel, flags, slot, node_cap, nodes, aux,
-                            pix_hits, fb);
+                            pix_hits, fb, nd);
+    if (wr || wt) spawn_rays(spawn, wr, wt, s0, s1, nd.P, nd.N, d, flags, slot);
 }
 
 // second half of k_trace for the rays that went through the deferred slow path
@@ -550,7 +593,8 @@ template <bool PRIMARY>
 __global__ void __launch_bounds__(128)
 k_trace_finish(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, const SlowRay* __restrict__ rays,
                const SlowRes* __restrict__ res, unsigned n_slow, Node* __restrict__ nodes, NodeAux* __restrict__ aux,
-               unsigned int* __restrict__ counters, uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap)
+               unsigned int* __restrict__ counters, uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap,
+               Spawn spawn)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = e < n_slow;
@@ -569,8 +613,12 @@ k_trace_finish(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, c
         else { parent = __float_as_int(queue[i].o.w); flags = __float_as_uint(queue[i].d.w); }
     }
     const unsigned slot = warp_alloc(&counters[0], hit);
+    bool wr, wt; unsigned s0, s1;
+    spawn_slots(sc, spawn, hit, flags, h.prim, wr, wt, s0, s1);
     if (!active) return;
-    commit_closest<PRIMARY>(sc.prims, hit, h, O, d, parent, pixel, flags, slot, node_cap, nodes, aux, pix_hits, fb);
+    Node nd;
+    commit_closest<PRIMARY>(sc.prims, hit, h, O, d, parent, pixel, flags, slot, node_cap, nodes, aux, pix_hits, fb, nd);
+    if (wr || wt) spawn_rays(spawn, wr, wt, s0, s1, nd.P, nd.N, d, flags, slot);
 }
 
 // ---- closest hit of the queued reflection / refraction rays, wavefront form ----------------
@@ -682,7 +730,7 @@ k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __
 __global__ void __launch_bounds__(128)
 k_commit(DeviceScene sc, const QRay* __restrict__ queue, unsigned n_items, const unsigned int* __restrict__ n_items_dev,
          const CHit* __restrict__ chits, Node* __restrict__ nodes, NodeAux* __restrict__ aux, unsigned int* __restrict__ counters,
-         uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap, SlowQ sq)
+         uint32_t* __restrict__ pix_hits, int16_t* __restrict__ fb, unsigned node_cap, SlowQ sq, Spawn spawn)
 {
     if (n_items_dev) n_items = min(n_items, __ldg(n_items_dev));
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -699,8 +747,12 @@ k_commit(DeviceScene sc, const QRay* __restrict__ queue, unsigned n_items, const
     }
     const int tr = finish_closest(sc, active, O, d, h, sq, (int)i);
     const unsigned slot = warp_alloc(&counters[0], tr == TR_HIT);
+    bool wr, wt; unsigned s0, s1;
+    spawn_slots(sc, spawn, active && tr == TR_HIT, flags, h.prim, wr, wt, s0, s1);
     if (!active || tr == TR_PENDING) return;
-    commit_closest<false>(sc.prims, tr == TR_HIT, h, O, d, parent, 0, flags, slot, node_cap, nodes, aux, pix_hits, fb);
+    Node nd;
+    commit_closest<false>(sc.prims, tr == TR_HIT, h, O, d, parent, 0, flags, slot, node_cap, nodes, aux, pix_hits, fb, nd);
+    if (wr || wt) spawn_rays(spawn, wr, wt, s0, s1, nd.P, nd.N, d, flags, slot);
 }
 
 // shading normal of a node (cpp:225-236): interpolated object-space vertex normals for a triangle
@@ -811,50 +863,10 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
 // reflection / refraction rays needs nothing from the shadow rays, and the chain spawn -> closest hit ->
 // commit -> next level is the critical path of the structure pass, while the shadow rays of a level and the
 // Phong terms they gate (the bulk of the work) only have to be done before the resolve pass.
-//   k_spawn       per hit node: NodeAux except `local`, children into the ray queue        (cpp:87-112)
-//   k_shade_local per hit node: sum of the unoccluded lights' Phong terms -> NodeAux::local (cpp:53-81)
+//   spawn_slots / spawn_rays  in the kernel that creates a hit node: NodeAux except `local`, children into the next
+//                             level's ray queue                                              (cpp:87-112)
+//   k_shade_local             per hit node: sum of the unoccluded lights' Phong terms -> NodeAux::local (cpp:53-81)
 // The two write disjoint bytes of NodeAux.
-__global__ void __launch_bounds__(128)
-k_spawn(DeviceScene sc, unsigned n0, unsigned n1, const Node* __restrict__ nodes, NodeAux* __restrict__ aux,
-        QRay* __restrict__ queue, unsigned int* __restrict__ counters)
-{
-    const unsigned i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < n1;
-    bool want_refl = false, want_refr = false;
-    V3 P = mk(0, 0, 0), N = mk(0, 0, 0), D = mk(0, 0, 0);
-    int bounces = 0;
-    if (active) {
-        const Node nd = nodes[i];
-        P = mk(nd.P.x, nd.P.y, nd.P.z); N = mk(nd.N.x, nd.N.y, nd.N.z); D = mk(nd.D.x, nd.D.y, nd.D.z);
-        const unsigned flags = __float_as_uint(nd.B.w);
-        bounces = (int)((flags >> NF_BOUNCE_SHIFT) & 0xffu);
-        const Material M = load_material(sc.materials, __ldg(sc.prim_material + __float_as_int(nd.P.w)));
-        uint2* a = reinterpret_cast<uint2*>(aux + i);                 // [0] local (k_shade_local's), [1] refl, [2] refr, [3] subtree sizes
-        a[1] = make_uint2(0u, 0u); a[2] = make_uint2(0u, 0u); a[3] = make_uint2(0u, 0u);   // Pixel() (cpp:91-92)
-        if (bounces > 0) { want_refl = M.Ks > 0; want_refr = M.Kt > 0; }     // cpp:87, 94, 108
-    }
-    const unsigned s0 = warp_alloc(&counters[1], want_refl);
-    const unsigned s1 = warp_alloc(&counters[1], want_refr);
-    if (!active) return;
-    const unsigned child_flags = (unsigned)(bounces - 1) << NF_BOUNCE_SHIFT;
-    if (want_refl) {
-        const V3 rdir = normalize(reflect(D, N));                             // cpp:96-97
-        const V3 ro = P + rdir * RT_SHADOW_OFFSET;                            // cpp:98
-        const V3 rd = normalize(rdir);                                        // Ray ctor
-        QRay q; q.o = make_float4(ro.x, ro.y, ro.z, __int_as_float((int)i));
-        q.d = make_float4(rd.x, rd.y, rd.z, __uint_as_float(child_flags));
-        queue[s0] = q;
-    }
-    if (want_refr) {
-        const V3 tdir = calculate_refraction(D, N, RT_IOR);                   // cpp:109
-        const V3 to = P + tdir * RT_SHADOW_OFFSET;                            // cpp:110
-        const V3 td = normalize(tdir);                                        // Ray ctor (zero stays zero, Q20)
-        QRay q; q.o = make_float4(to.x, to.y, to.z, __int_as_float((int)i));
-        q.d = make_float4(td.x, td.y, td.z, __uint_as_float(child_flags | NF_REFR));
-        queue[s1] = q;
-    }
-}
-
 __global__ void __launch_bounds__(128)
 k_shade_local(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __restrict__ nodes,
               NodeAux* __restrict__ aux, const uint32_t* __restrict__ occl)
@@ -1662,7 +1674,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     free_scene(c);
     frame_release(c);
     arena_release(c->scene_arena); arena_release(c->build_arena);
-    c->ndc.release(); c->lcg_pow.release(); c->lcg_tab.release(); c->rgb8.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->pre.release();
+    c->ndc.release(); c->lcg_pow.release(); c->lcg_tab.release(); c->rgb8.release(); c->nodes.release(); c->aux.release(); c->queue.release(); c->queue2.release(); c->pre.release();
     c->ao_state.release(); c->ao_hits.release(); c->pix_hits.release(); c->pix_scan.release();
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
     c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release(); c->chits.release();
@@ -1964,14 +1976,14 @@ static SlowQ slowq_any(rt580_context* c) {
     SlowQ q; q.rays = c->any_cap ? c->any_rays.p : nullptr; q.res = c->any_res.p; q.count = c->counters.p + 3; q.cap = c->any_cap;
     return q;
 }
-template <int MODE> static void launch_trace(rt580_context* c, bool primary, unsigned n_items, const unsigned* n_items_dev,
-                                             unsigned node_cap, unsigned slow_cap) {
+template <int MODE> static void launch_trace(rt580_context* c, bool primary, const QRay* queue, unsigned n_items, const unsigned* n_items_dev,
+                                             unsigned node_cap, unsigned slow_cap, Spawn spawn) {
     if (primary)
-        k_trace<MODE, true><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, n_items_dev, c->nodes.p, c->aux.p,
-                                                                      c->counters.p, c->pix_hits.p, c->fb.p, node_cap, slowq(c, slow_cap));
+        k_trace<MODE, true><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, queue, n_items, n_items_dev, c->nodes.p, c->aux.p,
+                                                                      c->counters.p, c->pix_hits.p, c->fb.p, node_cap, slowq(c, slow_cap), spawn);
     else
-        k_trace<MODE, false><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, c->queue.p, n_items, n_items_dev, c->nodes.p, c->aux.p,
-                                                                       c->counters.p, c->pix_hits.p, c->fb.p, node_cap, slowq(c, slow_cap));
+        k_trace<MODE, false><<<nblk(n_items, 128), 128, 0, c->stream>>>(c->sc, c->fp, queue, n_items, n_items_dev, c->nodes.p, c->aux.p,
+                                                                       c->counters.p, c->pix_hits.p, c->fb.p, node_cap, slowq(c, slow_cap), spawn);
     c->launches++;
 }
 template <int MODE> static void launch_shade(rt580_context* c, unsigned n0, unsigned n1, unsigned slow_cap) {
@@ -2262,63 +2274,49 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
     unsigned n_nodes = 0, slow_cap = 0, n_slow = 0;
     unsigned cnt[N_COUNTERS];
     c->slow_total = 0;
-    if (npix) {
-        if (slow_prepare(c, npix, &slow_cap)) return RT580_FAILURE;
-        DISPATCH_MODE(mode, launch_trace, c, true, npix, nullptr, (unsigned)c->nodes.cap, slow_cap);
-        if (read_counters(c, cnt)) return RT580_FAILURE;
-        n_nodes = cnt[0];
-        slow_run(c, false, slow_cap, cnt[2], &n_slow);
-        if (n_slow) {
-            k_trace_finish<true><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
-                                                                   c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
-                                                                   (unsigned)c->nodes.cap);
-            c->launches++;
-            if (read_counters(c, cnt)) return RT580_FAILURE;
-            n_nodes = cnt[0];
-        }
-    }
-    c->level_rays.push_back(npix);
-    c->level_off.push_back(n_nodes);
     unsigned long long rays_so_far = npix;
     bool any_open = false;      // shadow rays of earlier levels wait in the any-hit queue
     auto shadow_finish = [&](unsigned n) {
         k_shadow_finish<<<nblk(n, 128), 128, 0, st>>>(c->sc, c->fp, c->any_rays.p, c->any_res.p, n, c->nodes.p, c->aux.p);
     };
-    // the secondary rays of a level: their number stays on the device (counters[1])
-    auto launch_secondary = [&](unsigned q_max, unsigned slow_cap_) -> int {
-        if (mode == 0 && !c->one_thread_per_ray) {
-            CU(c->chits.ensure((size_t)q_max + 1, 0, st));
-            CU(cudaMemsetAsync(c->counters.p + 12, 0, sizeof(unsigned), st));
-            const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ch_blocks_per_sm;
-            k_closest<<<blocks, 128, 0, st>>>(c->sc, c->queue.p, c->counters.p + 1, q_max, c->counters.p + 12, c->chits.p,
-                                              c->ah_steps, c->ah_min_search, c->ah_batch_div);
-            k_commit<<<nblk(q_max, 128), 128, 0, st>>>(c->sc, c->queue.p, q_max, c->counters.p + 1, c->chits.p, c->nodes.p, c->aux.p,
-                                                       c->counters.p, c->pix_hits.p, c->fb.p, (unsigned)c->nodes.cap, slowq(c, slow_cap_));
-            c->launches += 2;
-        } else {
-            DISPATCH_MODE(mode, launch_trace, c, false, q_max, c->counters.p + 1, (unsigned)c->nodes.cap, slow_cap_);
+    const Spawn no_spawn = { nullptr, nullptr };
+    if (mode == 0) {
+        // ---- wavefront path over the LBVH -------------------------------------------------------------------
+        // The kernel that creates a hit node also spawns its children into the NEXT level's queue (two queues,
+        // two counters, alternating), so one host read after a level's closest-hit step returns both the new
+        // node count and the next queue's length.
+        DBuf<QRay>* Q[2] = { &c->queue, &c->queue2 };
+        unsigned int* qcnt[2] = { c->counters.p + 1, c->counters.p + 15 };
+        const int qidx[2] = { 1, 15 };
+        int cur = 0;
+        unsigned q = 0;
+        if (npix) {
+            CU(Q[0]->ensure(2 * (size_t)npix + 1, 0, st));
+            if (slow_prepare(c, npix, &slow_cap)) return RT580_FAILURE;
+            launch_trace<0>(c, true, nullptr, npix, nullptr, (unsigned)c->nodes.cap, slow_cap, Spawn{ Q[0]->p, qcnt[0] });
+            if (read_counters(c, cnt)) return RT580_FAILURE;
+            n_nodes = cnt[0]; q = cnt[qidx[0]];
+            slow_run(c, false, slow_cap, cnt[2], &n_slow);
+            if (n_slow) {
+                k_trace_finish<true><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, nullptr, c->slow_rays.p, c->slow_res.p, n_slow,
+                                                                       c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
+                                                                       (unsigned)c->nodes.cap, Spawn{ Q[0]->p, qcnt[0] });
+                c->launches++;
+                if (read_counters(c, cnt)) return RT580_FAILURE;
+                n_nodes = cnt[0]; q = cnt[qidx[0]];
+            }
         }
-        return RT580_SUCCESS;
-    };
-    for (int L = 0; L <= fp.depth; L++) {
-        const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
-        if (n1 == n0) break;
-        const unsigned q_max = (L < fp.depth) ? 2u * (n1 - n0) : 0u;       // every node spawns at most two rays
-        CU(c->queue.ensure((size_t)q_max + 1, 0, st));
-        if (q_max) {
-            // room for the next level before anything is launched: its size is only known on the device
-            // (a buffer that has to move must not be in use on the second stream)
-            if ((size_t)n1 + q_max > c->nodes.cap || (size_t)n1 + q_max > c->aux.cap) { if (sync_side(c)) return RT580_FAILURE; }
-            CU(c->nodes.ensure((size_t)n1 + q_max, n1, st));
-            CU(c->aux.ensure((size_t)n1 + q_max, n1, st));
-        }
-        CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
-        const unsigned long long n_sh = (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient;
-        if (mode == 0) {
+        c->level_rays.push_back(npix);
+        c->level_off.push_back(n_nodes);
+        for (int L = 0; L <= fp.depth; L++) {
+            const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
+            if (n1 == n0) break;
+            const unsigned long long n_sh = (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient;
             if (n_sh > 0xfffffff0ull) FAIL(RT580_FAILURE, "rt580_render_begin: too many shadow rays in one level");
+            const bool more = L < fp.depth && q > 0;
             const bool leaky = is_leaky(c, rays_so_far);
-            // Two chains per level.  Critical path, on the context's stream: spawn the children, find their closest
-            // hits, create the next level's nodes.  Beside it, on the second stream: the level's shadow rays
+            // Two chains per level.  Critical path, on the context's stream: the closest hits of the level's children
+            // and with them the next level's nodes and rays.  Beside it, on a side stream: the level's shadow rays
             // (k_shade_gen -> k_anyhit) and the Phong terms they gate; nothing needs those before the resolve pass.
             // Alone, each persistent traversal kernel ends in a tail that leaves most of the GPU idle, which is what
             // a rank of an 8-GPU run (1/8 of the rays per launch) spent a quarter of its structure pass on.
@@ -2339,14 +2337,30 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                 any_open = c->any_cap != 0;
             }
             if (sb != st) {
-                // everything the context's stream has done so far (the level's nodes, the queue counter) comes first
+                // everything the context's stream has done so far (the level's nodes) comes first
                 CU(cudaEventRecord(c->ev_level, st)); CU(cudaStreamWaitEvent(sb, c->ev_level, 0));
             }
-            k_spawn<<<nblk(n1 - n0, 128), 128, 0, st>>>(c->sc, n0, n1, c->nodes.p, c->aux.p, c->queue.p, c->counters.p);
-            c->launches++;
-            if (L < fp.depth) {
-                if (slow_prepare(c, q_max, &slow_cap)) return RT580_FAILURE;
-                if (launch_secondary(q_max, slow_cap)) return RT580_FAILURE;
+            if (more) {
+                // (a buffer that has to move must not be in use on a side stream)
+                if ((size_t)n1 + q > c->nodes.cap || (size_t)n1 + q > c->aux.cap) { if (sync_side(c)) return RT580_FAILURE; }
+                CU(c->nodes.ensure((size_t)n1 + q, n1, st));
+                CU(c->aux.ensure((size_t)n1 + q, n1, st));
+                CU(Q[cur ^ 1]->ensure(2 * (size_t)q + 1, 0, st));
+                CU(cudaMemsetAsync(qcnt[cur ^ 1], 0, sizeof(unsigned), st));
+                if (slow_prepare(c, q, &slow_cap)) return RT580_FAILURE;
+                const Spawn sp = { Q[cur ^ 1]->p, qcnt[cur ^ 1] };
+                if (!c->one_thread_per_ray) {
+                    CU(c->chits.ensure((size_t)q + 1, 0, st));
+                    CU(cudaMemsetAsync(c->counters.p + 12, 0, sizeof(unsigned), st));
+                    const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ch_blocks_per_sm;
+                    k_closest<<<blocks, 128, 0, st>>>(c->sc, Q[cur]->p, qcnt[cur], q, c->counters.p + 12, c->chits.p,
+                                                      c->ah_steps, c->ah_min_search, c->ah_batch_div);
+                    k_commit<<<nblk(q, 128), 128, 0, st>>>(c->sc, Q[cur]->p, q, nullptr, c->chits.p, c->nodes.p, c->aux.p,
+                                                           c->counters.p, c->pix_hits.p, c->fb.p, (unsigned)c->nodes.cap, slowq(c, slow_cap), sp);
+                    c->launches += 2;
+                } else {
+                    launch_trace<0>(c, false, Q[cur]->p, q, nullptr, (unsigned)c->nodes.cap, slow_cap, sp);
+                }
             }
             CU(occl.ensure((size_t)n_sh + 1, 0, sb));
             CU(cudaMemsetAsync(occl.p, 0, sizeof(uint32_t) * ((size_t)n_sh + 1), sb));
@@ -2364,7 +2378,55 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             k_shade_local<<<nblk(n1 - n0, 128), 128, 0, sb>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, occl.p);
             c->launches++;
             if (leaky && n_sh) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
-        } else {
+            rays_so_far += n_sh;
+            if (!more) break;
+            if (read_counters(c, cnt)) return RT580_FAILURE;
+            n_nodes = cnt[0];
+            unsigned q_next = cnt[qidx[cur ^ 1]];
+            slow_run(c, false, slow_cap, cnt[2], &n_slow);
+            if (n_slow) {
+                k_trace_finish<false><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, Q[cur]->p, c->slow_rays.p, c->slow_res.p, n_slow,
+                                                                        c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
+                                                                        (unsigned)c->nodes.cap, Spawn{ Q[cur ^ 1]->p, qcnt[cur ^ 1] });
+                c->launches++;
+                if (read_counters(c, cnt)) return RT580_FAILURE;
+                n_nodes = cnt[0]; q_next = cnt[qidx[cur ^ 1]];
+            }
+            c->level_rays.push_back(q);
+            c->level_off.push_back(n_nodes);
+            rays_so_far += q;
+            q = q_next; cur ^= 1;
+        }
+    } else {
+        // ---- tiny scenes / checker: the reference's linear loop, one thread per ray, k_shade spawns the children ----
+        if (npix) {
+            if (slow_prepare(c, npix, &slow_cap)) return RT580_FAILURE;
+            DISPATCH_MODE(mode, launch_trace, c, true, nullptr, npix, nullptr, (unsigned)c->nodes.cap, slow_cap, no_spawn);
+            if (read_counters(c, cnt)) return RT580_FAILURE;
+            n_nodes = cnt[0];
+            slow_run(c, false, slow_cap, cnt[2], &n_slow);
+            if (n_slow) {
+                k_trace_finish<true><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
+                                                                       c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
+                                                                       (unsigned)c->nodes.cap, no_spawn);
+                c->launches++;
+                if (read_counters(c, cnt)) return RT580_FAILURE;
+                n_nodes = cnt[0];
+            }
+        }
+        c->level_rays.push_back(npix);
+        c->level_off.push_back(n_nodes);
+        for (int L = 0; L <= fp.depth; L++) {
+            const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
+            if (n1 == n0) break;
+            const unsigned q_max = (L < fp.depth) ? 2u * (n1 - n0) : 0u;       // every node spawns at most two rays
+            CU(c->queue.ensure((size_t)q_max + 1, 0, st));
+            if (q_max) {
+                CU(c->nodes.ensure((size_t)n1 + q_max, n1, st));
+                CU(c->aux.ensure((size_t)n1 + q_max, n1, st));
+            }
+            CU(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(unsigned), st));
+            const unsigned long long n_sh = (unsigned long long)(n1 - n0) * (unsigned)c->sc.n_nonambient;
             if (slow_prepare(c, n_sh, &slow_cap)) return RT580_FAILURE;
             DISPATCH_MODE(mode, launch_shade, c, n0, n1, slow_cap);
             if (slow_cap) {
@@ -2375,29 +2437,28 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                     c->launches++;
                 }
             }
-        }
-        rays_so_far += n_sh;
-        if (L == fp.depth) break;
-        if (mode != 0) {
+            rays_so_far += n_sh;
+            if (L == fp.depth) break;
+            // the queued reflection / refraction rays: their number stays on the device (counters[1])
             if (slow_prepare(c, q_max, &slow_cap)) return RT580_FAILURE;
-            if (launch_secondary(q_max, slow_cap)) return RT580_FAILURE;
-        }
-        if (read_counters(c, cnt)) return RT580_FAILURE;
-        const unsigned q = cnt[1];
-        if (q == 0) break;
-        n_nodes = cnt[0];
-        slow_run(c, false, slow_cap, cnt[2], &n_slow);
-        if (n_slow) {
-            k_trace_finish<false><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
-                                                                    c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
-                                                                    (unsigned)c->nodes.cap);
-            c->launches++;
+            DISPATCH_MODE(mode, launch_trace, c, false, c->queue.p, q_max, c->counters.p + 1, (unsigned)c->nodes.cap, slow_cap, no_spawn);
             if (read_counters(c, cnt)) return RT580_FAILURE;
+            const unsigned q = cnt[1];
+            if (q == 0) break;
             n_nodes = cnt[0];
+            slow_run(c, false, slow_cap, cnt[2], &n_slow);
+            if (n_slow) {
+                k_trace_finish<false><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
+                                                                        c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
+                                                                        (unsigned)c->nodes.cap, no_spawn);
+                c->launches++;
+                if (read_counters(c, cnt)) return RT580_FAILURE;
+                n_nodes = cnt[0];
+            }
+            c->level_rays.push_back(q);
+            c->level_off.push_back(n_nodes);
+            rays_so_far += q;
         }
-        c->level_rays.push_back(q);
-        c->level_off.push_back(n_nodes);
-        rays_so_far += q;
     }
     // the second stream's work belongs to the structure pass: the context's stream goes on when it is done
     if (join_side(c)) return RT580_FAILURE;
