@@ -2460,10 +2460,6 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             rays_so_far += q;
         }
     }
-    // the second stream's work belongs to the structure pass: the context's stream goes on when it is done
-    if (join_side(c)) return RT580_FAILURE;
-    if (any_open) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
-    c->any_cap = 0;
     c->rays_structure = rays_so_far;
     const double t_struct = now_ms();
     CU(cudaEventRecord(c->ev[1], st));
@@ -2477,6 +2473,13 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         if (exclusive_scan_u32(c, c->pix_hits.p, c->pix_scan.p, npix)) return RT580_FAILURE;
         k_row_counts<<<nblk(fp.n_rows, 128), 128, 0, st>>>(c->pix_hits.p, c->pix_scan.p, fp.W, fp.n_rows, c->row_vals.p); c->launches++;
     }
+    CU(cudaEventRecord(c->ev[7], st));
+    // The side streams' work (shadow rays and Phong terms of the last levels) belongs to the structure pass, but the
+    // order kernels above need none of it (they read the subtree sizes, the side streams write NodeAux::local): the
+    // context's stream waits for it only now, then the deferred shadow rays are answered.
+    if (join_side(c)) return RT580_FAILURE;
+    if (any_open) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
+    c->any_cap = 0;
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev[6], st));
     if (row_hit_nodes) {
@@ -2643,9 +2646,12 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
     if (read_counters(c, cnt)) return RT580_FAILURE;
     CU(cudaGetLastError());
     float ms = 0.f;
+    // structure = the main chain up to the order kernels + what the context's stream then still waited for the side
+    // streams and the deferred shadow rays; order = the order kernels of both halves
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.ms_structure = ms;
+    cudaEventElapsedTime(&ms, c->ev[7], c->ev[6]); c->stats.ms_structure += ms;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.ms_order = ms;
-    cudaEventElapsedTime(&ms, c->ev[1], c->ev[6]); c->stats.ms_order += ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[7]); c->stats.ms_order += ms;
     cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stats.ms_ao = ms;
     cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->stats.ms_resolve = ms;
     if (n_ao) { cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]); c->stats.ms_ao_kernel = ms; }
