@@ -477,3 +477,27 @@ def test_benchmark_scene_at_full_size(pkg, oracle):
     assert np.array_equal(got3, fb)
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("scene,spp", [("scene.json", 16), ("scene.json", 64), ("scene_point.json", 16)])
+def test_mesh_scene_at_1080p_sampled(pkg, oracle, oracle_scene, scene, spp):
+    """BASELINE configs 2 and 3 at their named size: the 4-teapot mesh scene (and its point-light variant) at
+    1920x1080, depth 4, 16 / 64 AO samples.  An open scene: rays escape, so the far-field replay, the linear
+    fallback and the "leaky" form of the deferred queues all run.  300 sampled pixels (half of them drawn from
+    the pixels that hit something) against the T1 oracle, seeded with the GPU's AO ordinals."""
+    W, H, depth = 1920, 1080, 4
+    rt = make_rt(pkg, scene, W, H, spp, depth)
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    fb, st = ctx.render(rt.render_params())
+    base = ctx.last_frame_ao_base(W * H)
+    flat = fb.reshape(-1, 3)
+    covered = np.flatnonzero((flat != np.array([254, 64, 205], np.int16)).any(axis=-1))
+    assert covered.size > 1000
+    rng = np.random.default_rng(2)
+    pix = np.unique(np.concatenate([rng.choice(W * H, 150, replace=False), rng.choice(covered, 150, replace=False)])).astype(np.int32)
+    ref, _, _ = oracle_scene(scene).render(W, H, spp, depth, pix=pix, ao_base=base[pix], nthreads=NT)
+    got = flat[pix]
+    assert np.array_equal(got, ref), "%d sampled pixels differ" % int((got != ref).any(axis=-1).sum())
+    assert st.far_scans + st.linear_fallbacks > 0
+    ctx.close()
