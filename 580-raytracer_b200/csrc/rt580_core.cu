@@ -5,17 +5,22 @@
 // The recursive reflect/refract Raycast becomes a breadth-first wavefront over "hit nodes":
 //
 //   level 0   k_trace<primary>     GenerateRay (cpp:832-858) + closest hit per pixel
-//   level L   k_shade              per hit node: shadow rays (cpp:53-81) + CalculateLocalColor,
-//                                  spawn reflection / refraction rays (cpp:94-112) into the
-//                                  ray queue with warp-ballot compaction
-//             k_trace<secondary>   closest hit of the queued rays -> level L+1 nodes
+//   level L   main chain           k_closest (persistent closest-hit traversal of the level's reflection / refraction
+//                                  rays) -> k_commit (large primitives, far field, node creation): level L+1 nodes.
+//                                  The kernel that creates a node spawns its children (cpp:94-112) into the next queue.
+//             side streams         k_shade_gen (shadow rays cpp:53-81: large primitives, clearance map) -> k_anyhit
+//                                  (persistent any-hit traversal) -> k_shade_local (CalculateLocalColor of the lit lights)
 //   order     k_subtree (bottom-up), scan over pixels, k_preorder (top-down): gives every hit
 //             node its ordinal in the reference's traversal order (scanline pixels x pre-order
 //             nodes), i.e. its position in the single AO random stream
-//   AO        k_ao                 one thread per (node, ambient light, sample): any-hit ray,
-//                                  stream position by modular exponentiation (Appendix C)
+//   AO        k_ao_gen             one thread per (node, ambient light, sample): stream position by modular
+//                                  exponentiation (Appendix C), hemisphere direction, large primitives first;
+//             k_anyhit             the rays those did not stop
 //   resolve   k_resolve (bottom-up per level): the integer Pixel algebra of cpp:39-51 and
 //             cpp:114-128, child colour written into the parent's slot, roots into the frame
+//
+// Tiny scenes (<= 64 primitives) and the brute-force checker run the reference's linear loop instead, one thread
+// per ray / node: k_trace<MODE>, k_shade<MODE>, k_ao<MODE>.
 //
 // AO never influences ray geometry (cpp:45 only scales a colour), so the tree of every pixel
 // is known before a single AO ray is traced; that is what makes the stream addressable.
@@ -777,14 +782,13 @@ __device__ __forceinline__ void shadow_ray(const Light& L, V3 P, V3& so, V3& sd,
     tmax = (L.type == RT580_LIGHT_POINT) ? distToLight : __int_as_float(0x7f800000);
 }
 
-// Per hit node of one level: direct lighting with shadow rays, then spawn the children.
-// PRETRACED: the shadow rays went through k_shade_gen + k_anyhit already (occl[(node - n0) * n_nonambient + j]
-// counts their occluders in the tree); only the large-primitive list is left to test here.
-template <int MODE, bool PRETRACED>
+// Per hit node of one level, one thread per node: direct lighting with inline shadow rays, then spawn the children.
+// The form the linear modes use (tiny scenes staged in shared memory, the brute-force checker); the wavefront path over
+// the LBVH splits this work over k_shade_gen / k_anyhit / k_shade_local and the node-creating kernels (below).
+template <int MODE>
 __global__ void __launch_bounds__(128)
 k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __restrict__ nodes,
-        NodeAux* __restrict__ aux, QRay* __restrict__ queue, unsigned int* __restrict__ counters, SlowQ sq,
-        const uint32_t* __restrict__ occl)
+        NodeAux* __restrict__ aux, QRay* __restrict__ queue, unsigned int* __restrict__ counters, SlowQ sq)
 {
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
@@ -811,17 +815,11 @@ k_shade(DeviceScene sc, FrameParams fp, unsigned n0, unsigned n1, const Node* __
     for (int li = 0; li < sc.n_lights; li++) {                        // cpp:39
         const Light L = load_light(sc.light_type, sc.light_f, li);
         if (L.type == RT580_LIGHT_AMBIENT) continue;                  // handled by k_ao / k_resolve
-        int tr;
-        if (PRETRACED) {
-            // occluders of this ray: tree (k_anyhit), large primitives (k_shade_gen), or still pending (k_shadow_finish)
-            tr = (active && __ldg(occl + (size_t)(i - n0) * sc.n_nonambient + j) != 0u) ? TR_HIT : TR_MISS;
-        } else {
-            V3 so, sd; float tmax;
-            shadow_ray(L, P, so, sd, tmax);
-            HitRec sh;
-            // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
-            tr = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh, sq, (int)i, li);
-        }
+        V3 so, sd; float tmax;
+        shadow_ray(L, P, so, sd, tmax);
+        HitRec sh;
+        // cpp:75: lit unless something is hit (point light: at distance <= distToLight)
+        const int tr = trace_ray<MODE, true>(sc, sp, active, so, sd, tmax, sh, sq, (int)i, li);
         // TR_PENDING: k_shade_finish adds this light's term once the deferred ray is answered
         if (active && tr == TR_MISS) local = pix_add(local, calculate_local_color(P, pf, L, M));   // cpp:77
         j++;
@@ -1987,8 +1985,8 @@ template <int MODE> static void launch_trace(rt580_context* c, bool primary, con
     c->launches++;
 }
 template <int MODE> static void launch_shade(rt580_context* c, unsigned n0, unsigned n1, unsigned slow_cap) {
-    k_shade<MODE, false><<<nblk(n1 - n0, 128), 128, 0, c->stream>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p,
-                                                                    c->counters.p, slowq(c, slow_cap), nullptr);
+    k_shade<MODE><<<nblk(n1 - n0, 128), 128, 0, c->stream>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, c->queue.p,
+                                                             c->counters.p, slowq(c, slow_cap));
     c->launches++;
 }
 template <int MODE> static void launch_ao(rt580_context* c, unsigned long long n_rays, unsigned slow_cap) {
