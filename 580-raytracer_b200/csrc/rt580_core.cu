@@ -362,11 +362,12 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
     __shared__ unsigned long long s_q[8][64];              // survivors of the filter: (ray << 32) | record
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned first = blockIdx.x * SLOW_RPB + warp * SLOW_RPW;
+    // ray j of the block's batch goes to warp j % 8: a batch of 5 rays keeps 5 warps busy, not 2
+    const unsigned first = blockIdx.x * SLOW_RPB + warp;
     bool my_live = false, my_lin = false;
     unsigned long long key0 = 0ull;
     if (lane < SLOW_RPW) {
-        const unsigned e = first + lane;
+        const unsigned e = first + lane * 8u;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
         if (e < n) {
             o = __ldg(&rays[e].o); d = __ldg(&rays[e].d);
@@ -431,7 +432,7 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
     if ((unsigned)lane < q_len) slow_exact<ANY>(sc, s_q[warp][lane], s_O[warp], s_D[warp], s_key[warp], s_found[warp]);
     __syncwarp();
     if (lane < SLOW_RPW && my_live) {
-        const unsigned e = first + lane;
+        const unsigned e = first + lane * 8u;
         if (ANY) { if (s_found[warp][lane]) res[e].found = 1; }
         else { const unsigned long long k = s_key[warp][lane]; if (k < key0) atomicMin(&res[e].key, k); }
     }
@@ -2069,10 +2070,10 @@ static void slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes
 {
     if (!n) return;
     const unsigned batches = nblk(n, SLOW_RPB);
-    unsigned slices = nblk(4u * (unsigned)c->prop.multiProcessorCount, batches);
+    unsigned slices = nblk(8u * (unsigned)c->prop.multiProcessorCount, batches);
     const unsigned max_slices = nblk((unsigned)c->sc.n_all, SLOW_TILE);
     if (slices > max_slices) slices = max_slices;
-    if (slices > 256u) slices = 256u;
+    if (slices > 1024u) slices = 1024u;
     if (slices < 1u) slices = 1u;
     const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_all, slices), SLOW_TILE) * SLOW_TILE);
     const dim3 grid(batches, slices);
