@@ -107,7 +107,7 @@ __host__ __device__ __forceinline__ unsigned long long slow_key(float t, int pri
 #define AH_MIN_BLOCKS 12
 #endif
 #define AH_STEPS 48        // at most this many inner-node steps between two leaf / refill phases
-#define AH_MIN_SEARCH 12   // leave the inner-node phase when fewer lanes than this still have an inner node
+#define AH_MIN_SEARCH 16   // leave the inner-node phase when fewer lanes than this still have an inner node
 #define AH_NONE 0x7fffffff // traversal cursor: nothing left
 #define AH_BATCH 512  // most rays a warp reserves per atomic on the queue counter (fewer when the queue is short)
 
@@ -192,7 +192,7 @@ struct rt580_context {
     DBuf<struct ARay> arays;       // one chunk of generated any-hit rays (AO samples / shadow rays)
     DBuf<uint32_t> occl;           // per shadow ray of the current level: occluders found
     DBuf<struct CHit> chits;       // per queued secondary ray: what the tree answered (k_closest -> k_commit)
-    int ch_blocks_per_sm = 10; bool one_thread_per_ray = false;   // RT580_CH_BLOCKS_PER_SM, RT580_ONE_THREAD_PER_RAY (A/B)
+    int ch_blocks_per_sm = 12; bool one_thread_per_ray = false;   // RT580_CH_BLOCKS_PER_SM, RT580_ONE_THREAD_PER_RAY (A/B)
     uint64_t slow_total = 0;
     int ah_batch_div = 4;
     int smap_res = SMAP_RES_DEFAULT;        // RT580_SMAP_RES
