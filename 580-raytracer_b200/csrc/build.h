@@ -28,6 +28,24 @@ void arena_release(DevArena& a);
 size_t build_tmp_bytes(int64_t n_in);
 size_t build_out_bytes(int64_t n_in, int64_t n_prims);
 
+// grow-only device buffer
+template <typename T> struct DBuf {
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n, size_t keep, cudaStream_t s) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = cap ? cap : 1024;
+        while (ncap < n) ncap = ncap + ncap / 2 + 1024;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; }
+        if (p) { cudaStreamSynchronize(s); cudaFree(p); }
+        p = q; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
 struct BuildInput {            // device pointers (already uploaded)
     const float4* tri_v0; const float4* tri_v1; const float4* tri_v2;
     const int32_t* tri_prim; int64_t n_tris;
@@ -49,11 +67,28 @@ struct BuildOutput {
     int n_dropped;             // zero-area triangles
     unsigned int max_depth;
     float pad, extent;
+    float pad_max;             // largest padding of a leaf box (pad + L_near): every near-field hit lies within it of its primitive
     float bounds_lo[3], bounds_hi[3];
     int launches;
 };
 
 bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmp, DevArena& outa, cudaStream_t stream, char* err,
                size_t errlen);
+
+// ---- far-field direction grid (fargrid.cuh, fargrid_build.cu) ----
+struct FgBuildInput {
+    const PrimRec* prims; const float4* far_old; int n_all;
+    int K;                      // cells per cube-face edge, 0: per-triangle constants only (no grid)
+    float extent;
+    float ob_lo[3], ob_hi[3], cam[3];
+    float4* fgA; float2* fgB; uint32_t* wide;       // [n_all] each (scene arena)
+    unsigned int* counters;                         // [2] scratch
+    DBuf<unsigned int>* counts; DBuf<unsigned long long>* start; DBuf<unsigned long long>* bsum; DBuf<uint32_t>* entries;
+};
+struct FgBuildOutput {
+    int K; int n_wide; unsigned long long n_entries; float t_min; float diag;
+};
+int fg_default_K(long long n_tris);
+bool fg_build(const FgBuildInput& in, FgBuildOutput* out, cudaStream_t stream, char* err, size_t errlen);
 
 }  // namespace rt580

@@ -157,6 +157,7 @@ __global__ void k_prim_setup(const float4* __restrict__ v0, const float4* __rest
         } else l_near = fminf(l_near, diam);
         if (!(l_near >= 0.0f)) l_near = diam;                                    // NaN guard
         const float pad = sp.pad + l_near;
+        if (!drop) atomicMax(n_dropped + 5, (unsigned)__float_as_int(l_near));          // >= 0: orders like its bits
         far[i] = make_float4(N.x, N.y, N.z, drop ? -1.0f : thr);
         big = !drop && diam > sp.big_diam;
         if (!drop) {
@@ -350,7 +351,7 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
 {
     const int64_t n_in = in.n_tris + in.n_spheres;
     out->prims = nullptr; out->nodes = nullptr; out->far = nullptr; out->far_tmin = 0.f; out->n_always = 0; out->always_idx = nullptr; out->leaf_of_prim = nullptr;
-    out->n_leaf = 0; out->n_big = 0; out->max_depth = 0; out->launches = 0;
+    out->n_leaf = 0; out->n_big = 0; out->max_depth = 0; out->launches = 0; out->pad_max = 0.f;
     if (n_in > 0x7ffffff0ll) { snprintf(err, errlen, "too many primitives (%lld)", (long long)n_in); return false; }
 
     int* d_bounds = nullptr; unsigned int* d_counters = nullptr;
@@ -391,7 +392,7 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
         sp.blo[k] = l;
         sp.inv_ext[k] = 2097152.0f / fmaxf(h - l, 1e-20f);
     }
-    out->pad = sp.pad; out->extent = E;
+    out->pad = sp.pad; out->extent = E; out->pad_max = sp.pad;
     for (int k = 0; k < 3; k++) { out->bounds_lo[k] = lo[k]; out->bounds_hi[k] = hi[k]; }
     if (n_in == 0) return true;
 
@@ -431,6 +432,7 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
     out->n_leaf = n; out->n_big = n_big;
     out->n_dropped = (int)hc[0];
     out->n_always = (int)hc[3];
+    { float ln; memcpy(&ln, &hc[5], 4); out->pad_max = sp.pad + ln; }
     {
         float max_thr; memcpy(&max_thr, &hc[2], 4);
         // far-field acceptance needs t >= T_far = 4E / thr; with sliver triangles (candidates for

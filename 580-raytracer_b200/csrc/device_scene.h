@@ -78,6 +78,18 @@ struct DeviceScene {
     // from the light to the nearest padded leaf box in each direction.  A shadow ray whose far end
     // (its origin, seen from the light) is nearer than that bound cannot meet a tree primitive: it
     // skips the traversal.  Pure culling, like the boxes of the tree itself.
+    // Far-field direction grid (fargrid.cuh): per cell of a cube map of RAY DIRECTIONS, the triangles a ray of that
+    // direction that leaves the scene can still "hit" 10^5..10^8 units away.  fg_K == 0: no grid (the O(n) scan runs).
+    const float4* fg_A;                     // [n_all] (N.xyz, D)   (-: spheres carry zeros)
+    const float2* fg_B;                     // [n_all] (T: lower bound of the ray parameter of a far-field hit, < 0: none; unused)
+    const unsigned long long* fg_start;     // [6 K K + 1]
+    const uint32_t* fg_entries;             // (k6 << 26) | index into prims: T for the cell = T * 2^(k6/4)
+    const uint32_t* fg_wide;                // [fg_n_wide] triangles whose far field begins too near for a direction index:
+    int32_t fg_n_wide;                      //             every ray that leaves the scene filters them
+    int32_t fg_K;
+    float fg_dmax;                          // bound on |N.O + D| over in-scene ray origins
+    // in-scene ray origins (fargrid.cuh in_scene): box around every primitive + padding + 0.25, and the camera
+    float ob_lo[3], ob_hi[3], ob_cam[3];
     const float* smap;             // [n_smap][6][smap_res][smap_res]
     int32_t smap_res;
     const int32_t* smap_of_light;  // [n_lights] map index, -1: none (not a point light, or a primitive too close to it)

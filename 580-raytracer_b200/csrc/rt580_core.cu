@@ -30,6 +30,7 @@
 #include "trace.cuh"
 #include "shade.cuh"
 #include "smap.cuh"
+#include "fargrid.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <ctime>
@@ -124,23 +125,6 @@ struct FrameParams {
     const uint32_t* lcg_tab;   // [4][256] 16807^(d * 256^k) mod (2^31-1): engine state at any step in 3 modular products
 };
 
-template <typename T> struct DBuf {
-    T* p = nullptr; size_t cap = 0;
-    cudaError_t ensure(size_t n, size_t keep, cudaStream_t s) {
-        if (n <= cap) return cudaSuccess;
-        size_t ncap = cap ? cap : 1024;
-        while (ncap < n) ncap = ncap + ncap / 2 + 1024;
-        T* q = nullptr;
-        cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T));
-        if (e != cudaSuccess) return e;
-        if (keep && p) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; }
-        if (p) { cudaStreamSynchronize(s); cudaFree(p); }
-        p = q; cap = ncap;
-        return cudaSuccess;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
 struct rt580_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -159,6 +143,11 @@ struct rt580_context {
     float4* d_vn = nullptr; int32_t* d_prim_material = nullptr; float* d_materials = nullptr;
     int32_t* d_light_type = nullptr; float* d_light_f = nullptr;
     DevArena scene_arena, build_arena;   // scene buffers / upload + build temporaries (grow-only)
+    // far-field direction grid (fargrid.cuh): lists of the scene, and the per-flush sort of the deferred rays by direction cell
+    DBuf<unsigned int> fg_counts; DBuf<unsigned long long> fg_start, fg_bsum; DBuf<uint32_t> fg_entries;
+    int fg_K_env = -1;                   // RT580_FAR_GRID: -1 default (by triangle count), 0 off, else cells per cube-face edge
+    unsigned long long fg_n_entries = 0; float fg_build_ms = 0.f;
+    DBuf<unsigned int> fgq_hist, fgq_start, fgq_cellof, fgq_rank, fgq_order, fgq_lin;
     bool have_scene = false;
     float build_ms = 0.f; unsigned bvh_depth = 0; float pad_extent = 0.f;
     // frame
@@ -241,7 +230,7 @@ __device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* s
     bool found = false, need = false, linear = false, pending = false;
     hit.t = ANY ? tmax : __int_as_float(0x7f800000); hit.leaf = -1; hit.prim = 0x7fffffff;
     if (active) {
-        if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent) {
+        if (sc.farfield && !in_scene(sc, O)) {
             // starts outside the extent the boxes were padded for: only the child of a far-field
             // "hit" can (one float ulp out there is larger than a triangle) -> reference's linear loop
             need = true; linear = true;
@@ -353,7 +342,8 @@ __device__ __forceinline__ void slow_exact(const DeviceScene& sc, unsigned long 
 }
 template <bool ANY>
 __global__ void __launch_bounds__(256)
-k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __restrict__ res, int chunk)
+k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __restrict__ res, int chunk,
+       const unsigned int* __restrict__ idx)     // idx != nullptr: the rays to answer are rays[idx[0 .. n)]
 {
     __shared__ float4 s_far[SLOW_TILE];
     __shared__ float4 s_O[8][SLOW_RPW], s_D[8][SLOW_RPW];
@@ -367,9 +357,10 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
     bool my_live = false, my_lin = false;
     unsigned long long key0 = 0ull;
     if (lane < SLOW_RPW) {
-        const unsigned e = first + lane * 8u;
+        const unsigned e0 = first + lane * 8u;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
-        if (e < n) {
+        if (e0 < n) {
+            const unsigned e = idx ? __ldg(idx + e0) : e0;
             o = __ldg(&rays[e].o); d = __ldg(&rays[e].d);
             my_lin = (__ldg(&rays[e].c).x & 1) != 0;
             my_live = true;
@@ -432,9 +423,193 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
     if ((unsigned)lane < q_len) slow_exact<ANY>(sc, s_q[warp][lane], s_O[warp], s_D[warp], s_key[warp], s_found[warp]);
     __syncwarp();
     if (lane < SLOW_RPW && my_live) {
-        const unsigned e = first + lane * 8u;
+        const unsigned e0 = first + lane * 8u;
+        const unsigned e = idx ? __ldg(idx + e0) : e0;
         if (ANY) { if (s_found[warp][lane]) res[e].found = 1; }
         else { const unsigned long long k = s_key[warp][lane]; if (k < key0) atomicMin(&res[e].key, k); }
+    }
+}
+
+// ---- deferred far-scan rays through the far-field direction grid (fargrid.cuh) ----------------------------
+// The deferred rays of a flush are sorted by the cell of their direction (counting sort: k_fg_bin, scan, k_fg_order);
+// a block then takes FG_RPB consecutive rays.  Rays of one cell form a segment: its list is staged through shared
+// memory in tiles (record = (N, thr) + (D, T), gathered by the list's primitive indices), warp w runs rays
+// w, w + 8, ... of the segment over the tile (lane = record), the survivors of the two-stage filter are queued
+// per warp and get the exact test 32 at a time, as in k_slow.  The rays that start outside the scene ("linear",
+// children of far-field hits) are left to k_slow through an index list.
+#define FG_RPB 32
+#define FG_RPW (FG_RPB / 8)
+#define FG_TILE 256
+__global__ void __launch_bounds__(256)
+k_fg_bin(const SlowRay* __restrict__ rays, unsigned n, int K, unsigned int* __restrict__ hist, unsigned int* __restrict__ cellof,
+         unsigned int* __restrict__ rank, unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (__ldg(&rays[e].c).x & 1) { lin_idx[atomicAdd(lin_count, 1u)] = e; cellof[e] = 0xffffffffu; return; }
+    const float4 d = __ldg(&rays[e].d);
+    const int cell = fg_cell_of_dir(mk(d.x, d.y, d.z), K);
+    if (cell < 0) { cellof[e] = 0xffffffffu; return; }           // zero / NaN direction: no triangle accepts it (cpp:371)
+    rank[e] = atomicAdd(hist + cell, 1u);
+    cellof[e] = (unsigned)cell;
+}
+__global__ void __launch_bounds__(256)
+k_fg_order(unsigned n, const unsigned int* __restrict__ cellof, const unsigned int* __restrict__ rank,
+           const unsigned int* __restrict__ cstart, unsigned int* __restrict__ order)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const unsigned cell = cellof[e];
+    if (cell != 0xffffffffu) order[cstart[cell] + rank[e]] = e;
+}
+
+template <bool ANY>
+__device__ __forceinline__ void fg_exact(const DeviceScene& sc, unsigned long long entry, const float4* __restrict__ s_O,
+                                         const float4* __restrict__ s_D, unsigned long long* s_key, int* s_found)
+{
+    const int j = (int)(entry >> 32);
+    const unsigned i = (unsigned)entry;
+    const float4 o = s_O[j], dd = s_D[j];
+    const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(s_key + j);
+    float t; int prim;
+    if (prim_test<true>(sc.prims + i, mk(o.x, o.y, o.z), mk(dd.x, dd.y, dd.z), __uint_as_float((unsigned)(key >> 32)),
+                        ANY ? 0x7fffffff : (int)(unsigned)(key & 0xffffffffull), t, prim)) {
+        if (ANY) s_found[j] = 1;
+        else atomicMin(s_key + j, slow_key(t, prim));
+    }
+}
+
+struct FgShared {
+    float4 A[FG_TILE];                      // N.xyz, thr (stage 1)
+    float2 B[FG_TILE];                      // D, T       (stage 2)
+    unsigned id[FG_TILE];
+    float4 O[FG_RPB], D[FG_RPB];
+    unsigned long long key[FG_RPB];
+    int found[FG_RPB];
+    unsigned cell[FG_RPB];
+    unsigned long long q[8][64];
+};
+
+// rays [j0, j1) of the block against one list
+template <bool ANY>
+__device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgShared& sh, int j0, int j1, const uint32_t* __restrict__ list,
+                                           unsigned long long len, bool has_k6, float dno)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // this warp's rays: j0 + warp + 8 k
+    float4 dj[FG_RPW], oj[FG_RPW];
+    unsigned live = 0u;
+#pragma unroll
+    for (int k = 0; k < FG_RPW; k++) {
+        const int j = j0 + warp + 8 * k;
+        if (j < j1) { dj[k] = sh.D[j]; oj[k] = sh.O[j]; live |= 1u << k; }
+        else { dj[k] = make_float4(0.f, 0.f, 0.f, 0.f); oj[k] = dj[k]; }
+    }
+    unsigned q_len = 0;
+    for (unsigned long long base = 0; base < len; base += FG_TILE) {
+        {
+            const unsigned long long idx = base + threadIdx.x;
+            float4 a = make_float4(0.f, 0.f, 0.f, -1.0f); float2 b = make_float2(0.f, 0.f); unsigned id = 0u;
+            if (idx < len) {
+                const unsigned ent = __ldg(list + idx);
+                id = has_k6 ? (ent & FG_ID_MASK) : ent;
+                const float4 fa = __ldg(sc.fg_A + id);
+                const float2 fb = __ldg(sc.fg_B + id);
+                const float T = fg_entry_T(fb.x, has_k6 ? (ent >> FG_ID_BITS) : 0u);
+                a = make_float4(fa.x, fa.y, fa.z, fb.y / T * 1.00001f + FG_ND_SLACK);
+                b = make_float2(fa.w, T);
+            }
+            sh.A[threadIdx.x] = a; sh.B[threadIdx.x] = b; sh.id[threadIdx.x] = id;
+        }
+        __syncthreads();
+        if (ANY) {
+#pragma unroll
+            for (int k = 0; k < FG_RPW; k++)
+                if (((live >> k) & 1u) && *reinterpret_cast<volatile int*>(&sh.found[j0 + warp + 8 * k])) live &= ~(1u << k);
+        }
+        if (live) {
+            const int n_slab = (int)min((unsigned long long)(FG_TILE / 32), (len - base + 31ull) / 32ull);
+            for (int s = 0; s < n_slab; s++) {
+                const int sl = s * 32 + lane;
+                const float4 fr = sh.A[sl];
+#pragma unroll
+                for (int k = 0; k < FG_RPW; k++) {
+                    if (!((live >> k) & 1u)) continue;
+                    const float nd = __fmaf_rn(fr.x, dj[k].x, __fmaf_rn(fr.y, dj[k].y, fr.z * dj[k].z));
+                    const float and_ = fabsf(nd);
+                    bool pass = and_ <= fr.w && and_ > FG_ND_MIN;                   // stage 1: the band of the cell
+                    if (!__any_sync(0xffffffffu, pass)) continue;
+                    if (pass) {
+                        // stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
+                        const float2 fb = sh.B[sl];
+                        const float no = __fmaf_rn(fr.x, oj[k].x, __fmaf_rn(fr.y, oj[k].y, __fmaf_rn(fr.z, oj[k].z, fb.x)));
+                        const float x = (and_ - FG_ND_SLACK) * fb.y * 0.999998f - dno;
+                        pass = fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                    if (mask == 0u) continue;
+                    if (pass) sh.q[warp][q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)(j0 + warp + 8 * k) << 32) | sh.id[sl];
+                    q_len += (unsigned)__popc(mask);
+                    if (q_len >= 32u) {
+                        __syncwarp();
+                        fg_exact<ANY>(sc, sh.q[warp][lane], sh.O, sh.D, sh.key, sh.found);
+                        __syncwarp();
+                        const unsigned long long tail = (lane + 32u < q_len) ? sh.q[warp][lane + 32] : 0ull;
+                        __syncwarp();
+                        if (lane + 32u < q_len) sh.q[warp][lane] = tail;
+                        q_len -= 32u;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncwarp();
+    if ((unsigned)lane < q_len) fg_exact<ANY>(sc, sh.q[warp][lane], sh.O, sh.D, sh.key, sh.found);
+    __syncthreads();
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(256)
+k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ order,
+          const unsigned int* __restrict__ cellof, const unsigned int* __restrict__ total_ptr)
+{
+    __shared__ FgShared sh;
+    __shared__ unsigned s_e[FG_RPB];
+    const unsigned total = __ldg(total_ptr);
+    const unsigned pos0 = blockIdx.x * FG_RPB;
+    if (pos0 >= total) return;
+    const int nb = (int)min((unsigned)FG_RPB, total - pos0);
+    if (threadIdx.x < (unsigned)nb) {
+        const unsigned e = order[pos0 + threadIdx.x];
+        const float4 o = __ldg(&rays[e].o), d = __ldg(&rays[e].d);
+        s_e[threadIdx.x] = e;
+        sh.O[threadIdx.x] = o; sh.D[threadIdx.x] = d;
+        sh.key[threadIdx.x] = ((unsigned long long)__float_as_uint(o.w) << 32) | (unsigned)__float_as_int(d.w);
+        sh.found[threadIdx.x] = 0;
+        sh.cell[threadIdx.x] = cellof[e];
+    }
+    __syncthreads();
+    // the float evaluation of N.O + D here vs in the reference (cpp:377, 381): both within 28 u E of the true value
+    const float dno = 3.4e-6f * sc.extent;
+    for (int j0 = 0; j0 < nb;) {
+        const unsigned cell = sh.cell[j0];
+        int j1 = j0 + 1;
+        while (j1 < nb && sh.cell[j1] == cell) j1++;
+        const unsigned long long b = __ldg(sc.fg_start + cell), e = __ldg(sc.fg_start + cell + 1);
+        fg_segment<ANY>(sc, sh, j0, j1, sc.fg_entries + b, e - b, true, dno);
+        j0 = j1;
+    }
+    if (sc.fg_n_wide > 0) fg_segment<ANY>(sc, sh, 0, nb, sc.fg_wide, (unsigned long long)sc.fg_n_wide, false, dno);
+    if (threadIdx.x < (unsigned)nb) {
+        const unsigned e = s_e[threadIdx.x];
+        if (ANY) { if (sh.found[threadIdx.x]) res[e].found = 1; }
+        else {
+            const unsigned long long k = sh.key[threadIdx.x];
+            if (k < res[e].key) res[e].key = k;
+        }
     }
 }
 
@@ -677,7 +852,7 @@ k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __
                         const float4 qo = __ldg(&queue[idx].o), qd = __ldg(&queue[idx].d);
                         O = mk(qo.x, qo.y, qo.z); d = mk(qd.x, qd.y, qd.z);
                         best_t = __int_as_float(0x7f800000); best_leaf = -1; best_prim = 0x7fffffff;
-                        if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent) {
+                        if (sc.farfield && !in_scene(sc, O)) {
                             CHit h; h.t = best_t; h.leaf = -2; h.prim = best_prim; h.pad = 0;   // not traversed: k_commit takes the linear loop
                             out[idx] = h;
                         } else if (sc.n_leaf > 0) {
@@ -1188,7 +1363,7 @@ k_ao_gen(DeviceScene sc, FrameParams fp, unsigned long long first, unsigned n, i
         r.b = make_float4(rd.y, rd.z, __uint_as_float(call), __int_as_float(0x7f800000));
         emit = true;
         // the large primitives first: most likely occluders, and the ray is not queued at all if one is hit
-        const bool far_origin = sc.farfield && fmaxf(fabsf(org.x), fmaxf(fabsf(org.y), fabsf(org.z))) > sc.extent;
+        const bool far_origin = sc.farfield && !in_scene(sc, org);
         if (!far_origin && sc.n_big > 0) {
             hit = big_any_nearest_first(s_big, sc.n_big, s_plane, s_mask, s_newn, sc.n_big_planes, sc.big_sphere_mask, org, rd);
             emit = !hit;
@@ -1229,7 +1404,7 @@ k_shade_gen(DeviceScene sc, unsigned n0, unsigned n_level, unsigned long long fi
         r.a = make_float4(so.x, so.y, so.z, sd.x);
         r.b = make_float4(sd.y, sd.z, __uint_as_float(id), tmax);
         emit = true;
-        const bool far_origin = sc.farfield && fmaxf(fabsf(so.x), fmaxf(fabsf(so.y), fabsf(so.z))) > sc.extent;
+        const bool far_origin = sc.farfield && !in_scene(sc, so);
         // the large primitives here (plane by plane, exact), so that k_shade only has to read the verdict; a ray one
         // of them stops is not queued (a far origin takes the reference's linear loop over ALL records instead)
         const bool in_free_box = sc.big_free_on && __ldg(sc.big_free_light + li) != 0 &&
@@ -1331,7 +1506,7 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
                         const float4 a = __ldg(&rays[idx].a), b = __ldg(&rays[idx].b);
                         O = mk(a.x, a.y, a.z); d = mk(a.w, b.x, b.y);
                         id = __float_as_uint(b.z); tmax = b.w;
-                        if (sc.farfield && fmaxf(fabsf(O.x), fmaxf(fabsf(O.y), fabsf(O.z))) > sc.extent) {
+                        if (sc.farfield && !in_scene(sc, O)) {
                             // child of a far-field hit: the reference's linear loop, deferred (trace.cuh)
                             if (sc.diag) atomicAdd(sc.diag + 1, 1u);
                             if (defer_any(sq, O, d, tmax, true, id + id_offset) && pending_mark) atomicOr(hit_count + id, pending_mark);
@@ -1654,6 +1829,7 @@ extern "C" int rt580_create(int device, rt580_context** out)
     if (const char* e = getenv("RT580_AH_BATCH_DIV")) c->ah_batch_div = atoi(e) > 0 ? atoi(e) : c->ah_batch_div;
     if (const char* e = getenv("RT580_CH_BLOCKS_PER_SM")) c->ch_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ch_blocks_per_sm;
     if (const char* e = getenv("RT580_ONE_THREAD_PER_RAY")) c->one_thread_per_ray = atoi(e) != 0;
+    if (const char* e = getenv("RT580_FAR_GRID")) c->fg_K_env = atoi(e) >= 0 ? atoi(e) : -1;
     *out = c;
     return RT580_SUCCESS;
 }
@@ -1680,6 +1856,8 @@ extern "C" void rt580_destroy(rt580_context* c)
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     for (int k = 0; k < 2; k++) { cudaStreamSynchronize(c->side[k]); cudaEventDestroy(c->ev_join[k]); cudaStreamDestroy(c->side[k]); }
     c->arays2.release(); c->occl2.release();
+    c->fg_counts.release(); c->fg_start.release(); c->fg_bsum.release(); c->fg_entries.release();
+    c->fgq_hist.release(); c->fgq_start.release(); c->fgq_cellof.release(); c->fgq_rank.release(); c->fgq_order.release(); c->fgq_lin.release();
     cudaEventDestroy(c->ev_level);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1725,7 +1903,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         int n_point = 0;
         for (int i = 0; i < s->n_lights; i++) if (s->light_type && s->light_type[i] == RT580_LIGHT_POINT) n_point++;
         if (n_point > SMAP_MAX) n_point = SMAP_MAX;
-        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 52 + 48 * 256 +
+        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4 + 28) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 52 + 48 * 256 +
                                    (size_t)n_point * 6 * c->smap_res * c->smap_res * sizeof(float);
         if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
             !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
@@ -1787,6 +1965,45 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->d_always = bo.always_idx; c->sc.always_idx = bo.always_idx; c->sc.n_always = bo.n_always;
     c->d_leaf_of_prim = bo.leaf_of_prim; c->sc.leaf_of_prim = bo.leaf_of_prim;
     c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_big = bo.n_big; c->sc.n_all = bo.n_leaf + bo.n_big;
+    {
+        // in-scene ray origins: every near-field hit lies within pad_max of its primitive's bounds, the rays of cpp:67 / 98 /
+        // 110 / 322 start 0.2 further along a unit vector; whatever starts outside that box (the children of far-field hits)
+        // takes the reference's own linear loop
+        const float margin = bo.pad_max + 0.2001f + 1e-5f * bo.extent;
+        for (int k = 0; k < 3; k++) {
+            c->sc.ob_lo[k] = bo.bounds_lo[k] - margin; c->sc.ob_hi[k] = bo.bounds_hi[k] + margin; c->sc.ob_cam[k] = s->origin_hint[k];
+        }
+        // far-field direction grid (fargrid.cuh)
+        c->sc.fg_A = nullptr; c->sc.fg_B = nullptr; c->sc.fg_start = nullptr; c->sc.fg_entries = nullptr; c->sc.fg_wide = nullptr;
+        c->sc.fg_n_wide = 0; c->sc.fg_K = 0; c->sc.fg_dmax = 0.f; c->fg_n_entries = 0; c->fg_build_ms = 0.f;
+        const int n_all = bo.n_leaf + bo.n_big;
+        if (n_all > 0) {
+            FgBuildInput fi{};
+            fi.prims = bo.prims; fi.far_old = bo.far; fi.n_all = n_all;
+            fi.K = c->fg_K_env >= 0 ? c->fg_K_env : fg_default_K(n_all);
+            if (fi.K > 4096) fi.K = 4096;
+            fi.extent = bo.extent;
+            for (int k = 0; k < 3; k++) { fi.ob_lo[k] = c->sc.ob_lo[k]; fi.ob_hi[k] = c->sc.ob_hi[k]; fi.cam[k] = c->sc.ob_cam[k]; }
+            fi.fgA = sa.take<float4>((size_t)n_all); fi.fgB = sa.take<float2>((size_t)n_all); fi.wide = sa.take<uint32_t>((size_t)n_all);
+            fi.counters = ta.take<unsigned int>(4);
+            if (!fi.fgA || !fi.fgB || !fi.wide || !fi.counters) FAIL(RT580_FAILURE, "rt580_upload_scene: arena exhausted (far-field grid)");
+            fi.counts = &c->fg_counts; fi.start = &c->fg_start; fi.bsum = &c->fg_bsum; fi.entries = &c->fg_entries;
+            FgBuildOutput fo{};
+            CU(cudaEventRecord(c->ev[8], st));
+            if (!fg_build(fi, &fo, st, err, sizeof err)) FAIL(RT580_FAILURE, "rt580_upload_scene: %s", err);
+            CU(cudaEventRecord(c->ev[9], st));
+            CU(cudaStreamSynchronize(st));
+            CU(cudaEventElapsedTime(&c->fg_build_ms, c->ev[8], c->ev[9]));
+            c->sc.fg_A = fi.fgA; c->sc.fg_B = fi.fgB; c->sc.fg_wide = fi.wide; c->sc.fg_n_wide = fo.n_wide;
+            c->sc.fg_K = fo.K; c->sc.fg_start = c->fg_start.p; c->sc.fg_entries = c->fg_entries.p;
+            c->fg_n_entries = fo.n_entries;
+            // no far-field hit nearer than the smallest of the tightened bounds (sliver list aside)
+            if (fo.t_min > c->sc.far_tmin) c->sc.far_tmin = fo.t_min;
+            if (getenv("RT580_DEBUG_TIMING"))
+                fprintf(stderr, "[rt580] far-field grid: K %d, %llu entries (%.1f per cell), %d wide, t_min %.4g, diag %.4g, build %.2f ms\n", fo.K, fo.n_entries,
+                        fo.K ? (double)fo.n_entries / (6.0 * fo.K * fo.K) : 0.0, fo.n_wide, fo.t_min, fo.diag, c->fg_build_ms);
+        }
+    }
     {
         // distinct planes of the large triangles (device_scene.h); at most 64 records, grouped on the host
         c->sc.big_planes = nullptr; c->sc.big_masks = nullptr; c->sc.big_plane_newn = nullptr; c->sc.big_sphere_mask = 0ull; c->sc.n_big_planes = 0;
@@ -2065,29 +2282,55 @@ static int any_prepare(rt580_context* c, unsigned long long max_rays, cudaStream
     c->any_cap = cap;
     return RT580_SUCCESS;
 }
-// Answer n recorded slow rays: 32 rays per block, the records sliced over blockIdx.y (k_slow).
-static void slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes* res, unsigned n)
+// Answer n recorded slow rays.  With a far-field direction grid: the rays are sorted by the cell of their direction
+// and answered from that cell's list (k_fg_scan); only the rays that start outside the scene ("linear") go through
+// k_slow's scan of every record.  Without a grid (small scenes) k_slow answers all of them.
+static int exclusive_scan_u32(rt580_context* c, const uint32_t* in, uint32_t* out, unsigned n);
+static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes* res, unsigned n)
 {
-    if (!n) return;
-    const unsigned batches = nblk(n, SLOW_RPB);
-    unsigned slices = nblk(8u * (unsigned)c->prop.multiProcessorCount, batches);
-    const unsigned max_slices = nblk((unsigned)c->sc.n_all, SLOW_TILE);
-    if (slices > max_slices) slices = max_slices;
-    if (slices > 1024u) slices = 1024u;
-    if (slices < 1u) slices = 1u;
-    const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_all, slices), SLOW_TILE) * SLOW_TILE);
-    const dim3 grid(batches, slices);
-    if (any) k_slow<true><<<grid, 256, 0, c->stream>>>(c->sc, rays, n, res, chunk);
-    else k_slow<false><<<grid, 256, 0, c->stream>>>(c->sc, rays, n, res, chunk);
-    c->launches++;
+    if (!n) return RT580_SUCCESS;
+    cudaStream_t st = c->stream;
+    const unsigned int* lin_idx = nullptr;
+    unsigned n_lin = n;
+    if (c->sc.fg_K > 0) {
+        const size_t n_cells = (size_t)6 * c->sc.fg_K * c->sc.fg_K;
+        CU(c->fgq_hist.ensure(n_cells + 2, 0, st)); CU(c->fgq_start.ensure(n_cells + 2, 0, st));
+        CU(c->fgq_cellof.ensure(n, 0, st)); CU(c->fgq_rank.ensure(n, 0, st)); CU(c->fgq_order.ensure(n, 0, st)); CU(c->fgq_lin.ensure((size_t)n + 1, 0, st));
+        CU(cudaMemsetAsync(c->fgq_hist.p, 0, sizeof(unsigned) * (n_cells + 2), st));
+        unsigned int* lin_count = c->fgq_hist.p + n_cells + 1;       // (the scan below covers n_cells + 1 elements: [n_cells] stays 0)
+        k_fg_bin<<<nblk(n, 256), 256, 0, st>>>(rays, n, c->sc.fg_K, c->fgq_hist.p, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_lin.p, lin_count);
+        if (exclusive_scan_u32(c, c->fgq_hist.p, c->fgq_start.p, (unsigned)(n_cells + 1))) return RT580_FAILURE;
+        k_fg_order<<<nblk(n, 256), 256, 0, st>>>(n, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_start.p, c->fgq_order.p);
+        if (any) k_fg_scan<true><<<nblk(n, FG_RPB), 256, 0, st>>>(c->sc, rays, res, c->fgq_order.p, c->fgq_cellof.p, c->fgq_start.p + n_cells);
+        else k_fg_scan<false><<<nblk(n, FG_RPB), 256, 0, st>>>(c->sc, rays, res, c->fgq_order.p, c->fgq_cellof.p, c->fgq_start.p + n_cells);
+        c->launches += 3;
+        CU(cudaMemcpyAsync(&n_lin, lin_count, sizeof n_lin, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        c->syncs++;
+        lin_idx = c->fgq_lin.p;
+    }
+    if (n_lin) {
+        const unsigned batches = nblk(n_lin, SLOW_RPB);
+        unsigned slices = nblk(8u * (unsigned)c->prop.multiProcessorCount, batches);
+        const unsigned max_slices = nblk((unsigned)c->sc.n_all, SLOW_TILE);
+        if (slices > max_slices) slices = max_slices;
+        if (slices > 1024u) slices = 1024u;
+        if (slices < 1u) slices = 1u;
+        const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_all, slices), SLOW_TILE) * SLOW_TILE);
+        const dim3 grid(batches, slices);
+        if (any) k_slow<true><<<grid, 256, 0, st>>>(c->sc, rays, n_lin, res, chunk, lin_idx);
+        else k_slow<false><<<grid, 256, 0, st>>>(c->sc, rays, n_lin, res, chunk, lin_idx);
+        c->launches++;
+    }
     c->slow_total += n;
+    return RT580_SUCCESS;
 }
 // Closest-hit queue: `n` rays were recorded (counter [2], read by the caller).
-static void slow_run(rt580_context* c, bool any, unsigned cap, unsigned n, unsigned* n_out)
+static int slow_run(rt580_context* c, bool any, unsigned cap, unsigned n, unsigned* n_out)
 {
     if (n > cap) n = cap;
-    slow_launch(c, any, c->slow_rays.p, c->slow_res.p, n);
     *n_out = n;
+    return slow_launch(c, any, c->slow_rays.p, c->slow_res.p, n);
 }
 
 // A scene "leaks" when a noticeable share of its rays needs the slow path (open scenes: every ray that
@@ -2109,7 +2352,7 @@ static int any_flush(rt580_context* c, Fin finish)
     if (cnt[3] > c->any_cap) return RT580_INTERNAL_OVERFLOW;      // rays were dropped: the caller repeats the pass
     const unsigned n = cnt[3];
     if (n) {
-        slow_launch(c, true, c->any_rays.p, c->any_res.p, n);
+        if (slow_launch(c, true, c->any_rays.p, c->any_res.p, n)) return RT580_FAILURE;
         finish(n);
         c->launches++;
         CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), c->stream));
@@ -2148,7 +2391,7 @@ static int anyhit_queue_pass(rt580_context* c, cudaStream_t st, int lane, unsign
             const unsigned long long next_n = rest < chunk ? rest : chunk;
             if (cnt[3] && (unsigned long long)cnt[3] + next_n > c->any_cap) {
                 const unsigned q = cnt[3] > c->any_cap ? c->any_cap : cnt[3];
-                slow_launch(c, true, c->any_rays.p, c->any_res.p, q);
+                if (slow_launch(c, true, c->any_rays.p, c->any_res.p, q)) return RT580_FAILURE;
                 k_ao_finish<<<nblk(q, 256), 256, 0, st>>>(c->any_rays.p, c->any_res.p, q, hits); c->launches++;
                 CU(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(unsigned), st));
             }
@@ -2179,10 +2422,19 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
     if (p->ao_spp < 1 || p->ao_spp > 65536) FAIL(RT580_INVALID_ARG, "rt580_render_begin: ao_spp %d outside [1,65536]", p->ao_spp);
     if (p->rng_mode != RT580_RNG_REFERENCE_LCG && p->rng_mode != RT580_RNG_COUNTER) FAIL(RT580_INVALID_ARG, "rt580_render_begin: bad rng_mode");
     if (p->traversal < 0 || p->traversal > 2) FAIL(RT580_INVALID_ARG, "rt580_render_begin: bad traversal");
-    for (int k = 0; k < 3; k++)
-        if (!(fabsf(p->camera_from[k]) + 1.0f <= c->pad_extent))
-            FAIL(RT580_INVALID_ARG, "rt580_render_begin: camera_from[%d]=%g lies outside the extent (%g) the BVH boxes were padded for; "
-                 "pass the camera as rt580_flat_scene::origin_hint", k, p->camera_from[k], c->pad_extent);
+    {
+        // the far-field bounds of the scene build hold for ray origins inside the scene's origin box and at the camera
+        // the scene was uploaded with
+        bool same = true, inside = true;
+        for (int k = 0; k < 3; k++) {
+            same = same && p->camera_from[k] == c->sc.ob_cam[k];
+            inside = inside && p->camera_from[k] >= c->sc.ob_lo[k] && p->camera_from[k] <= c->sc.ob_hi[k];
+        }
+        if (!same && !inside)
+            FAIL(RT580_INVALID_ARG, "rt580_render_begin: camera_from (%g, %g, %g) is neither the rt580_flat_scene::origin_hint the scene was "
+                 "uploaded with nor inside the scene's bounds; upload the scene with this camera as origin_hint",
+                 p->camera_from[0], p->camera_from[1], p->camera_from[2]);
+    }
     CU(cudaSetDevice(c->device));
     if (sync_side(c)) return RT580_FAILURE;        // (idle unless an earlier frame was abandoned on an error)
     const bool dbg_t = getenv("RT580_DEBUG_TIMING") != nullptr;
@@ -2295,7 +2547,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             launch_trace<0>(c, true, nullptr, npix, nullptr, (unsigned)c->nodes.cap, slow_cap, Spawn{ Q[0]->p, qcnt[0] });
             if (read_counters(c, cnt)) return RT580_FAILURE;
             n_nodes = cnt[0]; q = cnt[qidx[0]];
-            slow_run(c, false, slow_cap, cnt[2], &n_slow);
+            if (slow_run(c, false, slow_cap, cnt[2], &n_slow)) return RT580_FAILURE;
             if (n_slow) {
                 k_trace_finish<true><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, nullptr, c->slow_rays.p, c->slow_res.p, n_slow,
                                                                        c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
@@ -2382,7 +2634,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             if (read_counters(c, cnt)) return RT580_FAILURE;
             n_nodes = cnt[0];
             unsigned q_next = cnt[qidx[cur ^ 1]];
-            slow_run(c, false, slow_cap, cnt[2], &n_slow);
+            if (slow_run(c, false, slow_cap, cnt[2], &n_slow)) return RT580_FAILURE;
             if (n_slow) {
                 k_trace_finish<false><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, Q[cur]->p, c->slow_rays.p, c->slow_res.p, n_slow,
                                                                         c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
@@ -2403,7 +2655,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             DISPATCH_MODE(mode, launch_trace, c, true, nullptr, npix, nullptr, (unsigned)c->nodes.cap, slow_cap, no_spawn);
             if (read_counters(c, cnt)) return RT580_FAILURE;
             n_nodes = cnt[0];
-            slow_run(c, false, slow_cap, cnt[2], &n_slow);
+            if (slow_run(c, false, slow_cap, cnt[2], &n_slow)) return RT580_FAILURE;
             if (n_slow) {
                 k_trace_finish<true><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
                                                                        c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
@@ -2430,7 +2682,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             DISPATCH_MODE(mode, launch_shade, c, n0, n1, slow_cap);
             if (slow_cap) {
                 if (read_counters(c, cnt)) return RT580_FAILURE;
-                slow_run(c, true, slow_cap, cnt[2], &n_slow);
+                if (slow_run(c, true, slow_cap, cnt[2], &n_slow)) return RT580_FAILURE;
                 if (n_slow) {
                     k_shade_finish<<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->slow_rays.p, c->slow_res.p, n_slow, c->nodes.p, c->aux.p);
                     c->launches++;
@@ -2445,7 +2697,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
             const unsigned q = cnt[1];
             if (q == 0) break;
             n_nodes = cnt[0];
-            slow_run(c, false, slow_cap, cnt[2], &n_slow);
+            if (slow_run(c, false, slow_cap, cnt[2], &n_slow)) return RT580_FAILURE;
             if (n_slow) {
                 k_trace_finish<false><<<nblk(n_slow, 128), 128, 0, st>>>(c->sc, c->fp, c->queue.p, c->slow_rays.p, c->slow_res.p, n_slow,
                                                                         c->nodes.p, c->aux.p, c->counters.p, c->pix_hits.p, c->fb.p,
@@ -2608,7 +2860,7 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
             if (slow_cap) {
                 unsigned cnt[N_COUNTERS];
                 if (read_counters(c, cnt)) return RT580_FAILURE;
-                slow_run(c, true, slow_cap, cnt[2], &n_slow);
+                if (slow_run(c, true, slow_cap, cnt[2], &n_slow)) return RT580_FAILURE;
                 if (n_slow) { k_ao_finish<<<nblk(n_slow, 256), 256, 0, st>>>(c->slow_rays.p, c->slow_res.p, n_slow, c->ao_hits.p); c->launches++; }
             }
         }
