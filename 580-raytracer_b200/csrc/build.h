@@ -81,12 +81,12 @@ struct FgBuildInput {
     int K;                      // cells per cube-face edge, 0: per-triangle constants only (no grid)
     float extent;
     float ob_lo[3], ob_hi[3], cam[3];
-    float4* fgA; float2* fgB; uint32_t* wide;       // [n_all] each (scene arena)
-    unsigned int* counters;                         // [2] scratch
+    float4* fgA; float2* fgB; uint32_t* wide; uint32_t* sph;   // [n_all] each (scene arena)
+    unsigned int* counters;                         // [4] scratch
     DBuf<unsigned int>* counts; DBuf<unsigned long long>* start; DBuf<unsigned long long>* bsum; DBuf<uint32_t>* entries;
 };
 struct FgBuildOutput {
-    int K; int n_wide; unsigned long long n_entries; float t_min; float diag;
+    int K; int n_wide; int n_sph; unsigned long long n_entries; float t_min; float diag;
 };
 int fg_default_K(long long n_tris);
 bool fg_build(const FgBuildInput& in, FgBuildOutput* out, cudaStream_t stream, char* err, size_t errlen);

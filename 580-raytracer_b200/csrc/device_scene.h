@@ -88,6 +88,11 @@ struct DeviceScene {
     int32_t fg_n_wide;                      //             every ray that leaves the scene filters them
     int32_t fg_K;
     float fg_dmax;                          // bound on |N.O + D| over in-scene ray origins
+    const uint32_t* fg_sph;                 // [fg_n_sph] the spheres among prims (rays from outside the scene test them all when aimed at it)
+    int32_t fg_n_sph;
+    float fg_rmax;                          // largest sphere radius
+    float fg_center[3];                     // a point of the origin box: directions of far hit points are taken from here
+    float fg_tmin;                          // smallest T of the grid's triangles
     // in-scene ray origins (fargrid.cuh in_scene): box around every primitive + padding + 0.25, and the camera
     float ob_lo[3], ob_hi[3], ob_cam[3];
     const float* smap;             // [n_smap][6][smap_res][smap_res]

@@ -41,7 +41,7 @@ namespace rt580 {
 #define FG_U 5.9604644775390625e-8          /* 2^-24 */
 #define FG_ND_SLACK 4.0e-7f                 /* |N.d| evaluated with FMA here vs unfused in the reference: <= 6u apart */
 #define FG_ND_MIN 6.0e-7f                   /* |N.d| below this is below EPSILON in the reference as well (cpp:371) */
-#define FG_WIDE_FACTOR 64.0f                /* triangles whose far field begins nearer than this many extents: "wide" list */
+#define FG_WIDE_FACTOR 8.0f                 /* triangles whose far field begins nearer than this many scene diagonals: "wide" list */
 
 // in-scene ray origins: the box around all primitives (+ padding + the 0.2 offset of cpp:67/98/110/322) and the camera
 __device__ __forceinline__ bool in_scene(const DeviceScene& sc, V3 O) {
@@ -64,6 +64,21 @@ __device__ __forceinline__ int fg_cell_of_dir(V3 d, int K) {
     const int iu = min(K - 1, max(0, (int)floorf((fu + 1.f) * half)));
     const int iv = min(K - 1, max(0, (int)floorf((fv + 1.f) * half)));
     return ((a * 2 + (w < 0.f ? 1 : 0)) * K + iv) * K + iu;
+}
+
+// the same in double, for the walk along the arc of a ray from outside the scene (rt580_core.cu k_fg_arc): the cell must agree
+// with the walls the walk computes in double
+__device__ __forceinline__ int fg_cell_of_point_d(double x, double y, double z, int K) {
+    const double ax = fabs(x), ay = fabs(y), az = fabs(z);
+    const int a = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+    const double w = a == 0 ? x : (a == 1 ? y : z);
+    const double aw = fabs(w);
+    if (!(aw > 0.0)) return -1;
+    const double fu = (a == 0 ? y : (a == 1 ? z : x)) / aw, fv = (a == 0 ? z : (a == 1 ? x : y)) / aw;
+    const double half = 0.5 * (double)K;
+    const int iu = min(K - 1, max(0, (int)floor((fu + 1.0) * half)));
+    const int iv = min(K - 1, max(0, (int)floor((fv + 1.0) * half)));
+    return ((a * 2 + (w < 0.0 ? 1 : 0)) * K + iv) * K + iu;
 }
 
 // T for a list entry: the triangle's bound times 2^(k6 / 4), a hair below

@@ -29,7 +29,7 @@ __device__ __forceinline__ FgTri fg_tri(const PrimRec* __restrict__ prims, const
 {
     FgTri t; t.ok = false;
     const float2 B = fgB[i];
-    if (!(B.x > 0.f) || B.x < FG_WIDE_FACTOR * fp.extent) return t;            // no far field / wide list
+    if (!(B.x > 0.f) || B.x < FG_WIDE_FACTOR * fp.diag) return t;            // no far field / wide list
     const float4 ra = prims[i].a, rb = prims[i].b, rc = prims[i].c, rd = prims[i].d;
     const V3 v0 = mk(ra.x, ra.y, ra.z), v1 = mk(rb.x, rb.y, rb.z), v2 = mk(rc.x, rc.y, rc.z);
     t.N = mk(rd.x, rd.y, rd.z);
@@ -121,7 +121,8 @@ k_fg_raster(const PrimRec* __restrict__ prims, const float2* __restrict__ fgB, i
 // record of the build (bvh_build.cu: thr_old = 4E / T_old, rigorous, round 1) tightened by the bound of fargrid.cuh.
 __global__ void __launch_bounds__(256)
 k_fg_setup(const PrimRec* __restrict__ prims, const float4* __restrict__ far_old, int n_all, FgParams fp,
-           float4* __restrict__ fgA, float2* __restrict__ fgB, uint32_t* __restrict__ wide, unsigned int* __restrict__ counters)
+           float4* __restrict__ fgA, float2* __restrict__ fgB, uint32_t* __restrict__ wide, uint32_t* __restrict__ sph,
+           unsigned int* __restrict__ counters)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_all) return;
@@ -129,6 +130,7 @@ k_fg_setup(const PrimRec* __restrict__ prims, const float4* __restrict__ far_old
     const float thr_old = far_old[i].w;
     const bool tri = !(__float_as_int(rd.w) & RT_PRIM_SPHERE);
     fgA[i] = tri ? make_float4(rd.x, rd.y, rd.z, ra.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!tri) sph[atomicAdd(counters + 2, 1u)] = (unsigned)i;
     float T = -1.f, dmax = 0.f;
     if (tri && thr_old > 0.f && thr_old < 4.0f) {
         const double E = fp.extent, diag = fp.diag, u = FG_U;
@@ -155,7 +157,7 @@ k_fg_setup(const PrimRec* __restrict__ prims, const float4* __restrict__ far_old
             // the wedge test of the rasteriser takes N perpendicular to the two edges at v0 up to 2 %: slivers whose float
             // normal is off by more stay out of the direction index (wide list)
             degenerate = !(el > 0 && l1 > 0 && l2 > 0 && len(k1) > 0.98 * l1 && len(k2) > 0.98 * l2 && len(m) > 0.98 * el);
-            if (!degenerate && T_old >= (double)FG_WIDE_FACTOR * E) {
+            if (!degenerate && T_old >= (double)FG_WIDE_FACTOR * diag) {
                 const double s1 = len(x1) / (l1 * el), s2 = len(x2) / (l2 * el);      // sin of the angles at v1, v2
                 const double mu = 1.02 * diag / (T_old - diag) + 2e-6;
                 const double smin = fmin(s1, s2) - mu;
@@ -166,8 +168,8 @@ k_fg_setup(const PrimRec* __restrict__ prims, const float4* __restrict__ far_old
             }
         }
         T = (float)(Tn * (1.0 - 1e-6));
-        if (degenerate) T = fminf(T, 0.99f * FG_WIDE_FACTOR * fp.extent);
-        if (T < FG_WIDE_FACTOR * fp.extent) {
+        if (degenerate) T = fminf(T, 0.99f * FG_WIDE_FACTOR * fp.diag);
+        if (T < FG_WIDE_FACTOR * fp.diag) {
             const unsigned slot = atomicAdd(counters, 1u);
             wide[slot] = (unsigned)i;
         }
@@ -253,7 +255,7 @@ int fg_default_K(long long n_tris)
 
 bool fg_build(const FgBuildInput& in, FgBuildOutput* out, cudaStream_t stream, char* err, size_t errlen)
 {
-    out->K = 0; out->n_wide = 0; out->n_entries = 0; out->t_min = 3.0e38f;
+    out->K = 0; out->n_wide = 0; out->n_sph = 0; out->n_entries = 0; out->t_min = 3.0e38f;
     const int n = in.n_all;
     if (n <= 0) return true;
     FgParams fp{};
@@ -268,13 +270,13 @@ bool fg_build(const FgBuildInput& in, FgBuildOutput* out, cudaStream_t stream, c
     }
     fp.diag = (float)(sqrt(d2) * 1.00001 + 1e-3);
     out->diag = fp.diag;
-    CK(cudaMemsetAsync(in.counters, 0, 2 * sizeof(unsigned int), stream));
+    CK(cudaMemsetAsync(in.counters, 0, 4 * sizeof(unsigned int), stream));
     CK(cudaMemsetAsync(in.counters + 1, 0x7f, sizeof(unsigned int), stream));
-    k_fg_setup<<<(n + 255) / 256, 256, 0, stream>>>(in.prims, in.far_old, n, fp, in.fgA, in.fgB, in.wide, in.counters);
-    unsigned int hc[2];
+    k_fg_setup<<<(n + 255) / 256, 256, 0, stream>>>(in.prims, in.far_old, n, fp, in.fgA, in.fgB, in.wide, in.sph, in.counters);
+    unsigned int hc[4];
     CK(cudaMemcpyAsync(hc, in.counters, sizeof hc, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    out->n_wide = (int)hc[0];
+    out->n_wide = (int)hc[0]; out->n_sph = (int)hc[2];
     { float t; memcpy(&t, &hc[1], 4); out->t_min = (hc[1] == 0x7f7f7f7fu) ? 3.0e38f : t; }
     if (in.K <= 0) return true;
     if (n > FG_MAX_PRIMS) { snprintf(err, errlen, "far-field grid: %d primitives exceed the %d-bit entry index", n, FG_ID_BITS); return false; }

@@ -392,6 +392,15 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
         // record in the outer loop, the warp's rays in the inner one: one shared-memory load serves four filter tests
 #pragma unroll 2
         for (int k = 0; k < SLOW_TILE / 32; k++) {
+            if (ANY && lin_mask) {
+                // a ray from outside the scene is accepted by about every fortieth triangle it meets (float noise, fargrid.cuh):
+                // stop testing it as soon as one has
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < SLOW_RPW; j++)
+                    if (((live_mask >> j) & 1u) && *reinterpret_cast<volatile int*>(&s_found[warp][j])) live_mask &= ~(1u << j);
+                if (!live_mask) break;
+            }
             const int sl = k * 32 + lane, i = base + sl;
             const bool in_range = i < nl;
             const float4 fr = s_far[sl];
@@ -610,6 +619,283 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
             const unsigned long long k = sh.key[threadIdx.x];
             if (k < res[e].key) res[e].key = k;
         }
+    }
+}
+
+// ---- rays that start outside the scene (children of far-field hits, 10^5..10^8 units away) ------------------------
+// The reference sends them through the same loop over every triangle (cpp:476-521).  Out there they meet two kinds of
+// acceptors, answered by two kernels over the list of such rays:
+//   far regime   (k_fg_arc)   a triangle accepts the plane hit P far from itself: the direction of P seen from the scene
+//                             lies in the triangle's strip and |P| >= T (fargrid.cuh), i.e. the triangle is in the list
+//                             of the direction cell of P.  While t grows, the direction of P(t) = O + t d walks along a
+//                             great-circle arc from the direction of O to d: the cells on that arc are visited in order
+//                             of t, each one's entries filtered by T <= |P|, the rest tested exactly.
+//   near regime  (k_lin_near) the ray comes back to the scene and hits a triangle for real: a tree traversal with the
+//                             leaf boxes inflated by the rounding of P = O + t d for such an origin; plus the handful of
+//                             primitives the tree and the grid do not hold (large ones, slivers, the wide list), and all
+//                             spheres when the ray is aimed at the scene (cpp:426's discriminant is noise out there).
+#define ARC_WARPS 4
+template <bool ANY>
+__global__ void __launch_bounds__(32 * ARC_WARPS)
+k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
+         unsigned n_lin, unsigned int* __restrict__ stat)
+{
+    __shared__ unsigned s_q[ARC_WARPS][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned w = blockIdx.x * ARC_WARPS + wib;
+    if (w >= n_lin) return;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned e = __ldg(lin_idx + w);
+    const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
+    const V3 O = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z);
+    float tlim = ro.w; int plim = ANY ? 0x7fffffff : __float_as_int(rd.w);
+    if (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) return;                   // no triangle accepts a zero direction (cpp:371)
+    const float inf = __int_as_float(0x7f800000);
+    // The walk runs in double: far out, a float t no longer resolves a cell (ulp(t) / |P| exceeds the cells' slack when the ray
+    // has come a long way and passes near the scene); the cells it names are a superset of those the reference's float P visits.
+    const double Ax = (double)O.x - sc.fg_center[0], Ay = (double)O.y - sc.fg_center[1], Az = (double)O.z - sc.fg_center[2];
+    const double dx = d.x, dy = d.y, dz = d.z;
+    const int K = sc.fg_K;
+    const double h = 2.0 / (double)K;
+    const double aa = Ax * Ax + Ay * Ay + Az * Az, ad = Ax * dx + Ay * dy + Az * dz, dd = dx * dx + dy * dy + dz * dz;
+    const double dinf = (double)inf;
+    // (hole_lo, hole_hi): where |P(t)| < 0.9 T_min, no far-field acceptor exists
+    double hole_lo = dinf, hole_hi = -dinf;
+    {
+        const double Tm = 0.9 * (double)sc.fg_tmin;
+        const double disc = ad * ad - dd * (aa - Tm * Tm);
+        if (disc > 0.0 && dd > 0.0 && Tm < 1e18) { const double sq = sqrt(disc); hole_lo = (-ad - sq) / dd; hole_hi = (-ad + sq) / dd; }
+    }
+    bool found = false;
+    unsigned n_cells = 0, n_exact = 0;
+    unsigned q_len = 0;
+    const float Olen = fabsf(O.x) + fabsf(O.y) + fabsf(O.z);
+    const float dno_far = 1e-6f * (Olen + sc.extent);          // float evaluation of N.O + D here and in the reference: <= 8 u (|O|_1 + |D|) each
+    // the entries of one cell that can accept at |P| <= rmax, tested exactly
+    auto flush = [&](bool all_of_it) {
+        while (q_len >= 32u || (all_of_it && q_len > 0u)) {
+            __syncwarp();
+            float t = inf; int prim = 0x7fffffff;
+            if ((unsigned)lane < q_len) {
+                float tt; int pp;
+                if (prim_test<true>(sc.prims + s_q[wib][lane], O, d, tlim, plim, tt, pp)) { t = tt; prim = pp; }
+            }
+            n_exact += min(q_len, 32u);
+            if (ANY) { if (__any_sync(0xffffffffu, prim != 0x7fffffff)) found = true; }
+            else {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float t2 = __shfl_xor_sync(0xffffffffu, t, o); const int p2 = __shfl_xor_sync(0xffffffffu, prim, o);
+                    if (t2 < t || (t2 == t && p2 < prim)) { t = t2; prim = p2; }
+                }
+                if (prim != 0x7fffffff) { tlim = t; plim = prim; found = true; }
+            }
+            __syncwarp();
+            const unsigned tail = (lane + 32u < q_len) ? s_q[wib][lane + 32] : 0u;
+            __syncwarp();
+            if (lane + 32u < q_len) s_q[wib][lane] = tail;
+            q_len = q_len > 32u ? q_len - 32u : 0u;
+            __syncwarp();
+        }
+    };
+    auto process_cell = [&](int cell, float rmax) {
+        const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
+        n_cells++;
+        for (unsigned long long base = b; base < en; base += 32) {
+            const unsigned long long idx = base + lane;
+            bool pass = false; unsigned id = 0u;
+            if (idx < en) {
+                const unsigned ent = __ldg(sc.fg_entries + idx);
+                id = ent & FG_ID_MASK;
+                const float T = fg_entry_T(__ldg(sc.fg_B + id).x, ent >> FG_ID_BITS);
+                if (T <= rmax) {
+                    // The triangle is listed in every cell its strip crosses, but this ray meets its plane at one parameter
+                    // t = -(N.O + D) / (N.d) only: bracket it ([t_lo, t_hi] covers the float evaluation here and in cpp:367-381)
+                    // and ask for t > 0, t within the limit, and |P(t)| >= T somewhere in the bracket (|P(t)| is convex).
+                    const float4 fa = __ldg(sc.fg_A + id);
+                    const float nd = __fmaf_rn(fa.x, d.x, __fmaf_rn(fa.y, d.y, fa.z * d.z));
+                    const float no = __fmaf_rn(fa.x, O.x, __fmaf_rn(fa.y, O.y, __fmaf_rn(fa.z, O.z, fa.w)));
+                    const float and_ = fabsf(nd), ano = fabsf(no);
+                    pass = and_ > FG_ND_MIN && !(ano > dno_far && ((no < 0.f) == (nd < 0.f)));
+                    if (pass) {
+                        const float t_lo = fmaxf(ano - dno_far, 0.f) / (and_ + FG_ND_SLACK) * 0.999999f;
+                        pass = t_lo <= tlim;
+                        if (pass && and_ > 2.0f * FG_ND_SLACK) {
+                            const double t_hi = (double)(ano + dno_far) / (double)(and_ - FG_ND_SLACK) * 1.000001, tl = t_lo;
+                            const double p_lo = aa + tl * (2.0 * ad + tl * dd), p_hi = aa + t_hi * (2.0 * ad + t_hi * dd);
+                            const double need = fmax((double)T * 0.9999 - 2e-6 * Olen, 0.0);
+                            pass = fmax(p_lo, p_hi) >= need * need;
+                        }
+                    }
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (mask) {
+                if (pass) s_q[wib][q_len + (unsigned)__popc(mask & lt_mask)] = id;
+                q_len += (unsigned)__popc(mask);
+                flush(false);
+                if (ANY && found) return;
+            }
+        }
+        flush(true);
+    };
+    double t_end = ANY ? (double)tlim : dinf;
+    if (ANY && !(tlim < 3.0e38f)) {
+        // any hit, unbounded: the far end of the arc first - out there |P| exceeds every T, most entries accept
+        const int cell = fg_cell_of_dir(d, K);
+        if (cell >= 0) process_cell(cell, inf);
+    }
+    double t = 0.0;
+    unsigned n_it = 0;
+    const long long clk0 = clock64();
+    // after leaving a cell through a wall, the next cell is looked up a hair BEYOND that wall (nx, ny, nz: relative nudge), so a
+    // path that runs along a wall cannot bounce between the lookup and the wall arithmetic
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    for (int it = 0; it < 200000 && !(ANY && found); it++) {
+        n_it++;
+        if (!(t < t_end)) break;
+        if (t > hole_lo && t < hole_hi) { t = hole_hi; nx = ny = nz = 0.0; continue; }
+        const double Px = Ax + dx * t, Py = Ay + dy * t, Pz = Az + dz * t;
+        const double p2 = Px * Px + Py * Py + Pz * Pz;
+        const double plen = sqrt(p2);
+        const int cell = fg_cell_of_point_d(Px + nx * plen, Py + ny * plen, Pz + nz * plen, K);
+        const double adv = 3e-7 * plen + 1e-30;
+        if (cell < 0) { t = t + adv + 1e-9 * fmax(1.0, t); continue; }
+        const int face = cell / (K * K), iv = (cell / K) % K, iu = cell % K;
+        const int ax = face >> 1;
+        const double sg = (face & 1) ? -1.0 : 1.0;
+        const double Aw = (ax == 0 ? Ax : (ax == 1 ? Ay : Az)) * sg, dw = (ax == 0 ? dx : (ax == 1 ? dy : dz)) * sg;
+        const double Au = (ax == 0 ? Ay : (ax == 1 ? Az : Ax)), du = (ax == 0 ? dy : (ax == 1 ? dz : dx));
+        const double Av = (ax == 0 ? Az : (ax == 1 ? Ax : Ay)), dv = (ax == 0 ? dz : (ax == 1 ? dx : dy));
+        // where does P(t) leave the cell: f(t) = P_u - b P_w changes sign at the walls b = u0 (f >= 0 inside), u1 (f <= 0 inside),
+        // likewise v.  Only walls the ray moves OUT through count; one it is already beyond (rounding) means "leave now".
+        double t_exit = dinf;
+        int k_exit = -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool upper = (k & 1) != 0;
+            const double b = ((double)((k < 2 ? iu : iv) + (upper ? 1 : 0))) * h - 1.0;
+            const double f0 = (k < 2 ? Au : Av) - b * Aw, f1 = (k < 2 ? du : dv) - b * dw;
+            if (upper ? (f1 > 0.0) : (f1 < 0.0)) { const double tc = fmax(-f0 / f1, t); if (tc < t_exit) { t_exit = tc; k_exit = k; } }
+        }
+        // the nudge for the next lookup: across wall k_exit, i.e. along axis u (k < 2) or v, up (odd k) or down
+        nx = ny = nz = 0.0;
+        if (k_exit >= 0) {
+            const int na = k_exit < 2 ? (ax + 1) % 3 : (ax + 2) % 3;
+            const double nv = (k_exit & 1) ? 1e-9 : -1e-9;
+            if (na == 0) nx = nv; else if (na == 1) ny = nv; else nz = nv;
+        }
+        double t_out = fmin(t_exit, t_end);
+        if (t < hole_lo) t_out = fmin(t_out, hole_lo);
+        float rmax = inf;
+        if (t_out < 1e300) {
+            const double Qx = Ax + dx * t_out, Qy = Ay + dy * t_out, Qz = Az + dz * t_out;
+            const double r = sqrt(fmax(p2, Qx * Qx + Qy * Qy + Qz * Qz)) * 1.00001 + 1.0;      // |P(t)| is convex in t
+            rmax = r < 3.0e38 ? (float)r * 1.000001f : inf;
+        }
+        process_cell(cell, rmax);
+        if (!ANY) t_end = fmin(t_end, (double)tlim * 1.000001);              // (ties at equal t: the lower primitive index wins)
+        if (!(t_out < 1e300)) break;
+        t = t_out + adv;
+    }
+    if (lane == 0) {
+        if (stat) { atomicAdd(stat, 1u); atomicAdd(stat + 2, n_cells); atomicAdd(stat + 3, n_exact); atomicMax(stat + 1, n_it); }
+        if (n_lin < 100000000u && (clock64() - clk0) > 20000000ll) printf("[k_fg_arc] slow ray: any %d its %u cells %u exact %u found %d t %g t_end %g hole (%g %g) |A| %g cycles %lld\n", (int)ANY, n_it, n_cells, n_exact, (int)found, t, t_end, hole_lo, hole_hi, sqrt(aa), clock64() - clk0);
+        if (found) {
+            if (ANY) res[e].found = 1;
+            else atomicMin(&res[e].key, slow_key(tlim, plim));
+        }
+    }
+}
+
+// conservative ray / box test with the box inflated by `infl`
+__device__ __forceinline__ bool slab_inflated(float lox, float hix, float loy, float hiy, float loz, float hiz, float infl,
+                                              V3 O, V3 inv, float tcull, float& tnear)
+{
+    return slab(lox - infl, hix + infl, loy - infl, hiy + infl, loz - infl, hiz + infl, O, inv, tcull, tnear);
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(128)
+k_lin_near(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx, unsigned n_lin,
+           unsigned int* __restrict__ stat)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lin) return;
+    const unsigned e = __ldg(lin_idx + i);
+    if (ANY && res[e].found) return;
+    const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
+    const V3 O = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z);
+    HitRec best; best.t = ro.w; best.leaf = -1; best.prim = ANY ? 0x7fffffff : __float_as_int(rd.w);
+    if (!ANY) {                                                            // what k_fg_arc found bounds the search
+        const unsigned long long key = res[e].key;
+        const float kt = __uint_as_float((unsigned)(key >> 32)); const int kp = (int)(unsigned)(key & 0xffffffffull);
+        if (kt < best.t || (kt == best.t && kp < best.prim)) { best.t = kt; best.prim = kp; }
+    }
+    bool found = false;
+    unsigned n_tests = 0;
+    auto test = [&](int idx) {
+        float t; int prim;
+        n_tests++;
+        if (prim_test<true>(sc.prims + idx, O, d, best.t, ANY ? 0x7fffffff : best.prim, t, prim)) {
+            found = true;
+            if (!ANY) { best.t = t; best.prim = prim; }
+            return true;
+        }
+        return false;
+    };
+    // the primitives neither the tree nor the grid holds
+    for (int k = sc.n_leaf; k < sc.n_all; k++) if (test(k) && ANY) { res[e].found = 1; return; }
+    for (int k = 0; k < sc.n_always; k++) if (test(__ldg(sc.always_idx + k)) && ANY) { res[e].found = 1; return; }
+    for (int k = 0; k < sc.fg_n_wide; k++) if (test((int)__ldg(sc.fg_wide + k)) && ANY) { res[e].found = 1; return; }
+    const float Olen = sqrtf(O.x * O.x + O.y * O.y + O.z * O.z);
+    // spheres: |oc|^2 - r^2 and b^2 are ~R^2 in float, the discriminant b^2 - 4c (cpp:426) carries an error of ~32 u R^2: it can be
+    // positive only if the ray passes within ~1.4e-3 R + r of the centre, i.e. is aimed at the scene within that angle
+    if (sc.fg_n_sph > 0) {
+        const V3 A = mk(O.x - sc.fg_center[0], O.y - sc.fg_center[1], O.z - sc.fg_center[2]);
+        const float R = sqrtf(A.x * A.x + A.y * A.y + A.z * A.z);
+        bool aimed = true;
+        if (R > 1.0f && R < 1e30f) {
+            const float th = 4e-3f + (3.5f * sc.extent + sc.fg_rmax) / R * 1.1f;
+            if (th < 1.0f) aimed = (d.x * A.x + d.y * A.y + d.z * A.z) <= -(1.0f - 0.5f * th * th) * R + 1e-6f * R;
+        }
+        if (aimed)
+            for (int k = 0; k < sc.fg_n_sph; k++) if (test((int)__ldg(sc.fg_sph + k)) && ANY) { res[e].found = 1; return; }
+    }
+    // The tree, boxes inflated by how far the reference's float P = O + d t can lie from a triangle it accepts near itself
+    // when the origin is that far out (the leaf boxes are padded for in-scene origins only): off the plane by the rounding
+    // of t = num / nd (cpp:367-381: |num| carries <= 3 u |O|, nd <= 3 u, the quotient u: <= 7 u |O| for t ~ |O|), sideways by
+    // the rounding of d t (<= u t); 8.5 u (|O| + 2 E) covers both.
+    if (sc.n_leaf > 0 && Olen < 1e30f && !(d.x == 0.0f && d.y == 0.0f && d.z == 0.0f && sc.fg_n_sph == 0)) {
+        const float infl = 5.1e-7f * (Olen + 2.0f * sc.extent) + 1e-4f;
+        const V3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        int stack[RT_STACK_SIZE];
+        int sp = 0, node = 0;
+        for (;;) {
+            float4 xy0, xy1, z01; int4 kids;
+            load_node(sc.nodes + node, xy0, xy1, z01, kids);
+            float tn0, tn1;
+            const bool h0 = slab_inflated(xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, infl, O, inv, best.t, tn0);
+            const bool h1 = slab_inflated(xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, infl, O, inv, best.t, tn1);
+            int next;
+            if (h0 && h1) { if (sp < RT_STACK_SIZE) stack[sp++] = kids.y; next = kids.x; }
+            else if (h0) next = kids.x;
+            else if (h1) next = kids.y;
+            else { if (sp == 0) break; next = stack[--sp]; }
+            bool done = false;
+            while (next < 0) {
+                if (test(~next) && ANY) { res[e].found = 1; return; }
+                if (sp == 0) { done = true; break; }
+                next = stack[--sp];
+            }
+            if (done) break;
+            node = next;
+        }
+    }
+    if (stat && n_tests > 64u) { atomicAdd(stat, 1u); atomicAdd(stat + 1, n_tests >> 6); }
+    if (found) {
+        if (ANY) res[e].found = 1;
+        else atomicMin(&res[e].key, slow_key(best.t, best.prim));
     }
 }
 
@@ -1696,7 +1982,7 @@ template <int MODE, bool ANY>
 __global__ void __launch_bounds__(128)
 k_trace_rays(DeviceScene sc, long long n, const float* __restrict__ org, const float* __restrict__ dir,
              const float* __restrict__ tmax, int32_t* __restrict__ prim_out, float* __restrict__ t_out,
-             uint8_t* __restrict__ hit_out)
+             uint8_t* __restrict__ hit_out, SlowQ q)
 {
     __shared__ PrimRec s_prims[MODE == 1 ? RT_SMEM_PRIMS : 1];
     const PrimRec* sp = stage_prims<MODE>(sc, s_prims);
@@ -1705,11 +1991,28 @@ k_trace_rays(DeviceScene sc, long long n, const float* __restrict__ org, const f
     V3 O = mk(0, 0, 0), d = mk(0, 0, 0);
     if (active) { O = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]); d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]); }
     HitRec h;
-    const SlowQ noq = { nullptr, nullptr, nullptr, 0u };
-    const bool hit = trace_ray<MODE, ANY>(sc, sp, active, O, d, (ANY && active) ? tmax[i] : 0.f, h, noq, 0, 0) == TR_HIT;
-    if (!active) return;
+    // with a deferred queue (the frame path's: far-field grid, rays from outside the scene) the rays the tree cannot answer
+    // alone come back TR_PENDING and k_trace_rays_apply writes their answer; without one the warp serves them in place
+    const int tr = trace_ray<MODE, ANY>(sc, sp, active, O, d, (ANY && active) ? tmax[i] : 0.f, h, q, (int)i, 0);
+    if (!active || tr == TR_PENDING) return;
+    const bool hit = tr == TR_HIT;
     if (ANY) hit_out[i] = hit ? 1 : 0;
     else { prim_out[i] = hit ? h.prim : -1; t_out[i] = hit ? h.t : 0.f; }
+}
+template <bool ANY>
+__global__ void k_trace_rays_apply(const SlowRay* __restrict__ rays, const SlowRes* __restrict__ res, unsigned n_slow,
+                                   int32_t* __restrict__ prim_out, float* __restrict__ t_out, uint8_t* __restrict__ hit_out)
+{
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_slow) return;
+    const int i = rays[e].c.y;
+    if (ANY) hit_out[i] = res[e].found ? 1 : 0;
+    else {
+        const unsigned long long key = res[e].key;
+        const int prim = (int)(unsigned)(key & 0xffffffffull);
+        prim_out[i] = prim != 0x7fffffff ? prim : -1;
+        t_out[i] = prim != 0x7fffffff ? __uint_as_float((unsigned)(key >> 32)) : 0.f;
+    }
 }
 
 // traversal profile of arbitrary rays (BVH path): per ray node visits, leaf tests, far-field scans,
@@ -1899,11 +2202,11 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     CU(cudaStreamSynchronize(st));
     {
         char aerr[256] = "";
-        const size_t in_bytes = (size_t)s->n_tris * (6 * 16 + 8) + (size_t)s->n_spheres * (16 + 8) + 24 * 256;
+        const size_t in_bytes = (size_t)s->n_tris * (6 * 16 + 8) + (size_t)s->n_spheres * (16 + 8) + (size_t)s->n_prims * 4 + 8192 + 24 * 256;
         int n_point = 0;
         for (int i = 0; i < s->n_lights; i++) if (s->light_type && s->light_type[i] == RT580_LIGHT_POINT) n_point++;
         if (n_point > SMAP_MAX) n_point = SMAP_MAX;
-        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4 + 28) + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 52 + 48 * 256 +
+        const size_t shade_bytes = (size_t)s->n_prims * (48 + 4 + 28 + 8) + 6 * 256 * 256 * 4 + 4096 + (size_t)s->n_materials * 32 + (size_t)s->n_lights * 52 + 48 * 256 +
                                    (size_t)n_point * 6 * c->smap_res * c->smap_res * sizeof(float);
         if (!arena_reserve(c->build_arena, in_bytes + build_tmp_bytes(s->n_prims), aerr, sizeof aerr) ||
             !arena_reserve(c->scene_arena, shade_bytes + build_out_bytes(s->n_prims, s->n_prims), aerr, sizeof aerr))
@@ -1976,6 +2279,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         // far-field direction grid (fargrid.cuh)
         c->sc.fg_A = nullptr; c->sc.fg_B = nullptr; c->sc.fg_start = nullptr; c->sc.fg_entries = nullptr; c->sc.fg_wide = nullptr;
         c->sc.fg_n_wide = 0; c->sc.fg_K = 0; c->sc.fg_dmax = 0.f; c->fg_n_entries = 0; c->fg_build_ms = 0.f;
+        c->sc.fg_sph = nullptr; c->sc.fg_n_sph = 0; c->sc.fg_rmax = 0.f; c->sc.fg_tmin = 3.0e38f;
         const int n_all = bo.n_leaf + bo.n_big;
         if (n_all > 0) {
             FgBuildInput fi{};
@@ -1984,9 +2288,9 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
             if (fi.K > 4096) fi.K = 4096;
             fi.extent = bo.extent;
             for (int k = 0; k < 3; k++) { fi.ob_lo[k] = c->sc.ob_lo[k]; fi.ob_hi[k] = c->sc.ob_hi[k]; fi.cam[k] = c->sc.ob_cam[k]; }
-            fi.fgA = sa.take<float4>((size_t)n_all); fi.fgB = sa.take<float2>((size_t)n_all); fi.wide = sa.take<uint32_t>((size_t)n_all);
+            fi.fgA = sa.take<float4>((size_t)n_all); fi.fgB = sa.take<float2>((size_t)n_all); fi.wide = sa.take<uint32_t>((size_t)n_all); fi.sph = sa.take<uint32_t>((size_t)n_all);
             fi.counters = ta.take<unsigned int>(4);
-            if (!fi.fgA || !fi.fgB || !fi.wide || !fi.counters) FAIL(RT580_FAILURE, "rt580_upload_scene: arena exhausted (far-field grid)");
+            if (!fi.fgA || !fi.fgB || !fi.wide || !fi.sph || !fi.counters) FAIL(RT580_FAILURE, "rt580_upload_scene: arena exhausted (far-field grid)");
             fi.counts = &c->fg_counts; fi.start = &c->fg_start; fi.bsum = &c->fg_bsum; fi.entries = &c->fg_entries;
             FgBuildOutput fo{};
             CU(cudaEventRecord(c->ev[8], st));
@@ -1997,6 +2301,13 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
             c->sc.fg_A = fi.fgA; c->sc.fg_B = fi.fgB; c->sc.fg_wide = fi.wide; c->sc.fg_n_wide = fo.n_wide;
             c->sc.fg_K = fo.K; c->sc.fg_start = c->fg_start.p; c->sc.fg_entries = c->fg_entries.p;
             c->fg_n_entries = fo.n_entries;
+            c->sc.fg_sph = fi.sph; c->sc.fg_n_sph = fo.n_sph; c->sc.fg_tmin = fo.t_min;
+            {
+                float rmax = 0.f;
+                for (int64_t i = 0; i < s->n_spheres; i++) rmax = fmaxf(rmax, fabsf(s->sph_center_r[4 * i + 3]));
+                c->sc.fg_rmax = rmax;
+                for (int k = 0; k < 3; k++) c->sc.fg_center[k] = 0.5f * (c->sc.ob_lo[k] + c->sc.ob_hi[k]);
+            }
             // no far-field hit nearer than the smallest of the tightened bounds (sliver list aside)
             if (fo.t_min > c->sc.far_tmin) c->sc.far_tmin = fo.t_min;
             if (getenv("RT580_DEBUG_TIMING"))
@@ -2247,7 +2558,7 @@ static int exclusive_scan_u32(rt580_context* c, const uint32_t* in, uint32_t* ou
 // [6] any-hit rays generated for the running chunk, [7] any-hit rays fetched, [8..9] uint64: AO rays that
 // went through the tree.  All of them come back in one 64-byte copy + one stream sync (every host round
 // trip idles the GPU for ~10-20 us; with 8 ranks a frame is only ~10 ms long).
-#define N_COUNTERS 16
+#define N_COUNTERS 28     // [16..19] / [20..23] k_fg_arc any / closest: rays, -, cells visited, exact tests
 static int read_counters(rt580_context* c, unsigned out[N_COUNTERS]) {
     CU(cudaMemcpyAsync(out, c->counters.p, N_COUNTERS * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -2308,6 +2619,18 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         CU(cudaStreamSynchronize(st));
         c->syncs++;
         lin_idx = c->fgq_lin.p;
+    }
+    if (n_lin && lin_idx) {
+        // rays from outside the scene: far regime along the arc of the direction grid, near regime through the inflated tree
+        if (any) {
+            k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16);
+            k_lin_near<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 24);
+        } else {
+            k_fg_arc<false><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 20);
+            k_lin_near<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 26);
+        }
+        c->launches += 2;
+        n_lin = 0;
     }
     if (n_lin) {
         const unsigned batches = nblk(n_lin, SLOW_RPB);
@@ -2909,6 +3232,13 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
     c->stats.ms_total = c->stats.ms_structure + c->stats.ms_order + c->stats.ms_ao + c->stats.ms_resolve;
     c->stats.kernel_launches = c->launches;
     c->stats.far_scans = cnt[4]; c->stats.linear_fallbacks = cnt[5];
+    if (getenv("RT580_DEBUG_TIMING"))
+        fprintf(stderr, "[rt580] rays from outside the scene, far regime: any hit %u (%.1f cells, %.0f exact tests each), closest hit %u (%.1f cells, %.0f exact tests each)\n",
+                cnt[16], cnt[16] ? (double)cnt[18] / cnt[16] : 0.0, cnt[16] ? (double)cnt[19] / cnt[16] : 0.0,
+                cnt[20], cnt[20] ? (double)cnt[22] / cnt[20] : 0.0, cnt[20] ? (double)cnt[23] / cnt[20] : 0.0);
+    if (getenv("RT580_DEBUG_TIMING"))
+        fprintf(stderr, "[rt580] rays from outside the scene, near regime: any hit %u rays with > 64 exact tests (%.0f each), closest hit %u (%.0f each)\n",
+                cnt[24], cnt[24] ? 64.0 * cnt[25] / cnt[24] : 0.0, cnt[26], cnt[26] ? 64.0 * cnt[27] / cnt[26] : 0.0);
     if (mode == 0) {
         c->stats.ao_rays_traversed = (uint64_t)cnt[8] | ((uint64_t)cnt[9] << 32);
         c->stats.shadow_rays_traversed = (uint64_t)cnt[10] | ((uint64_t)cnt[11] << 32);
@@ -3019,10 +3349,10 @@ extern "C" int rt580_last_frame_ao_base(rt580_context* c, uint64_t* out)
 }
 
 // ---- checkers ---------------------------------------------------------------------------
-template <int MODE> static void launch_rays(rt580_context* c, bool any, long long n, const float* o, const float* d,
-                                            const float* tmax, int32_t* prim, float* t, uint8_t* hit) {
-    if (any) k_trace_rays<MODE, true><<<nblk(n, 128), 128, 0, c->stream>>>(c->sc, n, o, d, tmax, prim, t, hit);
-    else k_trace_rays<MODE, false><<<nblk(n, 128), 128, 0, c->stream>>>(c->sc, n, o, d, tmax, prim, t, hit);
+template <int MODE> static void launch_rays(rt580_context* c, const DeviceScene& sc, bool any, long long n, const float* o, const float* d,
+                                            const float* tmax, int32_t* prim, float* t, uint8_t* hit, SlowQ q) {
+    if (any) k_trace_rays<MODE, true><<<nblk(n, 128), 128, 0, c->stream>>>(sc, n, o, d, tmax, prim, t, hit, q);
+    else k_trace_rays<MODE, false><<<nblk(n, 128), 128, 0, c->stream>>>(sc, n, o, d, tmax, prim, t, hit, q);
 }
 
 static int trace_rays_common(rt580_context* c, bool any, int64_t n, const float* org3, const float* dir3, const float* tmax,
@@ -3030,23 +3360,46 @@ static int trace_rays_common(rt580_context* c, bool any, int64_t n, const float*
 {
     if (!c || !org3 || !dir3 || n < 0) FAIL(RT580_INVALID_ARG, "rt580_trace: bad argument");
     if (!c->have_scene) FAIL(RT580_FAILURE, "rt580_trace: no scene uploaded");
+    if (c->frame_begun) FAIL(RT580_FAILURE, "rt580_trace: a frame is in progress (rt580_render_begin without rt580_render_finish)");
     if (n == 0) return RT580_SUCCESS;
+    if (n > 0x7ffffff0ll) FAIL(RT580_INVALID_ARG, "rt580_trace: too many rays");
     CU(cudaSetDevice(c->device));
-    float *o = nullptr, *d = nullptr, *tm = nullptr, *t = nullptr; int32_t* pr = nullptr; uint8_t* h = nullptr;
-    CU(cudaMalloc(&o, sizeof(float) * 3 * n)); CU(cudaMalloc(&d, sizeof(float) * 3 * n));
-    CU(cudaMemcpy(o, org3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d, dir3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
-    if (any) { CU(cudaMalloc(&tm, sizeof(float) * n)); CU(cudaMemcpy(tm, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)); CU(cudaMalloc(&h, n)); }
-    else { CU(cudaMalloc(&t, sizeof(float) * n)); CU(cudaMalloc(&pr, sizeof(int32_t) * n)); }
+    struct Tmp {      // freed on every exit path
+        float *o = nullptr, *d = nullptr, *tm = nullptr, *t = nullptr; int32_t* pr = nullptr; uint8_t* h = nullptr;
+        ~Tmp() { cudaFree(o); cudaFree(d); cudaFree(tm); cudaFree(t); cudaFree(pr); cudaFree(h); }
+    } m;
+    CU(cudaMalloc(&m.o, sizeof(float) * 3 * n)); CU(cudaMalloc(&m.d, sizeof(float) * 3 * n));
+    CU(cudaMemcpy(m.o, org3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m.d, dir3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    if (any) { CU(cudaMalloc(&m.tm, sizeof(float) * n)); CU(cudaMemcpy(m.tm, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)); CU(cudaMalloc(&m.h, n)); }
+    else { CU(cudaMalloc(&m.t, sizeof(float) * n)); CU(cudaMalloc(&m.pr, sizeof(int32_t) * n)); }
     const int mode = pick_mode(c, traversal);
-    c->sc.farfield = 1;     // the checkers always run the exact path
-    c->sc.diag = nullptr;
-    DISPATCH_MODE(mode, launch_rays, c, any, (long long)n, o, d, tm, pr, t, h);
+    DeviceScene sc = c->sc;         // the checkers always run the exact path, on a copy: the context's settings stay as they are
+    sc.farfield = 1; sc.diag = nullptr;
+    SlowQ q = { nullptr, nullptr, nullptr, 0u };
+    const bool deferred = mode == 0 && c->sc.fg_K > 0;      // the frame path's machinery for the rays the tree cannot answer alone
+    if (deferred) {
+        CU(c->counters.ensure(N_COUNTERS, 0, c->stream));
+        CU(c->slow_rays.ensure((size_t)n, 0, c->stream)); CU(c->slow_res.ensure((size_t)n, 0, c->stream));
+        CU(cudaMemsetAsync(c->counters.p, 0, N_COUNTERS * sizeof(unsigned), c->stream));
+        q.rays = c->slow_rays.p; q.res = c->slow_res.p; q.count = c->counters.p + 2; q.cap = (unsigned)n;
+    }
+    DISPATCH_MODE(mode, launch_rays, c, sc, any, (long long)n, m.o, m.d, m.tm, m.pr, m.t, m.h, q);
+    if (deferred) {
+        unsigned n_slow = 0;
+        CU(cudaMemcpyAsync(&n_slow, q.count, sizeof n_slow, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (n_slow > q.cap) n_slow = q.cap;
+        if (n_slow) {
+            if (slow_launch(c, any, q.rays, q.res, n_slow)) return RT580_FAILURE;
+            if (any) k_trace_rays_apply<true><<<nblk(n_slow, 256), 256, 0, c->stream>>>(q.rays, q.res, n_slow, m.pr, m.t, m.h);
+            else k_trace_rays_apply<false><<<nblk(n_slow, 256), 256, 0, c->stream>>>(q.rays, q.res, n_slow, m.pr, m.t, m.h);
+        }
+    }
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
-    if (any) CU(cudaMemcpy(hit_out, h, n, cudaMemcpyDeviceToHost));
-    else { CU(cudaMemcpy(prim_out, pr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(t_out, t, sizeof(float) * n, cudaMemcpyDeviceToHost)); }
-    cudaFree(o); cudaFree(d); cudaFree(tm); cudaFree(t); cudaFree(pr); cudaFree(h);
+    if (any) CU(cudaMemcpy(hit_out, m.h, n, cudaMemcpyDeviceToHost));
+    else { CU(cudaMemcpy(prim_out, m.pr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(t_out, m.t, sizeof(float) * n, cudaMemcpyDeviceToHost)); }
     return RT580_SUCCESS;
 }
 
@@ -3070,18 +3423,18 @@ extern "C" int rt580_trace_profile(rt580_context* c, int64_t n, const float* org
     if (!c->have_scene) FAIL(RT580_FAILURE, "rt580_trace_profile: no scene uploaded");
     if (n == 0) return RT580_SUCCESS;
     CU(cudaSetDevice(c->device));
-    float *o = nullptr, *d = nullptr, *tm = nullptr; unsigned* cn = nullptr;
-    CU(cudaMalloc(&o, sizeof(float) * 3 * n)); CU(cudaMalloc(&d, sizeof(float) * 3 * n)); CU(cudaMalloc(&cn, sizeof(unsigned) * 4 * n));
-    CU(cudaMemcpy(o, org3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d, dir3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
-    if (tmax) { CU(cudaMalloc(&tm, sizeof(float) * n)); CU(cudaMemcpy(tm, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)); }
-    c->sc.farfield = 1; c->sc.diag = nullptr;
-    if (tmax) k_trace_profile<true><<<nblk(n, 128), 128, 0, c->stream>>>(c->sc, (long long)n, o, d, tm, cn);
-    else k_trace_profile<false><<<nblk(n, 128), 128, 0, c->stream>>>(c->sc, (long long)n, o, d, tm, cn);
+    struct Tmp { float *o = nullptr, *d = nullptr, *tm = nullptr; unsigned* cn = nullptr; ~Tmp() { cudaFree(o); cudaFree(d); cudaFree(tm); cudaFree(cn); } } m;
+    CU(cudaMalloc(&m.o, sizeof(float) * 3 * n)); CU(cudaMalloc(&m.d, sizeof(float) * 3 * n)); CU(cudaMalloc(&m.cn, sizeof(unsigned) * 4 * n));
+    CU(cudaMemcpy(m.o, org3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m.d, dir3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    if (tmax) { CU(cudaMalloc(&m.tm, sizeof(float) * n)); CU(cudaMemcpy(m.tm, tmax, sizeof(float) * n, cudaMemcpyHostToDevice)); }
+    DeviceScene sc = c->sc;         // a copy: the context's far-field / diagnostic settings stay as they are
+    sc.farfield = 1; sc.diag = nullptr;
+    if (tmax) k_trace_profile<true><<<nblk(n, 128), 128, 0, c->stream>>>(sc, (long long)n, m.o, m.d, m.tm, m.cn);
+    else k_trace_profile<false><<<nblk(n, 128), 128, 0, c->stream>>>(sc, (long long)n, m.o, m.d, m.tm, m.cn);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
-    CU(cudaMemcpy(counts4, cn, sizeof(unsigned) * 4 * n, cudaMemcpyDeviceToHost));
-    cudaFree(o); cudaFree(d); cudaFree(tm); cudaFree(cn);
+    CU(cudaMemcpy(counts4, m.cn, sizeof(unsigned) * 4 * n, cudaMemcpyDeviceToHost));
     return RT580_SUCCESS;
 }
 
