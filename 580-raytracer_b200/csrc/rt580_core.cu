@@ -100,7 +100,8 @@ __host__ __device__ __forceinline__ unsigned long long slow_key(float t, int pri
 #define SLOW_CAP_MAX (16u << 20)   // deferred closest-hit rays / any-hit rays of a leaky scene: one entry per ray of a chunk
 #define SLOW_ANY_CAP (4u << 20)    // deferred any-hit rays of a scene that hardly leaks (on overflow the pass is repeated "leaky")
 #define RT580_INTERNAL_OVERFLOW 100
-#define AH_CHUNK_TIGHT (32u << 20) // any-hit rays generated per chunk when the scene hardly leaks
+#define AH_CHUNK_TIGHT (32u << 20) // any-hit rays generated per chunk
+#define LEAKY_ANY_CAP (384u << 20) // deferred any-hit rays of one occlusion pass of a leaky scene
 #define OCCL_PENDING 0x40000000u   // shadow ray deferred to the end of the structure pass (k_shadow_finish decides)
 
 // k_anyhit (persistent any-hit traversal) constants
@@ -446,19 +447,23 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
 // w, w + 8, ... of the segment over the tile (lane = record), the survivors of the two-stage filter are queued
 // per warp and get the exact test 32 at a time, as in k_slow.  The rays that start outside the scene ("linear",
 // children of far-field hits) are left to k_slow through an index list.
-#define FG_RPB 32
-#define FG_RPW (FG_RPB / 8)
-#define FG_TILE 256
 __global__ void __launch_bounds__(256)
 k_fg_bin(const SlowRay* __restrict__ rays, unsigned n, int K, unsigned int* __restrict__ hist, unsigned int* __restrict__ cellof,
-         unsigned int* __restrict__ rank, unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count)
+         unsigned int* __restrict__ rank, unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count, int bin_lin)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    if (__ldg(&rays[e].c).x & 1) { lin_idx[atomicAdd(lin_count, 1u)] = e; cellof[e] = 0xffffffffu; return; }
+    const bool lin = (__ldg(&rays[e].c).x & 1) != 0;
+    // a ray from outside the scene: closest hit -> its own kernels (k_fg_arc walks its cells in order of t); any hit (bin_lin) ->
+    // first the cell of its direction like everybody else (out there, far along the ray, almost every entry accepts it)
+    if (lin && !bin_lin) { lin_idx[atomicAdd(lin_count, 1u)] = e; cellof[e] = 0xffffffffu; return; }
     const float4 d = __ldg(&rays[e].d);
     const int cell = fg_cell_of_dir(mk(d.x, d.y, d.z), K);
-    if (cell < 0) { cellof[e] = 0xffffffffu; return; }           // zero / NaN direction: no triangle accepts it (cpp:371)
+    if (cell < 0) {                                              // zero / NaN direction: no triangle accepts it (cpp:371)
+        if (lin) lin_idx[atomicAdd(lin_count, 1u)] = e;          // (spheres may: k_lin_near)
+        cellof[e] = 0xffffffffu;
+        return;
+    }
     rank[e] = atomicAdd(hist + cell, 1u);
     cellof[e] = (unsigned)cell;
 }
@@ -488,135 +493,152 @@ __device__ __forceinline__ void fg_exact(const DeviceScene& sc, unsigned long lo
     }
 }
 
-struct FgShared {
-    float4 A[FG_TILE];                      // N.xyz, thr (stage 1)
-    float2 B[FG_TILE];                      // D, T       (stage 2)
-    unsigned id[FG_TILE];
-    float4 O[FG_RPB], D[FG_RPB];
-    unsigned long long key[FG_RPB];
-    int found[FG_RPB];
-    unsigned cell[FG_RPB];
-    unsigned long long q[8][64];
+// One warp takes FG_G consecutive rays of the sorted order; the rays of one cell among them form a segment that runs over the
+// cell's list 32 entries at a time (lane = entry: its record is gathered once and serves every ray of the segment).
+#define FG_G 8
+#define FG_WARPS 4
+struct FgWarp {
+    float4 O[FG_G], D[FG_G];
+    unsigned long long key[FG_G];
+    int found[FG_G];
+    unsigned cell[FG_G], e[FG_G];
+    unsigned lin;                           // bit j: ray j starts outside the scene
+    unsigned long long q[64];
 };
 
-// rays [j0, j1) of the block against one list
 template <bool ANY>
-__device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgShared& sh, int j0, int j1, const uint32_t* __restrict__ list,
+__device__ __forceinline__ void fg_flush(const DeviceScene& sc, FgWarp& sh, unsigned& q_len, bool all_of_it)
+{
+    const int lane = threadIdx.x & 31;
+    while (q_len >= 32u || (all_of_it && q_len > 0u)) {
+        __syncwarp();
+        if ((unsigned)lane < q_len) fg_exact<ANY>(sc, sh.q[lane], sh.O, sh.D, sh.key, sh.found);
+        __syncwarp();
+        const unsigned long long tail = (lane + 32u < q_len) ? sh.q[lane + 32] : 0ull;
+        __syncwarp();
+        if (lane + 32u < q_len) sh.q[lane] = tail;
+        q_len = q_len > 32u ? q_len - 32u : 0u;
+        __syncwarp();
+    }
+}
+
+// rays [j0, j1) of the warp against one list
+template <bool ANY>
+__device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, int j0, int j1, const uint32_t* __restrict__ list,
                                            unsigned long long len, bool has_k6, float dno)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    // this warp's rays: j0 + warp + 8 k
-    float4 dj[FG_RPW], oj[FG_RPW];
-    unsigned live = 0u;
-#pragma unroll
-    for (int k = 0; k < FG_RPW; k++) {
-        const int j = j0 + warp + 8 * k;
-        if (j < j1) { dj[k] = sh.D[j]; oj[k] = sh.O[j]; live |= 1u << k; }
-        else { dj[k] = make_float4(0.f, 0.f, 0.f, 0.f); oj[k] = dj[k]; }
-    }
+    unsigned live = ((1u << j1) - 1u) & ~((1u << j0) - 1u);
+    const unsigned linm = ANY ? sh.lin : 0u;
     unsigned q_len = 0;
-    for (unsigned long long base = 0; base < len; base += FG_TILE) {
-        {
-            const unsigned long long idx = base + threadIdx.x;
-            float4 a = make_float4(0.f, 0.f, 0.f, -1.0f); float2 b = make_float2(0.f, 0.f); unsigned id = 0u;
-            if (idx < len) {
-                const unsigned ent = __ldg(list + idx);
-                id = has_k6 ? (ent & FG_ID_MASK) : ent;
-                const float4 fa = __ldg(sc.fg_A + id);
-                const float2 fb = __ldg(sc.fg_B + id);
-                const float T = fg_entry_T(fb.x, has_k6 ? (ent >> FG_ID_BITS) : 0u);
-                a = make_float4(fa.x, fa.y, fa.z, fb.y / T * 1.00001f + FG_ND_SLACK);
-                b = make_float2(fa.w, T);
-            }
-            sh.A[threadIdx.x] = a; sh.B[threadIdx.x] = b; sh.id[threadIdx.x] = id;
+    for (unsigned long long base = 0; base < len; base += 32) {
+        // this lane's entry: (N, thr) for stage 1, (D, T) for stage 2
+        const unsigned long long idx = base + lane;
+        float4 fr = make_float4(0.f, 0.f, 0.f, -1.0f); float eD = 0.f, eT = 0.f; unsigned id = 0u;
+        if (idx < len) {
+            const unsigned ent = __ldg(list + idx);
+            id = has_k6 ? (ent & FG_ID_MASK) : ent;
+            const float4 fa = __ldg(sc.fg_A + id);
+            const float2 fb = __ldg(sc.fg_B + id);
+            eT = fg_entry_T(fb.x, has_k6 ? (ent >> FG_ID_BITS) : 0u);
+            fr = make_float4(fa.x, fa.y, fa.z, fb.y / eT * 1.00001f + FG_ND_SLACK);
+            eD = fa.w;
         }
-        __syncthreads();
-        if (ANY) {
-#pragma unroll
-            for (int k = 0; k < FG_RPW; k++)
-                if (((live >> k) & 1u) && *reinterpret_cast<volatile int*>(&sh.found[j0 + warp + 8 * k])) live &= ~(1u << k);
+        if (ANY) {                                       // rays that are answered leave
+            __syncwarp();
+            for (int j = j0; j < j1; j++) if (((live >> j) & 1u) && *reinterpret_cast<volatile int*>(&sh.found[j])) live &= ~(1u << j);
+            if (!live) break;
         }
-        if (live) {
-            const int n_slab = (int)min((unsigned long long)(FG_TILE / 32), (len - base + 31ull) / 32ull);
-            for (int s = 0; s < n_slab; s++) {
-                const int sl = s * 32 + lane;
-                const float4 fr = sh.A[sl];
-#pragma unroll
-                for (int k = 0; k < FG_RPW; k++) {
-                    if (!((live >> k) & 1u)) continue;
-                    const float nd = __fmaf_rn(fr.x, dj[k].x, __fmaf_rn(fr.y, dj[k].y, fr.z * dj[k].z));
-                    const float and_ = fabsf(nd);
-                    bool pass = and_ <= fr.w && and_ > FG_ND_MIN;                   // stage 1: the band of the cell
-                    if (!__any_sync(0xffffffffu, pass)) continue;
-                    if (pass) {
-                        // stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
-                        const float2 fb = sh.B[sl];
-                        const float no = __fmaf_rn(fr.x, oj[k].x, __fmaf_rn(fr.y, oj[k].y, __fmaf_rn(fr.z, oj[k].z, fb.x)));
-                        const float x = (and_ - FG_ND_SLACK) * fb.y * 0.999998f - dno;
-                        pass = fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
-                    }
-                    const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                    if (mask == 0u) continue;
-                    if (pass) sh.q[warp][q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)(j0 + warp + 8 * k) << 32) | sh.id[sl];
-                    q_len += (unsigned)__popc(mask);
-                    if (q_len >= 32u) {
-                        __syncwarp();
-                        fg_exact<ANY>(sc, sh.q[warp][lane], sh.O, sh.D, sh.key, sh.found);
-                        __syncwarp();
-                        const unsigned long long tail = (lane + 32u < q_len) ? sh.q[warp][lane + 32] : 0ull;
-                        __syncwarp();
-                        if (lane + 32u < q_len) sh.q[warp][lane] = tail;
-                        q_len -= 32u;
-                        __syncwarp();
-                    }
+        for (int j = j0; j < j1; j++) {
+            if (!((live >> j) & 1u)) continue;
+            const float4 dj = sh.D[j];
+            const float nd = __fmaf_rn(fr.x, dj.x, __fmaf_rn(fr.y, dj.y, fr.z * dj.z));
+            const float and_ = fabsf(nd);
+            bool pass;
+            if (ANY && ((linm >> j) & 1u)) {
+                // From outside the scene the bounds of the list do not apply (they assume an in-scene origin); far along
+                // this ray, though, almost every triangle of the cell of its direction accepts it.  So: every entry whose
+                // plane lies ahead within the limit gets the exact test; a ray that finds no acceptor here goes on to
+                // k_fg_arc / k_lin_near, which are complete.
+                pass = fr.w >= 0.f && and_ > FG_ND_MIN;
+                if (pass) {
+                    const float4 oj = sh.O[j];
+                    const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
+                    const float dl = 1e-6f * (fabsf(oj.x) + fabsf(oj.y) + fabsf(oj.z) + sc.extent);
+                    const float ano = fabsf(no);
+                    pass = !(ano > dl && ((no < 0.f) == (nd < 0.f))) && fmaxf(ano - dl, 0.f) <= oj.w * (and_ + FG_ND_SLACK);   // (o.w: tmax)
+                }
+            } else {
+                pass = and_ <= fr.w && and_ > FG_ND_MIN;                    // stage 1: the band of the cell
+                if (!__any_sync(0xffffffffu, pass)) continue;
+                if (pass) {
+                    // stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
+                    const float4 oj = sh.O[j];
+                    const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
+                    const float x = (and_ - FG_ND_SLACK) * eT * 0.999998f - dno;
+                    pass = fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
                 }
             }
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (mask == 0u) continue;
+            if (pass) sh.q[q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)j << 32) | id;
+            q_len += (unsigned)__popc(mask);
+            fg_flush<ANY>(sc, sh, q_len, false);
         }
-        __syncthreads();
+        if (ANY && linm) fg_flush<ANY>(sc, sh, q_len, true);      // (so that the look at `found` above sees this slab's acceptors)
     }
-    __syncwarp();
-    if ((unsigned)lane < q_len) fg_exact<ANY>(sc, sh.q[warp][lane], sh.O, sh.D, sh.key, sh.found);
-    __syncthreads();
+    fg_flush<ANY>(sc, sh, q_len, true);
 }
 
 template <bool ANY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * FG_WARPS)
 k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ order,
-          const unsigned int* __restrict__ cellof, const unsigned int* __restrict__ total_ptr)
+          const unsigned int* __restrict__ cellof, const unsigned int* __restrict__ total_ptr,
+          unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count)
 {
-    __shared__ FgShared sh;
-    __shared__ unsigned s_e[FG_RPB];
+    __shared__ FgWarp shw[FG_WARPS];
+    FgWarp& sh = shw[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
     const unsigned total = __ldg(total_ptr);
-    const unsigned pos0 = blockIdx.x * FG_RPB;
+    const unsigned long long pos0 = ((unsigned long long)blockIdx.x * FG_WARPS + (threadIdx.x >> 5)) * FG_G;
     if (pos0 >= total) return;
-    const int nb = (int)min((unsigned)FG_RPB, total - pos0);
-    if (threadIdx.x < (unsigned)nb) {
-        const unsigned e = order[pos0 + threadIdx.x];
+    const int nb = (int)min((unsigned long long)FG_G, total - pos0);
+    bool my_lin = false;
+    if (lane < nb) {
+        const unsigned e = order[pos0 + lane];
         const float4 o = __ldg(&rays[e].o), d = __ldg(&rays[e].d);
-        s_e[threadIdx.x] = e;
-        sh.O[threadIdx.x] = o; sh.D[threadIdx.x] = d;
-        sh.key[threadIdx.x] = ((unsigned long long)__float_as_uint(o.w) << 32) | (unsigned)__float_as_int(d.w);
-        sh.found[threadIdx.x] = 0;
-        sh.cell[threadIdx.x] = cellof[e];
+        sh.e[lane] = e;
+        sh.O[lane] = o; sh.D[lane] = d;
+        sh.key[lane] = ((unsigned long long)__float_as_uint(o.w) << 32) | (unsigned)__float_as_int(d.w);
+        sh.found[lane] = 0;
+        sh.cell[lane] = cellof[e];
+        my_lin = ANY && (__ldg(&rays[e].c).x & 1) != 0;
     }
-    __syncthreads();
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, my_lin);
+        if (lane == 0) sh.lin = m;
+    }
+    __syncwarp();
     // the float evaluation of N.O + D here vs in the reference (cpp:377, 381): both within 28 u E of the true value
     const float dno = 3.4e-6f * sc.extent;
     for (int j0 = 0; j0 < nb;) {
         const unsigned cell = sh.cell[j0];
         int j1 = j0 + 1;
         while (j1 < nb && sh.cell[j1] == cell) j1++;
-        const unsigned long long b = __ldg(sc.fg_start + cell), e = __ldg(sc.fg_start + cell + 1);
-        fg_segment<ANY>(sc, sh, j0, j1, sc.fg_entries + b, e - b, true, dno);
+        const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
+        fg_segment<ANY>(sc, sh, j0, j1, sc.fg_entries + b, en - b, true, dno);
         j0 = j1;
     }
     if (sc.fg_n_wide > 0) fg_segment<ANY>(sc, sh, 0, nb, sc.fg_wide, (unsigned long long)sc.fg_n_wide, false, dno);
-    if (threadIdx.x < (unsigned)nb) {
-        const unsigned e = s_e[threadIdx.x];
-        if (ANY) { if (sh.found[threadIdx.x]) res[e].found = 1; }
-        else {
-            const unsigned long long k = sh.key[threadIdx.x];
+    __syncwarp();
+    if (lane < nb) {
+        const unsigned e = sh.e[lane];
+        if (ANY) {
+            if (sh.found[lane]) res[e].found = 1;
+            else if (my_lin) lin_idx[atomicAdd(lin_count, 1u)] = e;       // no acceptor in the cell of its direction: the complete search
+        } else {
+            const unsigned long long k = sh.key[lane];
             if (k < res[e].key) res[e].key = k;
         }
     }
@@ -733,7 +755,7 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
             if (mask) {
                 if (pass) s_q[wib][q_len + (unsigned)__popc(mask & lt_mask)] = id;
                 q_len += (unsigned)__popc(mask);
-                flush(false);
+                flush(ANY);                                  // any hit: test right away, the first acceptor ends the ray
                 if (ANY && found) return;
             }
         }
@@ -747,7 +769,6 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
     }
     double t = 0.0;
     unsigned n_it = 0;
-    const long long clk0 = clock64();
     // after leaving a cell through a wall, the next cell is looked up a hair BEYOND that wall (nx, ny, nz: relative nudge), so a
     // path that runs along a wall cannot bounce between the lookup and the wall arithmetic
     double nx = 0.0, ny = 0.0, nz = 0.0;
@@ -799,8 +820,8 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
         t = t_out + adv;
     }
     if (lane == 0) {
-        if (stat) { atomicAdd(stat, 1u); atomicAdd(stat + 2, n_cells); atomicAdd(stat + 3, n_exact); atomicMax(stat + 1, n_it); }
-        if (n_lin < 100000000u && (clock64() - clk0) > 20000000ll) printf("[k_fg_arc] slow ray: any %d its %u cells %u exact %u found %d t %g t_end %g hole (%g %g) |A| %g cycles %lld\n", (int)ANY, n_it, n_cells, n_exact, (int)found, t, t_end, hole_lo, hole_hi, sqrt(aa), clock64() - clk0);
+        // (statistics from one ray in 64: four atomics per ray on four addresses cost more than the walk itself)
+        if (stat && (w & 63u) == 0u) { atomicAdd(stat, 64u); atomicAdd(stat + 2, 64u * n_cells); atomicAdd(stat + 3, 64u * n_exact); atomicMax(stat + 1, n_it); }
         if (found) {
             if (ANY) res[e].found = 1;
             else atomicMin(&res[e].key, slow_key(tlim, plim));
@@ -815,10 +836,13 @@ __device__ __forceinline__ bool slab_inflated(float lox, float hix, float loy, f
     return slab(lox - infl, hix + infl, loy - infl, hiy + infl, loz - infl, hiz + infl, O, inv, tcull, tnear);
 }
 
+// (a ray from 10^8 units away is off by tens of units when it comes back: its inflated boxes cover half the scene.  One thread
+// walking all of that would hold its warp for milliseconds: past this many exact tests the ray goes to k_slow's block-wide scan)
+#define LIN_NEAR_BUDGET 192u
 template <bool ANY>
 __global__ void __launch_bounds__(128)
 k_lin_near(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx, unsigned n_lin,
-           unsigned int* __restrict__ stat)
+           unsigned int* __restrict__ stat, unsigned int* __restrict__ heavy_idx, unsigned int* __restrict__ heavy_count)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_lin) return;
@@ -832,7 +856,7 @@ k_lin_near(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict
         const float kt = __uint_as_float((unsigned)(key >> 32)); const int kp = (int)(unsigned)(key & 0xffffffffull);
         if (kt < best.t || (kt == best.t && kp < best.prim)) { best.t = kt; best.prim = kp; }
     }
-    bool found = false;
+    bool found = false, heavy = false;
     unsigned n_tests = 0;
     auto test = [&](int idx) {
         float t; int prim;
@@ -889,9 +913,11 @@ k_lin_near(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict
                 next = stack[--sp];
             }
             if (done) break;
+            if (n_tests > LIN_NEAR_BUDGET) { heavy = true; break; }
             node = next;
         }
     }
+    if (heavy) heavy_idx[atomicAdd(heavy_count, 1u)] = e;       // the block-wide linear scan (k_slow) finishes this one
     if (stat && n_tests > 64u) { atomicAdd(stat, 1u); atomicAdd(stat + 1, n_tests >> 6); }
     if (found) {
         if (ANY) res[e].found = 1;
@@ -2609,11 +2635,11 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         CU(c->fgq_cellof.ensure(n, 0, st)); CU(c->fgq_rank.ensure(n, 0, st)); CU(c->fgq_order.ensure(n, 0, st)); CU(c->fgq_lin.ensure((size_t)n + 1, 0, st));
         CU(cudaMemsetAsync(c->fgq_hist.p, 0, sizeof(unsigned) * (n_cells + 2), st));
         unsigned int* lin_count = c->fgq_hist.p + n_cells + 1;       // (the scan below covers n_cells + 1 elements: [n_cells] stays 0)
-        k_fg_bin<<<nblk(n, 256), 256, 0, st>>>(rays, n, c->sc.fg_K, c->fgq_hist.p, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_lin.p, lin_count);
+        k_fg_bin<<<nblk(n, 256), 256, 0, st>>>(rays, n, c->sc.fg_K, c->fgq_hist.p, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_lin.p, lin_count, any ? 1 : 0);
         if (exclusive_scan_u32(c, c->fgq_hist.p, c->fgq_start.p, (unsigned)(n_cells + 1))) return RT580_FAILURE;
         k_fg_order<<<nblk(n, 256), 256, 0, st>>>(n, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_start.p, c->fgq_order.p);
-        if (any) k_fg_scan<true><<<nblk(n, FG_RPB), 256, 0, st>>>(c->sc, rays, res, c->fgq_order.p, c->fgq_cellof.p, c->fgq_start.p + n_cells);
-        else k_fg_scan<false><<<nblk(n, FG_RPB), 256, 0, st>>>(c->sc, rays, res, c->fgq_order.p, c->fgq_cellof.p, c->fgq_start.p + n_cells);
+        if (any) k_fg_scan<true><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, c->fgq_order.p, c->fgq_cellof.p, c->fgq_start.p + n_cells, c->fgq_lin.p, lin_count);
+        else k_fg_scan<false><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, c->fgq_order.p, c->fgq_cellof.p, c->fgq_start.p + n_cells, c->fgq_lin.p, lin_count);
         c->launches += 3;
         CU(cudaMemcpyAsync(&n_lin, lin_count, sizeof n_lin, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -2621,16 +2647,24 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         lin_idx = c->fgq_lin.p;
     }
     if (n_lin && lin_idx) {
-        // rays from outside the scene: far regime along the arc of the direction grid, near regime through the inflated tree
+        // rays from outside the scene: far regime along the arc of the direction grid, near regime through the inflated tree;
+        // the few whose inflated boxes cover much of the scene come back in a list for the linear scan below
+        CU(c->fgq_rank.ensure((size_t)n_lin + 1, 0, st));        // (free again: k_fg_order has consumed the ranks)
+        unsigned int* heavy_idx = c->fgq_rank.p;
+        unsigned int* heavy_count = c->fgq_hist.p;               // (free again as well)
+        CU(cudaMemsetAsync(heavy_count, 0, sizeof(unsigned), st));
         if (any) {
             k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16);
-            k_lin_near<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 24);
+            k_lin_near<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 24, heavy_idx, heavy_count);
         } else {
             k_fg_arc<false><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 20);
-            k_lin_near<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 26);
+            k_lin_near<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 26, heavy_idx, heavy_count);
         }
         c->launches += 2;
-        n_lin = 0;
+        CU(cudaMemcpyAsync(&n_lin, heavy_count, sizeof n_lin, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        c->syncs++;
+        lin_idx = heavy_idx;
     }
     if (n_lin) {
         const unsigned batches = nblk(n_lin, SLOW_RPB);
@@ -2694,7 +2728,7 @@ static int anyhit_queue_pass(rt580_context* c, cudaStream_t st, int lane, unsign
 {
     DBuf<ARay>& rays = lane ? c->arays2 : c->arays;
     unsigned int* ctr = c->counters.p + (lane ? 13 : 6);           // [0] rays emitted, [1] rays fetched
-    const unsigned long long chunk = leaky ? (unsigned long long)SLOW_CAP_MAX : (unsigned long long)AH_CHUNK_TIGHT;
+    const unsigned long long chunk = (unsigned long long)AH_CHUNK_TIGHT;
     CU(rays.ensure((size_t)(total < chunk ? total : chunk), 0, st));
     const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ah_blocks_per_sm;
     for (unsigned long long first = 0; first < total; first += chunk) {
@@ -2707,8 +2741,8 @@ static int anyhit_queue_pass(rt580_context* c, cudaStream_t st, int lane, unsign
                                          c->ah_steps, c->ah_min_search, c->ah_batch_div);
         c->launches++;
         const unsigned long long rest = total - first - n;
-        if (leaky && ao && c->any_cap && rest) {
-            // the queue must be able to take every ray of the next chunk
+        if (leaky && ao && c->any_cap && rest && (unsigned long long)c->any_cap < total) {
+            // the queue must be able to take every ray of the next chunk (a queue that holds the whole pass needs no check)
             unsigned cnt[N_COUNTERS];
             if (read_counters(c, cnt)) return RT580_FAILURE;
             const unsigned long long next_n = rest < chunk ? rest : chunk;
@@ -3156,7 +3190,9 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
         if (mode == 0) {
             for (int attempt = 0; ; attempt++) {
                 const bool leaky = is_leaky(c, c->rays_structure);
-                if (any_prepare(c, leaky ? SLOW_CAP_MAX : c->slow_any_cap, st)) return RT580_FAILURE;
+                // leaky (open scene): one queue for the escaping rays of the whole pass - the more rays a flush sorts by direction
+                // cell, the more of them share a cell's list (64 B per entry: 180 GB of HBM take it)
+                if (any_prepare(c, leaky ? (n_ao < (unsigned long long)LEAKY_ANY_CAP ? n_ao : (unsigned long long)LEAKY_ANY_CAP) : c->slow_any_cap, st)) return RT580_FAILURE;
                 const int rc = anyhit_queue_pass(c, st, 0, n_ao, c->ao_hits.p, 0u, 0u, leaky, true,
                     [&](unsigned long long first, unsigned n, ARay* rays, unsigned int* ctr) {
                         k_ao_gen<<<nblk(n, 256), 256, 0, st>>>(c->sc, fp, first, n, n_amb, c->nodes.p, c->ao_state.p, rays, ctr, c->ao_hits.p);
