@@ -52,6 +52,8 @@ struct BuildInput {            // device pointers (already uploaded)
     const float4* sph; const int32_t* sph_prim; int64_t n_spheres;
     float origin_hint[3];      // camera position: bounds |ray origin| for the box padding
     int64_t n_prims;           // primitives in reference order
+    int64_t first_tri;         // input index of the triangle that comes first in reference order (-1: no triangle): a ray with a NaN in
+                               // it "hits" that one (cpp:371, 382, 396 all compare false), whatever its area
 };
 
 struct BuildOutput {
@@ -64,6 +66,7 @@ struct BuildOutput {
     int32_t* leaf_of_prim;     // [n_prims] inverse of the Morton permutation (-1 for dropped triangles)
     int n_leaf;                // primitives in the tree
     int n_big;                 // large primitives after them in `prims` / `far`
+    int nan_leaf;              // prims[nan_leaf]: the record of that first triangle, kept outside the tree and the lists (-1: none)
     int n_dropped;             // zero-area triangles
     unsigned int max_depth;
     float pad, extent;

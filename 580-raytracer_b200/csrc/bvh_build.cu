@@ -343,7 +343,7 @@ size_t build_tmp_bytes(int64_t n_in)
 size_t build_out_bytes(int64_t n_in, int64_t n_prims)
 {
     const size_t n = (size_t)(n_in > 0 ? n_in : 1), np = (size_t)(n_prims > 0 ? n_prims : 1);
-    return n * (64 + 64 + 16 + 4) + np * 4 + 16 * 256 + 4096;   // prims, nodes, far, always_idx | leaf_of_prim
+    return n * (64 + 64 + 16 + 4) + np * 4 + 16 * 256 + 4096 + 64;   // prims (+ 1), nodes, far, always_idx | leaf_of_prim
 }
 
 bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena& outa, cudaStream_t stream, char* err,
@@ -351,7 +351,7 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
 {
     const int64_t n_in = in.n_tris + in.n_spheres;
     out->prims = nullptr; out->nodes = nullptr; out->far = nullptr; out->far_tmin = 0.f; out->n_always = 0; out->always_idx = nullptr; out->leaf_of_prim = nullptr;
-    out->n_leaf = 0; out->n_big = 0; out->max_depth = 0; out->launches = 0; out->pad_max = 0.f;
+    out->n_leaf = 0; out->n_big = 0; out->max_depth = 0; out->launches = 0; out->pad_max = 0.f; out->nan_leaf = -1;
     if (n_in > 0x7ffffff0ll) { snprintf(err, errlen, "too many primitives (%lld)", (long long)n_in); return false; }
 
     int* d_bounds = nullptr; unsigned int* d_counters = nullptr;
@@ -442,11 +442,15 @@ bool build_bvh(const BuildInput& in, BuildOutput* out, DevArena& tmpa, DevArena&
     if (n_all > 0) {
         PrimRec* prims = nullptr; BvhNode* nodes = nullptr; float4* far = nullptr;
         float4 *nlo = nullptr, *nhi = nullptr; int2* kids = nullptr; int* parent = nullptr; unsigned int* arrive = nullptr;
-        TAKE(prims, outa, PrimRec, n_all); TAKE(nodes, outa, BvhNode, n > 1 ? n - 1 : 1); TAKE(far, outa, float4, n_all);
+        TAKE(prims, outa, PrimRec, (size_t)n_all + 1); TAKE(nodes, outa, BvhNode, n > 1 ? n - 1 : 1); TAKE(far, outa, float4, n_all);
         TAKE(nlo, tmpa, float4, 2 * (size_t)n + 2); TAKE(nhi, tmpa, float4, 2 * (size_t)n + 2);
         TAKE(kids, tmpa, int2, n + 1); TAKE(parent, tmpa, int, 2 * (size_t)n + 2); TAKE(arrive, tmpa, unsigned int, n + 1);
         int blocks = (n_all + 255) / 256;
         k_gather<<<blocks, 256, 0, stream>>>(rec, blo, bhi, far_in, ids2, n, n_all, prims, far, nlo, nhi); out->launches++;
+        if (in.first_tri >= 0 && in.first_tri < in.n_tris) {
+            CK(cudaMemcpyAsync(prims + n_all, rec + in.first_tri, sizeof(PrimRec), cudaMemcpyDeviceToDevice, stream));
+            out->nan_leaf = n_all;
+        }
         if (n > 1) {
             CK(cudaMemsetAsync(arrive, 0, sizeof(unsigned int) * n, stream));
             k_hierarchy<<<blocks, 256, 0, stream>>>(keys2, n, kids, parent); out->launches++;

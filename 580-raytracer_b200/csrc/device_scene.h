@@ -63,6 +63,8 @@ struct DeviceScene {
     float big_free_lo[3], big_free_hi[3];
     const int32_t* big_free_light;          // [n_lights]
     int32_t big_free_on;
+    int32_t nan_leaf, nan_prim; // a ray with a NaN in it: every compare of cpp:371 / 382 / 396 is false, the reference's loop keeps the FIRST
+                               // triangle of the scene (cpp:487-499), at t = NaN.  prims[nan_leaf] is its record (outside tree and lists), -1: no triangle
     int32_t n_all;             // n_leaf + n_big: what the linear loops and the far-field scan walk
     int32_t n_prims;           // primitives in reference order (incl. dropped ones)
     const float4* vn;          // [n_prims][3] object-space vertex normals (Q10); unused for spheres

