@@ -30,7 +30,7 @@ EXPORTS = [
     "rt580_scene_info_get", "rt580_get_stream",
     "rt580_render", "rt580_render_begin", "rt580_render_finish", "rt580_row_counts_to_device", "rt580_render_finish_interleaved",
     "rt580_frame_export", "rt580_frame_import", "rt580_frame_release", "rt580_frame_read", "rt580_frame_rgb8", "rt580_trace_closest", "rt580_trace_any", "rt580_trace_profile",
-    "rt580_last_frame_ao_base", "rt580_hemisphere_stream", "rt580_powf",
+    "rt580_last_frame_ao_base", "rt580_hemisphere_stream", "rt580_powf", "rt580_set_profiling", "rt580_frame_profile",
     "rt580_raytracer_new", "rt580_raytracer_delete", "rt580_raytracer_set_assets_path", "rt580_raytracer_set_options", "rt580_raytracer_set_quiet",
     "rt580_raytracer_load_scene_json", "rt580_raytracer_render", "rt580_raytracer_flush_ppm",
     "rt580_raytracer_framebuffer", "rt580_raytracer_stats", "rt580_raytracer_flat_scene",
@@ -103,6 +103,24 @@ class Stats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
+N_CLASSES = 10
+CLASS_NAMES = ["primary", "closest", "shadow_gen", "shadow_tree", "ao_gen", "ao_tree", "far_any", "far_closest", "order", "resolve"]
+
+
+class Profile(ctypes.Structure):
+    _fields_ = [
+        ("ms", ctypes.c_float * N_CLASSES), ("rays", ctypes.c_uint64 * N_CLASSES), ("launches", ctypes.c_uint32 * N_CLASSES),
+        ("reserved", ctypes.c_uint32),
+        ("nodes_any", ctypes.c_uint64), ("leaves_any", ctypes.c_uint64), ("nodes_closest", ctypes.c_uint64), ("leaves_closest", ctypes.c_uint64),
+    ]
+
+    def as_dict(self):
+        d = {n: {"ms": float(self.ms[i]), "rays": int(self.rays[i]), "launches": int(self.launches[i])} for i, n in enumerate(CLASS_NAMES)}
+        d["visits"] = {"nodes_any": int(self.nodes_any), "leaves_any": int(self.leaves_any),
+                       "nodes_closest": int(self.nodes_closest), "leaves_closest": int(self.leaves_closest)}
+        return d
+
+
 def build(verbose=False):
     """Compile librt580.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     out = None if verbose else subprocess.DEVNULL
@@ -150,6 +168,8 @@ def lib():
         L.rt580_last_frame_ao_base.argtypes = [vp, vp]
         L.rt580_hemisphere_stream.argtypes = [vp, vp, ctypes.c_uint64, i32, vp]
         L.rt580_powf.argtypes = [vp, i64, vp, vp, vp]
+        L.rt580_set_profiling.argtypes = [vp, i32]
+        L.rt580_frame_profile.argtypes = [vp, ctypes.POINTER(Profile)]
         L.rt580_raytracer_new.restype = vp
         L.rt580_raytracer_new.argtypes = [i32, i32]
         L.rt580_raytracer_delete.argtypes = [vp]
@@ -321,6 +341,15 @@ class Context:
             tptr = tmax.ctypes.data
         _check(lib().rt580_trace_profile(self._h, n, org.ctypes.data, dirs.ctypes.data, tptr, cnt.ctypes.data))
         return cnt
+
+    def set_profiling(self, count_visits):
+        _check(lib().rt580_set_profiling(self._h, 1 if count_visits else 0))
+
+    def frame_profile(self):
+        """Per-class device times and ray counts of the last finished frame (rt580.h RT580_CLASS_*)."""
+        pr = Profile()
+        _check(lib().rt580_frame_profile(self._h, ctypes.byref(pr)))
+        return pr
 
     def last_frame_ao_base(self, n_pixels):
         out = np.zeros(n_pixels, np.uint64)

@@ -85,7 +85,32 @@ k_fg_raster(const PrimRec* __restrict__ prims, const float2* __restrict__ fgB, i
         const float Ns = rows ? Nu : Nv, No = rows ? Nv : Nu;   // solved / iterated coefficient
         const float inv = 1.0f / Ns;
         const float halfw = Wd * fabsf(inv);
-        for (int r = lane; r < K; r += 32) {
+        // Rows worth visiting: with o the iterated coordinate, the strip's centre line is s(o) = -(No o + Nw) / Ns; it must lie on
+        // the face (|s| <= 1 + halfw) and inside the widened wedge (p.k >= -m |p| for both in-plane normals, p = (o, s(o), 1) in
+        // face coordinates): four affine inequalities c0 + c1 o >= 0, intersected with [-1, 1].  A superset: the cells are
+        // tested one by one below.
+        float o_lo = -1.f, o_hi = 1.f;
+        {
+            const float s0 = -Nw * inv, s1 = -No * inv;                       // s(o) = s0 + s1 o
+            auto clip = [&](float c0, float c1) {                             // keep c0 + c1 o >= 0
+                if (c1 > 0.f) o_lo = fmaxf(o_lo, -c0 / c1);
+                else if (c1 < 0.f) o_hi = fminf(o_hi, -c0 / c1);
+                else if (c0 < 0.f) o_hi = -2.f;
+            };
+            const float slack = 1.f + halfw + 2.f * fp.h;
+            clip(slack - s0, -s1); clip(slack + s0, s1);                      // |s(o)| <= 1 + halfw
+            const float m = (t.eps_o + 3.f * fp.r_c + t.thr1 + 1e-5f) * 1.7338f + halfw;
+            const V3 kk[2] = { t.k1, t.k2 };
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const float ku = fg_axis(kk[q], ua), kv = fg_axis(kk[q], va), kw = fg_axis(kk[q], a) * sg;
+                const float ks = rows ? ku : kv, ko = rows ? kv : ku;        // coefficient of the solved / iterated coordinate
+                clip(m + kw + ks * s0, ko + ks * s1);
+            }
+        }
+        if (o_hi < o_lo) continue;
+        const int r_lo = max(0, (int)floorf((o_lo + 1.f) / fp.h) - 1), r_hi = min(K - 1, (int)floorf((o_hi + 1.f) / fp.h) + 1);
+        for (int r = r_lo + lane; r <= r_hi; r += 32) {
             const float oc = ((float)r + 0.5f) * fp.h - 1.f;    // centre of the row in the iterated coordinate
             const float line = -(No * oc + Nw) * inv;
             const float lo = line - halfw, hi = line + halfw;
@@ -157,11 +182,15 @@ k_fg_setup(const PrimRec* __restrict__ prims, const float4* __restrict__ far_old
             // the wedge test of the rasteriser takes N perpendicular to the two edges at v0 up to 2 %: slivers whose float
             // normal is off by more stay out of the direction index (wide list)
             degenerate = !(el > 0 && l1 > 0 && l2 > 0 && len(k1) > 0.98 * l1 && len(k2) > 0.98 * l2 && len(m) > 0.98 * el);
-            if (!degenerate && T_old >= (double)FG_WIDE_FACTOR * diag) {
-                const double s1 = len(x1) / (l1 * el), s2 = len(x2) / (l2 * el);      // sin of the angles at v1, v2
-                const double mu = 1.02 * diag / (T_old - diag) + 2e-6;
-                const double smin = fmin(s1, s2) - mu;
-                if (smin > 0) {
+            if (!degenerate && T_old > 2.2 * diag) {
+                // the direction of P seen from v1 and the ray's own direction differ by at most mu (|O - v1| <= diag, |P - v1| >= T_old)
+                const double mu = asin(fmin(diag / (T_old - diag), 1.0)) * 1.002 + 2e-6;
+                auto dot3 = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+                const double me[3] = { -e[0], -e[1], -e[2] };
+                const double ang1 = atan2(len(x1), dot3(a1, e)), ang2 = atan2(len(x2), dot3(a2, me));   // angles at v1, v2
+                // over the widened wedge the angle between w and e runs from ang2 - mu to pi - ang1 + mu: sin is concave there
+                if (ang1 > mu && ang2 > mu) {
+                    const double smin = fmin(sin(ang1 - mu), sin(ang2 - mu));
                     const double TL = (len(m) * smin * (1.0 - 1e-4) - 9.3 * u * el) / (6.0001 * u * 0.57741 * 1.000001) * 0.98;
                     Tn = fmax(Tn, (TL - diag) * (1.0 - 1e-6));
                 }

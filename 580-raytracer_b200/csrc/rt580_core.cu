@@ -146,6 +146,7 @@ struct rt580_context {
     DevArena scene_arena, build_arena;   // scene buffers / upload + build temporaries (grow-only)
     // far-field direction grid (fargrid.cuh): lists of the scene, and the per-flush sort of the deferred rays by direction cell
     DBuf<unsigned int> fg_counts; DBuf<unsigned long long> fg_start, fg_bsum; DBuf<uint32_t> fg_entries;
+    FgBuildInput fg_in{}; bool fg_pending = false;   // the lists are built when a frame first needs them (far_grid_ensure)
     int fg_K_env = -1;                   // RT580_FAR_GRID: -1 default (by triangle count), 0 off, else cells per cube-face edge
     unsigned long long fg_n_entries = 0; float fg_build_ms = 0.f;
     DBuf<unsigned int> fgq_hist, fgq_start, fgq_cellof, fgq_rank, fgq_order, fgq_lin;
@@ -195,7 +196,33 @@ struct rt580_context {
     rt580_stats stats{};
     uint32_t launches = 0;
     std::vector<uint64_t> last_ao_base;   // host copy for the checker
+    // per-class device timers of the frame (rt580_frame_profile): pairs of CUDA events on the launching stream
+    std::vector<cudaEvent_t> tm_ev; std::vector<int> tm_cls; size_t tm_n = 0;
+    rt580_profile prof{};
+    DBuf<unsigned long long> visit_counts;   // [4] nodes / leaves of k_anyhit, nodes / leaves of k_closest
+    bool count_visits = false;            // rt580_set_profiling: the traversal kernels count node visits and leaf tests
 };
+static int tm_begin(rt580_context* c, int cls, cudaStream_t st) {
+    if (c->tm_n + 2 > c->tm_ev.size()) {
+        for (int k = 0; k < 2; k++) { cudaEvent_t e; CU(cudaEventCreate(&e)); c->tm_ev.push_back(e); }
+        c->tm_cls.resize(c->tm_ev.size() / 2);
+    }
+    c->tm_cls[c->tm_n / 2] = cls;
+    CU(cudaEventRecord(c->tm_ev[c->tm_n], st));
+    return RT580_SUCCESS;
+}
+static int tm_end(rt580_context* c, cudaStream_t st) {
+    CU(cudaEventRecord(c->tm_ev[c->tm_n + 1], st));
+    c->tm_n += 2;
+    return RT580_SUCCESS;
+}
+static void tm_resolve(rt580_context* c) {
+    for (size_t k = 0; k + 1 < c->tm_n; k += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]) == cudaSuccess) { c->prof.ms[c->tm_cls[k / 2]] += ms; c->prof.launches[c->tm_cls[k / 2]]++; }
+    }
+    c->tm_n = 0;
+}
 
 static void frame_release(rt580_context* c);
 
@@ -474,7 +501,7 @@ k_fg_bin(const SlowRay* __restrict__ rays, unsigned n, int K, unsigned int* __re
         cellof[e] = 0xffffffffu;
         return;
     }
-    rank[e] = atomicAdd(hist + cell, 1u);
+    if (hist) rank[e] = atomicAdd(hist + cell, 1u);
     cellof[e] = (unsigned)cell;
 }
 __global__ void __launch_bounds__(256)
@@ -604,19 +631,20 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
 template <bool ANY>
 __global__ void __launch_bounds__(32 * FG_WARPS)
 k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ order,
-          const unsigned int* __restrict__ cellof, const unsigned int* __restrict__ total_ptr,
+          const unsigned int* __restrict__ cellof, const unsigned int* __restrict__ total_ptr, unsigned n_direct,
           unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count)
 {
     __shared__ FgWarp shw[FG_WARPS];
     FgWarp& sh = shw[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const unsigned total = __ldg(total_ptr);
+    // order == nullptr: a small flush, not worth the sort by cell - the rays in queue order (n_direct of them)
+    const unsigned total = order ? __ldg(total_ptr) : n_direct;
     const unsigned long long pos0 = ((unsigned long long)blockIdx.x * FG_WARPS + (threadIdx.x >> 5)) * FG_G;
     if (pos0 >= total) return;
     const int nb = (int)min((unsigned long long)FG_G, total - pos0);
     bool my_lin = false;
     if (lane < nb) {
-        const unsigned e = order[pos0 + lane];
+        const unsigned e = order ? order[pos0 + lane] : (unsigned)(pos0 + lane);
         const float4 o = __ldg(&rays[e].o), d = __ldg(&rays[e].d);
         sh.e[lane] = e;
         sh.O[lane] = o; sh.D[lane] = d;
@@ -636,15 +664,18 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
         const unsigned cell = sh.cell[j0];
         int j1 = j0 + 1;
         while (j1 < nb && sh.cell[j1] == cell) j1++;
-        const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
-        fg_segment<ANY>(sc, sh, j0, j1, sc.fg_entries + b, en - b, true, dno);
+        if (cell != 0xffffffffu) {                       // (unsorted flush: rays without a cell - k_fg_bin has routed them elsewhere)
+            const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
+            fg_segment<ANY>(sc, sh, j0, j1, sc.fg_entries + b, en - b, true, dno);
+        } else for (int j = j0; j < j1; j++) sh.found[j] = -1;
         j0 = j1;
     }
     if (sc.fg_n_wide > 0) fg_segment<ANY>(sc, sh, 0, nb, sc.fg_wide, (unsigned long long)sc.fg_n_wide, false, dno);
     __syncwarp();
     if (lane < nb) {
         const unsigned e = sh.e[lane];
-        if (ANY) {
+        if (sh.found[lane] == -1) { }                                     // no cell: not this kernel's ray
+        else if (ANY) {
             if (sh.found[lane]) res[e].found = 1;
             else if (my_lin) lin_idx[atomicAdd(lin_count, 1u)] = e;       // no acceptor in the cell of its direction: the complete search
         } else {
@@ -1133,10 +1164,13 @@ k_trace_finish(DeviceScene sc, FrameParams fp, const QRay* __restrict__ queue, c
 // list, the sliver list and the far field, and creates the nodes exactly as k_trace does.
 struct __align__(16) CHit { float t; int leaf; int prim; int pad; };
 
+template <bool COUNT>
 __global__ void __launch_bounds__(128, AH_MIN_BLOCKS)
 k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __restrict__ n_ptr, unsigned n_bound,
-          unsigned int* __restrict__ next_ray, CHit* __restrict__ out, int ah_steps, int ah_min_search, int batch_div)
+          unsigned int* __restrict__ next_ray, CHit* __restrict__ out, int ah_steps, int ah_min_search, int batch_div,
+          unsigned long long* __restrict__ visit_counts)
 {
+    unsigned cnt_nodes = 0, cnt_leaves = 0;
     const unsigned n = min(__ldg(n_ptr), n_bound);
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -1200,6 +1234,7 @@ k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __
             const bool leaf_work = __any_sync(0xffffffffu, active && !searching);
             if (n_search == 0 || (n_search < ah_min_search && leaf_work)) break;
             if (searching) {
+                if (COUNT) cnt_nodes++;
                 float4 xy0, xy1, z01; int4 kids;
                 load_node(sc.nodes + cur, xy0, xy1, z01, kids);
                 float tn0, tn1;
@@ -1219,6 +1254,7 @@ k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __
         // phase 2: one leaf per lane, or the end of the ray
         if (active) {
             if (cur != AH_NONE && cur < 0) {
+                if (COUNT) cnt_leaves++;
                 float t; int prim;
                 if (prim_test<true>(sc.prims + (~cur), O, d, best_t, best_prim, t, prim)) { best_t = t; best_leaf = ~cur; best_prim = prim; }
                 cur = (sp > 0) ? stack[--sp] : AH_NONE;
@@ -1229,6 +1265,11 @@ k_closest(DeviceScene sc, const QRay* __restrict__ queue, const unsigned int* __
                 active = false;
             }
         }
+    }
+    if (COUNT) {
+        unsigned long long a = cnt_nodes, b = cnt_leaves;
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) { atomicAdd(visit_counts, a); atomicAdd(visit_counts + 1, b); }
     }
 }
 
@@ -1785,11 +1826,14 @@ __device__ __forceinline__ bool defer_any(const SlowQ& sq, V3 O, V3 d, float tma
 // Persistent any-hit traversal.  hit_count[id] += 1 for every ray that is occluded.  A ray the tree
 // cannot answer alone goes to the deferred queue `sq` under the id `id + id_offset`; with
 // `pending_mark` its hit_count entry is flagged so that the consumer knows the answer comes later.
+template <bool COUNT>
 __global__ void __launch_bounds__(128, AH_MIN_BLOCKS)
 k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __restrict__ n_ptr,
          unsigned int* __restrict__ next_ray, uint32_t* __restrict__ hit_count, SlowQ sq, unsigned id_offset,
-         unsigned pending_mark, unsigned long long* __restrict__ traversed_acc, int ah_steps, int ah_min_search, int batch_div)
+         unsigned pending_mark, unsigned long long* __restrict__ traversed_acc, int ah_steps, int ah_min_search, int batch_div,
+         unsigned long long* __restrict__ visit_counts)
 {
+    unsigned cnt_nodes = 0, cnt_leaves = 0;
     const unsigned n = __ldg(n_ptr);
     if (traversed_acc && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(traversed_acc, (unsigned long long)n);
     const int lane = threadIdx.x & 31;
@@ -1856,6 +1900,7 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
             const bool leaf_work = __any_sync(0xffffffffu, active && !searching);
             if (n_search == 0 || (n_search < ah_min_search && leaf_work)) break;
             if (searching) {
+                if (COUNT) cnt_nodes++;
                 float4 xy0, xy1, z01; int4 kids;
                 load_node(sc.nodes + cur, xy0, xy1, z01, kids);
                 float tn0, tn1;
@@ -1877,6 +1922,7 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
             bool found = false, done = false;
             if (cur == AH_NONE) done = true;
             else if (cur < 0) {
+                if (COUNT) cnt_leaves++;
                 float t; int prim;
                 if (prim_test<true>(sc.prims + (~cur), O, d, tmax, 0x7fffffff, t, prim)) { found = true; done = true; }
                 else if (sp > 0) cur = stack[--sp];
@@ -1896,6 +1942,11 @@ k_anyhit(DeviceScene sc, const ARay* __restrict__ rays, const unsigned int* __re
                 if (found) atomicAdd(hit_count + id, 1u);
             }
         }
+    }
+    if (COUNT) {
+        unsigned long long a = cnt_nodes, b = cnt_leaves;
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) { atomicAdd(visit_counts, a); atomicAdd(visit_counts + 1, b); }
     }
 }
 
@@ -2198,8 +2249,10 @@ extern "C" void rt580_destroy(rt580_context* c)
     c->scan_tmp.release(); c->row_vals.release(); c->fb.release(); c->counters.release();
     c->slow_rays.release(); c->slow_res.release(); c->any_rays.release(); c->any_res.release(); c->arays.release(); c->occl.release(); c->chits.release();
     for (auto& ev : c->ev) cudaEventDestroy(ev);
+    for (auto& ev : c->tm_ev) cudaEventDestroy(ev);
     for (int k = 0; k < 2; k++) { cudaStreamSynchronize(c->side[k]); cudaEventDestroy(c->ev_join[k]); cudaStreamDestroy(c->side[k]); }
     c->arays2.release(); c->occl2.release();
+    c->visit_counts.release();
     c->fg_counts.release(); c->fg_start.release(); c->fg_bsum.release(); c->fg_entries.release();
     c->fgq_hist.release(); c->fgq_start.release(); c->fgq_cellof.release(); c->fgq_rank.release(); c->fgq_order.release(); c->fgq_lin.release();
     cudaEventDestroy(c->ev_level);
@@ -2229,6 +2282,27 @@ template <typename T> static cudaError_t upload(DevArena& a, T** dst, const void
     if (!*dst) return cudaErrorMemoryAllocation;
     if (count) return cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s);
     return cudaSuccess;
+}
+
+// Build the lists of the far-field direction grid for the uploaded scene, if they are not there yet.
+static int far_grid_ensure(rt580_context* c)
+{
+    if (!c->fg_pending) return RT580_SUCCESS;
+    c->fg_pending = false;
+    cudaStream_t st = c->stream;
+    char err[256] = "";
+    FgBuildOutput fo{};
+    CU(cudaEventRecord(c->ev[10], st));
+    if (!fg_build(c->fg_in, &fo, st, err, sizeof err)) FAIL(RT580_FAILURE, "far-field grid: %s", err);
+    CU(cudaEventRecord(c->ev[11], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventElapsedTime(&c->fg_build_ms, c->ev[10], c->ev[11]));
+    c->sc.fg_K = fo.K; c->sc.fg_start = c->fg_start.p; c->sc.fg_entries = c->fg_entries.p; c->sc.fg_n_wide = fo.n_wide;
+    c->fg_n_entries = fo.n_entries;
+    if (getenv("RT580_DEBUG_TIMING"))
+        fprintf(stderr, "[rt580] far-field grid: K %d, %llu entries (%.1f per cell), %d wide, t_min %.4g, diag %.4g, build %.2f ms\n", fo.K, fo.n_entries,
+                fo.K ? (double)fo.n_entries / (6.0 * fo.K * fo.K) : 0.0, fo.n_wide, fo.t_min, fo.diag, c->fg_build_ms);
+    return RT580_SUCCESS;
 }
 
 extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
@@ -2321,31 +2395,27 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         for (int k = 0; k < 3; k++) {
             c->sc.ob_lo[k] = bo.bounds_lo[k] - margin; c->sc.ob_hi[k] = bo.bounds_hi[k] + margin; c->sc.ob_cam[k] = s->origin_hint[k];
         }
-        // far-field direction grid (fargrid.cuh)
+        // far-field direction grid (fargrid.cuh): the per-triangle constants now, the lists when a frame first needs them
+        // (far_grid_ensure: a closed scene never does, and would pay ~65 ms per upload of a million triangles for nothing)
         c->sc.fg_A = nullptr; c->sc.fg_B = nullptr; c->sc.fg_start = nullptr; c->sc.fg_entries = nullptr; c->sc.fg_wide = nullptr;
         c->sc.fg_n_wide = 0; c->sc.fg_K = 0; c->sc.fg_dmax = 0.f; c->fg_n_entries = 0; c->fg_build_ms = 0.f;
         c->sc.fg_sph = nullptr; c->sc.fg_n_sph = 0; c->sc.fg_rmax = 0.f; c->sc.fg_tmin = 3.0e38f;
+        c->fg_pending = false;
         const int n_all = bo.n_leaf + bo.n_big;
         if (n_all > 0) {
-            FgBuildInput fi{};
+            FgBuildInput& fi = c->fg_in;
+            fi = FgBuildInput{};
             fi.prims = bo.prims; fi.far_old = bo.far; fi.n_all = n_all;
-            fi.K = c->fg_K_env >= 0 ? c->fg_K_env : fg_default_K(n_all);
-            if (fi.K > 4096) fi.K = 4096;
+            fi.K = 0;                                    // constants only
             fi.extent = bo.extent;
             for (int k = 0; k < 3; k++) { fi.ob_lo[k] = c->sc.ob_lo[k]; fi.ob_hi[k] = c->sc.ob_hi[k]; fi.cam[k] = c->sc.ob_cam[k]; }
             fi.fgA = sa.take<float4>((size_t)n_all); fi.fgB = sa.take<float2>((size_t)n_all); fi.wide = sa.take<uint32_t>((size_t)n_all); fi.sph = sa.take<uint32_t>((size_t)n_all);
-            fi.counters = ta.take<unsigned int>(4);
+            fi.counters = sa.take<unsigned int>(4);
             if (!fi.fgA || !fi.fgB || !fi.wide || !fi.sph || !fi.counters) FAIL(RT580_FAILURE, "rt580_upload_scene: arena exhausted (far-field grid)");
             fi.counts = &c->fg_counts; fi.start = &c->fg_start; fi.bsum = &c->fg_bsum; fi.entries = &c->fg_entries;
             FgBuildOutput fo{};
-            CU(cudaEventRecord(c->ev[8], st));
             if (!fg_build(fi, &fo, st, err, sizeof err)) FAIL(RT580_FAILURE, "rt580_upload_scene: %s", err);
-            CU(cudaEventRecord(c->ev[9], st));
-            CU(cudaStreamSynchronize(st));
-            CU(cudaEventElapsedTime(&c->fg_build_ms, c->ev[8], c->ev[9]));
             c->sc.fg_A = fi.fgA; c->sc.fg_B = fi.fgB; c->sc.fg_wide = fi.wide; c->sc.fg_n_wide = fo.n_wide;
-            c->sc.fg_K = fo.K; c->sc.fg_start = c->fg_start.p; c->sc.fg_entries = c->fg_entries.p;
-            c->fg_n_entries = fo.n_entries;
             c->sc.fg_sph = fi.sph; c->sc.fg_n_sph = fo.n_sph; c->sc.fg_tmin = fo.t_min;
             {
                 float rmax = 0.f;
@@ -2355,9 +2425,10 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
             }
             // no far-field hit nearer than the smallest of the tightened bounds (sliver list aside)
             if (fo.t_min > c->sc.far_tmin) c->sc.far_tmin = fo.t_min;
-            if (getenv("RT580_DEBUG_TIMING"))
-                fprintf(stderr, "[rt580] far-field grid: K %d, %llu entries (%.1f per cell), %d wide, t_min %.4g, diag %.4g, build %.2f ms\n", fo.K, fo.n_entries,
-                        fo.K ? (double)fo.n_entries / (6.0 * fo.K * fo.K) : 0.0, fo.n_wide, fo.t_min, fo.diag, c->fg_build_ms);
+            fi.K = c->fg_K_env >= 0 ? c->fg_K_env : fg_default_K(n_all);
+            if (fi.K > 4096) fi.K = 4096;
+            c->fg_pending = fi.K > 0;
+            if (c->fg_pending && getenv("RT580_FAR_GRID_EAGER")) { if (far_grid_ensure(c)) return RT580_FAILURE; }
         }
     }
     {
@@ -2648,17 +2719,27 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
     cudaStream_t st = c->stream;
     const unsigned int* lin_idx = nullptr;
     unsigned n_lin = n;
+    if (tm_begin(c, any ? RT580_CLASS_FAR_ANY : RT580_CLASS_FAR_CLOSEST, st)) return RT580_FAILURE;
+    c->prof.rays[any ? RT580_CLASS_FAR_ANY : RT580_CLASS_FAR_CLOSEST] += n;
+    // the lists of the far-field grid are built when a flush is first large enough to need them (a closed scene defers a few
+    // hundred rays per frame: the scan of every record is cheaper than ~65 ms of build per million triangles)
+    if (c->fg_pending && n >= 2048u) { if (far_grid_ensure(c)) return RT580_FAILURE; }
     if (c->sc.fg_K > 0) {
         const size_t n_cells = (size_t)6 * c->sc.fg_K * c->sc.fg_K;
+        const bool sorted = n >= 32768u;                 // (below that the sort by cell - a histogram over 6 K^2 cells - costs more than it saves)
         CU(c->fgq_hist.ensure(n_cells + 2, 0, st)); CU(c->fgq_start.ensure(n_cells + 2, 0, st));
         CU(c->fgq_cellof.ensure(n, 0, st)); CU(c->fgq_rank.ensure(n, 0, st)); CU(c->fgq_order.ensure(n, 0, st)); CU(c->fgq_lin.ensure((size_t)n + 1, 0, st));
-        CU(cudaMemsetAsync(c->fgq_hist.p, 0, sizeof(unsigned) * (n_cells + 2), st));
         unsigned int* lin_count = c->fgq_hist.p + n_cells + 1;       // (the scan below covers n_cells + 1 elements: [n_cells] stays 0)
-        k_fg_bin<<<nblk(n, 256), 256, 0, st>>>(rays, n, c->sc.fg_K, c->fgq_hist.p, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_lin.p, lin_count, any ? 1 : 0);
-        if (exclusive_scan_u32(c, c->fgq_hist.p, c->fgq_start.p, (unsigned)(n_cells + 1))) return RT580_FAILURE;
-        k_fg_order<<<nblk(n, 256), 256, 0, st>>>(n, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_start.p, c->fgq_order.p);
-        if (any) k_fg_scan<true><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, c->fgq_order.p, c->fgq_cellof.p, c->fgq_start.p + n_cells, c->fgq_lin.p, lin_count);
-        else k_fg_scan<false><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, c->fgq_order.p, c->fgq_cellof.p, c->fgq_start.p + n_cells, c->fgq_lin.p, lin_count);
+        if (sorted) CU(cudaMemsetAsync(c->fgq_hist.p, 0, sizeof(unsigned) * (n_cells + 2), st));
+        else CU(cudaMemsetAsync(lin_count, 0, sizeof(unsigned), st));
+        k_fg_bin<<<nblk(n, 256), 256, 0, st>>>(rays, n, c->sc.fg_K, sorted ? c->fgq_hist.p : nullptr, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_lin.p, lin_count, any ? 1 : 0);
+        if (sorted) {
+            if (exclusive_scan_u32(c, c->fgq_hist.p, c->fgq_start.p, (unsigned)(n_cells + 1))) return RT580_FAILURE;
+            k_fg_order<<<nblk(n, 256), 256, 0, st>>>(n, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_start.p, c->fgq_order.p);
+        }
+        const unsigned int* order = sorted ? c->fgq_order.p : nullptr;
+        if (any) k_fg_scan<true><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
+        else k_fg_scan<false><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
         c->launches += 3;
         CU(cudaMemcpyAsync(&n_lin, lin_count, sizeof n_lin, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -2698,6 +2779,7 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         else k_slow<false><<<grid, 256, 0, st>>>(c->sc, rays, n_lin, res, chunk, lin_idx);
         c->launches++;
     }
+    if (tm_end(c, st)) return RT580_FAILURE;
     c->slow_total += n;
     return RT580_SUCCESS;
 }
@@ -2753,11 +2835,20 @@ static int anyhit_queue_pass(rt580_context* c, cudaStream_t st, int lane, unsign
     for (unsigned long long first = 0; first < total; first += chunk) {
         const unsigned n = (unsigned)((total - first) < chunk ? (total - first) : chunk);
         CU(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned), st));
+        if (tm_begin(c, ao ? RT580_CLASS_AO_GEN : RT580_CLASS_SHADOW_GEN, st)) return RT580_FAILURE;
         gen(first, n, rays.p, ctr);
+        if (tm_end(c, st)) return RT580_FAILURE;
         c->launches++;
-        k_anyhit<<<blocks, 128, 0, st>>>(c->sc, rays.p, ctr, ctr + 1, hits, slowq_any(c), id_offset,
-                                         pending_mark, reinterpret_cast<unsigned long long*>(c->counters.p + (ao ? 8 : 10)),
-                                         c->ah_steps, c->ah_min_search, c->ah_batch_div);
+        if (tm_begin(c, ao ? RT580_CLASS_AO_TREE : RT580_CLASS_SHADOW_TREE, st)) return RT580_FAILURE;
+        if (c->count_visits)
+            k_anyhit<true><<<blocks, 128, 0, st>>>(c->sc, rays.p, ctr, ctr + 1, hits, slowq_any(c), id_offset,
+                                                   pending_mark, reinterpret_cast<unsigned long long*>(c->counters.p + (ao ? 8 : 10)),
+                                                   c->ah_steps, c->ah_min_search, c->ah_batch_div, c->visit_counts.p);
+        else
+            k_anyhit<false><<<blocks, 128, 0, st>>>(c->sc, rays.p, ctr, ctr + 1, hits, slowq_any(c), id_offset,
+                                                    pending_mark, reinterpret_cast<unsigned long long*>(c->counters.p + (ao ? 8 : 10)),
+                                                    c->ah_steps, c->ah_min_search, c->ah_batch_div, nullptr);
+        if (tm_end(c, st)) return RT580_FAILURE;
         c->launches++;
         const unsigned long long rest = total - first - n;
         if (leaky && ao && c->any_cap && rest && (unsigned long long)c->any_cap < total) {
@@ -2837,6 +2928,10 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
     cudaStream_t st = c->stream;
     c->launches = 0; c->syncs = 0;
     memset(&c->stats, 0, sizeof c->stats);
+    memset(&c->prof, 0, sizeof c->prof);
+    c->tm_n = 0;
+    CU(c->visit_counts.ensure(4, 0, st));
+    CU(cudaMemsetAsync(c->visit_counts.p, 0, 4 * sizeof(unsigned long long), st));
 
     // primary-ray tables: cpp:834-846 evaluated in double on the host, exactly as the reference
     // does per pixel (tan is libm's; hoisting is bit-exact because it is a pure function of x / y);
@@ -2920,7 +3015,9 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         if (npix) {
             CU(Q[0]->ensure(2 * (size_t)npix + 1, 0, st));
             if (slow_prepare(c, npix, &slow_cap)) return RT580_FAILURE;
+            if (tm_begin(c, RT580_CLASS_PRIMARY, st)) return RT580_FAILURE;
             launch_trace<0>(c, true, nullptr, npix, nullptr, (unsigned)c->nodes.cap, slow_cap, Spawn{ Q[0]->p, qcnt[0] });
+            if (tm_end(c, st)) return RT580_FAILURE;
             if (read_counters(c, cnt)) return RT580_FAILURE;
             n_nodes = cnt[0]; q = cnt[qidx[0]];
             if (slow_run(c, false, slow_cap, cnt[2], &n_slow)) return RT580_FAILURE;
@@ -2980,10 +3077,16 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                     CU(c->chits.ensure((size_t)q + 1, 0, st));
                     CU(cudaMemsetAsync(c->counters.p + 12, 0, sizeof(unsigned), st));
                     const unsigned blocks = (unsigned)c->prop.multiProcessorCount * (unsigned)c->ch_blocks_per_sm;
-                    k_closest<<<blocks, 128, 0, st>>>(c->sc, Q[cur]->p, qcnt[cur], q, c->counters.p + 12, c->chits.p,
-                                                      c->ah_steps, c->ah_min_search, c->ah_batch_div);
+                    if (tm_begin(c, RT580_CLASS_CLOSEST, st)) return RT580_FAILURE;
+                    if (c->count_visits)
+                        k_closest<true><<<blocks, 128, 0, st>>>(c->sc, Q[cur]->p, qcnt[cur], q, c->counters.p + 12, c->chits.p,
+                                                                c->ah_steps, c->ah_min_search, c->ah_batch_div, c->visit_counts.p + 2);
+                    else
+                        k_closest<false><<<blocks, 128, 0, st>>>(c->sc, Q[cur]->p, qcnt[cur], q, c->counters.p + 12, c->chits.p,
+                                                                 c->ah_steps, c->ah_min_search, c->ah_batch_div, nullptr);
                     k_commit<<<nblk(q, 128), 128, 0, st>>>(c->sc, Q[cur]->p, q, nullptr, c->chits.p, c->nodes.p, c->aux.p,
                                                            c->counters.p, c->pix_hits.p, c->fb.p, (unsigned)c->nodes.cap, slowq(c, slow_cap), sp);
+                    if (tm_end(c, st)) return RT580_FAILURE;
                     c->launches += 2;
                 } else {
                     launch_trace<0>(c, false, Q[cur]->p, q, nullptr, (unsigned)c->nodes.cap, slow_cap, sp);
@@ -3002,7 +3105,9 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
                     });
                 if (rc) return rc;
             }
+            if (tm_begin(c, RT580_CLASS_SHADOW_GEN, sb)) return RT580_FAILURE;
             k_shade_local<<<nblk(n1 - n0, 128), 128, 0, sb>>>(c->sc, c->fp, n0, n1, c->nodes.p, c->aux.p, occl.p);
+            if (tm_end(c, sb)) return RT580_FAILURE;
             c->launches++;
             if (leaky && n_sh) { const int fr = any_flush(c, shadow_finish); if (fr) return fr; }
             rays_so_far += n_sh;
@@ -3091,6 +3196,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
     const double t_struct = now_ms();
     CU(cudaEventRecord(c->ev[1], st));
     // order: subtree sizes bottom-up, per-pixel exclusive scan, per-row totals
+    if (tm_begin(c, RT580_CLASS_ORDER, st)) return RT580_FAILURE;
     const int n_levels = (int)c->level_off.size() - 1;
     for (int L = n_levels - 1; L >= 0; L--) {
         const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
@@ -3100,6 +3206,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
         if (exclusive_scan_u32(c, c->pix_hits.p, c->pix_scan.p, npix)) return RT580_FAILURE;
         k_row_counts<<<nblk(fp.n_rows, 128), 128, 0, st>>>(c->pix_hits.p, c->pix_scan.p, fp.W, fp.n_rows, c->row_vals.p); c->launches++;
     }
+    if (tm_end(c, st)) return RT580_FAILURE;
     CU(cudaEventRecord(c->ev[7], st));
     // The side streams' work (shadow rays and Phong terms of the last levels) belongs to the structure pass, but the
     // order kernels above need none of it (they read the subtree sizes, the side streams write NodeAux::local): the
@@ -3192,6 +3299,7 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
     CU(c->ao_state.ensure((size_t)n_calls + 1, 0, st));
     CU(c->ao_hits.ensure((size_t)n_calls + 1, 0, st));
     CU(cudaMemsetAsync(c->ao_hits.p, 0, sizeof(uint32_t) * (n_calls + 1), st));
+    if (tm_begin(c, RT580_CLASS_ORDER, st)) return RT580_FAILURE;
     for (int L = 0; L < n_levels; L++) {
         const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
         if (n1 > n0) {
@@ -3200,6 +3308,7 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
             c->launches++;
         }
     }
+    if (tm_end(c, st)) return RT580_FAILURE;
     CU(cudaEventRecord(c->ev[3], st));
     const unsigned long long n_ao = n_calls * (unsigned long long)fp.spp;
     if (n_ao > 0xffffffffull * 128ull) FAIL(RT580_FAILURE, "rt580_render_finish: AO ray count exceeds one launch");
@@ -3244,6 +3353,7 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
         }
     }
     CU(cudaEventRecord(c->ev[4], st));
+    if (tm_begin(c, RT580_CLASS_RESOLVE, st)) return RT580_FAILURE;
     for (int L = n_levels - 1; L >= 0; L--) {
         const unsigned n0 = (unsigned)c->level_off[L], n1 = (unsigned)c->level_off[L + 1];
         if (n1 > n0) {
@@ -3251,6 +3361,7 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
             c->launches++;
         }
     }
+    if (tm_end(c, st)) return RT580_FAILURE;
     CU(cudaEventRecord(c->ev[5], st));
     if (c->frame && npix) {
         // multi-GPU: this rank's rows straight into the whole frame on rank 0 (own memory or peer mapping)
@@ -3299,8 +3410,35 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
         c->stats.shadow_rays_traversed = (uint64_t)cnt[10] | ((uint64_t)cnt[11] << 32);
     } else c->stats.shadow_rays_traversed = c->stats.rays_shadow;
     if (stats) *stats = c->stats;
+    {
+        tm_resolve(c);
+        rt580_profile& pr = c->prof;
+        pr.rays[RT580_CLASS_PRIMARY] = c->stats.rays_primary; pr.rays[RT580_CLASS_CLOSEST] = c->stats.rays_secondary;
+        pr.rays[RT580_CLASS_SHADOW_GEN] = c->stats.rays_shadow; pr.rays[RT580_CLASS_SHADOW_TREE] = c->stats.shadow_rays_traversed;
+        pr.rays[RT580_CLASS_AO_GEN] = c->stats.rays_ao; pr.rays[RT580_CLASS_AO_TREE] = c->stats.ao_rays_traversed;
+        pr.rays[RT580_CLASS_ORDER] = c->stats.hit_nodes; pr.rays[RT580_CLASS_RESOLVE] = c->stats.hit_nodes;
+        if (c->count_visits && c->visit_counts.p) {
+            unsigned long long v[4] = { 0, 0, 0, 0 };
+            CU(cudaMemcpy(v, c->visit_counts.p, sizeof v, cudaMemcpyDeviceToHost));
+            pr.nodes_any = v[0]; pr.leaves_any = v[1]; pr.nodes_closest = v[2]; pr.leaves_closest = v[3];
+        }
+    }
     c->frame_begun = false;
     c->fb_pixels = npix;
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_set_profiling(rt580_context* c, int count_visits)
+{
+    if (!c) FAIL(RT580_INVALID_ARG, "rt580_set_profiling: ctx is NULL");
+    c->count_visits = count_visits != 0;
+    return RT580_SUCCESS;
+}
+extern "C" int rt580_frame_profile(rt580_context* c, rt580_profile* out)
+{
+    if (!c || !out) FAIL(RT580_INVALID_ARG, "rt580_frame_profile: NULL argument");
+    if (c->frame_begun) FAIL(RT580_FAILURE, "rt580_frame_profile: the frame is not finished");
+    *out = c->prof;
     return RT580_SUCCESS;
 }
 
@@ -3432,6 +3570,7 @@ static int trace_rays_common(rt580_context* c, bool any, int64_t n, const float*
     DeviceScene sc = c->sc;         // the checkers always run the exact path, on a copy: the context's settings stay as they are
     sc.farfield = 1; sc.diag = nullptr;
     SlowQ q = { nullptr, nullptr, nullptr, 0u };
+    if (mode == 0 && far_grid_ensure(c)) return RT580_FAILURE;
     const bool deferred = mode == 0 && c->sc.fg_K > 0;      // the frame path's machinery for the rays the tree cannot answer alone
     if (deferred) {
         CU(c->counters.ensure(N_COUNTERS, 0, c->stream));

@@ -159,4 +159,5 @@ CONFIGS = {
     "c4_room": dict(n_teapots=977, n_spheres=1000, room=True),    # 1,000,448 teapot triangles + 1k spheres in a closed room
     "c4_open": dict(n_teapots=977, n_spheres=1000, room=False),   # same on an open floor (rays escape)
     "c5_room": dict(n_teapots=9766, n_spheres=0, room=True),      # 10,000,384 triangles
+    "c5_open": dict(n_teapots=9766, n_spheres=0, room=False),     # same on an open floor (BASELINE configs[4] as SURVEY 8d specifies it)
 }

@@ -139,6 +139,29 @@ typedef struct rt580_stats {
                                       clearance map proved that no tree primitive lies before the light */
 } rt580_stats;
 
+/* Where the device time of a frame goes: the kernels of the hot path grouped by the kind of ray they serve.  ms = sum of the
+ * launches' durations, CUDA events on the launching stream (classes on different streams overlap: the sum can exceed
+ * the frame time); rays = what the class processed.  One ray = one IntersectScene call of the reference (cpp:473). */
+#define RT580_N_CLASSES        10
+#define RT580_CLASS_PRIMARY     0   /* GenerateRay + closest hit of the camera rays (cpp:832-858, cpp:30)                 */
+#define RT580_CLASS_CLOSEST     1   /* closest hit of the reflection / refraction rays through the tree (cpp:103, 111)    */
+#define RT580_CLASS_SHADOW_GEN  2   /* shadow rays: generation, large primitives, clearance maps, Phong terms (cpp:53-81) */
+#define RT580_CLASS_SHADOW_TREE 3   /* any hit of the shadow rays through the tree                                         */
+#define RT580_CLASS_AO_GEN      4   /* AO sample rays: random stream, hemisphere directions, large primitives (cpp:269-292, 320-322) */
+#define RT580_CLASS_AO_TREE     5   /* any hit of the AO rays through the tree (cpp:325)                                   */
+#define RT580_CLASS_FAR_ANY     6   /* far-field replay for any-hit rays that left the scene / start outside it           */
+#define RT580_CLASS_FAR_CLOSEST 7   /* the same for closest-hit rays                                                        */
+#define RT580_CLASS_ORDER       8   /* subtree sizes, scans, pre-order ordinals, stream seeds          */
+#define RT580_CLASS_RESOLVE     9   /* integer Pixel algebra bottom-up, frame store (cpp:39-51, 114-128)                   */
+typedef struct rt580_profile {
+    float    ms[RT580_N_CLASSES];
+    uint64_t rays[RT580_N_CLASSES];
+    uint32_t launches[RT580_N_CLASSES];
+    uint32_t reserved;
+    /* with rt580_set_profiling(ctx, 1): inner-node visits and leaf (primitive) tests of the tree kernels, summed over their rays */
+    uint64_t nodes_any, leaves_any, nodes_closest, leaves_closest;
+} rt580_profile;
+
 /* ---- context ------------------------------------------------------------------------- */
 int  rt580_create(int device, rt580_context** out);
 void rt580_destroy(rt580_context* ctx);
@@ -208,6 +231,11 @@ int  rt580_frame_export(rt580_context* ctx, int32_t width, int32_t height, void*
 int  rt580_frame_import(rt580_context* ctx, const void* ipc_handle64, int32_t width, int32_t height);
 int  rt580_frame_release(rt580_context* ctx);
 int  rt580_frame_read(rt580_context* ctx, int16_t* fb_out);
+
+/* The class breakdown of the last finished frame.  rt580_set_profiling(ctx, 1) makes the tree kernels of the following frames
+ * count node visits and leaf tests as well (a few percent slower: not for timed runs). */
+int  rt580_set_profiling(rt580_context* ctx, int count_visits);
+int  rt580_frame_profile(rt580_context* ctx, rt580_profile* out);
 
 /* ---- checkers (used by the parity tests; same kernels as the frame path) ---------------- */
 /* Closest hit of n arbitrary rays: prim_out = primitive order index or -1, t_out = distance. */
