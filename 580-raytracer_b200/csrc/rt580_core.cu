@@ -150,6 +150,7 @@ struct rt580_context {
     int fg_K_env = -1;                   // RT580_FAR_GRID: -1 default (by triangle count), 0 off, else cells per cube-face edge
     unsigned long long fg_n_entries = 0; float fg_build_ms = 0.f;
     DBuf<unsigned int> fgq_hist, fgq_start, fgq_cellof, fgq_rank, fgq_order, fgq_lin;
+    DBuf<struct ArcItem> arc_items;
     bool have_scene = false;
     float build_ms = 0.f; unsigned bvh_depth = 0; float pad_extent = 0.f;
     // frame
@@ -534,6 +535,7 @@ __device__ __forceinline__ void fg_exact(const DeviceScene& sc, unsigned long lo
 // cell's list 32 entries at a time (lane = entry: its record is gathered once and serves every ray of the segment).
 #define FG_G 8
 #define FG_WARPS 4
+#define FG_U4 1      // list entries per lane and iteration (4 was measured slower: the rays from outside the scene stop after a few entries)
 struct FgWarp {
     float4 O[FG_G], D[FG_G];
     unsigned long long key[FG_G];
@@ -569,61 +571,73 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
     unsigned live = ((1u << j1) - 1u) & ~((1u << j0) - 1u);
     const unsigned linm = ANY ? sh.lin : 0u;
     unsigned q_len = 0;
-    for (unsigned long long base = 0; base < len; base += 32) {
-        // this lane's entry: (N, thr) for stage 1, (D, T) for stage 2
-        const unsigned long long idx = base + lane;
-        float4 fr = make_float4(0.f, 0.f, 0.f, -1.0f); float eD = 0.f, eT = 0.f; unsigned id = 0u;
-        if (idx < len) {
-            const unsigned ent = __ldg(list + idx);
-            id = has_k6 ? (ent & FG_ID_MASK) : ent;
-            const float4 fa = __ldg(sc.fg_A + id);
-            const float2 fb = __ldg(sc.fg_B + id);
-            eT = fg_entry_T(fb.x, has_k6 ? (ent >> FG_ID_BITS) : 0u);
-            fr = make_float4(fa.x, fa.y, fa.z, fb.y / eT * 1.00001f + FG_ND_SLACK);
-            eD = fa.w;
-        }
-        if (ANY) {                                       // rays that are answered leave
-            __syncwarp();
-            for (int j = j0; j < j1; j++) if (((live >> j) & 1u) && *reinterpret_cast<volatile int*>(&sh.found[j])) live &= ~(1u << j);
-            if (!live) break;
-        }
-        for (int j = j0; j < j1; j++) {
-            if (!((live >> j) & 1u)) continue;
-            const float4 dj = sh.D[j];
-            const float nd = __fmaf_rn(fr.x, dj.x, __fmaf_rn(fr.y, dj.y, fr.z * dj.z));
-            const float and_ = fabsf(nd);
-            bool pass;
-            if (ANY && ((linm >> j) & 1u)) {
-                // From outside the scene the bounds of the list do not apply (they assume an in-scene origin); far along
-                // this ray, though, almost every triangle of the cell of its direction accepts it.  So: every entry whose
-                // plane lies ahead within the limit gets the exact test; a ray that finds no acceptor here goes on to
-                // k_fg_arc / k_lin_near, which are complete.
-                pass = fr.w >= 0.f && and_ > FG_ND_MIN;
-                if (pass) {
-                    const float4 oj = sh.O[j];
-                    const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
-                    const float dl = 1e-6f * (fabsf(oj.x) + fabsf(oj.y) + fabsf(oj.z) + sc.extent);
-                    const float ano = fabsf(no);
-                    pass = !(ano > dl && ((no < 0.f) == (nd < 0.f))) && fmaxf(ano - dl, 0.f) <= oj.w * (and_ + FG_ND_SLACK);   // (o.w: tmax)
-                }
-            } else {
-                pass = and_ <= fr.w && and_ > FG_ND_MIN;                    // stage 1: the band of the cell
-                if (!__any_sync(0xffffffffu, pass)) continue;
-                if (pass) {
-                    // stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
-                    const float4 oj = sh.O[j];
-                    const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
-                    const float x = (and_ - FG_ND_SLACK) * eT * 0.999998f - dno;
-                    pass = fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
-                }
+    for (unsigned long long base = 0; base < len; base += 32 * FG_U4) {
+        // this lane's FG_U4 entries (independent gathers in flight together: the loop is bound by their latency):
+        // (N, thr) for stage 1, (D, T) for stage 2
+        float4 frs[FG_U4]; float eDs[FG_U4], eTs[FG_U4]; unsigned ids[FG_U4], ents[FG_U4];
+#pragma unroll
+        for (int u = 0; u < FG_U4; u++) { const unsigned long long idx = base + 32 * u + lane; ents[u] = idx < len ? __ldg(list + idx) : 0xffffffffu; }
+#pragma unroll
+        for (int u = 0; u < FG_U4; u++) {
+            frs[u] = make_float4(0.f, 0.f, 0.f, -1.0f); eDs[u] = 0.f; eTs[u] = 0.f; ids[u] = 0u;
+            if (base + 32 * u + lane < len) {
+                const unsigned ent = ents[u];
+                ids[u] = has_k6 ? (ent & FG_ID_MASK) : ent;
+                const float4 fa = __ldg(sc.fg_A + ids[u]);
+                const float2 fb = __ldg(sc.fg_B + ids[u]);
+                eTs[u] = fg_entry_T(fb.x, has_k6 ? (ent >> FG_ID_BITS) : 0u);
+                frs[u] = make_float4(fa.x, fa.y, fa.z, fb.y / eTs[u] * 1.00001f + FG_ND_SLACK);
+                eDs[u] = fa.w;
             }
-            const unsigned mask = __ballot_sync(0xffffffffu, pass);
-            if (mask == 0u) continue;
-            if (pass) sh.q[q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)j << 32) | id;
-            q_len += (unsigned)__popc(mask);
-            fg_flush<ANY>(sc, sh, q_len, false);
         }
-        if (ANY && linm) fg_flush<ANY>(sc, sh, q_len, true);      // (so that the look at `found` above sees this slab's acceptors)
+#pragma unroll
+        for (int u = 0; u < FG_U4; u++) {
+            if (base + 32 * u >= len) break;
+            const float4 fr = frs[u]; const float eD = eDs[u], eT = eTs[u]; const unsigned id = ids[u];
+            if (ANY) {                                       // rays that are answered leave
+                __syncwarp();
+                for (int j = j0; j < j1; j++) if (((live >> j) & 1u) && *reinterpret_cast<volatile int*>(&sh.found[j])) live &= ~(1u << j);
+                if (!live) break;
+            }
+            for (int j = j0; j < j1; j++) {
+                if (!((live >> j) & 1u)) continue;
+                const float4 dj = sh.D[j];
+                const float nd = __fmaf_rn(fr.x, dj.x, __fmaf_rn(fr.y, dj.y, fr.z * dj.z));
+                const float and_ = fabsf(nd);
+                bool pass;
+                if (ANY && ((linm >> j) & 1u)) {
+                    // From outside the scene the bounds of the list do not apply (they assume an in-scene origin); far along
+                    // this ray, though, almost every triangle of the cell of its direction accepts it.  So: every entry whose
+                    // plane lies ahead within the limit gets the exact test; a ray that finds no acceptor here goes on to
+                    // k_fg_arc / k_lin_near, which are complete.
+                    pass = fr.w >= 0.f && and_ > FG_ND_MIN;
+                    if (pass) {
+                        const float4 oj = sh.O[j];
+                        const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
+                        const float dl = 1e-6f * (fabsf(oj.x) + fabsf(oj.y) + fabsf(oj.z) + sc.extent);
+                        const float ano = fabsf(no);
+                        pass = !(ano > dl && ((no < 0.f) == (nd < 0.f))) && fmaxf(ano - dl, 0.f) <= oj.w * (and_ + FG_ND_SLACK);   // (o.w: tmax)
+                    }
+                } else {
+                    pass = and_ <= fr.w && and_ > FG_ND_MIN;                    // stage 1: the band of the cell
+                    if (!__any_sync(0xffffffffu, pass)) continue;
+                    if (pass) {
+                        // stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
+                        const float4 oj = sh.O[j];
+                        const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
+                        const float x = (and_ - FG_ND_SLACK) * eT * 0.999998f - dno;
+                        pass = fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
+                    }
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                if (mask == 0u) continue;
+                if (pass) sh.q[q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)j << 32) | id;
+                q_len += (unsigned)__popc(mask);
+                fg_flush<ANY>(sc, sh, q_len, false);
+            }
+            if (ANY && linm) fg_flush<ANY>(sc, sh, q_len, true);      // (so that the look at `found` above sees this slab's acceptors)
+        }
+        if (ANY && !live) break;
     }
     fg_flush<ANY>(sc, sh, q_len, true);
 }
@@ -698,50 +712,41 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
 //                             primitives the tree and the grid do not hold (large ones, slivers, the wide list), and all
 //                             spheres when the ray is aimed at the scene (cpp:426's discriminant is noise out there).
 #define ARC_WARPS 4
+#define ARC_INLINE_CELLS 6      // cells a ray's own warp works through; the rest of a long arc becomes work items (k_fg_arc_items)
+struct ArcItem { unsigned e; int cell; float rmax; };
+
+// one ray of a warp against the lists of cells of the direction grid: the state both arc kernels share
 template <bool ANY>
-__global__ void __launch_bounds__(32 * ARC_WARPS)
-k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
-         unsigned n_lin, unsigned int* __restrict__ stat)
-{
-    __shared__ unsigned s_q[ARC_WARPS][64];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned w = blockIdx.x * ARC_WARPS + wib;
-    if (w >= n_lin) return;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned e = __ldg(lin_idx + w);
-    const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
-    const V3 O = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z);
-    float tlim = ro.w; int plim = ANY ? 0x7fffffff : __float_as_int(rd.w);
-    if (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) return;                   // no triangle accepts a zero direction (cpp:371)
-    const float inf = __int_as_float(0x7f800000);
-    // The walk runs in double: far out, a float t no longer resolves a cell (ulp(t) / |P| exceeds the cells' slack when the ray
-    // has come a long way and passes near the scene); the cells it names are a superset of those the reference's float P visits.
-    const double Ax = (double)O.x - sc.fg_center[0], Ay = (double)O.y - sc.fg_center[1], Az = (double)O.z - sc.fg_center[2];
-    const double dx = d.x, dy = d.y, dz = d.z;
-    const int K = sc.fg_K;
-    const double h = 2.0 / (double)K;
-    const double aa = Ax * Ax + Ay * Ay + Az * Az, ad = Ax * dx + Ay * dy + Az * dz, dd = dx * dx + dy * dy + dz * dz;
-    const double dinf = (double)inf;
-    // (hole_lo, hole_hi): where |P(t)| < 0.9 T_min, no far-field acceptor exists
-    double hole_lo = dinf, hole_hi = -dinf;
-    {
-        const double Tm = 0.9 * (double)sc.fg_tmin;
-        const double disc = ad * ad - dd * (aa - Tm * Tm);
-        if (disc > 0.0 && dd > 0.0 && Tm < 1e18) { const double sq = sqrt(disc); hole_lo = (-ad - sq) / dd; hole_hi = (-ad + sq) / dd; }
+struct ArcRay {
+    const DeviceScene& sc;
+    unsigned* q;                       // the warp's queue of candidates [64]
+    V3 O, d;
+    float tlim; int plim;              // any hit: tmax; closest hit: the best (t, prim) so far
+    bool found;
+    unsigned q_len, n_cells, n_exact;
+    double aa, ad, dd;                 // |P(t)|^2 = aa + 2 t ad + t^2 dd, P relative to the grid's centre
+    float Olen, dno_far;
+
+    __device__ __forceinline__ ArcRay(const DeviceScene& sc_, unsigned* q_, float4 ro, float4 rd) : sc(sc_), q(q_) {
+        O = mk(ro.x, ro.y, ro.z); d = mk(rd.x, rd.y, rd.z);
+        tlim = ro.w; plim = ANY ? 0x7fffffff : __float_as_int(rd.w);
+        found = false; q_len = 0; n_cells = 0; n_exact = 0;
+        const double Ax = (double)O.x - sc.fg_center[0], Ay = (double)O.y - sc.fg_center[1], Az = (double)O.z - sc.fg_center[2];
+        aa = Ax * Ax + Ay * Ay + Az * Az; ad = Ax * (double)d.x + Ay * (double)d.y + Az * (double)d.z;
+        dd = (double)d.x * d.x + (double)d.y * d.y + (double)d.z * d.z;
+        Olen = fabsf(O.x) + fabsf(O.y) + fabsf(O.z);
+        dno_far = 1e-6f * (Olen + sc.extent);      // float evaluation of N.O + D here and in the reference: <= 8 u (|O|_1 + |D|) each
     }
-    bool found = false;
-    unsigned n_cells = 0, n_exact = 0;
-    unsigned q_len = 0;
-    const float Olen = fabsf(O.x) + fabsf(O.y) + fabsf(O.z);
-    const float dno_far = 1e-6f * (Olen + sc.extent);          // float evaluation of N.O + D here and in the reference: <= 8 u (|O|_1 + |D|) each
-    // the entries of one cell that can accept at |P| <= rmax, tested exactly
-    auto flush = [&](bool all_of_it) {
+    // the queued candidates get the reference's exact test, 32 at a time
+    __device__ __forceinline__ void flush(bool all_of_it) {
+        const int lane = threadIdx.x & 31;
+        const float inf = __int_as_float(0x7f800000);
         while (q_len >= 32u || (all_of_it && q_len > 0u)) {
             __syncwarp();
             float t = inf; int prim = 0x7fffffff;
             if ((unsigned)lane < q_len) {
                 float tt; int pp;
-                if (prim_test<true>(sc.prims + s_q[wib][lane], O, d, tlim, plim, tt, pp)) { t = tt; prim = pp; }
+                if (prim_test<true>(sc.prims + q[lane], O, d, tlim, plim, tt, pp)) { t = tt; prim = pp; }
             }
             n_exact += min(q_len, 32u);
             if (ANY) { if (__any_sync(0xffffffffu, prim != 0x7fffffff)) found = true; }
@@ -754,66 +759,110 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
                 if (prim != 0x7fffffff) { tlim = t; plim = prim; found = true; }
             }
             __syncwarp();
-            const unsigned tail = (lane + 32u < q_len) ? s_q[wib][lane + 32] : 0u;
+            const unsigned tail = (lane + 32u < q_len) ? q[lane + 32] : 0u;
             __syncwarp();
-            if (lane + 32u < q_len) s_q[wib][lane] = tail;
+            if (lane + 32u < q_len) q[lane] = tail;
             q_len = q_len > 32u ? q_len - 32u : 0u;
             __syncwarp();
         }
-    };
-    auto process_cell = [&](int cell, float rmax) {
+    }
+    // the entries of one cell that can accept at |P| <= rmax
+    __device__ __forceinline__ void cell(int cell, float rmax) {
+        const int lane = threadIdx.x & 31;
+        const unsigned lt_mask = (1u << lane) - 1u;
         const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
         n_cells++;
-        for (unsigned long long base = b; base < en; base += 32) {
-            const unsigned long long idx = base + lane;
-            bool pass = false; unsigned id = 0u;
-            if (idx < en) {
-                const unsigned ent = __ldg(sc.fg_entries + idx);
-                id = ent & FG_ID_MASK;
-                const float T = fg_entry_T(__ldg(sc.fg_B + id).x, ent >> FG_ID_BITS);
-                if (T <= rmax) {
-                    // The triangle is listed in every cell its strip crosses, but this ray meets its plane at one parameter
-                    // t = -(N.O + D) / (N.d) only: bracket it ([t_lo, t_hi] covers the float evaluation here and in cpp:367-381)
-                    // and ask for t > 0, t within the limit, and |P(t)| >= T somewhere in the bracket (|P(t)| is convex).
-                    const float4 fa = __ldg(sc.fg_A + id);
-                    const float nd = __fmaf_rn(fa.x, d.x, __fmaf_rn(fa.y, d.y, fa.z * d.z));
-                    const float no = __fmaf_rn(fa.x, O.x, __fmaf_rn(fa.y, O.y, __fmaf_rn(fa.z, O.z, fa.w)));
-                    const float and_ = fabsf(nd), ano = fabsf(no);
-                    pass = and_ > FG_ND_MIN && !(ano > dno_far && ((no < 0.f) == (nd < 0.f)));
-                    if (pass) {
-                        const float t_lo = fmaxf(ano - dno_far, 0.f) / (and_ + FG_ND_SLACK) * 0.999999f;
-                        pass = t_lo <= tlim;
-                        if (pass && and_ > 2.0f * FG_ND_SLACK) {
-                            const double t_hi = (double)(ano + dno_far) / (double)(and_ - FG_ND_SLACK) * 1.000001, tl = t_lo;
-                            const double p_lo = aa + tl * (2.0 * ad + tl * dd), p_hi = aa + t_hi * (2.0 * ad + t_hi * dd);
-                            const double need = fmax((double)T * 0.9999 - 2e-6 * Olen, 0.0);
-                            pass = fmax(p_lo, p_hi) >= need * need;
+        for (unsigned long long base = b; base < en; base += 32 * FG_U4) {
+            // FG_U4 entries per lane: their gathers are in flight together (the loop is bound by that latency)
+            unsigned ents[FG_U4], ids[FG_U4]; float Ts[FG_U4]; float4 fas[FG_U4];
+#pragma unroll
+            for (int u = 0; u < FG_U4; u++) { const unsigned long long idx = base + 32 * u + lane; ents[u] = idx < en ? __ldg(sc.fg_entries + idx) : 0xffffffffu; }
+#pragma unroll
+            for (int u = 0; u < FG_U4; u++) {
+                ids[u] = ents[u] & FG_ID_MASK; Ts[u] = __int_as_float(0x7f800000); fas[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + 32 * u + lane < en) { Ts[u] = fg_entry_T(__ldg(sc.fg_B + ids[u]).x, ents[u] >> FG_ID_BITS); fas[u] = __ldg(sc.fg_A + ids[u]); }
+            }
+#pragma unroll
+            for (int u = 0; u < FG_U4; u++) {
+                if (base + 32 * u >= en) break;
+                bool pass = false; const unsigned id = ids[u];
+                if (base + 32 * u + lane < en) {
+                    const float T = Ts[u];
+                    if (T <= rmax) {
+                        // The triangle is listed in every cell its strip crosses, but this ray meets its plane at one parameter
+                        // t = -(N.O + D) / (N.d) only: bracket it ([t_lo, t_hi] covers the float evaluation here and in cpp:367-381)
+                        // and ask for t > 0, t within the limit, and |P(t)| >= T somewhere in the bracket (|P(t)| is convex).
+                        const float4 fa = fas[u];
+                        const float nd = __fmaf_rn(fa.x, d.x, __fmaf_rn(fa.y, d.y, fa.z * d.z));
+                        const float no = __fmaf_rn(fa.x, O.x, __fmaf_rn(fa.y, O.y, __fmaf_rn(fa.z, O.z, fa.w)));
+                        const float and_ = fabsf(nd), ano = fabsf(no);
+                        pass = and_ > FG_ND_MIN && !(ano > dno_far && ((no < 0.f) == (nd < 0.f)));
+                        if (pass) {
+                            const float t_lo = fmaxf(ano - dno_far, 0.f) / (and_ + FG_ND_SLACK) * 0.999999f;
+                            pass = t_lo <= tlim;
+                            if (pass && and_ > 2.0f * FG_ND_SLACK) {
+                                const double t_hi = (double)(ano + dno_far) / (double)(and_ - FG_ND_SLACK) * 1.000001, tl = t_lo;
+                                const double p_lo = aa + tl * (2.0 * ad + tl * dd), p_hi = aa + t_hi * (2.0 * ad + t_hi * dd);
+                                const double need = fmax((double)T * 0.9999 - 2e-6 * Olen, 0.0);
+                                pass = fmax(p_lo, p_hi) >= need * need;
+                            }
                         }
                     }
                 }
-            }
-            const unsigned mask = __ballot_sync(0xffffffffu, pass);
-            if (mask) {
-                if (pass) s_q[wib][q_len + (unsigned)__popc(mask & lt_mask)] = id;
-                q_len += (unsigned)__popc(mask);
-                flush(ANY);                                  // any hit: test right away, the first acceptor ends the ray
-                if (ANY && found) return;
+                const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                if (mask) {
+                    if (pass) q[q_len + (unsigned)__popc(mask & lt_mask)] = id;
+                    q_len += (unsigned)__popc(mask);
+                    flush(ANY);                                  // any hit: test right away, the first acceptor ends the ray
+                    if (ANY && found) return;
+                }
             }
         }
         flush(true);
-    };
-    double t_end = ANY ? (double)tlim : dinf;
-    if (ANY && !(tlim < 3.0e38f)) {
+    }
+};
+
+template <bool ANY>
+__global__ void __launch_bounds__(32 * ARC_WARPS)
+k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
+         unsigned n_lin, unsigned int* __restrict__ stat, int end_cell_done, ArcItem* __restrict__ items, unsigned int* __restrict__ n_items,
+         unsigned item_cap)
+{
+    __shared__ unsigned s_q[ARC_WARPS][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned w = blockIdx.x * ARC_WARPS + wib;
+    if (w >= n_lin) return;
+    const unsigned e = __ldg(lin_idx + w);
+    const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
+    if (rd.x == 0.0f && rd.y == 0.0f && rd.z == 0.0f) return;                // no triangle accepts a zero direction (cpp:371)
+    ArcRay<ANY> R(sc, s_q[wib], ro, rd);
+    const float inf = __int_as_float(0x7f800000);
+    // The walk runs in double: far out, a float t no longer resolves a cell (ulp(t) / |P| exceeds the cells' slack when the ray
+    // has come a long way and passes near the scene); the cells it names are a superset of those the reference's float P visits.
+    const double Ax = (double)R.O.x - sc.fg_center[0], Ay = (double)R.O.y - sc.fg_center[1], Az = (double)R.O.z - sc.fg_center[2];
+    const double dx = R.d.x, dy = R.d.y, dz = R.d.z;
+    const int K = sc.fg_K;
+    const double h = 2.0 / (double)K;
+    const double dinf = (double)inf;
+    // (hole_lo, hole_hi): where |P(t)| < 0.9 T_min, no far-field acceptor exists
+    double hole_lo = dinf, hole_hi = -dinf;
+    {
+        const double Tm = 0.9 * (double)sc.fg_tmin;
+        const double disc = R.ad * R.ad - R.dd * (R.aa - Tm * Tm);
+        if (disc > 0.0 && R.dd > 0.0 && Tm < 1e18) { const double sq = sqrt(disc); hole_lo = (-R.ad - sq) / R.dd; hole_hi = (-R.ad + sq) / R.dd; }
+    }
+    double t_end = ANY ? (double)R.tlim : dinf;
+    if (ANY && !(R.tlim < 3.0e38f) && !end_cell_done) {
         // any hit, unbounded: the far end of the arc first - out there |P| exceeds every T, most entries accept
-        const int cell = fg_cell_of_dir(d, K);
-        if (cell >= 0) process_cell(cell, inf);
+        const int cell = fg_cell_of_dir(R.d, K);
+        if (cell >= 0) R.cell(cell, inf);
     }
     double t = 0.0;
-    unsigned n_it = 0;
+    unsigned n_it = 0, n_emitted = 0;
     // after leaving a cell through a wall, the next cell is looked up a hair BEYOND that wall (nx, ny, nz: relative nudge), so a
     // path that runs along a wall cannot bounce between the lookup and the wall arithmetic
     double nx = 0.0, ny = 0.0, nz = 0.0;
-    for (int it = 0; it < 200000 && !(ANY && found); it++) {
+    for (int it = 0; it < 200000 && !(ANY && R.found); it++) {
         n_it++;
         if (!(t < t_end)) break;
         if (t > hole_lo && t < hole_hi) { t = hole_hi; nx = ny = nz = 0.0; continue; }
@@ -855,18 +904,55 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
             const double r = sqrt(fmax(p2, Qx * Qx + Qy * Qy + Qz * Qz)) * 1.00001 + 1.0;      // |P(t)| is convex in t
             rmax = r < 3.0e38 ? (float)r * 1.000001f : inf;
         }
-        process_cell(cell, rmax);
-        if (!ANY) t_end = fmin(t_end, (double)tlim * 1.000001);              // (ties at equal t: the lower primitive index wins)
+        // the first cells here; the rest of a long arc (a ray that finds nothing walks hundreds of cells) as work items, one warp each
+        bool inline_cell = R.n_cells < ARC_INLINE_CELLS || items == nullptr;
+        if (!inline_cell) {
+            unsigned slot = 0;
+            if (lane == 0) slot = atomicAdd(n_items, 1u);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < item_cap) { if (lane == 0) { ArcItem itx; itx.e = e; itx.cell = cell; itx.rmax = rmax; items[slot] = itx; } n_emitted++; }
+            else inline_cell = true;                                         // (the item list is full)
+        }
+        if (inline_cell) {
+            R.cell(cell, rmax);
+            if (!ANY) t_end = fmin(t_end, (double)R.tlim * 1.000001);        // (ties at equal t: the lower primitive index wins)
+        }
         if (!(t_out < 1e300)) break;
         t = t_out + adv;
     }
     if (lane == 0) {
         // (statistics from one ray in 64: four atomics per ray on four addresses cost more than the walk itself)
-        if (stat && (w & 63u) == 0u) { atomicAdd(stat, 64u); atomicAdd(stat + 2, 64u * n_cells); atomicAdd(stat + 3, 64u * n_exact); atomicMax(stat + 1, n_it); }
-        if (found) {
+        if (stat && (w & 63u) == 0u) { atomicAdd(stat, 64u); atomicAdd(stat + 2, 64u * (R.n_cells + n_emitted)); atomicAdd(stat + 3, 64u * R.n_exact); atomicMax(stat + 1, n_it); }
+        if (R.found) {
             if (ANY) res[e].found = 1;
-            else atomicMin(&res[e].key, slow_key(tlim, plim));
+            else atomicMin(&res[e].key, slow_key(R.tlim, R.plim));
         }
+    }
+}
+
+// the cells of the long arcs, one warp per (ray, cell)
+template <bool ANY>
+__global__ void __launch_bounds__(32 * ARC_WARPS)
+k_fg_arc_items(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const ArcItem* __restrict__ items, unsigned n_items)
+{
+    __shared__ unsigned s_q[ARC_WARPS][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned w = blockIdx.x * ARC_WARPS + wib;
+    if (w >= n_items) return;
+    const ArcItem itx = items[w];
+    const unsigned e = itx.e;
+    if (ANY && *reinterpret_cast<volatile int*>(&res[e].found)) return;
+    const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
+    ArcRay<ANY> R(sc, s_q[wib], ro, rd);
+    if (!ANY) {                                                              // what has been found so far bounds the search
+        const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&res[e].key);
+        const float kt = __uint_as_float((unsigned)(key >> 32)); const int kp = (int)(unsigned)(key & 0xffffffffull);
+        if (kt < R.tlim || (kt == R.tlim && kp < R.plim)) { R.tlim = kt; R.plim = kp; }
+    }
+    R.cell(itx.cell, itx.rmax);
+    if (lane == 0 && R.found) {
+        if (ANY) res[e].found = 1;
+        else atomicMin(&res[e].key, slow_key(R.tlim, R.plim));
     }
 }
 
@@ -2254,6 +2340,7 @@ extern "C" void rt580_destroy(rt580_context* c)
     c->arays2.release(); c->occl2.release();
     c->visit_counts.release();
     c->fg_counts.release(); c->fg_start.release(); c->fg_bsum.release(); c->fg_entries.release();
+    c->arc_items.release();
     c->fgq_hist.release(); c->fgq_start.release(); c->fgq_cellof.release(); c->fgq_rank.release(); c->fgq_order.release(); c->fgq_lin.release();
     cudaEventDestroy(c->ev_level);
     cudaStreamDestroy(c->stream);
@@ -2752,18 +2839,33 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         CU(c->fgq_rank.ensure((size_t)n_lin + 1, 0, st));        // (free again: k_fg_order has consumed the ranks)
         unsigned int* heavy_idx = c->fgq_rank.p;
         unsigned int* heavy_count = c->fgq_hist.p;               // (free again as well)
-        CU(cudaMemsetAsync(heavy_count, 0, sizeof(unsigned), st));
+        CU(cudaMemsetAsync(heavy_count, 0, 2 * sizeof(unsigned), st));
+        // (the cells of long arcs become work items: up to 8 per ray of the list, the rest is walked in place)
+        const unsigned item_cap = n_lin > (1u << 26) ? (1u << 29) : n_lin * 8u + 65536u;
+        CU(c->arc_items.ensure(item_cap, 0, st));
+        unsigned int* n_items = heavy_count + 1;
+        CU(cudaMemsetAsync(n_items, 0, sizeof(unsigned), st));
         if (any) {
-            k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16);
+            k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16, c->sc.fg_K > 0 ? 1 : 0,
+                                                                             c->arc_items.p, n_items, item_cap);
             k_lin_near<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 24, heavy_idx, heavy_count);
         } else {
-            k_fg_arc<false><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 20);
+            k_fg_arc<false><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 20, 0,
+                                                                              c->arc_items.p, n_items, item_cap);
             k_lin_near<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 26, heavy_idx, heavy_count);
         }
         c->launches += 2;
-        CU(cudaMemcpyAsync(&n_lin, heavy_count, sizeof n_lin, cudaMemcpyDeviceToHost, st));
+        unsigned hc2[2] = { 0u, 0u };
+        CU(cudaMemcpyAsync(hc2, heavy_count, sizeof hc2, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         c->syncs++;
+        const unsigned n_it = hc2[1] < item_cap ? hc2[1] : item_cap;
+        if (n_it) {
+            if (any) k_fg_arc_items<true><<<nblk(n_it, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, c->arc_items.p, n_it);
+            else k_fg_arc_items<false><<<nblk(n_it, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, c->arc_items.p, n_it);
+            c->launches++;
+        }
+        n_lin = hc2[0];
         lin_idx = heavy_idx;
     }
     if (n_lin) {
