@@ -570,6 +570,8 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned live = ((1u << j1) - 1u) & ~((1u << j0) - 1u);
     const unsigned linm = ANY ? sh.lin : 0u;
+    if (!has_k6) live &= ~linm;       // the wide list: rays from outside the scene meet it in k_fg_arc (with the filter that holds out there)
+    if (!live) return;
     unsigned q_len = 0;
     for (unsigned long long base = 0; base < len; base += 32 * FG_U4) {
         // this lane's FG_U4 entries (independent gathers in flight together: the loop is bound by their latency):
@@ -709,7 +711,7 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
 //                             of t, each one's entries filtered by T <= |P|, the rest tested exactly.
 //   near regime  (k_lin_near) the ray comes back to the scene and hits a triangle for real: a tree traversal with the
 //                             leaf boxes inflated by the rounding of P = O + t d for such an origin; plus the handful of
-//                             primitives the tree and the grid do not hold (large ones, slivers, the wide list), and all
+//                             primitives the tree and the grid do not hold (large ones, slivers), and all
 //                             spheres when the ray is aimed at the scene (cpp:426's discriminant is noise out there).
 #define ARC_WARPS 4
 #define ARC_INLINE_CELLS 6      // cells a ray's own warp works through; the rest of a long arc becomes work items (k_fg_arc_items)
@@ -768,19 +770,23 @@ struct ArcRay {
     }
     // the entries of one cell that can accept at |P| <= rmax
     __device__ __forceinline__ void cell(int cell, float rmax) {
-        const int lane = threadIdx.x & 31;
-        const unsigned lt_mask = (1u << lane) - 1u;
         const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
         n_cells++;
+        list(sc.fg_entries, b, en, true, rmax);
+    }
+    // the same over any list of primitive indices (has_k6: entries of the grid, with their 6-bit factor on T)
+    __device__ __forceinline__ void list(const uint32_t* __restrict__ entries, unsigned long long b, unsigned long long en, bool has_k6, float rmax) {
+        const int lane = threadIdx.x & 31;
+        const unsigned lt_mask = (1u << lane) - 1u;
         for (unsigned long long base = b; base < en; base += 32 * FG_U4) {
             // FG_U4 entries per lane: their gathers are in flight together (the loop is bound by that latency)
             unsigned ents[FG_U4], ids[FG_U4]; float Ts[FG_U4]; float4 fas[FG_U4];
 #pragma unroll
-            for (int u = 0; u < FG_U4; u++) { const unsigned long long idx = base + 32 * u + lane; ents[u] = idx < en ? __ldg(sc.fg_entries + idx) : 0xffffffffu; }
+            for (int u = 0; u < FG_U4; u++) { const unsigned long long idx = base + 32 * u + lane; ents[u] = idx < en ? __ldg(entries + idx) : 0xffffffffu; }
 #pragma unroll
             for (int u = 0; u < FG_U4; u++) {
-                ids[u] = ents[u] & FG_ID_MASK; Ts[u] = __int_as_float(0x7f800000); fas[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (base + 32 * u + lane < en) { Ts[u] = fg_entry_T(__ldg(sc.fg_B + ids[u]).x, ents[u] >> FG_ID_BITS); fas[u] = __ldg(sc.fg_A + ids[u]); }
+                ids[u] = has_k6 ? (ents[u] & FG_ID_MASK) : ents[u]; Ts[u] = __int_as_float(0x7f800000); fas[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + 32 * u + lane < en) { Ts[u] = fg_entry_T(__ldg(sc.fg_B + ids[u]).x, has_k6 ? (ents[u] >> FG_ID_BITS) : 0u); fas[u] = __ldg(sc.fg_A + ids[u]); }
             }
 #pragma unroll
             for (int u = 0; u < FG_U4; u++) {
@@ -920,6 +926,8 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
         if (!(t_out < 1e300)) break;
         t = t_out + adv;
     }
+    // the triangles too small for the direction index (fg_wide): anywhere along the ray, same filter
+    if (sc.fg_n_wide > 0 && !(ANY && R.found)) R.list(sc.fg_wide, 0ull, (unsigned long long)sc.fg_n_wide, false, inf);
     if (lane == 0) {
         // (statistics from one ray in 64: four atomics per ray on four addresses cost more than the walk itself)
         if (stat && (w & 63u) == 0u) { atomicAdd(stat, 64u); atomicAdd(stat + 2, 64u * (R.n_cells + n_emitted)); atomicAdd(stat + 3, 64u * R.n_exact); atomicMax(stat + 1, n_it); }
@@ -998,7 +1006,6 @@ k_lin_near(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict
     // the primitives neither the tree nor the grid holds
     for (int k = sc.n_leaf; k < sc.n_all; k++) if (test(k) && ANY) { res[e].found = 1; return; }
     for (int k = 0; k < sc.n_always; k++) if (test(__ldg(sc.always_idx + k)) && ANY) { res[e].found = 1; return; }
-    for (int k = 0; k < sc.fg_n_wide; k++) if (test((int)__ldg(sc.fg_wide + k)) && ANY) { res[e].found = 1; return; }
     const float Olen = sqrtf(O.x * O.x + O.y * O.y + O.z * O.z);
     // spheres: |oc|^2 - r^2 and b^2 are ~R^2 in float, the discriminant b^2 - 4c (cpp:426) carries an error of ~32 u R^2: it can be
     // positive only if the ray passes within ~1.4e-3 R + r of the centre, i.e. is aimed at the scene within that angle

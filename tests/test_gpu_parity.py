@@ -694,3 +694,64 @@ def test_bvh_equals_brute_force_at_a_million_primitives(pkg):
     assert np.array_equal(t1[p2 >= 0].view(np.uint32), t2[p2 >= 0].view(np.uint32))
     assert (p2 >= 0).sum() > 50000 and ((p2 >= 0) & (t2 > 1e4)).sum() > 1000 and (p2 < 0).sum() > 5000
     ctx.close()
+
+
+def test_ten_million_triangles_sampled(pkg, oracle):
+    """BASELINE config 5's scene - c5_open: 9766 teapot instances = 10,000,384 triangles over an open floor - far field exact, at a
+    reduced resolution (the exact frame at 7680x4320 is dominated by rays that start 10^5..10^8 units outside the scene:
+    nine of ten rays that leave a scene of 10^7 triangles are "hit" by float noise, cpp:392): 96 sampled pixels against the
+    T1 oracle's linear loop over all ten million triangles, and the same frame from two interleaved row sets."""
+    import bench
+    name, W, H, spp, depth = "c5_open", 480, 270, 16, 4
+    d = bench.scene_dir(name)
+    ctx, rt, fb, st, pix, got, ref, hits_ref = _sampled_pixels_against_the_oracle(pkg, oracle, d, name, W, H, spp, depth, 96, 5)
+    assert np.array_equal(got, ref), "%d of %d sampled pixels differ from the oracle" % (int((got != ref).any(axis=-1).sum()), len(pix))
+    assert st.linear_fallbacks > st.rays // 3              # the rays from outside the scene are the bulk of this frame
+    p = rt.render_params()
+    counts, ps = [], []
+    for r in range(2):
+        q = p.copy()
+        q.row_first, q.row_step, q.n_rows = pkg.rows_for_rank(H, r, 2)
+        ps.append(q)
+    bands = []
+    c0 = ctx.render_begin(ps[0])
+    ctx2 = pkg.Context(0)
+    ctx2.upload_scene(rt.flat_scene())
+    c1 = ctx2.render_begin(ps[1])
+    bases = pkg.row_bases_from_counts(H, 2, [c0, c1])
+    bands.append(ctx.render_finish(ps[0], bases[0])[0])
+    bands.append(ctx2.render_finish(ps[1], bases[1])[0])
+    assert np.array_equal(pkg.interleave_rows(H, W, 2, bands), fb)
+    ctx.close(); ctx2.close()
+
+
+def test_bvh_equals_brute_force_at_ten_million_primitives(pkg):
+    """SURVEY 8c check (i) at C5 scale: LBVH (+ far-field machinery) against the GPU's brute-force loop over all 10,000,386
+    primitives of c5_open on 30,000 rays: same primitive, same t bits."""
+    import bench
+    name = "c5_open"
+    d = bench.scene_dir(name)
+    rt = pkg.Raytracer(7680, 4320)
+    rt.SetAssetsPath(d)
+    assert rt.LoadSceneJSON(name + ".json") == pkg.RT_SUCCESS
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    E = ctx.scene_info().extent
+    rng = np.random.default_rng(10)
+    n = 30000
+    a = rng.uniform(-0.65 * E, 0.65 * E, (n, 3)); a[:, 1] = rng.uniform(-0.3, 9, n)
+    b = rng.uniform(-0.65 * E, 0.65 * E, (n, 3)); b[:, 1] = rng.uniform(-0.3, 9, n)
+    O = a.astype(np.float32)
+    dd = b - a
+    up = rng.random(n) < 0.3
+    dd[up] = rng.normal(size=(int(up.sum()), 3)); dd[up, 1] = np.abs(dd[up, 1])
+    Of, df, _, _ = _rays_from_outside(rng, n // 4, E)
+    O[-(n // 4):] = Of; dd[-(n // 4):] = df
+    dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    dd = dd.astype(np.float32)
+    p1, t1 = ctx.trace_closest(O, dd, pkg.TRAVERSAL_BVH)
+    p2, t2 = ctx.trace_closest(O, dd, pkg.TRAVERSAL_BRUTE_FORCE)
+    assert np.array_equal(p1, p2), "%d rays hit another primitive" % int((p1 != p2).sum())
+    assert np.array_equal(t1[p2 >= 0].view(np.uint32), t2[p2 >= 0].view(np.uint32))
+    assert (p2 >= 0).sum() > 15000 and ((p2 >= 0) & (t2 > 1e4)).sum() > 1000
+    ctx.close()
