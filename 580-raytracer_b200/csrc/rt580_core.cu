@@ -528,7 +528,9 @@ __device__ __forceinline__ void fg_exact(const DeviceScene& sc, unsigned long lo
                         ANY ? 0x7fffffff : (int)(unsigned)(key & 0xffffffffull), t, prim)) {
         if (ANY) s_found[j] = 1;
         else atomicMin(s_key + j, slow_key(t, prim));
+        if (sc.diag) atomicAdd(sc.diag + 25, 1u);
     }
+    if (sc.diag) atomicAdd(sc.diag + 24, 1u);
 }
 
 // One warp takes FG_G consecutive rays of the sorted order; the rays of one cell among them form a segment that runs over the
@@ -620,6 +622,11 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
                         const float ano = fabsf(no);
                         pass = !(ano > dl && ((no < 0.f) == (nd < 0.f))) && fmaxf(ano - dl, 0.f) <= oj.w * (and_ + FG_ND_SLACK);   // (o.w: tmax)
                     }
+                    // About every other such entry accepts: the first four candidates of a slab are enough (four per ray fill one
+                    // batch of exact tests for the eight rays of a segment).  The others are dropped, which is why k_fg_arc starts
+                    // over with the complete cell for the few rays that leave here unanswered.
+                    const unsigned m0 = __ballot_sync(0xffffffffu, pass);
+                    pass = pass && __popc(m0 & lt_mask) < 4;
                 } else {
                     pass = and_ <= fr.w && and_ > FG_ND_MIN;                    // stage 1: the band of the cell
                     if (!__any_sync(0xffffffffu, pass)) continue;
@@ -714,6 +721,7 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
 //                             primitives the tree and the grid do not hold (large ones, slivers), and all
 //                             spheres when the ray is aimed at the scene (cpp:426's discriminant is noise out there).
 #define ARC_WARPS 4
+#define ARC_MAX_CELLS 48u
 #define ARC_INLINE_CELLS 6      // cells a ray's own warp works through; the rest of a long arc becomes work items (k_fg_arc_items)
 struct ArcItem { unsigned e; int cell; float rmax; };
 
@@ -832,7 +840,7 @@ template <bool ANY>
 __global__ void __launch_bounds__(32 * ARC_WARPS)
 k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
          unsigned n_lin, unsigned int* __restrict__ stat, int end_cell_done, ArcItem* __restrict__ items, unsigned int* __restrict__ n_items,
-         unsigned item_cap)
+         unsigned item_cap, unsigned int* __restrict__ heavy_idx, unsigned int* __restrict__ heavy_count)     // heavy_*: the rays given up (-> k_far_linear)
 {
     __shared__ unsigned s_q[ARC_WARPS][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -910,7 +918,13 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
             const double r = sqrt(fmax(p2, Qx * Qx + Qy * Qy + Qz * Qz)) * 1.00001 + 1.0;      // |P(t)| is convex in t
             rmax = r < 3.0e38 ? (float)r * 1.000001f : inf;
         }
-        // the first cells here; the rest of a long arc (a ray that finds nothing walks hundreds of cells) as work items, one warp each
+        // A ray that finds nothing walks on and on (an arc of 90 degrees is ~650 cells of a 1024-cell face), one warp, cell after
+        // cell: past ARC_MAX_CELLS it goes to the block-wide scan of every record (k_slow), which is complete and scales.
+        if (heavy_idx && R.n_cells + n_emitted >= ARC_MAX_CELLS) {
+            if (lane == 0) heavy_idx[atomicAdd(heavy_count, 1u)] = e;
+            break;
+        }
+        // the first cells here; the rest of the arc as work items, one warp each
         bool inline_cell = R.n_cells < ARC_INLINE_CELLS || items == nullptr;
         if (!inline_cell) {
             unsigned slot = 0;
@@ -1056,6 +1070,127 @@ k_lin_near(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict
     if (found) {
         if (ANY) res[e].found = 1;
         else atomicMin(&res[e].key, slow_key(best.t, best.prim));
+    }
+}
+
+// The far regime of a ray from outside the scene by a scan of every triangle's far-field constants (N, D, T): for the rays
+// whose arc over the direction grid runs on and on without an acceptor (k_fg_arc gives them up after ARC_MAX_CELLS cells).
+// Same block layout as k_slow (32 rays per block, the records streamed through shared memory in tiles, slices of the record
+// range over blockIdx.y), but the filter is the bracket test of ArcRay::list - plane ahead, t within the limit, |P(t)| >= T
+// somewhere in the bracket of t - so only a few records per ray reach the exact test.  The near regime, spheres and the
+// primitives outside the tree are k_lin_near's.
+template <bool ANY>
+__global__ void __launch_bounds__(256)
+k_far_linear(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __restrict__ res, int chunk,
+             const unsigned int* __restrict__ idx)
+{
+    __shared__ float4 s_A[SLOW_TILE];
+    __shared__ float s_T[SLOW_TILE];
+    __shared__ float4 s_O[8][SLOW_RPW], s_D[8][SLOW_RPW];
+    __shared__ unsigned long long s_key[8][SLOW_RPW];
+    __shared__ int s_found[8][SLOW_RPW];
+    __shared__ unsigned long long s_q[8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned first = blockIdx.x * SLOW_RPB + warp;
+    bool my_live = false;
+    unsigned long long key0 = 0ull;
+    if (lane < SLOW_RPW) {
+        const unsigned e0 = first + lane * 8u;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
+        if (e0 < n) {
+            const unsigned e = __ldg(idx + e0);
+            o = __ldg(&rays[e].o); d = __ldg(&rays[e].d);
+            my_live = !(d.x == 0.f && d.y == 0.f && d.z == 0.f);
+            if (ANY) { if (*reinterpret_cast<volatile int*>(&res[e].found)) my_live = false; }
+            else {
+                const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&res[e].key);     // what has been found so far bounds the search
+                const unsigned long long kr = ((unsigned long long)__float_as_uint(o.w) << 32) | (unsigned)__float_as_int(d.w);
+                if (k < kr) { o.w = __uint_as_float((unsigned)(k >> 32)); d.w = __int_as_float((int)(unsigned)(k & 0xffffffffull)); }
+            }
+        }
+        s_O[warp][lane] = o; s_D[warp][lane] = d;
+        key0 = ((unsigned long long)__float_as_uint(o.w) << 32) | (unsigned)__float_as_int(d.w);
+        s_key[warp][lane] = key0;
+        s_found[warp][lane] = 0;
+    }
+    unsigned live_mask = __ballot_sync(0xffffffffu, my_live) & ((1u << SLOW_RPW) - 1u);
+    __syncwarp();
+    float4 dj[SLOW_RPW], oj[SLOW_RPW];
+    float aa[SLOW_RPW], ad[SLOW_RPW], dd[SLOW_RPW], dl[SLOW_RPW];
+#pragma unroll
+    for (int j = 0; j < SLOW_RPW; j++) {
+        dj[j] = s_D[warp][j]; oj[j] = s_O[warp][j];
+        const float ax = oj[j].x - sc.fg_center[0], ay = oj[j].y - sc.fg_center[1], az = oj[j].z - sc.fg_center[2];
+        aa[j] = ax * ax + ay * ay + az * az; ad[j] = ax * dj[j].x + ay * dj[j].y + az * dj[j].z;
+        dd[j] = dj[j].x * dj[j].x + dj[j].y * dj[j].y + dj[j].z * dj[j].z;
+        dl[j] = 1e-6f * (fabsf(oj[j].x) + fabsf(oj[j].y) + fabsf(oj[j].z) + sc.extent);
+    }
+    unsigned q_len = 0;
+    const int nl = min(sc.n_all, ((int)blockIdx.y + 1) * chunk);
+    for (int base = (int)blockIdx.y * chunk; base < nl; base += SLOW_TILE) {
+        {
+            const int i = base + (int)threadIdx.x;
+            s_A[threadIdx.x] = (i < nl) ? __ldg(sc.fg_A + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s_T[threadIdx.x] = (i < nl) ? __ldg(sc.fg_B + i).x : -1.0f;        // (< 0: no far field - spheres)
+        }
+        __syncthreads();
+        if (ANY) {
+#pragma unroll
+            for (int j = 0; j < SLOW_RPW; j++)
+                if (((live_mask >> j) & 1u) && *reinterpret_cast<volatile int*>(&s_found[warp][j])) live_mask &= ~(1u << j);
+        }
+#pragma unroll 2
+        for (int k = 0; k < SLOW_TILE / 32; k++) {
+            const int sl = k * 32 + lane, i = base + sl;
+            const float4 fa = s_A[sl];
+            const float T = s_T[sl];
+#pragma unroll
+            for (int j = 0; j < SLOW_RPW; j++) {
+                if (!((live_mask >> j) & 1u)) continue;
+                const float nd = __fmaf_rn(fa.x, dj[j].x, __fmaf_rn(fa.y, dj[j].y, fa.z * dj[j].z));
+                const float no = __fmaf_rn(fa.x, oj[j].x, __fmaf_rn(fa.y, oj[j].y, __fmaf_rn(fa.z, oj[j].z, fa.w)));
+                const float and_ = fabsf(nd), ano = fabsf(no);
+                bool pass = T > 0.f && and_ > FG_ND_MIN && !(ano > dl[j] && ((no < 0.f) == (nd < 0.f)));
+                if (pass) {
+                    const float tlim = __uint_as_float((unsigned)(*reinterpret_cast<volatile unsigned long long*>(&s_key[warp][j]) >> 32));
+                    const float t_lo = fmaxf(ano - dl[j], 0.f) / (and_ + FG_ND_SLACK) * 0.999999f;
+                    pass = t_lo <= tlim;
+                    if (pass && and_ > 2.0f * FG_ND_SLACK) {
+                        // |P(t)|^2 = aa + 2 t ad + t^2 dd in float: every term carries <= 3e-7 of its magnitude
+                        const float t_hi = (ano + dl[j]) / (and_ - FG_ND_SLACK) * 1.000001f;
+                        const float e_lo = 4e-7f * (aa[j] + 2.0f * t_lo * fabsf(ad[j]) + t_lo * t_lo * dd[j]);
+                        const float e_hi = 4e-7f * (aa[j] + 2.0f * t_hi * fabsf(ad[j]) + t_hi * t_hi * dd[j]);
+                        const float p_lo = aa[j] + t_lo * (2.0f * ad[j] + t_lo * dd[j]) + e_lo, p_hi = aa[j] + t_hi * (2.0f * ad[j] + t_hi * dd[j]) + e_hi;
+                        const float need = fmaxf(T * 0.9999f - 2e-6f * (fabsf(oj[j].x) + fabsf(oj[j].y) + fabsf(oj[j].z)), 0.f);
+                        pass = !(fmaxf(p_lo, p_hi) < need * need);           // (an overflow to inf or a NaN passes)
+                    }
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                if (mask == 0u) continue;
+                if (pass) s_q[warp][q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)j << 32) | (unsigned)i;
+                q_len += (unsigned)__popc(mask);
+                if (q_len >= 32u) {
+                    __syncwarp();
+                    slow_exact<ANY>(sc, s_q[warp][lane], s_O[warp], s_D[warp], s_key[warp], s_found[warp]);
+                    __syncwarp();
+                    const unsigned long long tail = (lane + 32u < q_len) ? s_q[warp][lane + 32] : 0ull;
+                    __syncwarp();
+                    if (lane + 32u < q_len) s_q[warp][lane] = tail;
+                    q_len -= 32u;
+                    __syncwarp();
+                }
+            }
+        }
+        if (!__syncthreads_or(live_mask ? 1 : 0)) break;
+    }
+    __syncwarp();
+    if ((unsigned)lane < q_len) slow_exact<ANY>(sc, s_q[warp][lane], s_O[warp], s_D[warp], s_key[warp], s_found[warp]);
+    __syncwarp();
+    if (lane < SLOW_RPW && first + lane * 8u < n) {
+        const unsigned e = __ldg(idx + first + lane * 8u);
+        if (ANY) { if (s_found[warp][lane]) res[e].found = 1; }
+        else { const unsigned long long k = s_key[warp][lane]; if (k < key0) atomicMin(&res[e].key, k); }
     }
 }
 
@@ -2768,7 +2903,7 @@ static int exclusive_scan_u32(rt580_context* c, const uint32_t* in, uint32_t* ou
 // [6] any-hit rays generated for the running chunk, [7] any-hit rays fetched, [8..9] uint64: AO rays that
 // went through the tree.  All of them come back in one 64-byte copy + one stream sync (every host round
 // trip idles the GPU for ~10-20 us; with 8 ranks a frame is only ~10 ms long).
-#define N_COUNTERS 28     // [16..19] / [20..23] k_fg_arc any / closest: rays, -, cells visited, exact tests
+#define N_COUNTERS 32     // [16..19] / [20..23] k_fg_arc any / closest: rays, -, cells visited, exact tests
 static int read_counters(rt580_context* c, unsigned out[N_COUNTERS]) {
     CU(cudaMemcpyAsync(out, c->counters.p, N_COUNTERS * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -2843,26 +2978,26 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
     if (n_lin && lin_idx) {
         // rays from outside the scene: far regime along the arc of the direction grid, near regime through the inflated tree;
         // the few whose inflated boxes cover much of the scene come back in a list for the linear scan below
-        CU(c->fgq_rank.ensure((size_t)n_lin + 1, 0, st));        // (free again: k_fg_order has consumed the ranks)
-        unsigned int* heavy_idx = c->fgq_rank.p;
-        unsigned int* heavy_count = c->fgq_hist.p;               // (free again as well)
-        CU(cudaMemsetAsync(heavy_count, 0, 2 * sizeof(unsigned), st));
+        CU(c->fgq_rank.ensure(2 * (size_t)n_lin + 2, 0, st));    // (free again: k_fg_order has consumed the ranks)
+        unsigned int* heavy_idx = c->fgq_rank.p;                 // k_lin_near's: inflated boxes cover much of the scene -> k_slow
+        unsigned int* farheavy_idx = c->fgq_rank.p + n_lin + 1;  // k_fg_arc's: the arc runs on without an acceptor -> k_far_linear
+        unsigned int* heavy_count = c->fgq_hist.p;               // (free again as well) [0] heavy, [1] arc items, [2] far-heavy
+        CU(cudaMemsetAsync(heavy_count, 0, 3 * sizeof(unsigned), st));
         // (the cells of long arcs become work items: up to 8 per ray of the list, the rest is walked in place)
         const unsigned item_cap = n_lin > (1u << 26) ? (1u << 29) : n_lin * 8u + 65536u;
         CU(c->arc_items.ensure(item_cap, 0, st));
         unsigned int* n_items = heavy_count + 1;
-        CU(cudaMemsetAsync(n_items, 0, sizeof(unsigned), st));
         if (any) {
-            k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16, c->sc.fg_K > 0 ? 1 : 0,
-                                                                             c->arc_items.p, n_items, item_cap);
+            k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16, 0,
+                                                                             c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
             k_lin_near<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 24, heavy_idx, heavy_count);
         } else {
             k_fg_arc<false><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 20, 0,
-                                                                              c->arc_items.p, n_items, item_cap);
+                                                                              c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
             k_lin_near<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 26, heavy_idx, heavy_count);
         }
         c->launches += 2;
-        unsigned hc2[2] = { 0u, 0u };
+        unsigned hc2[3] = { 0u, 0u, 0u };
         CU(cudaMemcpyAsync(hc2, heavy_count, sizeof hc2, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         c->syncs++;
@@ -2870,6 +3005,20 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         if (n_it) {
             if (any) k_fg_arc_items<true><<<nblk(n_it, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, c->arc_items.p, n_it);
             else k_fg_arc_items<false><<<nblk(n_it, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, c->arc_items.p, n_it);
+            c->launches++;
+        }
+        if (hc2[2]) {
+            const unsigned nf = hc2[2];
+            const unsigned batches = nblk(nf, SLOW_RPB);
+            unsigned slices = nblk(8u * (unsigned)c->prop.multiProcessorCount, batches);
+            const unsigned max_slices = nblk((unsigned)c->sc.n_all, SLOW_TILE);
+            if (slices > max_slices) slices = max_slices;
+            if (slices > 1024u) slices = 1024u;
+            if (slices < 1u) slices = 1u;
+            const int chunk = (int)(nblk(nblk((unsigned)c->sc.n_all, slices), SLOW_TILE) * SLOW_TILE);
+            const dim3 grid(batches, slices);
+            if (any) k_far_linear<true><<<grid, 256, 0, st>>>(c->sc, rays, nf, res, chunk, farheavy_idx);
+            else k_far_linear<false><<<grid, 256, 0, st>>>(c->sc, rays, nf, res, chunk, farheavy_idx);
             c->launches++;
         }
         n_lin = hc2[0];
@@ -3511,6 +3660,7 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
         fprintf(stderr, "[rt580] rays from outside the scene, far regime: any hit %u (%.1f cells, %.0f exact tests each), closest hit %u (%.1f cells, %.0f exact tests each)\n",
                 cnt[16], cnt[16] ? (double)cnt[18] / cnt[16] : 0.0, cnt[16] ? (double)cnt[19] / cnt[16] : 0.0,
                 cnt[20], cnt[20] ? (double)cnt[22] / cnt[20] : 0.0, cnt[20] ? (double)cnt[23] / cnt[20] : 0.0);
+    if (getenv("RT580_DEBUG_TIMING")) fprintf(stderr, "[rt580] k_fg_scan exact tests %u accepted %u\n", cnt[28], cnt[29]);
     if (getenv("RT580_DEBUG_TIMING"))
         fprintf(stderr, "[rt580] rays from outside the scene, near regime: any hit %u rays with > 64 exact tests (%.0f each), closest hit %u (%.0f each)\n",
                 cnt[24], cnt[24] ? 64.0 * cnt[25] / cnt[24] : 0.0, cnt[26], cnt[26] ? 64.0 * cnt[27] / cnt[26] : 0.0);
