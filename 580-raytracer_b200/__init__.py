@@ -240,7 +240,7 @@ class Context:
     def render(self, params: RenderParams, out=None):
         """Whole frame (or the rows in params) -> host int16 [n_rows][width][3]; `out`: a preallocated
         array to fill (e.g. over page-locked memory, host_array())."""
-        n_rows = params.n_rows or params.height
+        n_rows = max(params.n_rows, 0) or (params.height if params.n_rows == 0 else 0)
         fb = np.empty((n_rows, params.width, 3), np.int16) if out is None else out
         assert fb.dtype == np.int16 and fb.size == n_rows * params.width * 3 and fb.flags["C_CONTIGUOUS"]
         st = Stats()
@@ -250,7 +250,7 @@ class Context:
     def render_begin(self, params: RenderParams, want_counts=True):
         """Structure pass.  Returns the per-row hit-node counts, or None with want_counts=False
         (they then stay on the device for row_counts_to_device)."""
-        n_rows = params.n_rows or params.height
+        n_rows = max(params.n_rows, 0) or (params.height if params.n_rows == 0 else 0)
         if not want_counts:
             _check(lib().rt580_render_begin(self._h, ctypes.byref(params), None))
             return None
@@ -297,7 +297,7 @@ class Context:
 
     def render_finish(self, params: RenderParams, row_ao_base=None, out=None, device_ptr=None):
         """out: host int16 array, or device_ptr: raw CUDA pointer (e.g. torch tensor data_ptr())."""
-        n_rows = params.n_rows or params.height
+        n_rows = max(params.n_rows, 0) or (params.height if params.n_rows == 0 else 0)
         st = Stats()
         base_ptr = None
         if row_ao_base is not None:
@@ -488,7 +488,7 @@ def rows_for_rank(height, rank, world):
     """Interleaved row partition: rank r renders rows r, r+world, ... (load balance: in the
     mesh scenes most rows are background).  -> (row_first, row_step, n_rows)"""
     if rank >= height:
-        return (0, 1, 0)
+        return (0, world, -1)            # n_rows < 0: this rank renders no row (n_rows == 0 would mean the whole frame, rt580.h)
     return (rank, world, (height - rank + world - 1) // world)
 
 
@@ -499,11 +499,13 @@ def row_bases_from_counts(height, world, counts_per_rank):
     per_row = np.zeros(height, np.uint64)
     for r in range(world):
         first, step, n = rows_for_rank(height, r, world)
+        n = max(n, 0)
         per_row[first:first + n * step:step] = np.asarray(counts_per_rank[r][:n], np.uint64)
     excl = np.concatenate([[np.uint64(0)], np.cumsum(per_row, dtype=np.uint64)[:-1]]) if height else per_row
     out = []
     for r in range(world):
         first, step, n = rows_for_rank(height, r, world)
+        n = max(n, 0)
         out.append(np.ascontiguousarray(excl[first:first + n * step:step], np.uint64))
     return out
 
@@ -513,6 +515,6 @@ def interleave_rows(height, width, world, bands):
     fb = np.empty((height, width, 3), np.int16)
     for r in range(world):
         first, step, n = rows_for_rank(height, r, world)
-        if n:
+        if n > 0:
             fb[first:first + n * step:step] = bands[r][:n]
     return fb

@@ -2236,14 +2236,14 @@ k_gamma_rgb8(const int16_t* __restrict__ fb, unsigned long long n, const uint8_t
     lut[threadIdx.x] = lut_g[threadIdx.x];
     __syncthreads();
     const unsigned long long i4 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 4ull;
-    if (i4 + 4ull <= n) {
+    if (i4 + 4ull <= n && (reinterpret_cast<uintptr_t>(out) & 3u) == 0u) {        // (a caller's device pointer need not be 4-byte aligned)
         const short4 v = *reinterpret_cast<const short4*>(fb + i4);
         uchar4 o;
         o.x = lut[min(max((int)v.x, 0), 255)]; o.y = lut[min(max((int)v.y, 0), 255)];
         o.z = lut[min(max((int)v.z, 0), 255)]; o.w = lut[min(max((int)v.w, 0), 255)];
         *reinterpret_cast<uchar4*>(out + i4) = o;
     } else {
-        for (unsigned long long i = i4; i < n; i++) out[i] = lut[min(max((int)fb[i], 0), 255)];
+        for (unsigned long long i = i4; i < n && i < i4 + 4ull; i++) out[i] = lut[min(max((int)fb[i], 0), 255)];
     }
 }
 
@@ -3168,6 +3168,7 @@ static int render_begin_impl(rt580_context* c, const rt580_render_params* p, uin
     FrameParams& fp = c->fp;
     fp.W = p->width; fp.H = p->height;
     if (p->n_rows == 0) { fp.row_first = 0; fp.row_step = 1; fp.n_rows = p->height; }
+    else if (p->n_rows < 0) { fp.row_first = 0; fp.row_step = p->row_step > 0 ? p->row_step : 1; fp.n_rows = 0; }     // this context renders no row (more ranks than rows)
     else { fp.row_first = p->row_first; fp.row_step = p->row_step; fp.n_rows = p->n_rows; }
     if (fp.n_rows < 0 || fp.row_step < 1 || fp.row_first < 0 || (fp.n_rows > 0 && fp.row_first + (long long)(fp.n_rows - 1) * fp.row_step >= fp.H))
         FAIL(RT580_INVALID_ARG, "rt580_render_begin: rows (first %d step %d count %d) outside the %d-row frame", fp.row_first, fp.row_step, fp.n_rows, fp.H);
@@ -3773,7 +3774,7 @@ extern "C" int rt580_frame_read(rt580_context* c, int16_t* fb_out)
 extern "C" int rt580_render(rt580_context* c, const rt580_render_params* p, int16_t* fb_out, rt580_stats* stats)
 {
     if (!c || !p) FAIL(RT580_INVALID_ARG, "rt580_render: NULL argument");
-    const int n_rows = p->n_rows ? p->n_rows : p->height;
+    const int n_rows = p->n_rows == 0 ? p->height : (p->n_rows < 0 ? 0 : p->n_rows);
     std::vector<uint64_t> rows((size_t)(n_rows > 0 ? n_rows : 0) + 1);
     int st = rt580_render_begin(c, p, rows.data());
     if (st != RT580_SUCCESS) return st;

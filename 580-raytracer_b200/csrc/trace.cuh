@@ -13,7 +13,9 @@
 
 namespace rt580 {
 
-#define RT_STACK_SIZE 64
+// The LBVH's depth is bounded by its keys: 63 Morton bits, then the 32 index bits that order equal keys (bvh_build.cu delta()):
+// a stack of 96 entries holds any tree the build can produce (clustered centroids, thousands of coincident instances).
+#define RT_STACK_SIZE 96
 #define RT_SLAB_WIDEN 4.76837158e-7f   // 2^-21: > 3 roundings of (plane - o) * (1/d), see DESIGN.md
 
 // 32 bytes per lane in one instruction (LDG.E.256, sm_100): a 64-byte node or primitive record is two

@@ -99,7 +99,8 @@ typedef struct rt580_render_params {
     int32_t rng_mode;              /* RT580_RNG_*                                          */
     int32_t traversal;             /* RT580_TRAVERSAL_*                                    */
     /* rows rendered by this context: row_first + k*row_step, k in [0,n_rows).
-     * n_rows == 0 means the whole frame (row_first 0, step 1). */
+     * n_rows == 0 means the whole frame (row_first 0, step 1); n_rows < 0 means no row at all (a rank beyond the
+     * frame's height: it still takes part in the exchange, with row_step = the number of ranks). */
     int32_t row_first, row_step, n_rows;
     int32_t farfield;              /* RT580_FARFIELD_*                                     */
 } rt580_render_params;
@@ -191,7 +192,9 @@ int  rt580_render(rt580_context* ctx, const rt580_render_params* params, int16_t
 
 /* The last finished frame (its rows on this context) as 8-bit RGB, the body of the reference's PPM
  * (cpp:809-823): rgb = lut256[value] with the caller's table of u8(powf(c / 255.0f, 1 / 2.2f) * 255.0f),
- * c = 0..255, evaluated with the host's powf.  rgb_out: [n_rows][width][3] bytes, host or device. */
+ * c = 0..255, evaluated with the host's powf.  rgb_out: [n_rows][width][3] bytes, host or device (any alignment).
+ * Values outside [0, 255] are clamped to the table's ends; the hot path only stores values in [0, 255] (cpp:128 clamps,
+ * the background is a constant), so this never differs from the host's FlushFrameBufferToPPM on a rendered frame. */
 int  rt580_frame_rgb8(rt580_context* ctx, const uint8_t* lut256, uint8_t* rgb_out, int out_on_device);
 
 /* Split form for several ranks (one context per GPU, rows partitioned):
@@ -227,6 +230,9 @@ int  rt580_render_finish(rt580_context* ctx, const uint64_t* row_ao_base, int16_
 int  rt580_row_counts_to_device(rt580_context* ctx, uint64_t* dst_device, int32_t max_rows);
 int  rt580_render_finish_interleaved(rt580_context* ctx, const uint64_t* all_counts_device, int32_t world, int32_t rank,
                                      int32_t max_rows, int16_t* fb_out, int fb_on_device, rt580_stats* stats);
+/* Release order of a shared frame: every importing context calls rt580_frame_release (cudaIpcCloseMemHandle) BEFORE the
+ * exporting context releases (or re-exports) the allocation; freeing an exported region that is still mapped elsewhere is
+ * undefined behaviour in CUDA.  A barrier between the two is the caller's (bench.py: Rig.release_frame). */
 int  rt580_frame_export(rt580_context* ctx, int32_t width, int32_t height, void* ipc_handle64);
 int  rt580_frame_import(rt580_context* ctx, const void* ipc_handle64, int32_t width, int32_t height);
 int  rt580_frame_release(rt580_context* ctx);

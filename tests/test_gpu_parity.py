@@ -755,3 +755,111 @@ def test_bvh_equals_brute_force_at_ten_million_primitives(pkg):
     assert np.array_equal(t1[p2 >= 0].view(np.uint32), t2[p2 >= 0].view(np.uint32))
     assert (p2 >= 0).sum() > 15000 and ((p2 >= 0) & (t2 > 1e4)).sum() > 1000
     ctx.close()
+
+
+def test_deep_tree_of_clustered_centroids(pkg, oracle, tmp_path):
+    """An LBVH over centroids clustered at every scale is a chain: triangles at 2^20, 2^19, ... 2^-2 along x, then along y, then
+    along z (each halving peels one leaf off: ~66 levels), and 1500 coincident triangles at the far end (equal Morton keys:
+    ordered by index, another ~11 levels).  Round 1 refused such scenes (depth > 64); the traversal stack now holds any tree
+    the build can produce.  Same frame as the oracle, bit for bit."""
+    import json
+    import shutil
+    d = str(tmp_path)
+    shutil.copy(os.path.join(ASSETS, "1triangle.json"), d)
+    shapes = []
+    mat = {"Cs": [0.8, 0.5, 0.3], "Ka": 0.3, "Kd": 0.7, "Ks": 0.4, "Kt": 0.0, "n": 10}
+
+    def tri(pos, k):
+        shapes.append({"id": "t%d" % len(shapes), "geometry": "1triangle", "material": dict(mat, Cs=[0.3 + 0.1 * (k % 7), 0.5, 0.9 - 0.1 * (k % 5)]),
+                       "transforms": [{"S": [1, 1, 1]}, {"T": pos}]})
+    for axis in range(3):
+        for k in range(23):
+            pos = [0.0, 0.0, 0.0]
+            pos[axis] = float(2.0 ** (20 - k))
+            tri(pos, k)
+    for k in range(1500):
+        tri([0.0, 0.0, 0.0], k)
+    scene = {"scene": {"shapes": shapes,
+                       "lights": [{"type": "ambient", "color": [1, 1, 1], "intensity": 0.3},
+                                  {"type": "directional", "color": [1, 1, 1], "intensity": 0.9, "from": [2, 5, 9], "to": [0, 0, 0]}],
+                       "camera": {"from": [3, 2, 12], "to": [0, 0, 0], "bounds": [0.1, 10, 1, -1, 1, -1], "resolution": [8, 8]}}}
+    with open(os.path.join(d, "deep.json"), "w") as f:
+        json.dump(scene, f)
+    W, H, spp, depth = 96, 64, 2, 2
+    rt = pkg.Raytracer(W, H)
+    rt.SetAssetsPath(d)
+    rt.SetOptions(depth=depth, ao_spp=spp, traversal=pkg.TRAVERSAL_BVH)
+    assert rt.LoadSceneJSON("deep.json") == pkg.RT_SUCCESS
+    assert rt.Render("") == pkg.RT_SUCCESS, pkg.lib().rt580_last_error().decode()
+    st = rt.stats()
+    assert st.bvh_max_depth > 64, "the scene did not produce a deep tree (depth %d)" % st.bvh_max_depth
+    orc = oracle.Oracle(oracle.load_scene_json(d, "deep.json"))
+    ref, rays, _ = orc.render(W, H, spp, depth, nthreads=NT)
+    assert st.rays == rays
+    assert np.array_equal(rt.frame_buffer(), ref)
+
+
+def test_more_ranks_than_rows(pkg):
+    """rows_for_rank hands a rank beyond the frame's height n_rows = -1 ("no row"; 0 would mean the whole frame, rt580.h): it
+    takes part in the exchange with empty hands, and the assembled frame is still the single-context frame."""
+    import torch
+    scene, W, H, spp, depth = "simpleSphereScene.json", 64, 3, 4, 2
+    whole, st_whole = render(pkg, scene, W, H, spp, depth)
+    rt = make_rt(pkg, scene, W, H, spp, depth)
+    world = 5
+    assert pkg.rows_for_rank(H, 4, world)[2] == -1
+    max_rows = (H + world - 1) // world
+    all_d = torch.zeros((world, max_rows), dtype=torch.int64, device="cuda")
+    ctxs, got, rays = [], np.zeros((H, W, 3), np.int16), 0
+    for r in range(world):
+        c = pkg.Context(0)
+        c.upload_scene(rt.flat_scene())
+        c.frame_export(W, H)
+        p = rt.render_params().copy()
+        p.row_first, p.row_step, p.n_rows = pkg.rows_for_rank(H, r, world)
+        c.render_begin(p, want_counts=False)
+        c.row_counts_to_device(all_d[r].data_ptr(), max_rows)
+        ctxs.append(c)
+    torch.cuda.synchronize()
+    for r in range(world):
+        st = ctxs[r].render_finish_interleaved(all_d.data_ptr(), world, r, max_rows)
+        rays += st.rays
+        first, step, n = pkg.rows_for_rank(H, r, world)
+        if n > 0:
+            got[first:first + n * step:step] = ctxs[r].frame_read(W, H)[first:first + n * step:step]
+    assert rays == st_whole.rays and np.array_equal(got, whole)
+    for c in ctxs:
+        c.close()
+
+
+def test_ao_directions_match_libm_on_two_million_samples(pkg, oracle):
+    """cpp:277-278 computes (float)(r * cos a), (float)(r * sin a) through the C library's DOUBLE cos / sin; neither glibc's nor
+    CUDA's is correctly rounded, so equality of the float results is a property to measure, not one that holds by construction:
+    2,097,152 consecutive samples of the reference stream (and the same number from far down the stream), device vs host."""
+    ctx = pkg.Context(0)
+    for normal, step in [((0.0, 1.0, 0.0), 0), ((0.3, -0.2, 0.93), 3_000_000_001)]:
+        n = 1 << 21
+        a = ctx.hemisphere_stream(normal, step, n)
+        b = oracle.hemisphere_stream(normal, step, n)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "%d directions differ" % int((a.view(np.uint32) != b.view(np.uint32)).any(axis=1).sum())
+    ctx.close()
+
+
+def test_ppm_body_into_a_misaligned_device_buffer(pkg, oracle):
+    """rt580_frame_rgb8 with out_on_device and a destination that is not 4-byte aligned (advisor finding, round 1)."""
+    import torch
+    scene, W, H, spp, depth = "simpleSphereScene.json", 61, 37, 2, 1
+    rt = make_rt(pkg, scene, W, H, spp, depth)
+    ctx = pkg.Context(0)
+    ctx.upload_scene(rt.flat_scene())
+    fb, _ = ctx.render(rt.render_params())
+    lut = np.ascontiguousarray(oracle.gamma_encode(np.arange(256, dtype=np.int16)), np.uint8)
+    buf = torch.zeros(W * H * 3 + 8, dtype=torch.uint8, device="cuda")
+    for off in (0, 1, 3):
+        buf.zero_()
+        st = pkg.lib().rt580_frame_rgb8(ctx._h, lut.ctypes.data, buf.data_ptr() + off, 1)
+        assert st == pkg.RT_SUCCESS, pkg.lib().rt580_last_error().decode()
+        torch.cuda.synchronize()
+        got = buf[off:off + W * H * 3].cpu().numpy().reshape(H, W, 3)
+        assert np.array_equal(got, oracle.gamma_encode(fb))
+    ctx.close()
