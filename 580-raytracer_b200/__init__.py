@@ -34,7 +34,7 @@ EXPORTS = [
     "rt580_raytracer_new", "rt580_raytracer_delete", "rt580_raytracer_set_assets_path", "rt580_raytracer_set_options", "rt580_raytracer_set_quiet",
     "rt580_raytracer_load_scene_json", "rt580_raytracer_render", "rt580_raytracer_flush_ppm",
     "rt580_raytracer_framebuffer", "rt580_raytracer_stats", "rt580_raytracer_flat_scene",
-    "rt580_raytracer_render_params",
+    "rt580_raytracer_render_params", "rt580_raytracer_set_gpus", "rt580_raytracer_set_mesh_cache", "rt580_raytracer_mesh_cache_hits",
 ]
 
 
@@ -178,6 +178,9 @@ def lib():
         L.rt580_raytracer_set_options.argtypes = [vp, i32, i32, i32, i32, i32, i32]
         L.rt580_raytracer_set_quiet.argtypes = [vp, i32]
         L.rt580_raytracer_load_scene_json.argtypes = [vp, ctypes.c_char_p]
+        L.rt580_raytracer_set_gpus.argtypes = [vp, i32]
+        L.rt580_raytracer_set_mesh_cache.argtypes = [vp, ctypes.c_char_p]
+        L.rt580_raytracer_mesh_cache_hits.argtypes = [vp]
         L.rt580_raytracer_render.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_flush_ppm.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_framebuffer.restype = vp
@@ -400,6 +403,15 @@ class Raytracer:
         self._opts.update(kw)
         o = self._opts
         return lib().rt580_raytracer_set_options(self._h, o["depth"], o["ao_spp"], o["rng_mode"], o["traversal"], o["device"], o["farfield"])
+
+    def SetGpus(self, n_gpus):
+        return lib().rt580_raytracer_set_gpus(self._h, n_gpus)
+
+    def SetMeshCacheDir(self, directory):
+        return lib().rt580_raytracer_set_mesh_cache(self._h, (directory or "").encode())
+
+    def MeshCacheHits(self):
+        return lib().rt580_raytracer_mesh_cache_hits(self._h)
 
     def LoadSceneJSON(self, scene_path):
         return lib().rt580_raytracer_load_scene_json(self._h, scene_path.encode())

@@ -36,6 +36,17 @@ int rt580_raytracer_set_quiet(rt580_raytracer* h, int quiet) {
     h->rt->SetQuiet(quiet != 0);
     return RT_SUCCESS;
 }
+int rt580_raytracer_set_gpus(rt580_raytracer* h, int n_gpus) {
+    if (!h || n_gpus < 1) return RT_INVALID_ARG;
+    h->rt->SetGpus(n_gpus);
+    return RT_SUCCESS;
+}
+int rt580_raytracer_set_mesh_cache(rt580_raytracer* h, const char* dir) {
+    if (!h) return RT_INVALID_ARG;
+    h->rt->SetMeshCacheDir(dir ? dir : "");
+    return RT_SUCCESS;
+}
+int rt580_raytracer_mesh_cache_hits(rt580_raytracer* h) { return h ? h->rt->MeshCacheHits() : -1; }
 int rt580_raytracer_load_scene_json(rt580_raytracer* h, const char* scene) {
     if (!h || !scene) return RT_INVALID_ARG;
     try { return h->rt->LoadSceneJSON(scene); } catch (...) { return RT_FAILURE; }

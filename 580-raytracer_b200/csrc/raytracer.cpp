@@ -9,6 +9,7 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 namespace {
 
@@ -102,7 +103,53 @@ Raytracer::Raytracer(int width, int height) : mWidth(width), mHeight(height) {
 
 Raytracer::~Raytracer() {
     if (mCtx) rt580_destroy(mCtx);
+    for (rt580_context* c : mPeers) if (c) rt580_destroy(c);
     delete mScene;
+}
+
+// ---- binary mesh cache -------------------------------------------------------------------------------
+// file = header { magic "RT580MSH", version, json size, FNV-1a 64 of the json bytes, type, radius, triangle count } + triangles
+namespace {
+struct MeshCacheHeader { char magic[8]; uint32_t version; uint32_t type; uint64_t json_size; uint64_t json_hash; float radius; uint32_t pad; uint64_t n_tris; };
+uint64_t fnv1a64(const std::string& s) {
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+}  // namespace
+
+bool Raytracer::LoadMeshFromCache(const std::string& path, const std::string& jsonText, Mesh& mesh) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f.is_open()) return false;
+    MeshCacheHeader h;
+    if (!f.read(reinterpret_cast<char*>(&h), sizeof h)) return false;
+    if (memcmp(h.magic, "RT580MSH", 8) != 0 || h.version != 1u || h.json_size != (uint64_t)jsonText.size() || h.json_hash != fnv1a64(jsonText)) return false;
+    if (h.type > 1u || h.n_tris > (1ull << 32)) return false;
+    static_assert(sizeof(Triangle) == 18 * sizeof(float), "Triangle is 18 packed floats");
+    mesh.type = h.type == 0u ? Mesh::RT_POLYGON : Mesh::RT_SPHERE;
+    mesh.radius = h.radius;
+    mesh.triangles.resize((size_t)h.n_tris);
+    if (h.n_tris && !f.read(reinterpret_cast<char*>(mesh.triangles.data()), (std::streamsize)(h.n_tris * sizeof(Triangle)))) return false;
+    char extra;
+    return !f.read(&extra, 1);               // nothing may follow
+}
+
+void Raytracer::StoreMeshInCache(const std::string& path, const std::string& jsonText, const Mesh& mesh) {
+    const std::string tmp = path + ".tmp";
+    {
+        std::ofstream f(tmp, std::ios::binary);
+        if (!f.is_open()) return;            // a read-only cache directory is not an error
+        MeshCacheHeader h;
+        memset(&h, 0, sizeof h);
+        memcpy(h.magic, "RT580MSH", 8);
+        h.version = 1u; h.type = mesh.type == Mesh::RT_POLYGON ? 0u : 1u;
+        h.json_size = (uint64_t)jsonText.size(); h.json_hash = fnv1a64(jsonText);
+        h.radius = mesh.radius; h.n_tris = (uint64_t)mesh.triangles.size();
+        f.write(reinterpret_cast<const char*>(&h), sizeof h);
+        if (!mesh.triangles.empty()) f.write(reinterpret_cast<const char*>(mesh.triangles.data()), (std::streamsize)(mesh.triangles.size() * sizeof(Triangle)));
+        if (!f.good()) { f.close(); std::remove(tmp.c_str()); return; }
+    }
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
 }
 
 // cpp:528-586: S * (Rz * Ry * Rx) * T (Q11); trig through double libm of a float radian (Q27)
@@ -138,6 +185,16 @@ int Raytracer::LoadMesh(const std::string meshName) {
         std::cout << "File with name " << mAssetsPath << meshName << ".json" << " could not be found";
         return RT_FAILURE;
     }
+    std::string cachePath;
+    if (!mMeshCacheDir.empty()) {
+        cachePath = mMeshCacheDir + (mMeshCacheDir.back() == '/' ? "" : "/") + meshName + ".rt580mesh";
+        Mesh cached;
+        if (LoadMeshFromCache(cachePath, text, cached)) {        // the cache was written from exactly these JSON bytes
+            mScene->meshMap[meshName] = std::move(cached);
+            mMeshCacheHits++;
+            return RT_SUCCESS;
+        }
+    }
     jsonmin::ValuePtr doc = jsonmin::parse(text);                // throws like the reference's `file >> jsonData`
     const jsonmin::Value& data = doc->at("data");
     Mesh mesh;
@@ -165,6 +222,7 @@ int Raytracer::LoadMesh(const std::string meshName) {
         std::cout << "Mesh " << meshName << " has unsupported type " << shapeType << "\n";
         return RT_FAILURE;
     }
+    if (!cachePath.empty()) StoreMeshInCache(cachePath, text, mesh);
     mScene->meshMap[meshName] = std::move(mesh);
     return RT_SUCCESS;
 }
@@ -188,6 +246,7 @@ int Raytracer::LoadSceneJSON(const std::string scenePath) {
         delete mScene;
         mScene = new Scene();
         mSceneUploaded = false;
+        for (size_t k = 0; k < mPeerUploaded.size(); k++) mPeerUploaded[k] = 0;
         const jsonmin::Value& scene = doc->at("scene");
         if (scene.contains("shapes")) {
             const jsonmin::Value& shapes = scene.at("shapes");
@@ -309,6 +368,7 @@ int Raytracer::FlattenScene() {
         mLightF.insert(mLightF.end(), row, row + 10);
     }
     mSceneUploaded = false;
+    for (size_t k = 0; k < mPeerUploaded.size(); k++) mPeerUploaded[k] = 0;
     return RT_SUCCESS;
 }
 
@@ -398,10 +458,74 @@ int Raytracer::RenderToFrameBuffer() {
     rt580_render_params rp;
     if (GetRenderParams(&rp) != RT_SUCCESS) return RT_FAILURE;      // InitializeRenderer(), cpp:917
     if (EnsureContext() != RT_SUCCESS) return RT_FAILURE;
+    if (mGpus > 1) return RenderMultiGpu(rp);
     static_assert(sizeof(Pixel) == 6, "Pixel must be 3 packed shorts (h:373-374)");
     const int st = rt580_render(mCtx, &rp, reinterpret_cast<int16_t*>(mFrameBuffer.data()), &mStats);   // cpp:921-932
     if (st != RT580_SUCCESS) std::cerr << "Raytracer: " << rt580_last_error() << "\n";
     return st;
+}
+
+// The frame on several GPUs of this process: rows interleaved (row y on GPU y % n), the structure pass of every GPU first, then
+// the exchange - the hit-node counts per row, prefix-summed in scanline order, give every row its place in the reference's
+// single random stream (h:592) - then the occlusion + resolve passes, each GPU's rows into the frame buffer.
+int Raytracer::RenderMultiGpu(const rt580_render_params& rp) {
+    const int n = mGpus;
+    mPeers.resize((size_t)n - 1, nullptr);
+    mPeerUploaded.resize((size_t)n - 1, 0);
+    rt580_flat_scene fs;
+    if (GetFlatScene(&fs) != RT_SUCCESS) return RT_FAILURE;
+    std::vector<rt580_context*> ctx((size_t)n);
+    ctx[0] = mCtx;
+    std::vector<int> status((size_t)n, RT580_SUCCESS);
+    std::vector<std::string> errs((size_t)n);
+    auto on_all = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int g = 0; g < n; g++) th.emplace_back([&, g] { status[g] = fn(g); if (status[g] != RT580_SUCCESS) errs[g] = rt580_last_error(); });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < n; g++) if (status[g] != RT580_SUCCESS) { std::cerr << "Raytracer: GPU " << g << ": " << errs[g] << "\n"; return status[g]; }
+        return (int)RT580_SUCCESS;
+    };
+    int st = on_all([&](int g) -> int {
+        if (g == 0) return RT580_SUCCESS;
+        if (!mPeers[g - 1]) { const int s2 = rt580_create(mDevice + g, &mPeers[g - 1]); if (s2 != RT580_SUCCESS) return s2; }
+        ctx[g] = mPeers[g - 1];
+        if (!mPeerUploaded[g - 1]) { const int s2 = rt580_upload_scene(ctx[g], &fs); if (s2 != RT580_SUCCESS) return s2; mPeerUploaded[g - 1] = 1; }
+        return RT580_SUCCESS;
+    });
+    if (st != RT580_SUCCESS) return st;
+    std::vector<rt580_render_params> ps((size_t)n, rp);
+    std::vector<std::vector<uint64_t>> counts((size_t)n);
+    for (int g = 0; g < n; g++) {
+        const int rows = g < mHeight ? (mHeight - g + n - 1) / n : 0;
+        ps[g].row_first = rows ? g : 0; ps[g].row_step = n; ps[g].n_rows = rows ? rows : -1;
+        counts[g].assign((size_t)rows + 1, 0);
+    }
+    st = on_all([&](int g) { return rt580_render_begin(ctx[g], &ps[g], counts[g].data()); });
+    if (st != RT580_SUCCESS) return st;
+    uint64_t run = 0;                                    // exclusive prefix over the rows in scanline order (cpp:921-922)
+    for (int y = 0; y < mHeight; y++) { uint64_t& c = counts[y % n][y / n]; const uint64_t v = c; c = run; run += v; }
+    std::vector<Rt580HostVector<int16_t>> bands((size_t)n);
+    std::vector<rt580_stats> stats((size_t)n);
+    for (int g = 0; g < n; g++) bands[g].resize((size_t)(ps[g].n_rows > 0 ? ps[g].n_rows : 0) * mWidth * 3 + 1);
+    st = on_all([&](int g) { return rt580_render_finish(ctx[g], counts[g].data(), bands[g].data(), 0, &stats[g]); });
+    if (st != RT580_SUCCESS) return st;
+    int16_t* fb = reinterpret_cast<int16_t*>(mFrameBuffer.data());
+    for (int y = 0; y < mHeight; y++)
+        memcpy(fb + (size_t)y * mWidth * 3, bands[y % n].data() + (size_t)(y / n) * mWidth * 3, (size_t)mWidth * 6);
+    mStats = stats[0];
+    for (int g = 1; g < n; g++) {                        // rays add up, times are the slowest GPU's
+        mStats.rays_primary += stats[g].rays_primary; mStats.rays_secondary += stats[g].rays_secondary;
+        mStats.rays_shadow += stats[g].rays_shadow; mStats.rays_ao += stats[g].rays_ao;
+        mStats.hit_nodes += stats[g].hit_nodes; mStats.ao_calls += stats[g].ao_calls;
+        mStats.far_scans += stats[g].far_scans; mStats.linear_fallbacks += stats[g].linear_fallbacks;
+        mStats.ao_rays_traversed += stats[g].ao_rays_traversed; mStats.shadow_rays_traversed += stats[g].shadow_rays_traversed;
+        mStats.kernel_launches += stats[g].kernel_launches;
+        if (stats[g].ms_total > mStats.ms_total) {
+            mStats.ms_total = stats[g].ms_total; mStats.ms_structure = stats[g].ms_structure; mStats.ms_order = stats[g].ms_order;
+            mStats.ms_ao = stats[g].ms_ao; mStats.ms_resolve = stats[g].ms_resolve; mStats.ms_ao_kernel = stats[g].ms_ao_kernel;
+        }
+    }
+    return RT_SUCCESS;
 }
 
 // cpp:916-935
@@ -411,7 +535,7 @@ int Raytracer::Render(const std::string outputName) {
     // cpp:934 FlushFrameBufferToPPM: the gamma table is applied on the device and the PPM body comes back
     // as 3 bytes per pixel (rt580_frame_rgb8); the host restatement below is the fallback and the
     // public method (it writes whatever the frame buffer holds, like the reference's)
-    if (mCtx && mWidth > 0 && mHeight > 0) {
+    if (mCtx && mGpus == 1 && mWidth > 0 && mHeight > 0) {
         unsigned char lut[256];
         for (int c = 0; c < 256; c++) lut[c] = static_cast<unsigned char>(std::pow(c / 255.0f, 1.0f / 2.2f) * 255.0f);   // cpp:816-818
         Rt580HostVector<unsigned char> body((size_t)mWidth * mHeight * 3);

@@ -90,6 +90,15 @@ public:
     void SetDevice(int device) { mDevice = device; }
     void SetFarField(int mode) { mFarField = mode; }
     void SetQuiet(bool q) { mQuiet = q; }                              // silence the loader's cout chatter (cpp:592, 772)
+    // Rows of the frame interleaved over the first n GPUs of this process (row y on GPU y % n), one context each; the per-row
+    // hit-node counts that position every row in the reference's single random stream (h:592) are exchanged on the host.
+    void SetGpus(int n) { mGpus = n < 1 ? 1 : n; }
+    // Binary cache of parsed meshes: "<dir>/<mesh>.rt580mesh" next to / instead of re-parsing "<mesh>.json"
+    // (teapot.json: 472 KB of text for 1024 triangles).  Keyed by the JSON's size and a hash of its bytes: the JSON stays the
+    // source of truth, a stale or damaged cache file is ignored and rewritten.  Empty = no cache (the default).
+    void SetMeshCacheDir(const std::string& dir) { mMeshCacheDir = dir; }
+    int  MeshCacheHits() const { return mMeshCacheHits; }
+    rt580_context* Context() const { return mCtx; }
     int  RenderToFrameBuffer();                                        // Render without the PPM
     const Pixel* FrameBuffer() const { return mFrameBuffer.data(); }
     int Width() const { return mWidth; }
@@ -103,6 +112,9 @@ private:
     int InitializeRenderer();                                          // h:604
     int FlattenScene();
     int EnsureContext();
+    int RenderMultiGpu(const rt580_render_params& rp);
+    bool LoadMeshFromCache(const std::string& path, const std::string& jsonText, Mesh& mesh);
+    void StoreMeshInCache(const std::string& path, const std::string& jsonText, const Mesh& mesh);
 
     std::string mAssetsPath = "Assets/";
     int mWidth, mHeight;
@@ -124,6 +136,11 @@ private:
     int64_t mNumPrims = 0;
 
     rt580_context* mCtx = nullptr;
+    std::vector<rt580_context*> mPeers;    // contexts on GPUs 1 .. mGpus-1 (SetGpus)
+    std::vector<char> mPeerUploaded;      // char, not bool: written from one thread per GPU
+    int mGpus = 1;
+    std::string mMeshCacheDir;
+    int mMeshCacheHits = 0;
     bool mSceneUploaded = false;
     rt580_stats mStats{};
 };

@@ -528,9 +528,7 @@ __device__ __forceinline__ void fg_exact(const DeviceScene& sc, unsigned long lo
                         ANY ? 0x7fffffff : (int)(unsigned)(key & 0xffffffffull), t, prim)) {
         if (ANY) s_found[j] = 1;
         else atomicMin(s_key + j, slow_key(t, prim));
-        if (sc.diag) atomicAdd(sc.diag + 25, 1u);
     }
-    if (sc.diag) atomicAdd(sc.diag + 24, 1u);
 }
 
 // One warp takes FG_G consecutive rays of the sorted order; the rays of one cell among them form a segment that runs over the
@@ -3661,7 +3659,6 @@ static int render_finish_impl(rt580_context* c, const uint64_t* row_ao_base, boo
         fprintf(stderr, "[rt580] rays from outside the scene, far regime: any hit %u (%.1f cells, %.0f exact tests each), closest hit %u (%.1f cells, %.0f exact tests each)\n",
                 cnt[16], cnt[16] ? (double)cnt[18] / cnt[16] : 0.0, cnt[16] ? (double)cnt[19] / cnt[16] : 0.0,
                 cnt[20], cnt[20] ? (double)cnt[22] / cnt[20] : 0.0, cnt[20] ? (double)cnt[23] / cnt[20] : 0.0);
-    if (getenv("RT580_DEBUG_TIMING")) fprintf(stderr, "[rt580] k_fg_scan exact tests %u accepted %u\n", cnt[28], cnt[29]);
     if (getenv("RT580_DEBUG_TIMING"))
         fprintf(stderr, "[rt580] rays from outside the scene, near regime: any hit %u rays with > 64 exact tests (%.0f each), closest hit %u (%.0f each)\n",
                 cnt[24], cnt[24] ? 64.0 * cnt[25] / cnt[24] : 0.0, cnt[26], cnt[26] ? 64.0 * cnt[27] / cnt[26] : 0.0);

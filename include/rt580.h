@@ -269,6 +269,12 @@ int  rt580_raytracer_set_assets_path(rt580_raytracer* rt, const char* dir);  /* 
 int  rt580_raytracer_set_options(rt580_raytracer* rt, int depth, int ao_spp, int rng_mode, int traversal,
                                  int device, int farfield);                  /* h:563, cpp:317        */
 int  rt580_raytracer_set_quiet(rt580_raytracer* rt, int quiet);              /* mute cpp:592 / cpp:772 prints */
+/* rows of the frame interleaved over GPUs device .. device + n_gpus - 1 of this process: the frame is bit-identical */
+int  rt580_raytracer_set_gpus(rt580_raytracer* rt, int n_gpus);
+/* binary cache of parsed meshes, "<dir>/<mesh>.rt580mesh", validated against the JSON's size and hash;
+ * NULL or "" = off.  The loaded meshes are bit-identical with or without it (cpp:568-643 stays the source of truth). */
+int  rt580_raytracer_set_mesh_cache(rt580_raytracer* rt, const char* dir);
+int  rt580_raytracer_mesh_cache_hits(rt580_raytracer* rt);
 int  rt580_raytracer_load_scene_json(rt580_raytracer* rt, const char* scene);/* h:572 LoadSceneJSON   */
 int  rt580_raytracer_render(rt580_raytracer* rt, const char* output_ppm);    /* h:586 Render          */
 int  rt580_raytracer_flush_ppm(rt580_raytracer* rt, const char* output_ppm); /* h:573                 */

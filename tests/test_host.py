@@ -142,3 +142,87 @@ def test_row_partition_helpers(pkg):
     per_row[1::2] = counts[1]
     excl = np.concatenate([[0], np.cumsum(per_row)[:-1]]).astype(np.uint64)
     assert np.array_equal(bases[0], excl[0::2]) and np.array_equal(bases[1], excl[1::2])
+
+
+def test_mesh_cache_is_bit_identical_and_self_healing(pkg, tmp_path):
+    """the binary mesh cache next to LoadMesh (cpp:568-643).  The flattened scene with the cache, cold and warm, is
+    the scene without it, byte for byte; a cache whose JSON changed, or that is truncated / corrupted, is ignored and rewritten;
+    a cache directory that cannot be written is not an error."""
+    scene = "simpleScene.json"                                       # teapot + spheres: polygon and sphere meshes
+
+    def load(cache_dir):
+        rt = pkg.Raytracer(16, 16)
+        rt.SetAssetsPath(ASSETS)
+        if cache_dir is not None:
+            rt.SetMeshCacheDir(cache_dir)
+        assert rt.LoadSceneJSON(scene) == pkg.RT_SUCCESS
+        arr = pkg.flat_scene_arrays(rt.flat_scene())
+        return {k: np.array(v, copy=True) for k, v in arr.items() if isinstance(v, np.ndarray)}, rt.MeshCacheHits()
+
+    def same(a, b):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k].tobytes() == b[k].tobytes(), k
+
+    plain, hits = load(None)
+    assert hits == 0
+    cdir = str(tmp_path / "cache")
+    os.makedirs(cdir)
+    cold, hits = load(cdir)
+    assert hits == 0
+    files = sorted(os.listdir(cdir))
+    assert files and all(f.endswith(".rt580mesh") for f in files)
+    same(plain, cold)
+    warm, hits = load(cdir)
+    assert hits == len(files)
+    same(plain, warm)
+    # truncated and bit-flipped cache files: fall back to the JSON, rewrite
+    victim = os.path.join(cdir, files[0])
+    good = open(victim, "rb").read()
+    open(victim, "wb").write(good[:len(good) // 2])
+    again, hits = load(cdir)
+    assert hits == len(files) - 1
+    same(plain, again)
+    assert open(victim, "rb").read() == good
+    open(victim, "wb").write(good[:16] + bytes([good[16] ^ 1]) + good[17:])    # the recorded JSON size no longer matches
+    again, hits = load(cdir)
+    assert hits == len(files) - 1
+    same(plain, again)
+    # the JSON changes (other assets directory, same mesh name, different bytes): the old cache entry must not be used
+    import shutil
+    adir = tmp_path / "assets"
+    shutil.copytree(ASSETS, str(adir))
+    cam = {"from": [0, 0, 5], "to": [0, 0, 0], "bounds": [0.1, 10, 1, -1, 1, -1], "resolution": [8, 8]}
+    sc = {"scene": {"shapes": [{"id": "s", "geometry": "1sphere", "material": {"Cs": [1, 1, 1], "Ka": 1, "Kd": 1, "Ks": 0, "Kt": 0, "n": 1},
+                                "transforms": []}], "lights": [], "camera": cam}}
+    (adir / "one.json").write_text(json.dumps(sc))
+
+    def radius():
+        rt = pkg.Raytracer(8, 8)
+        rt.SetAssetsPath(str(adir))
+        rt.SetMeshCacheDir(cdir)
+        assert rt.LoadSceneJSON("one.json") == pkg.RT_SUCCESS
+        return float(pkg.flat_scene_arrays(rt.flat_scene())["sph_center_r"][0][3]), rt.MeshCacheHits()
+
+    r0, h0 = radius()
+    r1, h1 = radius()
+    assert (h0, h1) == (0, 1) and r0 == r1
+    text = (adir / "1sphere.json").read_text()
+    (adir / "1sphere.json").write_text(text + "\n")                          # same mesh, other bytes: the key changes
+    r2, h2 = radius()
+    assert h2 == 0 and r2 == r0
+    # a directory that does not exist: loads fine, writes nothing
+    nowhere, hits = load(str(tmp_path / "no" / "such" / "dir"))
+    assert hits == 0
+    same(plain, nowhere)
+
+
+def test_far_field_bound_holds_against_float_arithmetic():
+    """fargrid.cuh's necessary condition for a far-field accept, against the reference's float evaluation of cpp:392
+    (tools/far_bound_check.py, 4e5 adversarial samples per distance factor here; 2.4e7 in DESIGN.md 2.1)."""
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "far_bound_check.py"), "400000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "accepts below the bound: 0" in r.stdout
