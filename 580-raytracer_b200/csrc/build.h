@@ -87,6 +87,7 @@ struct FgBuildInput {
     float4* fgA; float2* fgB; uint32_t* wide; uint32_t* sph;   // [n_all] each (scene arena)
     unsigned int* counters;                         // [4] scratch
     DBuf<unsigned int>* counts; DBuf<unsigned long long>* start; DBuf<unsigned long long>* bsum; DBuf<uint32_t>* entries;
+    DBuf<unsigned int>* cell_tmin;                  // [6 K K] smallest T per cell (float bits)
 };
 struct FgBuildOutput {
     int K; int n_wide; int n_sph; unsigned long long n_entries; float t_min; float diag;

@@ -86,6 +86,7 @@ struct DeviceScene {
     const float2* fg_B;                     // [n_all] (T: lower bound of the ray parameter of a far-field hit, < 0: none; unused)
     const unsigned long long* fg_start;     // [6 K K + 1]
     const uint32_t* fg_entries;             // (k6 << 26) | index into prims: T for the cell = T * 2^(k6/4)
+    const unsigned int* fg_cell_tmin;       // [6 K K] float bits: the smallest T among the cell's entries (all ones: empty cell)
     const uint32_t* fg_wide;                // [fg_n_wide] triangles whose far field begins too near for a direction index:
     int32_t fg_n_wide;                      //             every ray that leaves the scene filters them
     int32_t fg_K;

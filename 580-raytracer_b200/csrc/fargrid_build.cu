@@ -67,7 +67,8 @@ __device__ __forceinline__ float fg_cell_T(const FgTri& t, V3 c, const FgParams&
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 k_fg_raster(const PrimRec* __restrict__ prims, const float2* __restrict__ fgB, int n_all, FgParams fp,
-            unsigned int* __restrict__ counts, const unsigned long long* __restrict__ start, uint32_t* __restrict__ entries)
+            unsigned int* __restrict__ counts, const unsigned long long* __restrict__ start, uint32_t* __restrict__ entries,
+            unsigned int* __restrict__ cell_tmin)
 {
     const int i = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -136,6 +137,7 @@ k_fg_raster(const PrimRec* __restrict__ prims, const float2* __restrict__ fgB, i
                     k6 = max(0, min(63, k6));
                     const unsigned pos = atomicAdd(counts + cell, 1u);
                     entries[start[cell] + pos] = ((unsigned)k6 << FG_ID_BITS) | (unsigned)i;
+                    atomicMin(cell_tmin + cell, __float_as_uint(fg_entry_T(t.Ti, (unsigned)k6)));    // (positive floats order like their bits)
                 }
             }
         }
@@ -316,7 +318,7 @@ bool fg_build(const FgBuildInput& in, FgBuildOutput* out, cudaStream_t stream, c
     CK(in.bsum->ensure((size_t)n_blocks + 2, 0, stream));
     CK(cudaMemsetAsync(in.counts->p, 0, sizeof(unsigned int) * (n_cells + 1), stream));
     const unsigned grid = (unsigned)(((size_t)n * 32 + 255) / 256);
-    k_fg_raster<false><<<grid, 256, 0, stream>>>(in.prims, in.fgB, n, fp, in.counts->p, nullptr, nullptr);
+    k_fg_raster<false><<<grid, 256, 0, stream>>>(in.prims, in.fgB, n, fp, in.counts->p, nullptr, nullptr, nullptr);
     k_fg_scan_reduce<<<n_blocks, 256, 0, stream>>>(in.counts->p, n_cells, in.bsum->p);
     k_fg_scan_top<<<1, 1024, 0, stream>>>(in.bsum->p, n_blocks, in.start->p + n_cells);
     k_fg_scan_apply<<<n_blocks, 256, 0, stream>>>(in.counts->p, n_cells, in.bsum->p, in.start->p);
@@ -326,7 +328,9 @@ bool fg_build(const FgBuildInput& in, FgBuildOutput* out, cudaStream_t stream, c
     CK(cudaGetLastError());
     CK(in.entries->ensure((size_t)total + 1, 0, stream));
     CK(cudaMemsetAsync(in.counts->p, 0, sizeof(unsigned int) * (n_cells + 1), stream));
-    k_fg_raster<true><<<grid, 256, 0, stream>>>(in.prims, in.fgB, n, fp, in.counts->p, in.start->p, in.entries->p);
+    CK(in.cell_tmin->ensure(n_cells + 1, 0, stream));
+    CK(cudaMemsetAsync(in.cell_tmin->p, 0xff, sizeof(unsigned int) * (n_cells + 1), stream));
+    k_fg_raster<true><<<grid, 256, 0, stream>>>(in.prims, in.fgB, n, fp, in.counts->p, in.start->p, in.entries->p, in.cell_tmin->p);
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
     out->K = in.K; out->n_entries = total;

@@ -145,12 +145,12 @@ struct rt580_context {
     int32_t* d_light_type = nullptr; float* d_light_f = nullptr;
     DevArena scene_arena, build_arena;   // scene buffers / upload + build temporaries (grow-only)
     // far-field direction grid (fargrid.cuh): lists of the scene, and the per-flush sort of the deferred rays by direction cell
-    DBuf<unsigned int> fg_counts; DBuf<unsigned long long> fg_start, fg_bsum; DBuf<uint32_t> fg_entries;
+    DBuf<unsigned int> fg_counts; DBuf<unsigned long long> fg_start, fg_bsum; DBuf<uint32_t> fg_entries; DBuf<unsigned int> fg_cell_tmin;
     FgBuildInput fg_in{}; bool fg_pending = false;   // the lists are built when a frame first needs them (far_grid_ensure)
     int fg_K_env = -1;                   // RT580_FAR_GRID: -1 default (by triangle count), 0 off, else cells per cube-face edge
     unsigned long long fg_n_entries = 0; float fg_build_ms = 0.f;
-    DBuf<unsigned int> fgq_hist, fgq_start, fgq_cellof, fgq_rank, fgq_order, fgq_lin;
-    DBuf<struct ArcItem> arc_items;
+    DBuf<unsigned int> fgq_hist, fgq_start, fgq_cellof, fgq_rank, fgq_order, fgq_lin, fgq_first;
+    DBuf<struct ArcItem> arc_items; DBuf<unsigned char> arc_pre;
     bool have_scene = false;
     float build_ms = 0.f; unsigned bvh_depth = 0; float pad_extent = 0.f;
     // frame
@@ -487,19 +487,26 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
 // children of far-field hits) are left to k_slow through an index list.
 __global__ void __launch_bounds__(256)
 k_fg_bin(const SlowRay* __restrict__ rays, unsigned n, int K, unsigned int* __restrict__ hist, unsigned int* __restrict__ cellof,
-         unsigned int* __restrict__ rank, unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count, int bin_lin)
+         unsigned int* __restrict__ rank, unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count, int bin_lin,
+         unsigned int* __restrict__ first_idx, unsigned int* __restrict__ first_count)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const bool lin = (__ldg(&rays[e].c).x & 1) != 0;
     // a ray from outside the scene: closest hit -> its own kernels (k_fg_arc walks its cells in order of t); any hit (bin_lin) ->
-    // first the cell of its direction like everybody else (out there, far along the ray, almost every entry accepts it)
+    // first the cell of its direction (k_fg_lin_first: out there, far along the ray, almost every entry of that cell accepts it)
     if (lin && !bin_lin) { lin_idx[atomicAdd(lin_count, 1u)] = e; cellof[e] = 0xffffffffu; return; }
     const float4 d = __ldg(&rays[e].d);
     const int cell = fg_cell_of_dir(mk(d.x, d.y, d.z), K);
     if (cell < 0) {                                              // zero / NaN direction: no triangle accepts it (cpp:371)
         if (lin) lin_idx[atomicAdd(lin_count, 1u)] = e;          // (spheres may: k_lin_near)
         cellof[e] = 0xffffffffu;
+        return;
+    }
+    if (lin) {                                                   // not part of the sorted order: k_fg_scan never sees it
+        first_idx[atomicAdd(first_count, 1u)] = e;
+        cellof[e] = (unsigned)cell;
+        if (hist) rank[e] = 0xffffffffu;
         return;
     }
     if (hist) rank[e] = atomicAdd(hist + cell, 1u);
@@ -512,7 +519,7 @@ k_fg_order(unsigned n, const unsigned int* __restrict__ cellof, const unsigned i
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const unsigned cell = cellof[e];
-    if (cell != 0xffffffffu) order[cstart[cell] + rank[e]] = e;
+    if (cell != 0xffffffffu && rank[e] != 0xffffffffu) order[cstart[cell] + rank[e]] = e;
 }
 
 template <bool ANY>
@@ -541,7 +548,6 @@ struct FgWarp {
     unsigned long long key[FG_G];
     int found[FG_G];
     unsigned cell[FG_G], e[FG_G];
-    unsigned lin;                           // bit j: ray j starts outside the scene
     unsigned long long q[64];
 };
 
@@ -569,9 +575,6 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned live = ((1u << j1) - 1u) & ~((1u << j0) - 1u);
-    const unsigned linm = ANY ? sh.lin : 0u;
-    if (!has_k6) live &= ~linm;       // the wide list: rays from outside the scene meet it in k_fg_arc (with the filter that holds out there)
-    if (!live) return;
     unsigned q_len = 0;
     for (unsigned long long base = 0; base < len; base += 32 * FG_U4) {
         // this lane's FG_U4 entries (independent gathers in flight together: the loop is bound by their latency):
@@ -606,35 +609,14 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
                 const float4 dj = sh.D[j];
                 const float nd = __fmaf_rn(fr.x, dj.x, __fmaf_rn(fr.y, dj.y, fr.z * dj.z));
                 const float and_ = fabsf(nd);
-                bool pass;
-                if (ANY && ((linm >> j) & 1u)) {
-                    // From outside the scene the bounds of the list do not apply (they assume an in-scene origin); far along
-                    // this ray, though, almost every triangle of the cell of its direction accepts it.  So: every entry whose
-                    // plane lies ahead within the limit gets the exact test; a ray that finds no acceptor here goes on to
-                    // k_fg_arc / k_lin_near, which are complete.
-                    pass = fr.w >= 0.f && and_ > FG_ND_MIN;
-                    if (pass) {
-                        const float4 oj = sh.O[j];
-                        const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
-                        const float dl = 1e-6f * (fabsf(oj.x) + fabsf(oj.y) + fabsf(oj.z) + sc.extent);
-                        const float ano = fabsf(no);
-                        pass = !(ano > dl && ((no < 0.f) == (nd < 0.f))) && fmaxf(ano - dl, 0.f) <= oj.w * (and_ + FG_ND_SLACK);   // (o.w: tmax)
-                    }
-                    // About every other such entry accepts: the first four candidates of a slab are enough (four per ray fill one
-                    // batch of exact tests for the eight rays of a segment).  The others are dropped, which is why k_fg_arc starts
-                    // over with the complete cell for the few rays that leave here unanswered.
-                    const unsigned m0 = __ballot_sync(0xffffffffu, pass);
-                    pass = pass && __popc(m0 & lt_mask) < 4;
-                } else {
-                    pass = and_ <= fr.w && and_ > FG_ND_MIN;                    // stage 1: the band of the cell
-                    if (!__any_sync(0xffffffffu, pass)) continue;
-                    if (pass) {
-                        // stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
-                        const float4 oj = sh.O[j];
-                        const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
-                        const float x = (and_ - FG_ND_SLACK) * eT * 0.999998f - dno;
-                        pass = fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
-                    }
+                bool pass = and_ <= fr.w && and_ > FG_ND_MIN;                   // stage 1: the band of the cell
+                if (!__any_sync(0xffffffffu, pass)) continue;
+                if (pass) {
+                    // stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
+                    const float4 oj = sh.O[j];
+                    const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
+                    const float x = (and_ - FG_ND_SLACK) * eT * 0.999998f - dno;
+                    pass = fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
                 }
                 const unsigned mask = __ballot_sync(0xffffffffu, pass);
                 if (mask == 0u) continue;
@@ -642,7 +624,6 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
                 q_len += (unsigned)__popc(mask);
                 fg_flush<ANY>(sc, sh, q_len, false);
             }
-            if (ANY && linm) fg_flush<ANY>(sc, sh, q_len, true);      // (so that the look at `found` above sees this slab's acceptors)
         }
         if (ANY && !live) break;
     }
@@ -671,12 +652,9 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
         sh.O[lane] = o; sh.D[lane] = d;
         sh.key[lane] = ((unsigned long long)__float_as_uint(o.w) << 32) | (unsigned)__float_as_int(d.w);
         sh.found[lane] = 0;
-        sh.cell[lane] = cellof[e];
-        my_lin = ANY && (__ldg(&rays[e].c).x & 1) != 0;
-    }
-    {
-        const unsigned m = __ballot_sync(0xffffffffu, my_lin);
-        if (lane == 0) sh.lin = m;
+        // (unsorted flush, any hit: the rays from outside the scene are k_fg_lin_first's)
+        my_lin = ANY && !order && (__ldg(&rays[e].c).x & 1) != 0;
+        sh.cell[lane] = my_lin ? 0xffffffffu : cellof[e];
     }
     __syncwarp();
     // the float evaluation of N.O + D here vs in the reference (cpp:377, 381): both within 28 u E of the true value
@@ -698,12 +676,37 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
         if (sh.found[lane] == -1) { }                                     // no cell: not this kernel's ray
         else if (ANY) {
             if (sh.found[lane]) res[e].found = 1;
-            else if (my_lin) lin_idx[atomicAdd(lin_count, 1u)] = e;       // no acceptor in the cell of its direction: the complete search
         } else {
             const unsigned long long k = sh.key[lane];
             if (k < res[e].key) res[e].key = k;
         }
     }
+}
+
+// Any-hit rays from outside the scene, first attempt: far along such a ray almost every triangle listed in the cell of its
+// direction accepts the plane hit (the bounds of the list assume an in-scene origin, so they are not used: every entry gets the
+// reference's test, whose plane half rejects cheaply).  One thread per ray walks the list of that one cell until the first
+// acceptor - two or three entries on average.  A ray that finds none goes on to k_fg_arc / k_lin_near, which are complete.
+__global__ void __launch_bounds__(128)
+k_fg_lin_first(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ first_idx,
+               const unsigned int* __restrict__ first_count, const unsigned int* __restrict__ cellof,
+               unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= __ldg(first_count)) return;
+    const unsigned e = first_idx[i];
+    const float4 o = __ldg(&rays[e].o), d = __ldg(&rays[e].d);
+    const V3 O = mk(o.x, o.y, o.z), D = mk(d.x, d.y, d.z);
+    const unsigned cell = cellof[e];
+    const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
+    bool found = false;
+    for (unsigned long long k = b; k < en && !found; k++) {
+        const unsigned id = __ldg(sc.fg_entries + k) & FG_ID_MASK;
+        float t; int prim;
+        found = prim_test<true>(sc.prims + id, O, D, o.w, 0x7fffffff, t, prim);
+    }
+    if (found) res[e].found = 1;
+    else lin_idx[atomicAdd(lin_count, 1u)] = e;
 }
 
 // ---- rays that start outside the scene (children of far-field hits, 10^5..10^8 units away) ------------------------
@@ -719,7 +722,7 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
 //                             primitives the tree and the grid do not hold (large ones, slivers), and all
 //                             spheres when the ray is aimed at the scene (cpp:426's discriminant is noise out there).
 #define ARC_WARPS 4
-#define ARC_MAX_CELLS 48u
+#define ARC_MAX_CELLS 512u
 #define ARC_INLINE_CELLS 6      // cells a ray's own warp works through; the rest of a long arc becomes work items (k_fg_arc_items)
 struct ArcItem { unsigned e; int cell; float rmax; };
 
@@ -775,6 +778,9 @@ struct ArcRay {
         }
     }
     // the entries of one cell that can accept at |P| <= rmax
+    __device__ __forceinline__ bool cell_can_accept(int cell, float rmax) const {      // some entry of the cell has T <= rmax
+        return __uint_as_float(__ldg(sc.fg_cell_tmin + cell)) <= rmax;                    // (empty cell: NaN)
+    }
     __device__ __forceinline__ void cell(int cell, float rmax) {
         const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
         n_cells++;
@@ -834,10 +840,118 @@ struct ArcRay {
     }
 };
 
+// The walk of one ray over the cells of the direction grid, in order of t.  It runs in double: far out, a float t no longer
+// resolves a cell (ulp(t) / |P| exceeds the cells' slack when the ray has come a long way and passes near the scene); the cells
+// it names are a superset of those the reference's float P visits.
+struct ArcWalk {
+    double Ax, Ay, Az, dx, dy, dz;     // P(t) = A + t d relative to the grid's centre
+    double hole_lo, hole_hi;           // where |P(t)| < 0.9 T_min no far-field acceptor exists
+    double t_end, t;
+    // after leaving a cell through a wall, the next cell is looked up a hair BEYOND that wall (relative nudge along one axis), so
+    // a path that runs along a wall cannot bounce between the lookup and the wall arithmetic.  0: none, 1 + 2 axis + (negative)
+    int nudge;
+    unsigned n_it;
+    int K;
+
+    __device__ __forceinline__ void init(const DeviceScene& sc, V3 O, V3 d, double aa, double ad, double dd, double t_end_) {
+        Ax = (double)O.x - sc.fg_center[0]; Ay = (double)O.y - sc.fg_center[1]; Az = (double)O.z - sc.fg_center[2];
+        dx = d.x; dy = d.y; dz = d.z;
+        K = sc.fg_K;
+        const double dinf = (double)__int_as_float(0x7f800000);
+        hole_lo = dinf; hole_hi = -dinf;
+        const double Tm = 0.9 * (double)sc.fg_tmin;
+        const double disc = ad * ad - dd * (aa - Tm * Tm);
+        if (disc > 0.0 && dd > 0.0 && Tm < 1e18) { const double sq = sqrt(disc); hole_lo = (-ad - sq) / dd; hole_hi = (-ad + sq) / dd; }
+        t_end = t_end_; t = 0.0; nudge = 0; n_it = 0;
+    }
+    // the next cell of the arc, the parameter at which the ray enters it and the largest |P| inside it; false: the arc is over
+    __device__ __forceinline__ bool next(int& cell_out, double& t_in, float& rmax) {
+        const float inf = __int_as_float(0x7f800000);
+        const double dinf = (double)inf;
+        const double h = 2.0 / (double)K;
+        while (n_it < 200000u) {
+            n_it++;
+            if (!(t < t_end)) return false;
+            if (t > hole_lo && t < hole_hi) { t = hole_hi; nudge = 0; continue; }
+            const double Px = Ax + dx * t, Py = Ay + dy * t, Pz = Az + dz * t;
+            const double p2 = Px * Px + Py * Py + Pz * Pz;
+            const double plen = sqrt(p2);
+            const double nv = nudge ? (((nudge - 1) & 1) ? 1e-9 : -1e-9) * plen : 0.0;
+            const int nax = nudge ? ((nudge - 1) >> 1) : -1;
+            const int cell = fg_cell_of_point_d(Px + (nax == 0 ? nv : 0.0), Py + (nax == 1 ? nv : 0.0), Pz + (nax == 2 ? nv : 0.0), K);
+            const double adv = 3e-7 * plen + 1e-30;
+            if (cell < 0) { t = t + adv + 1e-9 * fmax(1.0, t); continue; }
+            const int face = cell / (K * K), iv = (cell / K) % K, iu = cell % K;
+            const int ax = face >> 1;
+            const double sg = (face & 1) ? -1.0 : 1.0;
+            const double Aw = (ax == 0 ? Ax : (ax == 1 ? Ay : Az)) * sg, dw = (ax == 0 ? dx : (ax == 1 ? dy : dz)) * sg;
+            const double Au = (ax == 0 ? Ay : (ax == 1 ? Az : Ax)), du = (ax == 0 ? dy : (ax == 1 ? dz : dx));
+            const double Av = (ax == 0 ? Az : (ax == 1 ? Ax : Ay)), dv = (ax == 0 ? dz : (ax == 1 ? dx : dy));
+            // where does P(t) leave the cell: f(t) = P_u - b P_w changes sign at the walls b = u0 (f >= 0 inside), u1 (f <= 0 inside),
+            // likewise v.  Only walls the ray moves OUT through count; one it is already beyond (rounding) means "leave now".
+            double t_exit = dinf;
+            int k_exit = -1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool upper = (k & 1) != 0;
+                const double b = ((double)((k < 2 ? iu : iv) + (upper ? 1 : 0))) * h - 1.0;
+                const double f0 = (k < 2 ? Au : Av) - b * Aw, f1 = (k < 2 ? du : dv) - b * dw;
+                if (upper ? (f1 > 0.0) : (f1 < 0.0)) { const double tc = fmax(-f0 / f1, t); if (tc < t_exit) { t_exit = tc; k_exit = k; } }
+            }
+            // the nudge for the next lookup: across wall k_exit, i.e. along axis u (k < 2) or v, up (odd k) or down
+            nudge = 0;
+            if (k_exit >= 0) nudge = 1 + 2 * (k_exit < 2 ? (ax + 1) % 3 : (ax + 2) % 3) + ((k_exit & 1) ? 1 : 0);
+            double t_out = fmin(t_exit, t_end);
+            if (t < hole_lo) t_out = fmin(t_out, hole_lo);
+            rmax = inf;
+            if (t_out < 1e300) {
+                const double Qx = Ax + dx * t_out, Qy = Ay + dy * t_out, Qz = Az + dz * t_out;
+                const double r = sqrt(fmax(p2, Qx * Qx + Qy * Qy + Qz * Qz)) * 1.00001 + 1.0;      // |P(t)| is convex in t
+                rmax = r < 3.0e38 ? (float)r * 1.000001f : inf;
+            }
+            cell_out = cell; t_in = t;
+            t = (t_out < 1e300) ? t_out + adv : dinf;                        // (inf: the next call ends the arc)
+            return true;
+        }
+        return false;
+    }
+};
+
+// The first cells of every arc, one THREAD per ray (the walk is serial arithmetic: a warp per ray would run it 32 times over).
+// k_fg_arc takes the cells from here and goes on walking by itself only when these did not settle the ray.
+#define ARC_PRE 4
+struct ArcPre { double t; double t_in[ARC_PRE]; int cell[ARC_PRE]; float rmax[ARC_PRE]; int n; int nudge; unsigned n_it; int done; };
+
+template <bool ANY>
+__global__ void __launch_bounds__(128)
+k_fg_arc_pre(DeviceScene sc, const SlowRay* __restrict__ rays, const unsigned int* __restrict__ lin_idx, unsigned n_lin, ArcPre* __restrict__ pre)
+{
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_lin) return;
+    const unsigned e = __ldg(lin_idx + w);
+    const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
+    ArcPre out;
+    out.n = 0; out.done = 1; out.t = 0.0; out.nudge = 0; out.n_it = 0;
+    if (!(rd.x == 0.0f && rd.y == 0.0f && rd.z == 0.0f)) {
+        ArcRay<ANY> R(sc, nullptr, ro, rd);
+        ArcWalk W;
+        W.init(sc, R.O, R.d, R.aa, R.ad, R.dd, ANY ? (double)R.tlim : (double)__int_as_float(0x7f800000));
+        out.done = 0;
+        while (out.n < ARC_PRE) {
+            int cell; double t_in; float rmax;
+            if (!W.next(cell, t_in, rmax)) { out.done = 1; break; }
+            if (!R.cell_can_accept(cell, rmax)) continue;
+            out.cell[out.n] = cell; out.t_in[out.n] = t_in; out.rmax[out.n] = rmax; out.n++;
+        }
+        out.t = W.t; out.nudge = W.nudge; out.n_it = W.n_it;
+    }
+    pre[w] = out;
+}
+
 template <bool ANY>
 __global__ void __launch_bounds__(32 * ARC_WARPS)
 k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
-         unsigned n_lin, unsigned int* __restrict__ stat, int end_cell_done, ArcItem* __restrict__ items, unsigned int* __restrict__ n_items,
+         unsigned n_lin, unsigned int* __restrict__ stat, const ArcPre* __restrict__ pre, ArcItem* __restrict__ items, unsigned int* __restrict__ n_items,
          unsigned item_cap, unsigned int* __restrict__ heavy_idx, unsigned int* __restrict__ heavy_count)     // heavy_*: the rays given up (-> k_far_linear)
 {
     __shared__ unsigned s_q[ARC_WARPS][64];
@@ -849,94 +963,45 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
     if (rd.x == 0.0f && rd.y == 0.0f && rd.z == 0.0f) return;                // no triangle accepts a zero direction (cpp:371)
     ArcRay<ANY> R(sc, s_q[wib], ro, rd);
     const float inf = __int_as_float(0x7f800000);
-    // The walk runs in double: far out, a float t no longer resolves a cell (ulp(t) / |P| exceeds the cells' slack when the ray
-    // has come a long way and passes near the scene); the cells it names are a superset of those the reference's float P visits.
-    const double Ax = (double)R.O.x - sc.fg_center[0], Ay = (double)R.O.y - sc.fg_center[1], Az = (double)R.O.z - sc.fg_center[2];
-    const double dx = R.d.x, dy = R.d.y, dz = R.d.z;
-    const int K = sc.fg_K;
-    const double h = 2.0 / (double)K;
-    const double dinf = (double)inf;
-    // (hole_lo, hole_hi): where |P(t)| < 0.9 T_min, no far-field acceptor exists
-    double hole_lo = dinf, hole_hi = -dinf;
-    {
-        const double Tm = 0.9 * (double)sc.fg_tmin;
-        const double disc = R.ad * R.ad - R.dd * (R.aa - Tm * Tm);
-        if (disc > 0.0 && R.dd > 0.0 && Tm < 1e18) { const double sq = sqrt(disc); hole_lo = (-R.ad - sq) / R.dd; hole_hi = (-R.ad + sq) / R.dd; }
+    double t_end = ANY ? (double)R.tlim : (double)inf;
+    // the cells k_fg_arc_pre has found (any hit, unbounded: the cell of the ray's direction, where |P| exceeds every T, has been
+    // through k_fg_lin_first before the ray came here)
+    const int pre_n = pre[w].n;
+    for (int k = 0; k < pre_n && !(ANY && R.found); k++) {
+        if (!(pre[w].t_in[k] < t_end)) break;
+        R.cell(pre[w].cell[k], pre[w].rmax[k]);
+        if (!ANY) t_end = fmin(t_end, (double)R.tlim * 1.000001);            // (ties at equal t: the lower primitive index wins)
     }
-    double t_end = ANY ? (double)R.tlim : dinf;
-    if (ANY && !(R.tlim < 3.0e38f) && !end_cell_done) {
-        // any hit, unbounded: the far end of the arc first - out there |P| exceeds every T, most entries accept
-        const int cell = fg_cell_of_dir(R.d, K);
-        if (cell >= 0) R.cell(cell, inf);
-    }
-    double t = 0.0;
-    unsigned n_it = 0, n_emitted = 0;
-    // after leaving a cell through a wall, the next cell is looked up a hair BEYOND that wall (nx, ny, nz: relative nudge), so a
-    // path that runs along a wall cannot bounce between the lookup and the wall arithmetic
-    double nx = 0.0, ny = 0.0, nz = 0.0;
-    for (int it = 0; it < 200000 && !(ANY && R.found); it++) {
-        n_it++;
-        if (!(t < t_end)) break;
-        if (t > hole_lo && t < hole_hi) { t = hole_hi; nx = ny = nz = 0.0; continue; }
-        const double Px = Ax + dx * t, Py = Ay + dy * t, Pz = Az + dz * t;
-        const double p2 = Px * Px + Py * Py + Pz * Pz;
-        const double plen = sqrt(p2);
-        const int cell = fg_cell_of_point_d(Px + nx * plen, Py + ny * plen, Pz + nz * plen, K);
-        const double adv = 3e-7 * plen + 1e-30;
-        if (cell < 0) { t = t + adv + 1e-9 * fmax(1.0, t); continue; }
-        const int face = cell / (K * K), iv = (cell / K) % K, iu = cell % K;
-        const int ax = face >> 1;
-        const double sg = (face & 1) ? -1.0 : 1.0;
-        const double Aw = (ax == 0 ? Ax : (ax == 1 ? Ay : Az)) * sg, dw = (ax == 0 ? dx : (ax == 1 ? dy : dz)) * sg;
-        const double Au = (ax == 0 ? Ay : (ax == 1 ? Az : Ax)), du = (ax == 0 ? dy : (ax == 1 ? dz : dx));
-        const double Av = (ax == 0 ? Az : (ax == 1 ? Ax : Ay)), dv = (ax == 0 ? dz : (ax == 1 ? dx : dy));
-        // where does P(t) leave the cell: f(t) = P_u - b P_w changes sign at the walls b = u0 (f >= 0 inside), u1 (f <= 0 inside),
-        // likewise v.  Only walls the ray moves OUT through count; one it is already beyond (rounding) means "leave now".
-        double t_exit = dinf;
-        int k_exit = -1;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const bool upper = (k & 1) != 0;
-            const double b = ((double)((k < 2 ? iu : iv) + (upper ? 1 : 0))) * h - 1.0;
-            const double f0 = (k < 2 ? Au : Av) - b * Aw, f1 = (k < 2 ? du : dv) - b * dw;
-            if (upper ? (f1 > 0.0) : (f1 < 0.0)) { const double tc = fmax(-f0 / f1, t); if (tc < t_exit) { t_exit = tc; k_exit = k; } }
+    unsigned n_it = pre[w].n_it, n_emitted = 0;
+    if (!pre[w].done && !(ANY && R.found)) {
+        ArcWalk W;
+        W.init(sc, R.O, R.d, R.aa, R.ad, R.dd, t_end);
+        W.t = pre[w].t; W.nudge = pre[w].nudge;
+        while (!(ANY && R.found)) {
+            int cell; double t_in; float rmax;
+            if (!W.next(cell, t_in, rmax)) break;
+            if (!R.cell_can_accept(cell, rmax)) continue;                    // every T of this cell exceeds |P| on this stretch
+            // A ray that finds nothing walks on and on (an arc of 90 degrees is ~650 cells of a 1024-cell face), one warp, cell after
+            // cell: past ARC_MAX_CELLS it goes to the block-wide scan of every record (k_far_linear), which is complete and scales.
+            if (heavy_idx && R.n_cells + n_emitted >= ARC_MAX_CELLS) {
+                if (lane == 0) heavy_idx[atomicAdd(heavy_count, 1u)] = e;
+                break;
+            }
+            // the first cells here; the rest of the arc as work items, one warp each
+            bool inline_cell = R.n_cells < ARC_INLINE_CELLS || items == nullptr;
+            if (!inline_cell) {
+                unsigned slot = 0;
+                if (lane == 0) slot = atomicAdd(n_items, 1u);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot < item_cap) { if (lane == 0) { ArcItem itx; itx.e = e; itx.cell = cell; itx.rmax = rmax; items[slot] = itx; } n_emitted++; }
+                else inline_cell = true;                                     // (the item list is full)
+            }
+            if (inline_cell) {
+                R.cell(cell, rmax);
+                if (!ANY) W.t_end = fmin(W.t_end, (double)R.tlim * 1.000001);
+            }
         }
-        // the nudge for the next lookup: across wall k_exit, i.e. along axis u (k < 2) or v, up (odd k) or down
-        nx = ny = nz = 0.0;
-        if (k_exit >= 0) {
-            const int na = k_exit < 2 ? (ax + 1) % 3 : (ax + 2) % 3;
-            const double nv = (k_exit & 1) ? 1e-9 : -1e-9;
-            if (na == 0) nx = nv; else if (na == 1) ny = nv; else nz = nv;
-        }
-        double t_out = fmin(t_exit, t_end);
-        if (t < hole_lo) t_out = fmin(t_out, hole_lo);
-        float rmax = inf;
-        if (t_out < 1e300) {
-            const double Qx = Ax + dx * t_out, Qy = Ay + dy * t_out, Qz = Az + dz * t_out;
-            const double r = sqrt(fmax(p2, Qx * Qx + Qy * Qy + Qz * Qz)) * 1.00001 + 1.0;      // |P(t)| is convex in t
-            rmax = r < 3.0e38 ? (float)r * 1.000001f : inf;
-        }
-        // A ray that finds nothing walks on and on (an arc of 90 degrees is ~650 cells of a 1024-cell face), one warp, cell after
-        // cell: past ARC_MAX_CELLS it goes to the block-wide scan of every record (k_slow), which is complete and scales.
-        if (heavy_idx && R.n_cells + n_emitted >= ARC_MAX_CELLS) {
-            if (lane == 0) heavy_idx[atomicAdd(heavy_count, 1u)] = e;
-            break;
-        }
-        // the first cells here; the rest of the arc as work items, one warp each
-        bool inline_cell = R.n_cells < ARC_INLINE_CELLS || items == nullptr;
-        if (!inline_cell) {
-            unsigned slot = 0;
-            if (lane == 0) slot = atomicAdd(n_items, 1u);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (slot < item_cap) { if (lane == 0) { ArcItem itx; itx.e = e; itx.cell = cell; itx.rmax = rmax; items[slot] = itx; } n_emitted++; }
-            else inline_cell = true;                                         // (the item list is full)
-        }
-        if (inline_cell) {
-            R.cell(cell, rmax);
-            if (!ANY) t_end = fmin(t_end, (double)R.tlim * 1.000001);        // (ties at equal t: the lower primitive index wins)
-        }
-        if (!(t_out < 1e300)) break;
-        t = t_out + adv;
+        n_it += W.n_it;
     }
     // the triangles too small for the direction index (fg_wide): anywhere along the ray, same filter
     if (sc.fg_n_wide > 0 && !(ANY && R.found)) R.list(sc.fg_wide, 0ull, (unsigned long long)sc.fg_n_wide, false, inf);
@@ -2479,9 +2544,9 @@ extern "C" void rt580_destroy(rt580_context* c)
     for (int k = 0; k < 2; k++) { cudaStreamSynchronize(c->side[k]); cudaEventDestroy(c->ev_join[k]); cudaStreamDestroy(c->side[k]); }
     c->arays2.release(); c->occl2.release();
     c->visit_counts.release();
-    c->fg_counts.release(); c->fg_start.release(); c->fg_bsum.release(); c->fg_entries.release();
-    c->arc_items.release();
-    c->fgq_hist.release(); c->fgq_start.release(); c->fgq_cellof.release(); c->fgq_rank.release(); c->fgq_order.release(); c->fgq_lin.release();
+    c->fg_counts.release(); c->fg_start.release(); c->fg_bsum.release(); c->fg_entries.release(); c->fg_cell_tmin.release();
+    c->arc_items.release(); c->arc_pre.release();
+    c->fgq_hist.release(); c->fgq_start.release(); c->fgq_cellof.release(); c->fgq_rank.release(); c->fgq_order.release(); c->fgq_lin.release(); c->fgq_first.release();
     cudaEventDestroy(c->ev_level);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -2524,7 +2589,7 @@ static int far_grid_ensure(rt580_context* c)
     CU(cudaEventRecord(c->ev[11], st));
     CU(cudaStreamSynchronize(st));
     CU(cudaEventElapsedTime(&c->fg_build_ms, c->ev[10], c->ev[11]));
-    c->sc.fg_K = fo.K; c->sc.fg_start = c->fg_start.p; c->sc.fg_entries = c->fg_entries.p; c->sc.fg_n_wide = fo.n_wide;
+    c->sc.fg_K = fo.K; c->sc.fg_start = c->fg_start.p; c->sc.fg_entries = c->fg_entries.p; c->sc.fg_cell_tmin = c->fg_cell_tmin.p; c->sc.fg_n_wide = fo.n_wide;
     c->fg_n_entries = fo.n_entries;
     if (getenv("RT580_DEBUG_TIMING"))
         fprintf(stderr, "[rt580] far-field grid: K %d, %llu entries (%.1f per cell), %d wide, t_min %.4g, diag %.4g, build %.2f ms\n", fo.K, fo.n_entries,
@@ -2624,7 +2689,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
         }
         // far-field direction grid (fargrid.cuh): the per-triangle constants now, the lists when a frame first needs them
         // (far_grid_ensure: a closed scene never does, and would pay ~65 ms per upload of a million triangles for nothing)
-        c->sc.fg_A = nullptr; c->sc.fg_B = nullptr; c->sc.fg_start = nullptr; c->sc.fg_entries = nullptr; c->sc.fg_wide = nullptr;
+        c->sc.fg_A = nullptr; c->sc.fg_B = nullptr; c->sc.fg_start = nullptr; c->sc.fg_entries = nullptr; c->sc.fg_cell_tmin = nullptr; c->sc.fg_wide = nullptr;
         c->sc.fg_n_wide = 0; c->sc.fg_K = 0; c->sc.fg_dmax = 0.f; c->fg_n_entries = 0; c->fg_build_ms = 0.f;
         c->sc.fg_sph = nullptr; c->sc.fg_n_sph = 0; c->sc.fg_rmax = 0.f; c->sc.fg_tmin = 3.0e38f;
         c->fg_pending = false;
@@ -2639,7 +2704,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
             fi.fgA = sa.take<float4>((size_t)n_all); fi.fgB = sa.take<float2>((size_t)n_all); fi.wide = sa.take<uint32_t>((size_t)n_all); fi.sph = sa.take<uint32_t>((size_t)n_all);
             fi.counters = sa.take<unsigned int>(4);
             if (!fi.fgA || !fi.fgB || !fi.wide || !fi.sph || !fi.counters) FAIL(RT580_FAILURE, "rt580_upload_scene: arena exhausted (far-field grid)");
-            fi.counts = &c->fg_counts; fi.start = &c->fg_start; fi.bsum = &c->fg_bsum; fi.entries = &c->fg_entries;
+            fi.counts = &c->fg_counts; fi.start = &c->fg_start; fi.bsum = &c->fg_bsum; fi.entries = &c->fg_entries; fi.cell_tmin = &c->fg_cell_tmin;
             FgBuildOutput fo{};
             if (!fg_build(fi, &fo, st, err, sizeof err)) FAIL(RT580_FAILURE, "rt580_upload_scene: %s", err);
             c->sc.fg_A = fi.fgA; c->sc.fg_B = fi.fgB; c->sc.fg_wide = fi.wide; c->sc.fg_n_wide = fo.n_wide;
@@ -2954,18 +3019,25 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
     if (c->sc.fg_K > 0) {
         const size_t n_cells = (size_t)6 * c->sc.fg_K * c->sc.fg_K;
         const bool sorted = n >= 32768u;                 // (below that the sort by cell - a histogram over 6 K^2 cells - costs more than it saves)
-        CU(c->fgq_hist.ensure(n_cells + 2, 0, st)); CU(c->fgq_start.ensure(n_cells + 2, 0, st));
+        CU(c->fgq_hist.ensure(n_cells + 3, 0, st)); CU(c->fgq_start.ensure(n_cells + 3, 0, st));
+        if (any) CU(c->fgq_first.ensure(n, 0, st));
         CU(c->fgq_cellof.ensure(n, 0, st)); CU(c->fgq_rank.ensure(n, 0, st)); CU(c->fgq_order.ensure(n, 0, st)); CU(c->fgq_lin.ensure((size_t)n + 1, 0, st));
         unsigned int* lin_count = c->fgq_hist.p + n_cells + 1;       // (the scan below covers n_cells + 1 elements: [n_cells] stays 0)
-        if (sorted) CU(cudaMemsetAsync(c->fgq_hist.p, 0, sizeof(unsigned) * (n_cells + 2), st));
-        else CU(cudaMemsetAsync(lin_count, 0, sizeof(unsigned), st));
-        k_fg_bin<<<nblk(n, 256), 256, 0, st>>>(rays, n, c->sc.fg_K, sorted ? c->fgq_hist.p : nullptr, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_lin.p, lin_count, any ? 1 : 0);
+        unsigned int* first_count = lin_count + 1;
+        if (sorted) CU(cudaMemsetAsync(c->fgq_hist.p, 0, sizeof(unsigned) * (n_cells + 3), st));
+        else CU(cudaMemsetAsync(lin_count, 0, 2 * sizeof(unsigned), st));
+        k_fg_bin<<<nblk(n, 256), 256, 0, st>>>(rays, n, c->sc.fg_K, sorted ? c->fgq_hist.p : nullptr, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_lin.p, lin_count, any ? 1 : 0,
+                                               c->fgq_first.p, first_count);
         if (sorted) {
             if (exclusive_scan_u32(c, c->fgq_hist.p, c->fgq_start.p, (unsigned)(n_cells + 1))) return RT580_FAILURE;
             k_fg_order<<<nblk(n, 256), 256, 0, st>>>(n, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_start.p, c->fgq_order.p);
         }
         const unsigned int* order = sorted ? c->fgq_order.p : nullptr;
-        if (any) k_fg_scan<true><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
+        if (any) {
+            k_fg_scan<true><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
+            k_fg_lin_first<<<nblk(n, 128), 128, 0, st>>>(c->sc, rays, res, c->fgq_first.p, first_count, c->fgq_cellof.p, c->fgq_lin.p, lin_count);
+            c->launches++;
+        }
         else k_fg_scan<false><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
         c->launches += 3;
         CU(cudaMemcpyAsync(&n_lin, lin_count, sizeof n_lin, cudaMemcpyDeviceToHost, st));
@@ -2985,21 +3057,26 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         const unsigned item_cap = n_lin > (1u << 26) ? (1u << 29) : n_lin * 8u + 65536u;
         CU(c->arc_items.ensure(item_cap, 0, st));
         unsigned int* n_items = heavy_count + 1;
+        CU(c->arc_pre.ensure((size_t)n_lin * sizeof(ArcPre), 0, st));
+        ArcPre* pre = reinterpret_cast<ArcPre*>(c->arc_pre.p);
         if (any) {
-            k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16, 0,
+            k_fg_arc_pre<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, lin_idx, n_lin, pre);
+            k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16, pre,
                                                                              c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
             k_lin_near<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 24, heavy_idx, heavy_count);
         } else {
-            k_fg_arc<false><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 20, 0,
+            k_fg_arc_pre<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, lin_idx, n_lin, pre);
+            k_fg_arc<false><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 20, pre,
                                                                               c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
             k_lin_near<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 26, heavy_idx, heavy_count);
         }
-        c->launches += 2;
+        c->launches += 3;
         unsigned hc2[3] = { 0u, 0u, 0u };
         CU(cudaMemcpyAsync(hc2, heavy_count, sizeof hc2, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         c->syncs++;
         const unsigned n_it = hc2[1] < item_cap ? hc2[1] : item_cap;
+        if (getenv("RT580_DEBUG_TIMING")) fprintf(stderr, "[rt580] %s flush of %u: %u from outside after the first cell; %u to k_slow, %u arc items, %u to k_far_linear\n", any ? "any-hit" : "closest-hit", n, n_lin, hc2[0], hc2[1], hc2[2]);
         if (n_it) {
             if (any) k_fg_arc_items<true><<<nblk(n_it, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, c->arc_items.p, n_it);
             else k_fg_arc_items<false><<<nblk(n_it, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, c->arc_items.p, n_it);

@@ -17,7 +17,7 @@ kern = collections.OrderedDict()      # kernel name -> {(file, line, text): [war
 cur_file = cur_fn = hdr = None
 done_sections = set()
 skip = False
-with open(path, newline="") as f:
+with open(path, newline="", errors="replace") as f:
     for r in csv.reader(f):
         if not r:
             continue
@@ -43,14 +43,19 @@ with open(path, newline="") as f:
             continue
         d = kern.setdefault(cur_fn, collections.OrderedDict())
         k = (cur_file, r[0], r[1].strip())
-        a = d.setdefault(k, [0, 0])
+        a = d.setdefault(k, [0, 0, 0])
         a[0] += n
         a[1] += t
+        try:
+            a[2] += int(r[hdr.index("# Samples")] or 0)
+        except ValueError:
+            pass
 for fn, d in kern.items():
     tot = sum(a[0] for a in d.values())
     tth = sum(a[1] for a in d.values())
-    print("== %s\n   warp instructions %d, avg active lanes %.1f" % (fn[:110], tot, tth / max(tot, 1)))
+    tsm = max(sum(a[2] for a in d.values()), 1)
+    print("== %s\n   warp instructions %d, avg active lanes %.1f; columns: share of instructions, share of stall samples" % (fn[:110], tot, tth / max(tot, 1)))
     for (fl, ln, text), a in sorted(d.items(), key=lambda kv: -kv[1][0])[:top]:
         if a[0] == 0:
             break
-        print("   %5.1f%%  lanes %4.1f  %s:%s  %s" % (100.0 * a[0] / tot, a[1] / a[0], fl, ln, text[:100]))
+        print("   %5.1f%% %5.1f%%  lanes %4.1f  %s:%s  %s" % (100.0 * a[0] / tot, 100.0 * a[2] / tsm, a[1] / a[0], fl, ln, text[:100]))
