@@ -540,7 +540,7 @@ __device__ __forceinline__ void fg_exact(const DeviceScene& sc, unsigned long lo
 
 // One warp takes FG_G consecutive rays of the sorted order; the rays of one cell among them form a segment that runs over the
 // cell's list 32 entries at a time (lane = entry: its record is gathered once and serves every ray of the segment).
-#define FG_G 8
+#define FG_G 32     // rays per warp: the rays of one cell among them share the gathers of that cell's list
 #define FG_WARPS 4
 #define FG_U4 1      // list entries per lane and iteration (4 was measured slower: the rays from outside the scene stop after a few entries)
 struct FgWarp {
@@ -574,7 +574,9 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned live = ((1u << j1) - 1u) & ~((1u << j0) - 1u);
+    unsigned live = (j1 >= 32 ? 0xffffffffu : ((1u << j1) - 1u)) & ~((1u << j0) - 1u);
+    // any hit: the rays that are answered leave (found[] changes in fg_flush only)
+    if (ANY) { live &= ~__ballot_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&sh.found[lane]) != 0); if (!live) return; }
     unsigned q_len = 0;
     for (unsigned long long base = 0; base < len; base += 32 * FG_U4) {
         // this lane's FG_U4 entries (independent gathers in flight together: the loop is bound by their latency):
@@ -599,13 +601,9 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
         for (int u = 0; u < FG_U4; u++) {
             if (base + 32 * u >= len) break;
             const float4 fr = frs[u]; const float eD = eDs[u], eT = eTs[u]; const unsigned id = ids[u];
-            if (ANY) {                                       // rays that are answered leave
-                __syncwarp();
-                for (int j = j0; j < j1; j++) if (((live >> j) & 1u) && *reinterpret_cast<volatile int*>(&sh.found[j])) live &= ~(1u << j);
-                if (!live) break;
-            }
-            for (int j = j0; j < j1; j++) {
-                if (!((live >> j) & 1u)) continue;
+            for (unsigned rest = live; rest;) {
+                const int j = __ffs((int)rest) - 1;
+                rest &= rest - 1u;
                 const float4 dj = sh.D[j];
                 const float nd = __fmaf_rn(fr.x, dj.x, __fmaf_rn(fr.y, dj.y, fr.z * dj.z));
                 const float and_ = fabsf(nd);
@@ -622,8 +620,12 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
                 if (mask == 0u) continue;
                 if (pass) sh.q[q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)j << 32) | id;
                 q_len += (unsigned)__popc(mask);
-                fg_flush<ANY>(sc, sh, q_len, false);
+                if (q_len >= 32u) {
+                    fg_flush<ANY>(sc, sh, q_len, false);
+                    if (ANY) { live &= ~__ballot_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&sh.found[lane]) != 0); rest &= live; }
+                }
             }
+            if (ANY && !live) break;
         }
         if (ANY && !live) break;
     }
