@@ -779,6 +779,32 @@ struct ArcRay {
             __syncwarp();
         }
     }
+    // The triangle (fa = (N, D), far field from T on) is listed in every cell its strip crosses, but this ray meets its plane at
+    // one parameter t = -(N.O + D) / (N.d) only: bracket it ([t_lo, t_hi] covers the float evaluation here and in cpp:367-381)
+    // and ask for t > 0, t within the limit, and |P(t)| >= T somewhere in the bracket (|P(t)| is convex).
+    __device__ __forceinline__ bool entry_can_accept(float4 fa, float T) const {
+        const float nd = __fmaf_rn(fa.x, d.x, __fmaf_rn(fa.y, d.y, fa.z * d.z));
+        const float no = __fmaf_rn(fa.x, O.x, __fmaf_rn(fa.y, O.y, __fmaf_rn(fa.z, O.z, fa.w)));
+        const float and_ = fabsf(nd), ano = fabsf(no);
+        bool pass = and_ > FG_ND_MIN && !(ano > dno_far && ((no < 0.f) == (nd < 0.f)));
+        if (pass) {
+            const float t_lo = fmaxf(ano - dno_far, 0.f) / (and_ + FG_ND_SLACK) * 0.999999f;
+            pass = t_lo <= tlim;
+            if (pass && and_ > 2.0f * FG_ND_SLACK) {
+                const double t_hi = (double)(ano + dno_far) / (double)(and_ - FG_ND_SLACK) * 1.000001, tl = t_lo;
+                const double p_lo = aa + tl * (2.0 * ad + tl * dd), p_hi = aa + t_hi * (2.0 * ad + t_hi * dd);
+                const double need = fmax((double)T * 0.9999 - 2e-6 * Olen, 0.0);
+                pass = fmax(p_lo, p_hi) >= need * need;
+            }
+        }
+        return pass;
+    }
+    // one candidate through the reference's test, by this thread alone
+    __device__ __forceinline__ void exact_one(unsigned id) {
+        float tt; int pp;
+        n_exact++;
+        if (prim_test<true>(sc.prims + id, O, d, tlim, plim, tt, pp)) { found = true; if (!ANY) { tlim = tt; plim = pp; } }
+    }
     // the entries of one cell that can accept at |P| <= rmax
     __device__ __forceinline__ bool cell_can_accept(int cell, float rmax) const {      // some entry of the cell has T <= rmax
         return __uint_as_float(__ldg(sc.fg_cell_tmin + cell)) <= rmax;                    // (empty cell: NaN)
@@ -806,29 +832,7 @@ struct ArcRay {
             for (int u = 0; u < FG_U4; u++) {
                 if (base + 32 * u >= en) break;
                 bool pass = false; const unsigned id = ids[u];
-                if (base + 32 * u + lane < en) {
-                    const float T = Ts[u];
-                    if (T <= rmax) {
-                        // The triangle is listed in every cell its strip crosses, but this ray meets its plane at one parameter
-                        // t = -(N.O + D) / (N.d) only: bracket it ([t_lo, t_hi] covers the float evaluation here and in cpp:367-381)
-                        // and ask for t > 0, t within the limit, and |P(t)| >= T somewhere in the bracket (|P(t)| is convex).
-                        const float4 fa = fas[u];
-                        const float nd = __fmaf_rn(fa.x, d.x, __fmaf_rn(fa.y, d.y, fa.z * d.z));
-                        const float no = __fmaf_rn(fa.x, O.x, __fmaf_rn(fa.y, O.y, __fmaf_rn(fa.z, O.z, fa.w)));
-                        const float and_ = fabsf(nd), ano = fabsf(no);
-                        pass = and_ > FG_ND_MIN && !(ano > dno_far && ((no < 0.f) == (nd < 0.f)));
-                        if (pass) {
-                            const float t_lo = fmaxf(ano - dno_far, 0.f) / (and_ + FG_ND_SLACK) * 0.999999f;
-                            pass = t_lo <= tlim;
-                            if (pass && and_ > 2.0f * FG_ND_SLACK) {
-                                const double t_hi = (double)(ano + dno_far) / (double)(and_ - FG_ND_SLACK) * 1.000001, tl = t_lo;
-                                const double p_lo = aa + tl * (2.0 * ad + tl * dd), p_hi = aa + t_hi * (2.0 * ad + t_hi * dd);
-                                const double need = fmax((double)T * 0.9999 - 2e-6 * Olen, 0.0);
-                                pass = fmax(p_lo, p_hi) >= need * need;
-                            }
-                        }
-                    }
-                }
+                if (base + 32 * u + lane < en) pass = Ts[u] <= rmax && entry_can_accept(fas[u], Ts[u]);
                 const unsigned mask = __ballot_sync(0xffffffffu, pass);
                 if (mask) {
                     if (pass) q[q_len + (unsigned)__popc(mask & lt_mask)] = id;
@@ -950,32 +954,70 @@ k_fg_arc_pre(DeviceScene sc, const SlowRay* __restrict__ rays, const unsigned in
     pre[w] = out;
 }
 
+// The cells k_fg_arc_pre has found, one warp per ray (lane = list entry: the gathers of a slab of 32 entries are in flight
+// together; one thread per ray, walking its ~150-entry lists alone, was measured 1.4x slower - a chain of dependent gathers).
+// This kernel holds no walk state, so that twice as many warps fit an SM as in k_fg_arc: the loop is bound by gather latency.
+// Rays whose arc goes on after these cells, and all unanswered rays when the scene has a list of triangles too small for the
+// direction index, are listed for k_fg_arc (`rest`).
+// (any hit, unbounded: the cell of the ray's direction, where |P| exceeds every T, has been through k_fg_lin_first already)
+#define ARC_FIRST_WARPS 8
 template <bool ANY>
-__global__ void __launch_bounds__(32 * ARC_WARPS)
-k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
-         unsigned n_lin, unsigned int* __restrict__ stat, const ArcPre* __restrict__ pre, ArcItem* __restrict__ items, unsigned int* __restrict__ n_items,
-         unsigned item_cap, unsigned int* __restrict__ heavy_idx, unsigned int* __restrict__ heavy_count)     // heavy_*: the rays given up (-> k_far_linear)
+__global__ void __launch_bounds__(32 * ARC_FIRST_WARPS, 4)
+k_fg_arc_first(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
+               unsigned n_lin, unsigned int* __restrict__ stat, const ArcPre* __restrict__ pre, unsigned int* __restrict__ rest_idx,
+               unsigned int* __restrict__ rest_count)
 {
-    __shared__ unsigned s_q[ARC_WARPS][64];
+    __shared__ unsigned s_q[ARC_FIRST_WARPS][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned w = blockIdx.x * ARC_WARPS + wib;
+    const unsigned w = blockIdx.x * ARC_FIRST_WARPS + wib;
     if (w >= n_lin) return;
     const unsigned e = __ldg(lin_idx + w);
     const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
     if (rd.x == 0.0f && rd.y == 0.0f && rd.z == 0.0f) return;                // no triangle accepts a zero direction (cpp:371)
     ArcRay<ANY> R(sc, s_q[wib], ro, rd);
-    const float inf = __int_as_float(0x7f800000);
-    double t_end = ANY ? (double)R.tlim : (double)inf;
-    // the cells k_fg_arc_pre has found (any hit, unbounded: the cell of the ray's direction, where |P| exceeds every T, has been
-    // through k_fg_lin_first before the ray came here)
+    double t_end = ANY ? (double)R.tlim : (double)__int_as_float(0x7f800000);
     const int pre_n = pre[w].n;
-    for (int k = 0; k < pre_n && !(ANY && R.found); k++) {
-        if (!(pre[w].t_in[k] < t_end)) break;
-        R.cell(pre[w].cell[k], pre[w].rmax[k]);
+    for (int c = 0; c < pre_n && !(ANY && R.found); c++) {
+        if (!(pre[w].t_in[c] < t_end)) break;
+        R.cell(pre[w].cell[c], pre[w].rmax[c]);
         if (!ANY) t_end = fmin(t_end, (double)R.tlim * 1.000001);            // (ties at equal t: the lower primitive index wins)
     }
-    unsigned n_it = pre[w].n_it, n_emitted = 0;
-    if (!pre[w].done && !(ANY && R.found)) {
+    if (lane != 0) return;
+    if (R.found) {
+        if (ANY) res[e].found = 1;
+        else atomicMin(&res[e].key, slow_key(R.tlim, R.plim));
+    }
+    const bool walk_on = !pre[w].done && pre[w].t < t_end;
+    if (!(ANY && R.found) && (walk_on || sc.fg_n_wide > 0)) rest_idx[atomicAdd(rest_count, 1u)] = w;
+    // (statistics from one ray in 64: atomics per ray on a few addresses cost more than the walk itself)
+    if (stat && (w & 63u) == 0u) { atomicAdd(stat, 64u); atomicAdd(stat + 2, 64u * R.n_cells); atomicAdd(stat + 3, 64u * R.n_exact); atomicMax(stat + 1, pre[w].n_it); }
+}
+
+// What the first cells did not settle: one warp per ray walks on along the arc.
+template <bool ANY>
+__global__ void __launch_bounds__(32 * ARC_WARPS)
+k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
+         const unsigned int* __restrict__ rest_idx, unsigned n_rest, unsigned int* __restrict__ stat, const ArcPre* __restrict__ pre,
+         ArcItem* __restrict__ items, unsigned int* __restrict__ n_items,
+         unsigned item_cap, unsigned int* __restrict__ heavy_idx, unsigned int* __restrict__ heavy_count)     // heavy_*: the rays given up (-> k_far_linear)
+{
+    __shared__ unsigned s_q[ARC_WARPS][64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned wr = blockIdx.x * ARC_WARPS + wib;
+    if (wr >= n_rest) return;
+    const unsigned w = __ldg(rest_idx + wr);
+    const unsigned e = __ldg(lin_idx + w);
+    const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
+    ArcRay<ANY> R(sc, s_q[wib], ro, rd);
+    const float inf = __int_as_float(0x7f800000);
+    double t_end = ANY ? (double)R.tlim : (double)inf;
+    if (!ANY) {                                                              // what the first cells have found bounds the search
+        const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&res[e].key);
+        const float kt = __uint_as_float((unsigned)(key >> 32)); const int kp = (int)(unsigned)(key & 0xffffffffull);
+        if (kt < R.tlim || (kt == R.tlim && kp < R.plim)) { R.tlim = kt; R.plim = kp; t_end = fmin(t_end, (double)kt * 1.000001); }
+    }
+    unsigned n_it = 0, n_emitted = 0;
+    if (!pre[w].done && pre[w].t < t_end) {
         ArcWalk W;
         W.init(sc, R.O, R.d, R.aa, R.ad, R.dd, t_end);
         W.t = pre[w].t; W.nudge = pre[w].nudge;
@@ -1009,7 +1051,7 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
     if (sc.fg_n_wide > 0 && !(ANY && R.found)) R.list(sc.fg_wide, 0ull, (unsigned long long)sc.fg_n_wide, false, inf);
     if (lane == 0) {
         // (statistics from one ray in 64: four atomics per ray on four addresses cost more than the walk itself)
-        if (stat && (w & 63u) == 0u) { atomicAdd(stat, 64u); atomicAdd(stat + 2, 64u * (R.n_cells + n_emitted)); atomicAdd(stat + 3, 64u * R.n_exact); atomicMax(stat + 1, n_it); }
+        if (stat && (w & 63u) == 0u) { atomicAdd(stat + 2, 64u * (R.n_cells + n_emitted)); atomicAdd(stat + 3, 64u * R.n_exact); atomicMax(stat + 1, n_it); }
         if (R.found) {
             if (ANY) res[e].found = 1;
             else atomicMin(&res[e].key, slow_key(R.tlim, R.plim));
@@ -3050,35 +3092,46 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
     if (n_lin && lin_idx) {
         // rays from outside the scene: far regime along the arc of the direction grid, near regime through the inflated tree;
         // the few whose inflated boxes cover much of the scene come back in a list for the linear scan below
-        CU(c->fgq_rank.ensure(2 * (size_t)n_lin + 2, 0, st));    // (free again: k_fg_order has consumed the ranks)
+        CU(c->fgq_rank.ensure(3 * (size_t)n_lin + 3, 0, st));    // (free again: k_fg_order has consumed the ranks)
         unsigned int* heavy_idx = c->fgq_rank.p;                 // k_lin_near's: inflated boxes cover much of the scene -> k_slow
         unsigned int* farheavy_idx = c->fgq_rank.p + n_lin + 1;  // k_fg_arc's: the arc runs on without an acceptor -> k_far_linear
-        unsigned int* heavy_count = c->fgq_hist.p;               // (free again as well) [0] heavy, [1] arc items, [2] far-heavy
-        CU(cudaMemsetAsync(heavy_count, 0, 3 * sizeof(unsigned), st));
+        unsigned int* rest_idx = c->fgq_rank.p + 2 * (size_t)n_lin + 2;   // k_fg_arc_first's: the arc goes on after its first cells -> k_fg_arc
+        unsigned int* heavy_count = c->fgq_hist.p;               // (free again as well) [0] heavy, [1] arc items, [2] far-heavy, [3] rest
+        CU(cudaMemsetAsync(heavy_count, 0, 4 * sizeof(unsigned), st));
         // (the cells of long arcs become work items: up to 8 per ray of the list, the rest is walked in place)
         const unsigned item_cap = n_lin > (1u << 26) ? (1u << 29) : n_lin * 8u + 65536u;
         CU(c->arc_items.ensure(item_cap, 0, st));
         unsigned int* n_items = heavy_count + 1;
         CU(c->arc_pre.ensure((size_t)n_lin * sizeof(ArcPre), 0, st));
         ArcPre* pre = reinterpret_cast<ArcPre*>(c->arc_pre.p);
+        unsigned int* stat = c->counters.p + (any ? 16 : 20);
         if (any) {
             k_fg_arc_pre<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, lin_idx, n_lin, pre);
-            k_fg_arc<true><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 16, pre,
-                                                                             c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
+            k_fg_arc_first<true><<<nblk(n_lin, ARC_FIRST_WARPS), 32 * ARC_FIRST_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, stat, pre, rest_idx, heavy_count + 3);
             k_lin_near<true><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 24, heavy_idx, heavy_count);
         } else {
             k_fg_arc_pre<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, lin_idx, n_lin, pre);
-            k_fg_arc<false><<<nblk(n_lin, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 20, pre,
-                                                                              c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
+            k_fg_arc_first<false><<<nblk(n_lin, ARC_FIRST_WARPS), 32 * ARC_FIRST_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, stat, pre, rest_idx, heavy_count + 3);
             k_lin_near<false><<<nblk(n_lin, 128), 128, 0, st>>>(c->sc, rays, res, lin_idx, n_lin, c->counters.p + 26, heavy_idx, heavy_count);
         }
         c->launches += 3;
-        unsigned hc2[3] = { 0u, 0u, 0u };
+        unsigned hc2[4] = { 0u, 0u, 0u, 0u };
         CU(cudaMemcpyAsync(hc2, heavy_count, sizeof hc2, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         c->syncs++;
+        const unsigned n_rest = hc2[3];
+        if (n_rest) {
+            if (any) k_fg_arc<true><<<nblk(n_rest, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, rest_idx, n_rest, stat, pre,
+                                                                              c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
+            else k_fg_arc<false><<<nblk(n_rest, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, rest_idx, n_rest, stat, pre,
+                                                                               c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
+            c->launches++;
+            CU(cudaMemcpyAsync(hc2 + 1, heavy_count + 1, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            c->syncs++;
+        }
         const unsigned n_it = hc2[1] < item_cap ? hc2[1] : item_cap;
-        if (getenv("RT580_DEBUG_TIMING")) fprintf(stderr, "[rt580] %s flush of %u: %u from outside after the first cell; %u to k_slow, %u arc items, %u to k_far_linear\n", any ? "any-hit" : "closest-hit", n, n_lin, hc2[0], hc2[1], hc2[2]);
+        if (getenv("RT580_DEBUG_TIMING")) fprintf(stderr, "[rt580] %s flush of %u: %u from outside after the first cell; %u walk on, %u to k_slow, %u arc items, %u to k_far_linear\n", any ? "any-hit" : "closest-hit", n, n_lin, n_rest, hc2[0], hc2[1], hc2[2]);
         if (n_it) {
             if (any) k_fg_arc_items<true><<<nblk(n_it, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, c->arc_items.p, n_it);
             else k_fg_arc_items<false><<<nblk(n_it, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, c->arc_items.p, n_it);
