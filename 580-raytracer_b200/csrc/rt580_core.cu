@@ -724,9 +724,8 @@ k_fg_lin_first(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __rest
 //                             primitives the tree and the grid do not hold (large ones, slivers), and all
 //                             spheres when the ray is aimed at the scene (cpp:426's discriminant is noise out there).
 #define ARC_WARPS 4
-#define ARC_MAX_CELLS 512u
-#define ARC_INLINE_CELLS 6      // cells a ray's own warp works through; the rest of a long arc becomes work items (k_fg_arc_items)
-struct ArcItem { unsigned e; int cell; float rmax; };
+#define ARC_MAX_CELLS 4096u
+struct ArcItem { unsigned e; int cell; float rmax; float t_in; };   // t_in: the ray is in the cell from this parameter on (a lower bound)
 
 // one ray of a warp against the lists of cells of the direction grid: the state both arc kernels share
 template <bool ANY>
@@ -739,6 +738,9 @@ struct ArcRay {
     unsigned q_len, n_cells, n_exact;
     double aa, ad, dd;                 // |P(t)|^2 = aa + 2 t ad + t^2 dd, P relative to the grid's centre
     float Olen, dno_far;
+    // list entries per lane and iteration, their gathers in flight together (the loop is bound by that latency): a closest-hit
+    // ray reads the whole list anyway; an any-hit ray mostly stops within the first slab
+    static constexpr int ARC_U = ANY ? 1 : 2;
 
     __device__ __forceinline__ ArcRay(const DeviceScene& sc_, unsigned* q_, float4 ro, float4 rd) : sc(sc_), q(q_) {
         O = mk(ro.x, ro.y, ro.z); d = mk(rd.x, rd.y, rd.z);
@@ -788,10 +790,11 @@ struct ArcRay {
         const float and_ = fabsf(nd), ano = fabsf(no);
         bool pass = and_ > FG_ND_MIN && !(ano > dno_far && ((no < 0.f) == (nd < 0.f)));
         if (pass) {
-            const float t_lo = fmaxf(ano - dno_far, 0.f) / (and_ + FG_ND_SLACK) * 0.999999f;
+            // (approximate divisions, 2 ulp: the factors leave room for them)
+            const float t_lo = __fdividef(fmaxf(ano - dno_far, 0.f), and_ + FG_ND_SLACK) * 0.999998f;
             pass = t_lo <= tlim;
             if (pass && and_ > 2.0f * FG_ND_SLACK) {
-                const double t_hi = (double)(ano + dno_far) / (double)(and_ - FG_ND_SLACK) * 1.000001, tl = t_lo;
+                const double t_hi = (double)(__fdividef(ano + dno_far, and_ - FG_ND_SLACK) * 1.000002f), tl = t_lo;
                 const double p_lo = aa + tl * (2.0 * ad + tl * dd), p_hi = aa + t_hi * (2.0 * ad + t_hi * dd);
                 const double need = fmax((double)T * 0.9999 - 2e-6 * Olen, 0.0);
                 pass = fmax(p_lo, p_hi) >= need * need;
@@ -818,18 +821,18 @@ struct ArcRay {
     __device__ __forceinline__ void list(const uint32_t* __restrict__ entries, unsigned long long b, unsigned long long en, bool has_k6, float rmax) {
         const int lane = threadIdx.x & 31;
         const unsigned lt_mask = (1u << lane) - 1u;
-        for (unsigned long long base = b; base < en; base += 32 * FG_U4) {
-            // FG_U4 entries per lane: their gathers are in flight together (the loop is bound by that latency)
-            unsigned ents[FG_U4], ids[FG_U4]; float Ts[FG_U4]; float4 fas[FG_U4];
+        for (unsigned long long base = b; base < en; base += 32 * ARC_U) {
+            // ARC_U entries per lane: their gathers are in flight together (the loop is bound by that latency)
+            unsigned ents[ARC_U], ids[ARC_U]; float Ts[ARC_U]; float4 fas[ARC_U];
 #pragma unroll
-            for (int u = 0; u < FG_U4; u++) { const unsigned long long idx = base + 32 * u + lane; ents[u] = idx < en ? __ldg(entries + idx) : 0xffffffffu; }
+            for (int u = 0; u < ARC_U; u++) { const unsigned long long idx = base + 32 * u + lane; ents[u] = idx < en ? __ldg(entries + idx) : 0xffffffffu; }
 #pragma unroll
-            for (int u = 0; u < FG_U4; u++) {
+            for (int u = 0; u < ARC_U; u++) {
                 ids[u] = has_k6 ? (ents[u] & FG_ID_MASK) : ents[u]; Ts[u] = __int_as_float(0x7f800000); fas[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (base + 32 * u + lane < en) { Ts[u] = fg_entry_T(__ldg(sc.fg_B + ids[u]).x, has_k6 ? (ents[u] >> FG_ID_BITS) : 0u); fas[u] = __ldg(sc.fg_A + ids[u]); }
             }
 #pragma unroll
-            for (int u = 0; u < FG_U4; u++) {
+            for (int u = 0; u < ARC_U; u++) {
                 if (base + 32 * u >= en) break;
                 bool pass = false; const unsigned id = ids[u];
                 if (base + 32 * u + lane < en) pass = Ts[u] <= rmax && entry_can_accept(fas[u], Ts[u]);
@@ -993,7 +996,10 @@ k_fg_arc_first(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __rest
     if (stat && (w & 63u) == 0u) { atomicAdd(stat, 64u); atomicAdd(stat + 2, 64u * R.n_cells); atomicAdd(stat + 3, 64u * R.n_exact); atomicMax(stat + 1, pre[w].n_it); }
 }
 
-// What the first cells did not settle: one warp per ray walks on along the arc.
+// What the first cells did not settle: the rest of the arc, one warp per ray.  The walk is serial arithmetic (~2 us per cell,
+// an arc of 90 degrees is ~650 cells of a 1024-cell face), so the warp splits the arc by ANGLE into 32 stretches, one per lane;
+// every lane walks its stretch and emits the cells that can accept as work items (k_fg_arc_items: one warp per (ray, cell)).
+// Neighbouring stretches may both name the cell they meet in: a cell tested twice costs time, nothing else.
 template <bool ANY>
 __global__ void __launch_bounds__(32 * ARC_WARPS)
 k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
@@ -1003,6 +1009,7 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
 {
     __shared__ unsigned s_q[ARC_WARPS][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned wr = blockIdx.x * ARC_WARPS + wib;
     if (wr >= n_rest) return;
     const unsigned w = __ldg(rest_idx + wr);
@@ -1010,48 +1017,63 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
     const float4 ro = __ldg(&rays[e].o), rd = __ldg(&rays[e].d);
     ArcRay<ANY> R(sc, s_q[wib], ro, rd);
     const float inf = __int_as_float(0x7f800000);
-    double t_end = ANY ? (double)R.tlim : (double)inf;
+    const double dinf = (double)inf;
+    double t_end = ANY ? (double)R.tlim : dinf;
     if (!ANY) {                                                              // what the first cells have found bounds the search
         const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&res[e].key);
         const float kt = __uint_as_float((unsigned)(key >> 32)); const int kp = (int)(unsigned)(key & 0xffffffffull);
         if (kt < R.tlim || (kt == R.tlim && kp < R.plim)) { R.tlim = kt; R.plim = kp; t_end = fmin(t_end, (double)kt * 1.000001); }
     }
-    unsigned n_it = 0, n_emitted = 0;
-    if (!pre[w].done && pre[w].t < t_end) {
+    unsigned n_emitted = 0, n_it = 0;
+    bool given_up = false;
+    const double t0 = pre[w].t;
+    if (!pre[w].done && t0 < t_end) {
+        // P(t) = A + t d seen from the centre: at angle theta(t) = atan2(t |d| s, |A| + t |d| c) from A, (c, s) = cos, sin of (A, d);
+        // t(theta) = |A| sin(theta) / (|d| sin(theta_max - theta)), theta_max = angle(A, d)
+        const double la = sqrt(R.aa), ld = sqrt(R.dd);
+        const double c = fmax(-1.0, fmin(1.0, R.ad / (la * ld))), sn = sqrt(fmax(0.0, 1.0 - c * c));
+        const double th_max = atan2(sn, c);
+        const double th0 = atan2(t0 * ld * sn, la + t0 * ld * c);
+        const double th1 = t_end < 1e300 ? atan2(t_end * ld * sn, la + t_end * ld * c) : th_max;
+        double ta = t0, tb = t_end;                                          // this lane's stretch [ta, tb)
+        if (lane > 0) { const double th = th0 + (th1 - th0) * (double)lane / 32.0; ta = la * sin(th) / (ld * sin(th_max - th)); }
+        if (lane < 31) { const double th = th0 + (th1 - th0) * (double)(lane + 1) / 32.0; tb = la * sin(th) / (ld * sin(th_max - th)); }
+        // a ray along A (or through the centre) has no angle to split; nor has an arc of a few cells: lane 0 walks all of it
+        const bool ok = th1 - th0 > 64.0 * (2.0 / (double)sc.fg_K) && ta >= t0 && tb <= t_end && ta <= tb;
+        const bool split = __all_sync(0xffffffffu, ok);
+        if (!split) { ta = t0; tb = lane == 0 ? t_end : t0; }
         ArcWalk W;
-        W.init(sc, R.O, R.d, R.aa, R.ad, R.dd, t_end);
-        W.t = pre[w].t; W.nudge = pre[w].nudge;
-        while (!(ANY && R.found)) {
-            int cell; double t_in; float rmax;
-            if (!W.next(cell, t_in, rmax)) break;
-            if (!R.cell_can_accept(cell, rmax)) continue;                    // every T of this cell exceeds |P| on this stretch
-            // A ray that finds nothing walks on and on (an arc of 90 degrees is ~650 cells of a 1024-cell face), one warp, cell after
-            // cell: past ARC_MAX_CELLS it goes to the block-wide scan of every record (k_far_linear), which is complete and scales.
-            if (heavy_idx && R.n_cells + n_emitted >= ARC_MAX_CELLS) {
-                if (lane == 0) heavy_idx[atomicAdd(heavy_count, 1u)] = e;
-                break;
+        W.init(sc, R.O, R.d, R.aa, R.ad, R.dd, tb);
+        W.t = ta; W.nudge = (lane == 0) ? pre[w].nudge : 0;
+        bool more = ta < tb;
+        while (__any_sync(0xffffffffu, more)) {
+            int cell = 0; double t_in = 0.0; float rmax = 0.f;
+            bool have = false;
+            if (more) {
+                more = W.next(cell, t_in, rmax);
+                have = more && R.cell_can_accept(cell, rmax);                // (no: every T of this cell exceeds |P| on this stretch)
             }
-            // the first cells here; the rest of the arc as work items, one warp each
-            bool inline_cell = R.n_cells < ARC_INLINE_CELLS || items == nullptr;
-            if (!inline_cell) {
-                unsigned slot = 0;
-                if (lane == 0) slot = atomicAdd(n_items, 1u);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (slot < item_cap) { if (lane == 0) { ArcItem itx; itx.e = e; itx.cell = cell; itx.rmax = rmax; items[slot] = itx; } n_emitted++; }
-                else inline_cell = true;                                     // (the item list is full)
+            const unsigned m = __ballot_sync(0xffffffffu, have);
+            if (!m) continue;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(n_items, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned slot = base + (unsigned)__popc(m & lt_mask);
+            if (have && slot < item_cap) {
+                ArcItem itx; itx.e = e; itx.cell = cell; itx.rmax = rmax; itx.t_in = (float)t_in * 0.99999f;
+                items[slot] = itx;
             }
-            if (inline_cell) {
-                R.cell(cell, rmax);
-                if (!ANY) W.t_end = fmin(W.t_end, (double)R.tlim * 1.000001);
-            }
+            n_emitted += (unsigned)__popc(m);
+            // an arc that runs on and on (or a full item list): the block-wide scan of every record (k_far_linear) is complete
+            if (base + (unsigned)__popc(m) > item_cap || (heavy_idx && n_emitted >= ARC_MAX_CELLS)) { given_up = true; break; }
         }
-        n_it += W.n_it;
+        n_it = W.n_it;
+        if (given_up && lane == 0) heavy_idx[atomicAdd(heavy_count, 1u)] = e;
     }
     // the triangles too small for the direction index (fg_wide): anywhere along the ray, same filter
-    if (sc.fg_n_wide > 0 && !(ANY && R.found)) R.list(sc.fg_wide, 0ull, (unsigned long long)sc.fg_n_wide, false, inf);
+    if (sc.fg_n_wide > 0) R.list(sc.fg_wide, 0ull, (unsigned long long)sc.fg_n_wide, false, inf);
     if (lane == 0) {
-        // (statistics from one ray in 64: four atomics per ray on four addresses cost more than the walk itself)
-        if (stat && (w & 63u) == 0u) { atomicAdd(stat + 2, 64u * (R.n_cells + n_emitted)); atomicAdd(stat + 3, 64u * R.n_exact); atomicMax(stat + 1, n_it); }
+        if (stat && (w & 63u) == 0u) { atomicAdd(stat + 2, 64u * n_emitted); atomicAdd(stat + 3, 64u * R.n_exact); atomicMax(stat + 1, n_it); }
         if (R.found) {
             if (ANY) res[e].found = 1;
             else atomicMin(&res[e].key, slow_key(R.tlim, R.plim));
@@ -1077,6 +1099,7 @@ k_fg_arc_items(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __rest
         const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(&res[e].key);
         const float kt = __uint_as_float((unsigned)(key >> 32)); const int kp = (int)(unsigned)(key & 0xffffffffull);
         if (kt < R.tlim || (kt == R.tlim && kp < R.plim)) { R.tlim = kt; R.plim = kp; }
+        if (itx.t_in > R.tlim) return;                                       // the ray has been answered nearer than this cell
     }
     R.cell(itx.cell, itx.rmax);
     if (lane == 0 && R.found) {
@@ -3099,7 +3122,7 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         unsigned int* heavy_count = c->fgq_hist.p;               // (free again as well) [0] heavy, [1] arc items, [2] far-heavy, [3] rest
         CU(cudaMemsetAsync(heavy_count, 0, 4 * sizeof(unsigned), st));
         // (the cells of long arcs become work items: up to 8 per ray of the list, the rest is walked in place)
-        const unsigned item_cap = n_lin > (1u << 26) ? (1u << 29) : n_lin * 8u + 65536u;
+        const unsigned item_cap = n_lin > (1u << 26) ? (1u << 29) : n_lin * 8u + (1u << 21);
         CU(c->arc_items.ensure(item_cap, 0, st));
         unsigned int* n_items = heavy_count + 1;
         CU(c->arc_pre.ensure((size_t)n_lin * sizeof(ArcPre), 0, st));
