@@ -83,7 +83,10 @@ __device__ __forceinline__ int fg_cell_of_point_d(double x, double y, double z, 
 
 // T for a list entry: the triangle's bound times 2^(k6 / 4), a hair below
 __device__ __forceinline__ float fg_entry_T(float Ti, unsigned k6) {
-    return Ti * exp2f(0.25f * (float)k6) * 0.999998f;
+    // 2^(k6 / 4) = 2^(k6 >> 2) * 2^((k6 & 3) / 4): a power of two built from its exponent bits, times one of four constants
+    // (the build rounds k6 down with 1e-3 to spare in the exponent, fargrid_build.cu: the constants' last bit does not matter)
+    const float frac = (k6 & 2u) ? ((k6 & 1u) ? 1.6817928f : 1.4142135f) : ((k6 & 1u) ? 1.1892071f : 1.0f);
+    return Ti * (frac * __uint_as_float((127u + (k6 >> 2)) << 23)) * 0.999998f;
 }
 
 }  // namespace rt580

@@ -593,7 +593,7 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
                 const float4 fa = __ldg(sc.fg_A + ids[u]);
                 const float2 fb = __ldg(sc.fg_B + ids[u]);
                 eTs[u] = fg_entry_T(fb.x, has_k6 ? (ent >> FG_ID_BITS) : 0u);
-                frs[u] = make_float4(fa.x, fa.y, fa.z, fb.y / eTs[u] * 1.00001f + FG_ND_SLACK);
+                frs[u] = make_float4(fa.x, fa.y, fa.z, __fdividef(fb.y, eTs[u]) * 1.00001f + FG_ND_SLACK);    // (2 ulp: within the factor)
                 eDs[u] = fa.w;
             }
         }
@@ -840,7 +840,9 @@ struct ArcRay {
                 if (mask) {
                     if (pass) q[q_len + (unsigned)__popc(mask & lt_mask)] = id;
                     q_len += (unsigned)__popc(mask);
-                    flush(ANY);                                  // any hit: test right away, the first acceptor ends the ray
+                    // any hit: the first acceptor ends the ray, but a batch of exact tests costs the same for 2 candidates as
+                    // for 32 (and a far-away ray is accepted by one candidate in ten or so): wait for a dozen
+                    if (q_len >= (ANY ? 12u : 32u)) flush(ANY);
                     if (ANY && found) return;
                 }
             }
