@@ -965,9 +965,9 @@ k_fg_arc_pre(DeviceScene sc, const SlowRay* __restrict__ rays, const unsigned in
 // Rays whose arc goes on after these cells, and all unanswered rays when the scene has a list of triangles too small for the
 // direction index, are listed for k_fg_arc (`rest`).
 // (any hit, unbounded: the cell of the ray's direction, where |P| exceeds every T, has been through k_fg_lin_first already)
-#define ARC_FIRST_WARPS 8
+#define ARC_FIRST_WARPS 4
 template <bool ANY>
-__global__ void __launch_bounds__(32 * ARC_FIRST_WARPS, 4)
+__global__ void __launch_bounds__(32 * ARC_FIRST_WARPS, 8)
 k_fg_arc_first(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
                unsigned n_lin, unsigned int* __restrict__ stat, const ArcPre* __restrict__ pre, unsigned int* __restrict__ rest_idx,
                unsigned int* __restrict__ rest_count)
