@@ -504,6 +504,8 @@ k_fg_bin(const SlowRay* __restrict__ rays, unsigned n, int K, unsigned int* __re
         return;
     }
     if (lin) {                                                   // not part of the sorted order: k_fg_scan never sees it
+        // a bounded ray (the shadow ray of a point light) ends long before it is "far along d": straight to the arc kernels
+        if (__ldg(&rays[e].o).w < 3.0e38f) { lin_idx[atomicAdd(lin_count, 1u)] = e; cellof[e] = 0xffffffffu; if (hist) rank[e] = 0xffffffffu; return; }
         first_idx[atomicAdd(first_count, 1u)] = e;
         cellof[e] = (unsigned)cell;
         if (hist) rank[e] = 0xffffffffu;
