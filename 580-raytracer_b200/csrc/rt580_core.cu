@@ -602,22 +602,18 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
 #pragma unroll
         for (int u = 0; u < FG_U4; u++) {
             if (base + 32 * u >= len) break;
-            const float4 fr = frs[u]; const float eD = eDs[u], eT = eTs[u]; const unsigned id = ids[u];
+            const float4 fr = frs[u]; const float eD = eDs[u], eT = eTs[u] * 0.999998f; const unsigned id = ids[u];
             for (unsigned rest = live; rest;) {
                 const int j = __ffs((int)rest) - 1;
                 rest &= rest - 1u;
-                const float4 dj = sh.D[j];
+                // both stages for all 32 entries at once, without a branch (one entry in seven passes stage 1: some lane always does)
+                const float4 dj = sh.D[j], oj = sh.O[j];
                 const float nd = __fmaf_rn(fr.x, dj.x, __fmaf_rn(fr.y, dj.y, fr.z * dj.z));
+                const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
                 const float and_ = fabsf(nd);
-                bool pass = and_ <= fr.w && and_ > FG_ND_MIN;                   // stage 1: the band of the cell
-                if (!__any_sync(0xffffffffu, pass)) continue;
-                if (pass) {
-                    // stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
-                    const float4 oj = sh.O[j];
-                    const float no = __fmaf_rn(fr.x, oj.x, __fmaf_rn(fr.y, oj.y, __fmaf_rn(fr.z, oj.z, eD)));
-                    const float x = (and_ - FG_ND_SLACK) * eT * 0.999998f - dno;
-                    pass = fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
-                }
+                // stage 1: the band of the cell; stage 2: t = -(N.O + D) / (N.d) >= T with this ray's origin, and t > 0
+                const float x = __fmaf_rn(and_ - FG_ND_SLACK, eT, -dno);         // (eT: T * 0.999998)
+                const bool pass = and_ <= fr.w && and_ > FG_ND_MIN && fabsf(no) >= x && (x <= dno || ((no < 0.f) != (nd < 0.f)));
                 const unsigned mask = __ballot_sync(0xffffffffu, pass);
                 if (mask == 0u) continue;
                 if (pass) sh.q[q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)j << 32) | id;
