@@ -466,6 +466,14 @@ def run_ours(args):
                     "traffic": traffic,
                     "traffic_source": (ncu or {}).get("source"),
                     "ncu": (ncu or {}).get("counters"),
+                    # what actually bounds the kernel: instruction issue (4 warp instructions per SM and clock), at the lane
+                    # utilisation an incoherent any-hit traversal reaches; instructions per ray from the committed ncu capture
+                    "issue": None if not ncu else {
+                        "achieved": ncu["counters"]["warp_instructions_per_ray"] * ao_rays / (ao_ms * 1e-3) / 1e9 if ao_ms > 0 else 0.0,
+                        "peak": dev["sm_count"] * 4 * sm_mhz * 1e6 / 1e9 * world, "unit": "G warp instructions/s",
+                        "frac": (ncu["counters"]["warp_instructions_per_ray"] * ao_rays / (ao_ms * 1e-3) / 1e9) / (dev["sm_count"] * 4 * sm_mhz * 1e6 / 1e9 * world) if ao_ms > 0 else None,
+                        "warp_instructions_per_ray": ncu["counters"]["warp_instructions_per_ray"],
+                        "active_lanes_per_instruction": ncu["counters"]["active_lanes_per_instruction"]},
                     "hbm": {"achieved": ao_rays * b_any / (ao_ms * 1e-3) / 1e9 if ao_ms > 0 else 0.0, "peak": float(peaks["hbm_gbs"]) * world, "unit": "GB/s",
                             "bytes_per_ray": b_any,
                             "note": "algorithmic node + primitive bytes per ray x rays / kernel time: what the L1 / L2 hierarchy serves; "

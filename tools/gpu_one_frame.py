@@ -27,8 +27,8 @@ def main():
     for _ in range(frames):
         t0 = time.time()
         fb, st = ctx.render(p)
-        print("frame %.1f ms wall; device %.2f (structure %.2f order %.2f ao %.2f resolve %.2f); rays %d (ao %d traversed %d) far_scans %d linear %d launches %d" % (
-            (time.time() - t0) * 1e3, st.ms_total, st.ms_structure, st.ms_order, st.ms_ao, st.ms_resolve, st.rays, st.rays_ao, st.ao_rays_traversed,
+        print("frame %.1f ms wall; device %.2f (structure %.2f order %.2f ao %.2f resolve %.2f); rays %d (ao %d traversed %d) shadow traversed %d far_scans %d linear %d launches %d" % (
+            (time.time() - t0) * 1e3, st.ms_total, st.ms_structure, st.ms_order, st.ms_ao, st.ms_resolve, st.rays, st.rays_ao, st.ao_rays_traversed, st.shadow_rays_traversed,
             st.far_scans, st.linear_fallbacks, st.kernel_launches), flush=True)
     ctx.close()
 
