@@ -34,6 +34,7 @@ EXPORTS = [
     "rt580_raytracer_new", "rt580_raytracer_delete", "rt580_raytracer_set_assets_path", "rt580_raytracer_set_options", "rt580_raytracer_set_quiet",
     "rt580_raytracer_load_scene_json", "rt580_raytracer_render", "rt580_raytracer_flush_ppm",
     "rt580_raytracer_framebuffer", "rt580_raytracer_stats", "rt580_raytracer_flat_scene",
+    "rt580_upload_instanced_scene", "rt580_flatten_instanced", "rt580_raytracer_set_device_flatten", "rt580_raytracer_instanced_scene",
     "rt580_raytracer_render_params", "rt580_raytracer_set_gpus", "rt580_raytracer_set_mesh_cache", "rt580_raytracer_mesh_cache_hits",
 ]
 
@@ -53,6 +54,17 @@ class FlatScene(ctypes.Structure):
         ("n_spheres", ctypes.c_int64), ("sph_center_r", ctypes.c_void_p), ("sph_prim", ctypes.c_void_p),
         ("sph_material", ctypes.c_void_p),
         ("n_materials", ctypes.c_int32), ("materials", ctypes.c_void_p),
+        ("n_lights", ctypes.c_int32), ("light_type", ctypes.c_void_p), ("light_f", ctypes.c_void_p),
+        ("origin_hint", ctypes.c_float * 3),
+    ]
+
+
+class InstancedScene(ctypes.Structure):
+    """rt580_instanced_scene: the scene before FlattenScene (meshes in object space, one model matrix per shape)."""
+    _fields_ = [
+        ("n_meshes", ctypes.c_int32), ("mesh_first", ctypes.c_void_p), ("mesh_tris", ctypes.c_void_p),
+        ("n_shapes", ctypes.c_int32), ("shape_mesh", ctypes.c_void_p), ("shape_matrix", ctypes.c_void_p),
+        ("shape_radius", ctypes.c_void_p), ("materials", ctypes.c_void_p),
         ("n_lights", ctypes.c_int32), ("light_type", ctypes.c_void_p), ("light_f", ctypes.c_void_p),
         ("origin_hint", ctypes.c_float * 3),
     ]
@@ -179,6 +191,10 @@ def lib():
         L.rt580_raytracer_set_quiet.argtypes = [vp, i32]
         L.rt580_raytracer_load_scene_json.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_set_gpus.argtypes = [vp, i32]
+        L.rt580_raytracer_set_device_flatten.argtypes = [vp, i32]
+        L.rt580_raytracer_instanced_scene.argtypes = [vp, ctypes.POINTER(InstancedScene)]
+        L.rt580_upload_instanced_scene.argtypes = [vp, ctypes.POINTER(InstancedScene)]
+        L.rt580_flatten_instanced.argtypes = [vp, ctypes.POINTER(InstancedScene)] + [vp] * 11
         L.rt580_raytracer_set_mesh_cache.argtypes = [vp, ctypes.c_char_p]
         L.rt580_raytracer_mesh_cache_hits.argtypes = [vp]
         L.rt580_raytracer_render.argtypes = [vp, ctypes.c_char_p]
@@ -229,6 +245,20 @@ class Context:
 
     def upload_scene(self, flat: FlatScene):
         _check(lib().rt580_upload_scene(self._h, ctypes.byref(flat)))
+
+    def upload_instanced_scene(self, inst: InstancedScene):
+        """The same scene from meshes + one model matrix per shape: FlattenScene runs on the device (rt580.h)."""
+        _check(lib().rt580_upload_instanced_scene(self._h, ctypes.byref(inst)))
+
+    def flatten_instanced(self, inst: InstancedScene, n_tris, n_spheres):
+        """The device flatten alone, copied back: arrays named as in flat_scene_arrays (a test hook)."""
+        f4 = lambda n: np.zeros((n, 4), np.float32)
+        i1 = lambda n: np.zeros(n, np.int32)
+        out = {"tri_v0": f4(n_tris), "tri_v1": f4(n_tris), "tri_v2": f4(n_tris), "tri_n0": f4(n_tris), "tri_n1": f4(n_tris), "tri_n2": f4(n_tris),
+               "tri_prim": i1(n_tris), "tri_material": i1(n_tris), "sph_center_r": f4(n_spheres), "sph_prim": i1(n_spheres), "sph_material": i1(n_spheres)}
+        order = ["tri_v0", "tri_v1", "tri_v2", "tri_n0", "tri_n1", "tri_n2", "tri_prim", "tri_material", "sph_center_r", "sph_prim", "sph_material"]
+        _check(lib().rt580_flatten_instanced(self._h, ctypes.byref(inst), *[out[k].ctypes.data if out[k].size else None for k in order]))
+        return out
 
     def scene_info(self):
         info = SceneInfo()
@@ -406,6 +436,16 @@ class Raytracer:
 
     def SetGpus(self, n_gpus):
         return lib().rt580_raytracer_set_gpus(self._h, n_gpus)
+
+    def SetDeviceFlatten(self, on=True):
+        return lib().rt580_raytracer_set_device_flatten(self._h, 1 if on else 0)
+
+    def instanced_scene(self):
+        inst = InstancedScene()
+        st = lib().rt580_raytracer_instanced_scene(self._h, ctypes.byref(inst))
+        if st != RT_SUCCESS:
+            raise Rt580Error(st, "no scene loaded")
+        return inst   # borrows the Raytracer's buffers: keep `self` alive while it is used
 
     def SetMeshCacheDir(self, directory):
         return lib().rt580_raytracer_set_mesh_cache(self._h, (directory or "").encode())

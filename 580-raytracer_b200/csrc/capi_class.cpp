@@ -46,6 +46,15 @@ int rt580_raytracer_set_mesh_cache(rt580_raytracer* h, const char* dir) {
     h->rt->SetMeshCacheDir(dir ? dir : "");
     return RT_SUCCESS;
 }
+int rt580_raytracer_set_device_flatten(rt580_raytracer* h, int on) {
+    if (!h) return RT_INVALID_ARG;
+    h->rt->SetDeviceFlatten(on != 0);
+    return RT_SUCCESS;
+}
+int rt580_raytracer_instanced_scene(rt580_raytracer* h, rt580_instanced_scene* out) {
+    if (!h || !out) return RT_INVALID_ARG;
+    return h->rt->GetInstancedScene(out);
+}
 int rt580_raytracer_mesh_cache_hits(rt580_raytracer* h) { return h ? h->rt->MeshCacheHits() : -1; }
 int rt580_raytracer_load_scene_json(rt580_raytracer* h, const char* scene) {
     if (!h || !scene) return RT_INVALID_ARG;

@@ -1,7 +1,7 @@
 // Command-line driver.  With no arguments it is the reference's main() (Raytracer.cpp:944-953):
 // 500x500, simpleSphereScene.json from ./Assets/, output.ppm.
 //   rt580_main [scene.json] [width] [height] [output.ppm] [assets_dir] [ao_spp] [depth]
-//              [--gpus N] [--bench FRAMES] [--farfield exact|off] [--device D] [--mesh-cache DIR] [--no-ppm]
+//              [--gpus N] [--bench FRAMES] [--farfield exact|off] [--device D] [--mesh-cache DIR] [--no-ppm] [--device-flatten]
 // --gpus N    rows interleaved over GPUs D .. D+N-1 of this process (Raytracer::SetGpus)
 // --bench K   render K frames (after one warm-up frame) and print SURVEY 8d's table for this configuration: rays by kind,
 //             ms per frame, Mrays/s (one ray = one IntersectScene call of the reference), and where the device time goes
@@ -18,6 +18,7 @@ int main(int argc, char** argv) {
     int gpus = 1, bench = 0, device = 0, farfield = RT580_FARFIELD_EXACT;
     bool ppm = true;
     std::string mesh_cache;
+    bool device_flatten = false;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -27,9 +28,10 @@ int main(int argc, char** argv) {
         else if (a == "--farfield") farfield = strcmp(next(), "off") == 0 ? RT580_FARFIELD_OFF : RT580_FARFIELD_EXACT;
         else if (a == "--mesh-cache") mesh_cache = next();
         else if (a == "--no-ppm") ppm = false;
+        else if (a == "--device-flatten") device_flatten = true;
         else if (a == "--help" || a == "-h") {
             fprintf(stderr, "usage: rt580_main [scene.json] [width] [height] [output.ppm] [assets_dir] [ao_spp] [depth] "
-                            "[--gpus N] [--bench FRAMES] [--farfield exact|off] [--device D] [--mesh-cache DIR] [--no-ppm]\n");
+                            "[--gpus N] [--bench FRAMES] [--farfield exact|off] [--device D] [--mesh-cache DIR] [--no-ppm] [--device-flatten]\n");
             return 0;
         } else pos.push_back(a);
     }
@@ -40,7 +42,7 @@ int main(int argc, char** argv) {
     if (pos.size() > 4) { std::string d = pos[4]; if (!d.empty() && d.back() != '/') d += '/'; rt.SetAssetsPath(d); }
     if (pos.size() > 5) rt.SetAmbientOcclusionSamples(atoi(pos[5].c_str()));
     if (pos.size() > 6) rt.SetBounces(atoi(pos[6].c_str()));
-    rt.SetGpus(gpus); rt.SetDevice(device); rt.SetFarField(farfield);
+    rt.SetGpus(gpus); rt.SetDevice(device); rt.SetFarField(farfield); rt.SetDeviceFlatten(device_flatten);
     if (!mesh_cache.empty()) rt.SetMeshCacheDir(mesh_cache);
     if (bench > 0) rt.SetQuiet(true);
     const auto t_load = std::chrono::steady_clock::now();

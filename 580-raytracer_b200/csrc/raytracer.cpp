@@ -372,6 +372,43 @@ int Raytracer::FlattenScene() {
     return RT_SUCCESS;
 }
 
+int Raytracer::GetInstancedScene(rt580_instanced_scene* out) {
+    if (!out || !mScene) return RT_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    mInstMeshFirst.assign(1, 0); mInstMeshTris.clear(); mInstMatrix.clear(); mInstRadius.clear(); mInstShapeMesh.clear();
+    std::map<std::string, int32_t> meshIndex;
+    for (const Shape& sh : mScene->shapes) {
+        auto it = mScene->meshMap.find(sh.geometryId);
+        if (it == mScene->meshMap.end()) return RT_FAILURE;
+        const Mesh& mesh = it->second;
+        int32_t mi = -1;
+        if (mesh.type == Mesh::RT_POLYGON) {
+            auto f = meshIndex.find(sh.geometryId);
+            if (f == meshIndex.end()) {
+                mi = (int32_t)meshIndex.size();
+                meshIndex[sh.geometryId] = mi;
+                static_assert(sizeof(Triangle) == 18 * sizeof(float), "Triangle is 18 packed floats");
+                const float* p = reinterpret_cast<const float*>(mesh.triangles.data());
+                mInstMeshTris.insert(mInstMeshTris.end(), p, p + mesh.triangles.size() * 18);
+                mInstMeshFirst.push_back((int64_t)(mInstMeshTris.size() / 18));
+            } else mi = f->second;
+        }
+        mInstShapeMesh.push_back(mi);
+        const Matrix M = ComputeModelMatrix(sh.transforms);                     // cpp:480
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) mInstMatrix.push_back(M.m[r][c]);
+        mInstRadius.push_back(mesh.radius);
+    }
+    out->n_meshes = (int32_t)meshIndex.size();
+    out->mesh_first = mInstMeshFirst.data(); out->mesh_tris = mInstMeshTris.data();
+    out->n_shapes = (int32_t)mInstShapeMesh.size();
+    out->shape_mesh = mInstShapeMesh.data(); out->shape_matrix = mInstMatrix.data(); out->shape_radius = mInstRadius.data();
+    out->materials = mMaterials.data();
+    out->n_lights = (int32_t)mLightType.size();
+    out->light_type = mLightType.data(); out->light_f = mLightF.data();
+    out->origin_hint[0] = mScene->camera.from.x; out->origin_hint[1] = mScene->camera.from.y; out->origin_hint[2] = mScene->camera.from.z;
+    return RT_SUCCESS;
+}
+
 int Raytracer::GetFlatScene(rt580_flat_scene* out) const {
     if (!out || !mScene) return RT_INVALID_ARG;
     memset(out, 0, sizeof *out);
@@ -439,8 +476,10 @@ int Raytracer::EnsureContext() {
     }
     if (!mSceneUploaded) {
         rt580_flat_scene fs;
+        rt580_instanced_scene is;
         if (GetFlatScene(&fs) != RT_SUCCESS) return RT_FAILURE;
-        if (rt580_upload_scene(mCtx, &fs) != RT580_SUCCESS) {
+        if (mDeviceFlatten && GetInstancedScene(&is) != RT_SUCCESS) return RT_FAILURE;
+        if ((mDeviceFlatten ? rt580_upload_instanced_scene(mCtx, &is) : rt580_upload_scene(mCtx, &fs)) != RT580_SUCCESS) {
             std::cerr << "Raytracer: " << rt580_last_error() << "\n";
             return RT_FAILURE;
         }
@@ -473,7 +512,9 @@ int Raytracer::RenderMultiGpu(const rt580_render_params& rp) {
     mPeers.resize((size_t)n - 1, nullptr);
     mPeerUploaded.resize((size_t)n - 1, 0);
     rt580_flat_scene fs;
+    rt580_instanced_scene is;
     if (GetFlatScene(&fs) != RT_SUCCESS) return RT_FAILURE;
+    if (mDeviceFlatten && GetInstancedScene(&is) != RT_SUCCESS) return RT_FAILURE;
     std::vector<rt580_context*> ctx((size_t)n);
     ctx[0] = mCtx;
     std::vector<int> status((size_t)n, RT580_SUCCESS);
@@ -489,7 +530,7 @@ int Raytracer::RenderMultiGpu(const rt580_render_params& rp) {
         if (g == 0) return RT580_SUCCESS;
         if (!mPeers[g - 1]) { const int s2 = rt580_create(mDevice + g, &mPeers[g - 1]); if (s2 != RT580_SUCCESS) return s2; }
         ctx[g] = mPeers[g - 1];
-        if (!mPeerUploaded[g - 1]) { const int s2 = rt580_upload_scene(ctx[g], &fs); if (s2 != RT580_SUCCESS) return s2; mPeerUploaded[g - 1] = 1; }
+        if (!mPeerUploaded[g - 1]) { const int s2 = mDeviceFlatten ? rt580_upload_instanced_scene(ctx[g], &is) : rt580_upload_scene(ctx[g], &fs); if (s2 != RT580_SUCCESS) return s2; mPeerUploaded[g - 1] = 1; }
         return RT580_SUCCESS;
     });
     if (st != RT580_SUCCESS) return st;

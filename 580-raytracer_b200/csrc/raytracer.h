@@ -97,6 +97,10 @@ public:
     // (teapot.json: 472 KB of text for 1024 triangles).  Keyed by the JSON's size and a hash of its bytes: the JSON stays the
     // source of truth, a stale or damaged cache file is ignored and rewritten.  Empty = no cache (the default).
     void SetMeshCacheDir(const std::string& dir) { mMeshCacheDir = dir; }
+    // FlattenScene's TransformPoint calls (cpp:353-355) on the device: the context receives the meshes in object
+    // space and one model matrix per shape instead of the flattened arrays.  Same bytes on the device, same frame.
+    void SetDeviceFlatten(bool on) { if (on != mDeviceFlatten) { mDeviceFlatten = on; mSceneUploaded = false; for (auto& u : mPeerUploaded) u = 0; } }
+    int  GetInstancedScene(rt580_instanced_scene* out);
     int  MeshCacheHits() const { return mMeshCacheHits; }
     rt580_context* Context() const { return mCtx; }
     int  RenderToFrameBuffer();                                        // Render without the PPM
@@ -139,6 +143,9 @@ private:
     std::vector<rt580_context*> mPeers;    // contexts on GPUs 1 .. mGpus-1 (SetGpus)
     std::vector<char> mPeerUploaded;      // char, not bool: written from one thread per GPU
     int mGpus = 1;
+    bool mDeviceFlatten = false;
+    // the un-flattened scene for rt580_upload_instanced_scene (built on demand by GetInstancedScene)
+    std::vector<int64_t> mInstMeshFirst; std::vector<float> mInstMeshTris, mInstMatrix, mInstRadius; std::vector<int32_t> mInstShapeMesh;
     std::string mMeshCacheDir;
     int mMeshCacheHits = 0;
     bool mSceneUploaded = false;

@@ -2664,7 +2664,114 @@ static int far_grid_ensure(rt580_context* c)
     return RT580_SUCCESS;
 }
 
-extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
+// ---- FlattenScene on the device ----------------------------------------------------------------------------
+// Matrix::TransformPoint (h:234-248): ((m0 x + m1 y) + m2 z) + m3 per row, unfused (this file is built -fmad=false), and the
+// division by w when w != 1 - the operations and the order of the reference, so the arrays equal the host's bit for bit.
+__device__ __forceinline__ float4 transform_point_ref(const float* __restrict__ M, float px, float py, float pz)
+{
+    float x = M[0] * px + M[1] * py + M[2] * pz + M[3];
+    float y = M[4] * px + M[5] * py + M[6] * pz + M[7];
+    float z = M[8] * px + M[9] * py + M[10] * pz + M[11];
+    const float w = M[12] * px + M[13] * py + M[14] * pz + M[15];
+    if (w != 1.0f) { x /= w; y /= w; z /= w; }
+    return make_float4(x, y, z, 0.0f);
+}
+struct FlatDev {
+    float4 *v0, *v1, *v2, *n0, *n1, *n2, *sph;
+    int32_t *tprim, *tmat, *sprim, *smat;
+};
+__global__ void __launch_bounds__(256)
+k_flatten_tris(long long n_tris, int n_shapes, const long long* __restrict__ shape_tri_first, const int32_t* __restrict__ shape_prim_first,
+               const int32_t* __restrict__ shape_mesh, const long long* __restrict__ mesh_first, const float* __restrict__ mesh_tris,
+               const float* __restrict__ shape_matrix, FlatDev out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    int lo = 0, hi = n_shapes;                       // the last shape whose first triangle is <= t (spheres and empty meshes: zero length)
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (shape_tri_first[mid] <= t) lo = mid; else hi = mid; }
+    const int k = lo;
+    const long long local = t - shape_tri_first[k];
+    const float* src = mesh_tris + (mesh_first[shape_mesh[k]] + local) * 18;
+    const float* M = shape_matrix + (size_t)k * 16;
+    out.v0[t] = transform_point_ref(M, src[0], src[1], src[2]);            // cpp:353
+    out.v1[t] = transform_point_ref(M, src[3], src[4], src[5]);            // cpp:354
+    out.v2[t] = transform_point_ref(M, src[6], src[7], src[8]);            // cpp:355
+    out.n0[t] = make_float4(src[9], src[10], src[11], 0.0f);               // object space
+    out.n1[t] = make_float4(src[12], src[13], src[14], 0.0f);
+    out.n2[t] = make_float4(src[15], src[16], src[17], 0.0f);
+    out.tprim[t] = shape_prim_first[k] + (int32_t)local;
+    out.tmat[t] = k;
+}
+__global__ void __launch_bounds__(256)
+k_flatten_spheres(int n_shapes, const int32_t* __restrict__ shape_mesh, const int32_t* __restrict__ shape_prim_first,
+                  const int32_t* __restrict__ shape_sph_index, const float* __restrict__ shape_matrix, const float* __restrict__ shape_radius, FlatDev out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_shapes || shape_mesh[k] >= 0) return;
+    const float* M = shape_matrix + (size_t)k * 16;
+    const int si = shape_sph_index[k];
+    out.sph[si] = make_float4(M[3], M[7], M[11], shape_radius[k]);         // h:212-214, cpp:423
+    out.sprim[si] = shape_prim_first[k];
+    out.smat[si] = k;
+}
+// host tables of an instanced scene + the kernels; the arrays come out of `ta`
+struct InstTables { std::vector<long long> tri_first; std::vector<int32_t> prim_first, sph_index; long long n_tris = 0, n_spheres = 0, n_prims = 0; int64_t first_tri = -1; int32_t first_prim = 0x7fffffff; };
+static int inst_tables(const rt580_instanced_scene* s, InstTables& T)
+{
+    if (!s || s->n_meshes < 0 || s->n_shapes < 0 || s->n_lights < 0) FAIL(RT580_INVALID_ARG, "instanced scene: negative count");
+    if ((s->n_meshes && (!s->mesh_first || (s->mesh_first[s->n_meshes] && !s->mesh_tris))) || (s->n_shapes && (!s->shape_mesh || !s->shape_matrix || !s->shape_radius || !s->materials)))
+        FAIL(RT580_INVALID_ARG, "instanced scene: NULL table");
+    T.tri_first.assign((size_t)s->n_shapes + 1, 0); T.prim_first.assign((size_t)s->n_shapes + 1, 0); T.sph_index.assign((size_t)s->n_shapes + 1, 0);
+    long long nt = 0, np = 0, ns = 0;
+    for (int k = 0; k < s->n_shapes; k++) {
+        T.tri_first[k] = nt; T.prim_first[k] = (int32_t)np; T.sph_index[k] = (int32_t)ns;
+        const int m = s->shape_mesh[k];
+        if (m >= s->n_meshes) FAIL(RT580_INVALID_ARG, "instanced scene: shape %d names mesh %d of %d", k, m, s->n_meshes);
+        if (m < 0) { ns++; np++; }
+        else {
+            const long long cnt = s->mesh_first[m + 1] - s->mesh_first[m];
+            if (cnt < 0) FAIL(RT580_INVALID_ARG, "instanced scene: mesh_first decreases");
+            if (cnt > 0 && T.first_tri < 0) { T.first_tri = nt; T.first_prim = (int32_t)np; }
+            nt += cnt; np += cnt;
+        }
+        if (np > 0x7ffffff0ll) FAIL(RT580_INVALID_ARG, "instanced scene: too many primitives");
+    }
+    T.tri_first[s->n_shapes] = nt;
+    T.n_tris = nt; T.n_spheres = ns; T.n_prims = np;
+    return RT580_SUCCESS;
+}
+static int flatten_on_device(const rt580_instanced_scene* s, const InstTables& T, DevArena& ta, cudaStream_t st, FlatDev* out)
+{
+    FlatDev f{};
+    const size_t nt = (size_t)T.n_tris, ns = (size_t)T.n_spheres;
+    f.v0 = ta.take<float4>(nt); f.v1 = ta.take<float4>(nt); f.v2 = ta.take<float4>(nt);
+    f.n0 = ta.take<float4>(nt); f.n1 = ta.take<float4>(nt); f.n2 = ta.take<float4>(nt);
+    f.tprim = ta.take<int32_t>(nt); f.tmat = ta.take<int32_t>(nt);
+    f.sph = ta.take<float4>(ns); f.sprim = ta.take<int32_t>(ns); f.smat = ta.take<int32_t>(ns);
+    long long *d_tri_first = nullptr, *d_mesh_first = nullptr; int32_t *d_prim_first = nullptr, *d_sph_index = nullptr, *d_shape_mesh = nullptr;
+    float *d_mesh_tris = nullptr, *d_matrix = nullptr, *d_radius = nullptr;
+    const size_t nsh = (size_t)s->n_shapes;
+    CU(upload(ta, &d_tri_first, T.tri_first.data(), nsh + 1, st));
+    CU(upload(ta, &d_prim_first, T.prim_first.data(), nsh + 1, st));
+    CU(upload(ta, &d_sph_index, T.sph_index.data(), nsh + 1, st));
+    CU(upload(ta, &d_shape_mesh, s->shape_mesh, nsh, st));
+    CU(upload(ta, &d_mesh_first, s->mesh_first, (size_t)s->n_meshes + (s->n_meshes ? 1 : 0), st));
+    CU(upload(ta, &d_mesh_tris, s->mesh_tris, s->n_meshes ? (size_t)s->mesh_first[s->n_meshes] * 18 : 0, st));
+    CU(upload(ta, &d_matrix, s->shape_matrix, nsh * 16, st));
+    CU(upload(ta, &d_radius, s->shape_radius, nsh, st));
+    if ((nt && (!f.v0 || !f.v1 || !f.v2 || !f.n0 || !f.n1 || !f.n2 || !f.tprim || !f.tmat)) || (ns && (!f.sph || !f.sprim || !f.smat)))
+        FAIL(RT580_FAILURE, "instanced scene: arena exhausted");
+    if (nt) k_flatten_tris<<<nblk_ll(T.n_tris, 256), 256, 0, st>>>(T.n_tris, s->n_shapes, d_tri_first, d_prim_first, d_shape_mesh, d_mesh_first, d_mesh_tris, d_matrix, f);
+    if (ns) k_flatten_spheres<<<nblk_ll(s->n_shapes, 256), 256, 0, st>>>(s->n_shapes, d_shape_mesh, d_prim_first, d_sph_index, d_matrix, d_radius, f);
+    CU(cudaGetLastError());
+    *out = f;
+    return RT580_SUCCESS;
+}
+static size_t inst_input_bytes(const rt580_instanced_scene* s) {
+    return (size_t)s->n_shapes * (8 + 4 + 4 + 4 + 64 + 4 + 64) + (size_t)(s->n_meshes + 1) * 8 + (s->n_meshes ? (size_t)s->mesh_first[s->n_meshes] * 72 : 0) + 32 * 256;
+}
+
+static int upload_scene_impl(rt580_context* c, const rt580_flat_scene* s, const rt580_instanced_scene* inst, const InstTables* IT)
 {
     if (!c || !s) FAIL(RT580_INVALID_ARG, "rt580_upload_scene: NULL argument");
     if (s->n_tris < 0 || s->n_spheres < 0 || s->n_prims != s->n_tris + s->n_spheres || s->n_lights < 0 || s->n_materials < 0)
@@ -2676,7 +2783,7 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     CU(cudaStreamSynchronize(st));
     {
         char aerr[256] = "";
-        const size_t in_bytes = (size_t)s->n_tris * (6 * 16 + 8) + (size_t)s->n_spheres * (16 + 8) + (size_t)s->n_prims * 4 + 8192 + 24 * 256;
+        const size_t in_bytes = (size_t)s->n_tris * (6 * 16 + 8) + (size_t)s->n_spheres * (16 + 8) + (size_t)s->n_prims * 4 + 8192 + 24 * 256 + (inst ? inst_input_bytes(inst) : 0);
         int n_point = 0;
         for (int i = 0; i < s->n_lights; i++) if (s->light_type && s->light_type[i] == RT580_LIGHT_POINT) n_point++;
         if (n_point > SMAP_MAX) n_point = SMAP_MAX;
@@ -2688,6 +2795,14 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     }
     DevArena& ta = c->build_arena; DevArena& sa = c->scene_arena;
     float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr, *sph = nullptr; int32_t *tprim = nullptr, *sprim = nullptr;
+    float4 *tn0 = nullptr, *tn1 = nullptr, *tn2 = nullptr; int32_t *tmat = nullptr, *smat = nullptr; unsigned int* d_bad = nullptr;
+    if (inst) {
+        FlatDev f{};
+        const int fst = flatten_on_device(inst, *IT, ta, st, &f);
+        if (fst != RT580_SUCCESS) return fst;
+        v0 = f.v0; v1 = f.v1; v2 = f.v2; tprim = f.tprim; sph = f.sph; sprim = f.sprim;
+        tn0 = f.n0; tn1 = f.n1; tn2 = f.n2; tmat = f.tmat; smat = f.smat;
+    } else {
     CU(upload(ta, &v0, s->tri_v0, (size_t)s->n_tris, st));
     CU(upload(ta, &v1, s->tri_v1, (size_t)s->n_tris, st));
     CU(upload(ta, &v2, s->tri_v2, (size_t)s->n_tris, st));
@@ -2695,12 +2810,12 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     CU(upload(ta, &sph, s->sph_center_r, (size_t)s->n_spheres, st));
     CU(upload(ta, &sprim, s->sph_prim, (size_t)s->n_spheres, st));
     // shading tables addressed by primitive order index: scattered on the device (k_scatter_shading)
-    float4 *tn0 = nullptr, *tn1 = nullptr, *tn2 = nullptr; int32_t *tmat = nullptr, *smat = nullptr; unsigned int* d_bad = nullptr;
     CU(upload(ta, &tn0, s->tri_n0, (size_t)s->n_tris, st));
     CU(upload(ta, &tn1, s->tri_n1, (size_t)s->n_tris, st));
     CU(upload(ta, &tn2, s->tri_n2, (size_t)s->n_tris, st));
     CU(upload(ta, &tmat, s->tri_material, (size_t)s->n_tris, st));
     CU(upload(ta, &smat, s->sph_material, (size_t)s->n_spheres, st));
+    }
     d_bad = ta.take<unsigned int>(1);
     c->d_vn = sa.take<float4>((size_t)s->n_prims * 3);
     c->d_prim_material = sa.take<int32_t>((size_t)s->n_prims);
@@ -2729,7 +2844,8 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     for (int k = 0; k < 3; k++) in.origin_hint[k] = s->origin_hint[k];
     in.first_tri = -1;
     int32_t first_prim = 0x7fffffff;
-    for (int64_t i = 0; i < s->n_tris; i++) if (s->tri_prim[i] < first_prim) { first_prim = s->tri_prim[i]; in.first_tri = i; }
+    if (inst) { in.first_tri = IT->first_tri; first_prim = IT->first_prim; }
+    else for (int64_t i = 0; i < s->n_tris; i++) if (s->tri_prim[i] < first_prim) { first_prim = s->tri_prim[i]; in.first_tri = i; }
     BuildOutput bo{};
     CU(cudaEventRecord(c->ev[10], st));
     char err[256] = "";
@@ -2778,7 +2894,8 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
             c->sc.fg_sph = fi.sph; c->sc.fg_n_sph = fo.n_sph; c->sc.fg_tmin = fo.t_min;
             {
                 float rmax = 0.f;
-                for (int64_t i = 0; i < s->n_spheres; i++) rmax = fmaxf(rmax, fabsf(s->sph_center_r[4 * i + 3]));
+                if (inst) { for (int k = 0; k < inst->n_shapes; k++) if (inst->shape_mesh[k] < 0) rmax = fmaxf(rmax, fabsf(inst->shape_radius[k])); }
+                else for (int64_t i = 0; i < s->n_spheres; i++) rmax = fmaxf(rmax, fabsf(s->sph_center_r[4 * i + 3]));
                 c->sc.fg_rmax = rmax;
                 for (int k = 0; k < 3; k++) c->sc.fg_center[k] = 0.5f * (c->sc.ob_lo[k] + c->sc.ob_hi[k]);
             }
@@ -2939,6 +3056,52 @@ extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
     c->have_scene = true;
     c->frame_begun = false;
     c->force_leaky = false;
+    return RT580_SUCCESS;
+}
+
+extern "C" int rt580_upload_scene(rt580_context* c, const rt580_flat_scene* s)
+{
+    return upload_scene_impl(c, s, nullptr, nullptr);
+}
+extern "C" int rt580_upload_instanced_scene(rt580_context* c, const rt580_instanced_scene* s)
+{
+    if (!c || !s) FAIL(RT580_INVALID_ARG, "rt580_upload_instanced_scene: NULL argument");
+    InstTables T;
+    const int st = inst_tables(s, T);
+    if (st != RT580_SUCCESS) return st;
+    rt580_flat_scene fs;
+    memset(&fs, 0, sizeof fs);
+    fs.n_prims = T.n_prims; fs.n_tris = T.n_tris; fs.n_spheres = T.n_spheres;
+    fs.n_materials = s->n_shapes; fs.materials = s->materials;
+    fs.n_lights = s->n_lights; fs.light_type = s->light_type; fs.light_f = s->light_f;
+    for (int k = 0; k < 3; k++) fs.origin_hint[k] = s->origin_hint[k];
+    return upload_scene_impl(c, &fs, s, &T);
+}
+extern "C" int rt580_flatten_instanced(rt580_context* c, const rt580_instanced_scene* s, float* tri_v0, float* tri_v1, float* tri_v2,
+                                       float* tri_n0, float* tri_n1, float* tri_n2, int32_t* tri_prim, int32_t* tri_material,
+                                       float* sph_center_r, int32_t* sph_prim, int32_t* sph_material)
+{
+    if (!c || !s) FAIL(RT580_INVALID_ARG, "rt580_flatten_instanced: NULL argument");
+    InstTables T;
+    const int ist = inst_tables(s, T);
+    if (ist != RT580_SUCCESS) return ist;
+    CU(cudaSetDevice(c->device));
+    free_scene(c);                                   // (the build arena is the scratch space: whatever scene was uploaded is gone)
+    cudaStream_t st = c->stream;
+    CU(cudaStreamSynchronize(st));
+    char aerr[256] = "";
+    if (!arena_reserve(c->build_arena, (size_t)T.n_tris * (6 * 16 + 8) + (size_t)T.n_spheres * 24 + inst_input_bytes(s) + 8192, aerr, sizeof aerr))
+        FAIL(RT580_FAILURE, "rt580_flatten_instanced: %s", aerr);
+    FlatDev f{};
+    const int fst = flatten_on_device(s, T, c->build_arena, st, &f);
+    if (fst != RT580_SUCCESS) return fst;
+    const size_t nt = (size_t)T.n_tris, ns = (size_t)T.n_spheres;
+    struct { void* dst; const void* src; size_t bytes; } cp[] = {
+        { tri_v0, f.v0, nt * 16 }, { tri_v1, f.v1, nt * 16 }, { tri_v2, f.v2, nt * 16 }, { tri_n0, f.n0, nt * 16 }, { tri_n1, f.n1, nt * 16 },
+        { tri_n2, f.n2, nt * 16 }, { tri_prim, f.tprim, nt * 4 }, { tri_material, f.tmat, nt * 4 }, { sph_center_r, f.sph, ns * 16 },
+        { sph_prim, f.sprim, ns * 4 }, { sph_material, f.smat, ns * 4 } };
+    for (auto& x : cp) if (x.dst && x.bytes) CU(cudaMemcpyAsync(x.dst, x.src, x.bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return RT580_SUCCESS;
 }
 

@@ -20,6 +20,7 @@ all_gather on the device, the rows stored into rank 0's frame over NVLink.  N > 
 region) that the assembled frame equals rank 0's own single-GPU frame bit for bit.
 """
 import argparse
+import ctypes
 import json
 import os
 import shutil
@@ -38,6 +39,7 @@ METRIC, UNIT = "Mrays/s", "Mrays/s"
 WORKLOAD = "c4_open"
 DEPTH, SPP = 4, 16
 CACHE = "/tmp/rt580_bench_scenes"
+HOST_FLATTEN = False     # --host-flatten
 NCU_CAPTURE = os.path.join(ROOT, "profiles", "r02_ncu_k_anyhit_c4_open.json")     # written by tools/ncu_capture_to_json.py
 
 WORKLOADS = {
@@ -173,6 +175,7 @@ class Rig:
         self.pkg, self.torch, self.dist = pkg, torch, dist
         self.rank, self.world, self.local = rank, world, local
         self.workload = workload
+        self.host_flatten = HOST_FLATTEN
         self.W, self.H, self.scene_text = WORKLOADS[workload]
         W, H = self.W, self.H
         d = scene_dir(workload) if rank == 0 else None
@@ -323,13 +326,23 @@ class Rig:
         pkg, torch, dist = self.pkg, self.torch, self.dist
         W, H, p = self.W, self.H, self.p
         flat = self.flat
-        h2d = int(flat.n_tris * (6 * 16 + 8) + flat.n_spheres * (16 + 8) + flat.n_materials * 32 + flat.n_lights * 44)
+        # the class's upload with SetDeviceFlatten: meshes in object space + one model matrix per shape (rt580_upload_instanced_scene,
+        # SURVEY 8f-2); --host-flatten uploads the flattened arrays instead (rt580_upload_scene)
+        inst = None if self.host_flatten else self.rt.instanced_scene()
+        if inst is None:
+            h2d = int(flat.n_tris * (6 * 16 + 8) + flat.n_spheres * (16 + 8) + flat.n_materials * 32 + flat.n_lights * 44)
+        else:
+            mesh_tris = int(np.frombuffer((ctypes.c_int64 * (inst.n_meshes + 1)).from_address(inst.mesh_first), np.int64)[-1]) if inst.n_meshes else 0
+            h2d = int(mesh_tris * 72 + (inst.n_meshes + 1) * 8 + inst.n_shapes * (64 + 4 + 4 + 32 + 16) + inst.n_lights * 44)
         d2h = int(p.n_rows * W * 6) if self.world == 1 else int(W * H * 6)
         host_out = pkg.HostArray((p.n_rows, W, 3), np.int16) if self.world == 1 else (pkg.HostArray((H, W, 3), np.int16) if self.rank == 0 else None)
 
         def one(upload):
             if upload:
-                self.ctx.upload_scene(flat)
+                if inst is None:
+                    self.ctx.upload_scene(flat)
+                else:
+                    self.ctx.upload_instanced_scene(inst)
             if self.world == 1:
                 self.ctx.render(p, out=host_out.array)
             else:
@@ -503,7 +516,8 @@ def run_ours(args):
                 "ray_classes": classes,
                 "scene_info": head_scene,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms["cold"],
-                        "includes": "rt580_upload_scene (H2D + LBVH + far-field grid build) + rt580_render (D2H int16 frame), every step",
+                        "includes": ("rt580_upload_scene (H2D of the flattened arrays" if HOST_FLATTEN else "rt580_upload_instanced_scene (H2D of meshes + model matrices, FlattenScene on the device") +
+                                    " + LBVH + far-field grid build) + rt580_render (D2H int16 frame), every step",
                         "resident": {"value": m["rays_total"] / (e2e_ms["resident"] * 1e-3) / 1e6, "ms_per_step": e2e_ms["resident"],
                                      "includes": "rt580_render with the scene already uploaded (what a second Raytracer::Render call costs): D2H int16 frame"}},
                 "verify": verify, "records": records, "gpu_launches": int(m["launches"]), "roofline": roofline, "cpu_baseline": cpu,
@@ -521,6 +535,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-flatten", action="store_true", help="e2e uploads the host-flattened arrays (rt580_upload_scene) instead of meshes + matrices")
     ap.add_argument("--farfield", default="exact", choices=["exact", "off"], help="debug only")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(WORKLOADS), help="headline workload")
     ap.add_argument("--records", default="c4_room,c5_open:off,c5_room", help="comma-separated workloads measured after the headline, "
@@ -529,6 +544,8 @@ def main():
     ap.add_argument("--width", type=int, default=0, help="debug only: override the frame width")
     ap.add_argument("--height", type=int, default=0, help="debug only: override the frame height")
     args = ap.parse_args()
+    global HOST_FLATTEN
+    HOST_FLATTEN = bool(args.host_flatten)
     if args.width and args.height:
         for k in list(WORKLOADS):
             WORKLOADS[k] = (args.width, args.height, WORKLOADS[k][2])

@@ -89,6 +89,25 @@ typedef struct rt580_flat_scene {
                                       BVH boxes; a render whose camera lies outside is refused */
 } rt580_flat_scene;
 
+/* The same scene BEFORE FlattenScene: meshes in object space once, one model matrix per shape.  The
+ * library applies Matrix::TransformPoint (h:234-248, the reference's operation order, unfused) on the device and produces
+ * exactly the arrays of rt580_flat_scene - c4: 150 KB over PCIe instead of 104 MB.  Shape k has material k; primitive order =
+ * (shape order, triangle order) as above. */
+typedef struct rt580_instanced_scene {
+    int32_t        n_meshes;
+    const int64_t* mesh_first;     /* [n_meshes + 1] first triangle of each mesh in mesh_tris                     */
+    const float*   mesh_tris;      /* [mesh_first[n_meshes]][18] pos[3].xyz then nrm[3].xyz, object space (h:436) */
+    int32_t        n_shapes;
+    const int32_t* shape_mesh;     /* [n_shapes] mesh index, or -1: a sphere (cpp:421-423)                        */
+    const float*   shape_matrix;   /* [n_shapes][16] row-major model matrix (ComputeModelMatrix, cpp:528-586)     */
+    const float*   shape_radius;   /* [n_shapes] sphere radius, unscaled (cpp:423); ignored for meshes            */
+    const float*   materials;      /* [n_shapes][8] Cs.rgb Ka Kd Ks Kt n                                          */
+    int32_t        n_lights;
+    const int32_t* light_type;
+    const float*   light_f;
+    float          origin_hint[3];
+} rt580_instanced_scene;
+
 typedef struct rt580_render_params {
     int32_t width, height;         /* Display xRes,yRes (h:420-425) - the ctor's, not the JSON's (Q23) */
     float   fov_degrees;           /* Display::fov, 60 in the reference (cpp:786)          */
@@ -181,6 +200,13 @@ void  rt580_host_free(void* p);
 
 /* ---- scene: H2D + per-triangle constants (cpp:362-365, 377, 389) + LBVH build ----------- */
 int  rt580_upload_scene(rt580_context* ctx, const rt580_flat_scene* scene);
+/* the same from the un-flattened scene: FlattenScene (cpp:348-365's TransformPoint calls, hoisted) runs on the device */
+int  rt580_upload_instanced_scene(rt580_context* ctx, const rt580_instanced_scene* scene);
+/* the device flatten alone, results copied back to host arrays laid out as in rt580_flat_scene (a test hook: the arrays
+ * must equal the host FlattenScene's byte for byte).  Any output pointer may be NULL. */
+int  rt580_flatten_instanced(rt580_context* ctx, const rt580_instanced_scene* scene, float* tri_v0, float* tri_v1, float* tri_v2,
+                             float* tri_n0, float* tri_n1, float* tri_n2, int32_t* tri_prim, int32_t* tri_material,
+                             float* sph_center_r, int32_t* sph_prim, int32_t* sph_material);
 /* device ms of the last upload's build kernels (setup, morton, sort, hierarchy, refit, pack) */
 int  rt580_build_ms(rt580_context* ctx, float* ms);
 int  rt580_scene_info_get(rt580_context* ctx, rt580_scene_info* out);
@@ -275,6 +301,9 @@ int  rt580_raytracer_set_gpus(rt580_raytracer* rt, int n_gpus);
  * NULL or "" = off.  The loaded meshes are bit-identical with or without it (cpp:568-643 stays the source of truth). */
 int  rt580_raytracer_set_mesh_cache(rt580_raytracer* rt, const char* dir);
 int  rt580_raytracer_mesh_cache_hits(rt580_raytracer* rt);
+/* FlattenScene on the device: Render uploads meshes + one model matrix per shape (rt580_upload_instanced_scene) */
+int  rt580_raytracer_set_device_flatten(rt580_raytracer* rt, int on);
+int  rt580_raytracer_instanced_scene(rt580_raytracer* rt, rt580_instanced_scene* out);   /* borrows the object's buffers */
 int  rt580_raytracer_load_scene_json(rt580_raytracer* rt, const char* scene);/* h:572 LoadSceneJSON   */
 int  rt580_raytracer_render(rt580_raytracer* rt, const char* output_ppm);    /* h:586 Render          */
 int  rt580_raytracer_flush_ppm(rt580_raytracer* rt, const char* output_ppm); /* h:573                 */

@@ -935,3 +935,30 @@ def test_class_on_several_contexts_of_one_gpu_equals_one_context(pkg):
         band, _ = c.render_finish(params[r], bases[r])
         frame[r::world] = band
     assert (frame == whole).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["simpleScene.json", "scene.json", "mix_small.json", "simpleSphereScene.json"])
+def test_device_flatten_equals_host_flatten(pkg, scene):
+    """FlattenScene's TransformPoint calls (cpp:353-355, h:234-248) on the device.  The arrays the device produces
+    from meshes + model matrices are the host's byte for byte (rotations, scales and translations in the transforms), and a frame
+    rendered from them is the same frame."""
+    W, H, spp, depth = 64, 40, 2, 3
+    rt = make_rt(pkg, scene, W, H, spp, depth)
+    host = pkg.flat_scene_arrays(rt.flat_scene())
+    inst = rt.instanced_scene()
+    ctx = pkg.Context(0)
+    dev = ctx.flatten_instanced(inst, int(rt.flat_scene().n_tris), int(rt.flat_scene().n_spheres))
+    for k, v in dev.items():
+        assert v.tobytes() == np.ascontiguousarray(host[k]).tobytes(), k
+    ctx.upload_instanced_scene(inst)
+    fb_dev, st_dev = ctx.render(rt.render_params())
+    ctx.upload_scene(rt.flat_scene())
+    fb_host, st_host = ctx.render(rt.render_params())
+    assert (fb_dev == fb_host).all() and st_dev.rays == st_host.rays
+    ctx.close()
+    # and through the class
+    rt2 = make_rt(pkg, scene, W, H, spp, depth)
+    rt2.SetDeviceFlatten(True)
+    assert rt2.Render("") == pkg.RT_SUCCESS
+    assert (rt2.frame_buffer() == fb_host).all()
