@@ -542,19 +542,22 @@ __device__ __forceinline__ void fg_exact(const DeviceScene& sc, unsigned long lo
 
 // One warp takes FG_G consecutive rays of the sorted order; the rays of one cell among them form a segment that runs over the
 // cell's list 32 entries at a time (lane = entry: its record is gathered once and serves every ray of the segment).
-#define FG_G 32     // rays per warp: the rays of one cell among them share the gathers of that cell's list
+// rays per warp (template G): the rays of one cell among them share the gathers of that cell's list - 32 where cells hold many
+// rays (the AO flush of a whole 4K frame: ~12 per cell); 8 where they hold one or two (closest-hit flushes, a rank's share of a
+// frame), so that four times as many warps wait on their gathers side by side
 #define FG_WARPS 4
 #define FG_U4 1      // list entries per lane and iteration (4 was measured slower: the rays from outside the scene stop after a few entries)
+template <int G>
 struct FgWarp {
-    float4 O[FG_G], D[FG_G];
-    unsigned long long key[FG_G];
-    int found[FG_G];
-    unsigned cell[FG_G], e[FG_G];
+    float4 O[G], D[G];
+    unsigned long long key[G];
+    int found[G];
+    unsigned cell[G], e[G];
     unsigned long long q[64];
 };
 
-template <bool ANY>
-__device__ __forceinline__ void fg_flush(const DeviceScene& sc, FgWarp& sh, unsigned& q_len, bool all_of_it)
+template <bool ANY, int G>
+__device__ __forceinline__ void fg_flush(const DeviceScene& sc, FgWarp<G>& sh, unsigned& q_len, bool all_of_it)
 {
     const int lane = threadIdx.x & 31;
     while (q_len >= 32u || (all_of_it && q_len > 0u)) {
@@ -570,15 +573,15 @@ __device__ __forceinline__ void fg_flush(const DeviceScene& sc, FgWarp& sh, unsi
 }
 
 // rays [j0, j1) of the warp against one list
-template <bool ANY>
-__device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, int j0, int j1, const uint32_t* __restrict__ list,
+template <bool ANY, int G>
+__device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp<G>& sh, int j0, int j1, const uint32_t* __restrict__ list,
                                            unsigned long long len, bool has_k6, float dno)
 {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned live = (j1 >= 32 ? 0xffffffffu : ((1u << j1) - 1u)) & ~((1u << j0) - 1u);
     // any hit: the rays that are answered leave (found[] changes in fg_flush only)
-    if (ANY) { live &= ~__ballot_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&sh.found[lane]) != 0); if (!live) return; }
+    if (ANY) { live &= ~__ballot_sync(0xffffffffu, (lane < G && *reinterpret_cast<volatile int*>(&sh.found[lane < G ? lane : 0]) != 0)); if (!live) return; }
     unsigned q_len = 0;
     for (unsigned long long base = 0; base < len; base += 32 * FG_U4) {
         // this lane's FG_U4 entries (independent gathers in flight together: the loop is bound by their latency):
@@ -619,31 +622,31 @@ __device__ __forceinline__ void fg_segment(const DeviceScene& sc, FgWarp& sh, in
                 if (pass) sh.q[q_len + (unsigned)__popc(mask & lt_mask)] = ((unsigned long long)j << 32) | id;
                 q_len += (unsigned)__popc(mask);
                 if (q_len >= 32u) {
-                    fg_flush<ANY>(sc, sh, q_len, false);
-                    if (ANY) { live &= ~__ballot_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&sh.found[lane]) != 0); rest &= live; }
+                    fg_flush<ANY, G>(sc, sh, q_len, false);
+                    if (ANY) { live &= ~__ballot_sync(0xffffffffu, (lane < G && *reinterpret_cast<volatile int*>(&sh.found[lane < G ? lane : 0]) != 0)); rest &= live; }
                 }
             }
             if (ANY && !live) break;
         }
         if (ANY && !live) break;
     }
-    fg_flush<ANY>(sc, sh, q_len, true);
+    fg_flush<ANY, G>(sc, sh, q_len, true);
 }
 
-template <bool ANY>
+template <bool ANY, int G>
 __global__ void __launch_bounds__(32 * FG_WARPS)
 k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ order,
           const unsigned int* __restrict__ cellof, const unsigned int* __restrict__ total_ptr, unsigned n_direct,
           unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count)
 {
-    __shared__ FgWarp shw[FG_WARPS];
-    FgWarp& sh = shw[threadIdx.x >> 5];
+    __shared__ FgWarp<G> shw[FG_WARPS];
+    FgWarp<G>& sh = shw[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     // order == nullptr: a small flush, not worth the sort by cell - the rays in queue order (n_direct of them)
     const unsigned total = order ? __ldg(total_ptr) : n_direct;
-    const unsigned long long pos0 = ((unsigned long long)blockIdx.x * FG_WARPS + (threadIdx.x >> 5)) * FG_G;
+    const unsigned long long pos0 = ((unsigned long long)blockIdx.x * FG_WARPS + (threadIdx.x >> 5)) * G;
     if (pos0 >= total) return;
-    const int nb = (int)min((unsigned long long)FG_G, total - pos0);
+    const int nb = (int)min((unsigned long long)G, total - pos0);
     bool my_lin = false;
     if (lane < nb) {
         const unsigned e = order ? order[pos0 + lane] : (unsigned)(pos0 + lane);
@@ -665,11 +668,11 @@ k_fg_scan(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict_
         while (j1 < nb && sh.cell[j1] == cell) j1++;
         if (cell != 0xffffffffu) {                       // (unsorted flush: rays without a cell - k_fg_bin has routed them elsewhere)
             const unsigned long long b = __ldg(sc.fg_start + cell), en = __ldg(sc.fg_start + cell + 1);
-            fg_segment<ANY>(sc, sh, j0, j1, sc.fg_entries + b, en - b, true, dno);
+            fg_segment<ANY, G>(sc, sh, j0, j1, sc.fg_entries + b, en - b, true, dno);
         } else for (int j = j0; j < j1; j++) sh.found[j] = -1;
         j0 = j1;
     }
-    if (sc.fg_n_wide > 0) fg_segment<ANY>(sc, sh, 0, nb, sc.fg_wide, (unsigned long long)sc.fg_n_wide, false, dno);
+    if (sc.fg_n_wide > 0) fg_segment<ANY, G>(sc, sh, 0, nb, sc.fg_wide, (unsigned long long)sc.fg_n_wide, false, dno);
     __syncwarp();
     if (lane < nb) {
         const unsigned e = sh.e[lane];
@@ -3263,12 +3266,15 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
             k_fg_order<<<nblk(n, 256), 256, 0, st>>>(n, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_start.p, c->fgq_order.p);
         }
         const unsigned int* order = sorted ? c->fgq_order.p : nullptr;
+        const bool dense = sorted && (unsigned long long)n >= 4ull * n_cells;      // rays per cell of the direction grid
         if (any) {
-            k_fg_scan<true><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
+            if (dense) k_fg_scan<true, 32><<<nblk(n, 32 * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
+            else k_fg_scan<true, 8><<<nblk(n, 8 * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
             k_fg_lin_first<<<nblk(n, 128), 128, 0, st>>>(c->sc, rays, res, c->fgq_first.p, first_count, c->fgq_cellof.p, c->fgq_lin.p, lin_count);
             c->launches++;
         }
-        else k_fg_scan<false><<<nblk(n, FG_G * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
+        else if (dense) k_fg_scan<false, 32><<<nblk(n, 32 * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
+        else k_fg_scan<false, 8><<<nblk(n, 8 * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
         c->launches += 3;
         CU(cudaMemcpyAsync(&n_lin, lin_count, sizeof n_lin, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
