@@ -71,7 +71,7 @@ def main():
     }
     res["counters"] = {k: v for k, v in res["counters"].items() if v}      # (metrics this ncu version does not have read as 0)
     with open(out, "w") as f:
-        json.dump(res, f, indent=1)
+        f.write(json.dumps(res) + "\n")          # one line, like the bench lines next to it
     print(json.dumps({k: v for k, v in res.items() if k != "per_launch"}, indent=1))
 
 
