@@ -491,28 +491,32 @@ k_fg_bin(const SlowRay* __restrict__ rays, unsigned n, int K, unsigned int* __re
          unsigned int* __restrict__ first_idx, unsigned int* __restrict__ first_count)
 {
     const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const bool lin = (__ldg(&rays[e].c).x & 1) != 0;
-    // a ray from outside the scene: closest hit -> its own kernels (k_fg_arc walks its cells in order of t); any hit (bin_lin) ->
-    // first the cell of its direction (k_fg_lin_first: out there, far along the ray, almost every entry of that cell accepts it)
-    if (lin && !bin_lin) { lin_idx[atomicAdd(lin_count, 1u)] = e; cellof[e] = 0xffffffffu; return; }
-    const float4 d = __ldg(&rays[e].d);
-    const int cell = fg_cell_of_dir(mk(d.x, d.y, d.z), K);
-    if (cell < 0) {                                              // zero / NaN direction: no triangle accepts it (cpp:371)
-        if (lin) lin_idx[atomicAdd(lin_count, 1u)] = e;          // (spheres may: k_lin_near)
-        cellof[e] = 0xffffffffu;
-        return;
+    const bool valid = e < n;
+    // where the ray goes: 0 nowhere (no cell: no triangle accepts a zero / NaN direction, cpp:371), 1 the sorted order of
+    // k_fg_scan, 2 the list of rays from outside for the arc kernels, 3 any-hit from outside, unbounded: k_fg_lin_first
+    int to = 0, cell = -1;
+    if (valid) {
+        const bool lin = (__ldg(&rays[e].c).x & 1) != 0;
+        // a ray from outside the scene: closest hit -> its own kernels (k_fg_arc* walk its cells in order of t); any hit (bin_lin)
+        // -> first the cell of its direction (k_fg_lin_first: out there, far along the ray, almost every entry of that cell accepts
+        // it), unless it is bounded (the shadow ray of a point light ends long before it is "far along d")
+        if (lin && !bin_lin) to = 2;
+        else {
+            const float4 d = __ldg(&rays[e].d);
+            cell = fg_cell_of_dir(mk(d.x, d.y, d.z), K);
+            if (cell < 0) to = lin ? 2 : 0;                      // (spheres may still accept it: k_lin_near)
+            else if (!lin) to = 1;
+            else to = (__ldg(&rays[e].o).w < 3.0e38f) ? 2 : 3;
+        }
     }
-    if (lin) {                                                   // not part of the sorted order: k_fg_scan never sees it
-        // a bounded ray (the shadow ray of a point light) ends long before it is "far along d": straight to the arc kernels
-        if (__ldg(&rays[e].o).w < 3.0e38f) { lin_idx[atomicAdd(lin_count, 1u)] = e; cellof[e] = 0xffffffffu; if (hist) rank[e] = 0xffffffffu; return; }
-        first_idx[atomicAdd(first_count, 1u)] = e;
-        cellof[e] = (unsigned)cell;
-        if (hist) rank[e] = 0xffffffffu;
-        return;
-    }
-    if (hist) rank[e] = atomicAdd(hist + cell, 1u);
-    cellof[e] = (unsigned)cell;
+    // (one atomic per warp and list: 86 M rays of a frame go to the same two counters)
+    const unsigned s2 = warp_alloc(lin_count, to == 2);
+    const unsigned s3 = warp_alloc(first_count, to == 3);
+    if (!valid) return;
+    if (to == 2) lin_idx[s2] = e;
+    if (to == 3) first_idx[s3] = e;
+    cellof[e] = (to == 1 || to == 3) ? (unsigned)cell : 0xffffffffu;
+    if (hist) rank[e] = to == 1 ? atomicAdd(hist + cell, 1u) : 0xffffffffu;
 }
 __global__ void __launch_bounds__(256)
 k_fg_order(unsigned n, const unsigned int* __restrict__ cellof, const unsigned int* __restrict__ rank,
