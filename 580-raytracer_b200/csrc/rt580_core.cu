@@ -147,6 +147,7 @@ struct rt580_context {
     // far-field direction grid (fargrid.cuh): lists of the scene, and the per-flush sort of the deferred rays by direction cell
     DBuf<unsigned int> fg_counts; DBuf<unsigned long long> fg_start, fg_bsum; DBuf<uint32_t> fg_entries; DBuf<unsigned int> fg_cell_tmin;
     FgBuildInput fg_in{}; bool fg_pending = false;   // the lists are built when a frame first needs them (far_grid_ensure)
+    unsigned arc_max_cells = 4096u;           // (ARC_MAX_CELLS) RT580_ARC_MAX_CELLS (tests: a small value forces the k_far_linear overflow path)
     int fg_K_env = -1;                   // RT580_FAR_GRID: -1 default (by triangle count), 0 off, else cells per cube-face edge
     unsigned long long fg_n_entries = 0; float fg_build_ms = 0.f;
     DBuf<unsigned int> fgq_hist, fgq_start, fgq_cellof, fgq_rank, fgq_order, fgq_lin, fgq_first;
@@ -1012,7 +1013,8 @@ __global__ void __launch_bounds__(32 * ARC_WARPS)
 k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__ res, const unsigned int* __restrict__ lin_idx,
          const unsigned int* __restrict__ rest_idx, unsigned n_rest, unsigned int* __restrict__ stat, const ArcPre* __restrict__ pre,
          ArcItem* __restrict__ items, unsigned int* __restrict__ n_items,
-         unsigned item_cap, unsigned int* __restrict__ heavy_idx, unsigned int* __restrict__ heavy_count)     // heavy_*: the rays given up (-> k_far_linear)
+         unsigned item_cap, unsigned int* __restrict__ heavy_idx, unsigned int* __restrict__ heavy_count,     // heavy_*: the rays given up (-> k_far_linear)
+         unsigned max_cells)
 {
     __shared__ unsigned s_q[ARC_WARPS][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1072,7 +1074,7 @@ k_fg_arc(DeviceScene sc, const SlowRay* __restrict__ rays, SlowRes* __restrict__
             }
             n_emitted += (unsigned)__popc(m);
             // an arc that runs on and on (or a full item list): the block-wide scan of every record (k_far_linear) is complete
-            if (base + (unsigned)__popc(m) > item_cap || (heavy_idx && n_emitted >= ARC_MAX_CELLS)) { given_up = true; break; }
+            if (base + (unsigned)__popc(m) > item_cap || (heavy_idx && n_emitted >= max_cells)) { given_up = true; break; }
         }
         n_it = W.n_it;
         if (given_up && lane == 0) heavy_idx[atomicAdd(heavy_count, 1u)] = e;
@@ -2590,6 +2592,7 @@ extern "C" int rt580_create(int device, rt580_context** out)
     if (const char* e = getenv("RT580_CH_BLOCKS_PER_SM")) c->ch_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ch_blocks_per_sm;
     if (const char* e = getenv("RT580_ONE_THREAD_PER_RAY")) c->one_thread_per_ray = atoi(e) != 0;
     if (const char* e = getenv("RT580_FAR_GRID")) c->fg_K_env = atoi(e) >= 0 ? atoi(e) : -1;
+    if (const char* e = getenv("RT580_ARC_MAX_CELLS")) { if (atoi(e) > 0) c->arc_max_cells = (unsigned)atoi(e); }
     *out = c;
     return RT580_SUCCESS;
 }
@@ -3318,9 +3321,9 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
         const unsigned n_rest = hc2[3];
         if (n_rest) {
             if (any) k_fg_arc<true><<<nblk(n_rest, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, rest_idx, n_rest, stat, pre,
-                                                                              c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
+                                                                              c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2, c->arc_max_cells);
             else k_fg_arc<false><<<nblk(n_rest, ARC_WARPS), 32 * ARC_WARPS, 0, st>>>(c->sc, rays, res, lin_idx, rest_idx, n_rest, stat, pre,
-                                                                               c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2);
+                                                                               c->arc_items.p, n_items, item_cap, farheavy_idx, heavy_count + 2, c->arc_max_cells);
             c->launches++;
             CU(cudaMemcpyAsync(hc2 + 1, heavy_count + 1, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));

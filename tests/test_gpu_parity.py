@@ -564,13 +564,15 @@ def _rays_from_outside(rng, n, extent):
     return O, dd.astype(np.float32), cls, R
 
 
-@pytest.mark.parametrize("n_teapots,grid", [(40, ""), (200, ""), (40, "32")])
+@pytest.mark.parametrize("n_teapots,grid", [(40, ""), (200, ""), (40, "32"), (40, "overflow")])
 def test_far_field_machinery_equals_the_linear_loop(pkg, tmp_path, monkeypatch, n_teapots, grid):
     """The rays the tree cannot answer alone - the ones that leave the scene (far-field direction grid, fargrid.cuh) and the ones
     that start 10^4..10^8 units outside it (arc walk over the grid, tree with inflated boxes) - against the GPU's own linear
     loop over every primitive (the reference's loop, cpp:476-521): same primitive, same t bits, same any-hit answer, on
     300,000 synthetic rays of five kinds over an open scene of 41K / 205K triangles."""
-    if grid:
+    if grid == "overflow":
+        monkeypatch.setenv("RT580_ARC_MAX_CELLS", "8")       # long arcs are given up early: the filtered scan of every record (k_far_linear)
+    elif grid:
         monkeypatch.setenv("RT580_FAR_GRID", grid)           # a coarse grid: long lists, many rays per cell
     rt = _synthetic_scene(pkg, str(tmp_path), "far", n_teapots=n_teapots, n_spheres=max(4, n_teapots // 2), seed=5)
     ctx = pkg.Context(0)
