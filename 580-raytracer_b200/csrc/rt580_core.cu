@@ -191,6 +191,9 @@ struct rt580_context {
     int smap_res = SMAP_RES_DEFAULT;        // RT580_SMAP_RES
     unsigned slow_any_cap = SLOW_ANY_CAP;   // RT580_SLOW_ANY_CAP: shrink it to exercise the overflow -> repeat path
     int ah_steps = AH_STEPS, ah_min_search = AH_MIN_SEARCH, ah_blocks_per_sm = 12;  // k_anyhit tuning (env RT580_AH_*)
+    // the same for a scene that leaks (open: half of the any-hit rays walk the whole tree and leave): measured best on c4_open,
+    // 37.3 against 39.9 ms for the AO rays; the closed room prefers the values above (11.8 against 12.8 ms for its shadow rays)
+    int ah_steps_leaky = 24, ah_min_search_leaky = 6;
     std::vector<size_t> level_off; // node index where each level starts (+ end)
     std::vector<uint64_t> level_rays;
     bool frame_begun = false;
@@ -2583,8 +2586,8 @@ extern "C" int rt580_create(int device, rt580_context** out)
     }
     if (getenv("RT580_NO_OVERLAP")) c->overlap = false;
     for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
-    if (const char* e = getenv("RT580_AH_STEPS")) c->ah_steps = atoi(e) > 0 ? atoi(e) : c->ah_steps;
-    if (const char* e = getenv("RT580_AH_MIN_SEARCH")) c->ah_min_search = atoi(e) > 0 ? atoi(e) : c->ah_min_search;
+    if (const char* e = getenv("RT580_AH_STEPS")) { if (atoi(e) > 0) c->ah_steps = c->ah_steps_leaky = atoi(e); }
+    if (const char* e = getenv("RT580_AH_MIN_SEARCH")) { if (atoi(e) > 0) c->ah_min_search = c->ah_min_search_leaky = atoi(e); }
     if (const char* e = getenv("RT580_AH_BLOCKS_PER_SM")) c->ah_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ah_blocks_per_sm;
     if (const char* e = getenv("RT580_SMAP_RES")) c->smap_res = (atoi(e) >= 16 && atoi(e) <= 4096) ? atoi(e) : c->smap_res;
     if (const char* e = getenv("RT580_SLOW_ANY_CAP")) c->slow_any_cap = atoi(e) > 0 ? (unsigned)atoi(e) : c->slow_any_cap;
@@ -3427,14 +3430,15 @@ static int anyhit_queue_pass(rt580_context* c, cudaStream_t st, int lane, unsign
         if (tm_end(c, st)) return RT580_FAILURE;
         c->launches++;
         if (tm_begin(c, ao ? RT580_CLASS_AO_TREE : RT580_CLASS_SHADOW_TREE, st)) return RT580_FAILURE;
+        const int ah_steps = leaky ? c->ah_steps_leaky : c->ah_steps, ah_min = leaky ? c->ah_min_search_leaky : c->ah_min_search;
         if (c->count_visits)
             k_anyhit<true><<<blocks, 128, 0, st>>>(c->sc, rays.p, ctr, ctr + 1, hits, slowq_any(c), id_offset,
                                                    pending_mark, reinterpret_cast<unsigned long long*>(c->counters.p + (ao ? 8 : 10)),
-                                                   c->ah_steps, c->ah_min_search, c->ah_batch_div, c->visit_counts.p);
+                                                   ah_steps, ah_min, c->ah_batch_div, c->visit_counts.p);
         else
             k_anyhit<false><<<blocks, 128, 0, st>>>(c->sc, rays.p, ctr, ctr + 1, hits, slowq_any(c), id_offset,
                                                     pending_mark, reinterpret_cast<unsigned long long*>(c->counters.p + (ao ? 8 : 10)),
-                                                    c->ah_steps, c->ah_min_search, c->ah_batch_div, nullptr);
+                                                    ah_steps, ah_min, c->ah_batch_div, nullptr);
         if (tm_end(c, st)) return RT580_FAILURE;
         c->launches++;
         const unsigned long long rest = total - first - n;
