@@ -147,6 +147,7 @@ struct rt580_context {
     // far-field direction grid (fargrid.cuh): lists of the scene, and the per-flush sort of the deferred rays by direction cell
     DBuf<unsigned int> fg_counts; DBuf<unsigned long long> fg_start, fg_bsum; DBuf<uint32_t> fg_entries; DBuf<unsigned int> fg_cell_tmin;
     FgBuildInput fg_in{}; bool fg_pending = false;   // the lists are built when a frame first needs them (far_grid_ensure)
+    int fg_dense_rays = 2;                    // RT580_FG_DENSE: rays per cell from which k_fg_scan takes 32 rays per warp
     unsigned arc_max_cells = 4096u;           // (ARC_MAX_CELLS) RT580_ARC_MAX_CELLS (tests: a small value forces the k_far_linear overflow path)
     int fg_K_env = -1;                   // RT580_FAR_GRID: -1 default (by triangle count), 0 off, else cells per cube-face edge
     unsigned long long fg_n_entries = 0; float fg_build_ms = 0.f;
@@ -2595,6 +2596,7 @@ extern "C" int rt580_create(int device, rt580_context** out)
     if (const char* e = getenv("RT580_CH_BLOCKS_PER_SM")) c->ch_blocks_per_sm = atoi(e) > 0 ? atoi(e) : c->ch_blocks_per_sm;
     if (const char* e = getenv("RT580_ONE_THREAD_PER_RAY")) c->one_thread_per_ray = atoi(e) != 0;
     if (const char* e = getenv("RT580_FAR_GRID")) c->fg_K_env = atoi(e) >= 0 ? atoi(e) : -1;
+    if (const char* e = getenv("RT580_FG_DENSE")) { if (atoi(e) > 0) c->fg_dense_rays = atoi(e); }
     if (const char* e = getenv("RT580_ARC_MAX_CELLS")) { if (atoi(e) > 0) c->arc_max_cells = (unsigned)atoi(e); }
     *out = c;
     return RT580_SUCCESS;
@@ -3276,7 +3278,7 @@ static int slow_launch(rt580_context* c, bool any, const SlowRay* rays, SlowRes*
             k_fg_order<<<nblk(n, 256), 256, 0, st>>>(n, c->fgq_cellof.p, c->fgq_rank.p, c->fgq_start.p, c->fgq_order.p);
         }
         const unsigned int* order = sorted ? c->fgq_order.p : nullptr;
-        const bool dense = sorted && (unsigned long long)n >= 4ull * n_cells;      // rays per cell of the direction grid
+        const bool dense = sorted && (unsigned long long)n >= (unsigned long long)c->fg_dense_rays * n_cells;      // rays per cell of the direction grid
         if (any) {
             if (dense) k_fg_scan<true, 32><<<nblk(n, 32 * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
             else k_fg_scan<true, 8><<<nblk(n, 8 * FG_WARPS), 32 * FG_WARPS, 0, st>>>(c->sc, rays, res, order, c->fgq_cellof.p, c->fgq_start.p + n_cells, n, c->fgq_lin.p, lin_count);
