@@ -484,12 +484,14 @@ k_slow(DeviceScene sc, const SlowRay* __restrict__ rays, unsigned n, SlowRes* __
 }
 
 // ---- deferred far-scan rays through the far-field direction grid (fargrid.cuh) ----------------------------
-// The deferred rays of a flush are sorted by the cell of their direction (counting sort: k_fg_bin, scan, k_fg_order);
-// a block then takes FG_RPB consecutive rays.  Rays of one cell form a segment: its list is staged through shared
-// memory in tiles (record = (N, thr) + (D, T), gathered by the list's primitive indices), warp w runs rays
-// w, w + 8, ... of the segment over the tile (lane = record), the survivors of the two-stage filter are queued
-// per warp and get the exact test 32 at a time, as in k_slow.  The rays that start outside the scene ("linear",
-// children of far-field hits) are left to k_slow through an index list.
+// A flush of deferred rays (slow_launch) goes three ways:
+//   rays that start in the scene            sorted by the cell of their direction (counting sort: k_fg_bin, scan, k_fg_order),
+//                                           then k_fg_scan: a warp takes 32 (or 8) consecutive rays of that order, the rays of
+//                                           one cell share the gathers of its list (lane = entry), a two-stage filter, the
+//                                           survivors queued per warp for the reference's exact test, 32 at a time;
+//   any-hit rays from outside, unbounded    k_fg_lin_first: the first acceptor in the cell of their direction, one thread per ray;
+//   every other ray from outside            the arc kernels: k_fg_arc_pre -> k_fg_arc_first -> k_fg_arc -> k_fg_arc_items,
+//                                           and k_lin_near for the part of the ray that comes back to the scene.
 __global__ void __launch_bounds__(256)
 k_fg_bin(const SlowRay* __restrict__ rays, unsigned n, int K, unsigned int* __restrict__ hist, unsigned int* __restrict__ cellof,
          unsigned int* __restrict__ rank, unsigned int* __restrict__ lin_idx, unsigned int* __restrict__ lin_count, int bin_lin,
